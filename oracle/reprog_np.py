@@ -1,0 +1,123 @@
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) for HOP's audio->text reprogramming cross-attention.
+
+numpy float64 restatement (forward + hand-derived backward) of
+``ReprogrammingLayer`` in the reference's ``model/HOP.py``:
+  __init__ parameter shapes   model/HOP.py:256-268
+  forward                     model/HOP.py:271-285
+  reprogramming               model/HOP.py:289-299
+Written from SURVEY.md Appendix A, not from the reference's code.  Product code
+must never import this; tests / smoke / bench's CPU legs use it as the checker.
+
+Parity status: no golden vectors exist in the reference; pinned against the
+reference module executed here (tests/golden/make_golden.py -> reprog_*.npz).
+
+Dropout: torch's RNG stream cannot be reproduced by a kernel, so the build
+defines its own counter-based mask (``dropout_keep``) that the CUDA kernel and
+this oracle share bit-for-bit; parity with the *reference* is checked at p=0.
+"""
+import numpy as np
+
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def _lowbias32(x):
+    """32-bit integer finaliser (xorshift-multiply), vectorised on uint64 holders."""
+    x = x & _M32
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x7FEB352D)) & _M32
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(0x846CA68B)) & _M32
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def dropout_keep(seed, idx, p):
+    """Keep-mask for flat element indices ``idx`` (uint64) under 64-bit ``seed``.
+
+    u = top 24 bits of h(idx_lo + h(idx_hi ^ seed_hi) ^ seed_lo); keep iff u >= p * 2^24 (integer compare).
+    The CUDA kernel (csrc/xattn.cu: keep_mask()) evaluates exactly this.
+    """
+    idx = np.asarray(idx, dtype=np.uint64)
+    seed = np.uint64(seed)
+    s_lo, s_hi = seed & _M32, seed >> np.uint64(32)
+    i_lo, i_hi = idx & _M32, idx >> np.uint64(32)
+    h = _lowbias32(((i_lo + _lowbias32(i_hi ^ s_hi)) & _M32) ^ s_lo)
+    thr = np.uint64(int(round(float(p) * (1 << 24))))
+    return (h >> np.uint64(8)) >= thr
+
+
+def forward(P, target, source, value, n_heads, p_drop=0.0, seed=0, keep=False):
+    """ReprogrammingLayer.forward.  target (B,L,dm); source,value (S,dllm).  Returns (B,L,dllm)."""
+    P = {k: np.asarray(v, dtype=np.float64) for k, v in P.items()}
+    x = np.asarray(target, np.float64)
+    src = np.asarray(source, np.float64)
+    val = np.asarray(value, np.float64)
+    B, L, _ = x.shape
+    S = src.shape[0]
+    H = n_heads
+    Q = (x @ P['query_projection.weight'].T + P['query_projection.bias']).reshape(B, L, H, -1)
+    K = (src @ P['key_projection.weight'].T + P['key_projection.bias']).reshape(S, H, -1)
+    V = (val @ P['value_projection.weight'].T + P['value_projection.bias']).reshape(S, H, -1)
+    E = Q.shape[-1]
+    scale = 1.0 / np.sqrt(E)
+    sc = np.einsum('blhe,she->bhls', Q, K) * scale
+    sc = sc - sc.max(axis=-1, keepdims=True)
+    pr = np.exp(sc)
+    pr /= pr.sum(axis=-1, keepdims=True)
+    if p_drop > 0:
+        idx = np.arange(B * H * L * S, dtype=np.uint64).reshape(B, H, L, S)
+        mask = dropout_keep(seed, idx, p_drop) / (1.0 - p_drop)
+    else:
+        mask = np.ones_like(pr)
+    pd = pr * mask
+    O = np.einsum('bhls,she->blhe', pd, V).reshape(B, L, H * E)
+    R = np.maximum(O, 0.0)
+    Y = R @ P['out_projection.weight'].T + P['out_projection.bias']
+    cache = dict(x=x, src=src, val=val, Q=Q, K=K, V=V, pr=pr, mask=mask, O=O, R=R, scale=scale) if keep else None
+    return Y, cache
+
+
+def backward(P, cache, dY, n_heads):
+    """Returns (dtarget, dsource, dvalue, grads-by-state_dict-name)."""
+    P = {k: np.asarray(v, dtype=np.float64) for k, v in P.items()}
+    c = cache
+    dY = np.asarray(dY, np.float64)
+    B, L, _ = dY.shape
+    H = n_heads
+    G = {}
+    G['out_projection.weight'] = np.einsum('blo,bli->oi', dY, c['R'])
+    G['out_projection.bias'] = dY.sum(axis=(0, 1))
+    dR = dY @ P['out_projection.weight']
+    dO = (dR * (c['O'] > 0)).reshape(B, L, H, -1)
+    dpd = np.einsum('blhe,she->bhls', dO, c['V'])
+    dV = np.einsum('bhls,blhe->she', c['pr'] * c['mask'], dO)
+    dpr = dpd * c['mask']
+    dsc = c['pr'] * (dpr - (dpr * c['pr']).sum(axis=-1, keepdims=True))
+    dQ = np.einsum('bhls,she->blhe', dsc, c['K']) * c['scale']
+    dK = np.einsum('bhls,blhe->she', dsc, c['Q']) * c['scale']
+    S = dK.shape[0]
+    dQf, dKf, dVf = dQ.reshape(B * L, -1), dK.reshape(S, -1), dV.reshape(S, -1)
+    xf = c['x'].reshape(B * L, -1)
+    G['query_projection.weight'] = dQf.T @ xf
+    G['query_projection.bias'] = dQf.sum(0)
+    G['key_projection.weight'] = dKf.T @ c['src']
+    G['key_projection.bias'] = dKf.sum(0)
+    G['value_projection.weight'] = dVf.T @ c['val']
+    G['value_projection.bias'] = dVf.sum(0)
+    dx = (dQf @ P['query_projection.weight']).reshape(c['x'].shape)
+    dsrc = dKf @ P['key_projection.weight']
+    dval = dVf @ P['value_projection.weight']
+    return dx, dsrc, dval, G
+
+
+def init_params(rng, d_model=128, n_heads=8, d_keys=128, d_llm=768):
+    def lin(o, i):
+        b = 1.0 / np.sqrt(i)
+        return rng.uniform(-b, b, size=(o, i)), rng.uniform(-b, b, size=(o,))
+    P = {}
+    for name, (o, i) in dict(query_projection=(d_keys * n_heads, d_model),
+                             key_projection=(d_keys * n_heads, d_llm),
+                             value_projection=(d_keys * n_heads, d_llm),
+                             out_projection=(d_llm, d_keys * n_heads)).items():
+        P[name + '.weight'], P[name + '.bias'] = lin(o, i)
+    return P
