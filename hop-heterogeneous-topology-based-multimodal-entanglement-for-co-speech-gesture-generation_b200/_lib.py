@@ -1,0 +1,106 @@
+"""ctypes binding of libhopk.so -- the only door between the Python mirror of the reference's
+module interface and the sm_100a kernels (C ABI declared in include/hopk.h).
+
+There is deliberately no fallback: if the shared library is missing or a kernel reports an error
+the call raises, so a silent eager/CPU path can never stand in for the CUDA one.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libhopk.so')
+MAX_LAYERS = 16
+
+_vp = C.c_void_p
+_LAYER_ARR = _vp * MAX_LAYERS
+
+
+class GwnetShape(C.Structure):
+    _fields_ = [('B', C.c_int), ('V', C.c_int), ('T', C.c_int), ('in_dim', C.c_int), ('out_dim', C.c_int),
+                ('C', C.c_int), ('S', C.c_int), ('E', C.c_int), ('L', C.c_int), ('dil', C.c_int * MAX_LAYERS),
+                ('rank', C.c_int), ('training', C.c_int), ('dtype', C.c_int)]
+
+
+class GwnetParams(C.Structure):
+    _fields_ = [('nodevec1', _vp), ('nodevec2', _vp), ('start_w', _vp), ('start_b', _vp),
+                ('filter_w', _LAYER_ARR), ('filter_b', _LAYER_ARR), ('gate_w', _LAYER_ARR), ('gate_b', _LAYER_ARR),
+                ('skip_w', _LAYER_ARR), ('skip_b', _LAYER_ARR), ('mlp_w', _LAYER_ARR), ('mlp_b', _LAYER_ARR),
+                ('bn_w', _LAYER_ARR), ('bn_b', _LAYER_ARR), ('bn_mean', _LAYER_ARR), ('bn_var', _LAYER_ARR),
+                ('bn_nbt', _LAYER_ARR), ('end1_w', _vp), ('end1_b', _vp), ('end2_w', _vp), ('end2_b', _vp)]
+
+
+class GwnetGrads(C.Structure):
+    _fields_ = [('nodevec1', _vp), ('nodevec2', _vp), ('start_w', _vp), ('start_b', _vp),
+                ('filter_w', _LAYER_ARR), ('filter_b', _LAYER_ARR), ('gate_w', _LAYER_ARR), ('gate_b', _LAYER_ARR),
+                ('skip_w', _LAYER_ARR), ('skip_b', _LAYER_ARR), ('mlp_w', _LAYER_ARR), ('mlp_b', _LAYER_ARR),
+                ('bn_w', _LAYER_ARR), ('bn_b', _LAYER_ARR),
+                ('end1_w', _vp), ('end1_b', _vp), ('end2_w', _vp), ('end2_b', _vp)]
+
+
+# every symbol include/hopk.h declares, with its ctypes signature (restype int unless noted)
+_i, _f, _u64, _sz = C.c_int, C.c_float, C.c_uint64, C.c_size_t
+_SHP, _PRM, _GRD = C.POINTER(GwnetShape), C.POINTER(GwnetParams), C.POINTER(GwnetGrads)
+_I64x4 = C.c_int64 * 4
+SIGNATURES = {
+    'hopk_last_error': (C.c_char_p, []),
+    'hopk_version': (_i, []),
+    'hopk_gwnet_workspace_bytes': (_sz, [_SHP]),
+    'hopk_gwnet_scratch_bytes': (_sz, [_SHP]),
+    'hopk_gwnet_out_steps': (_i, [_SHP]),
+    'hopk_gwnet_forward': (_i, [_SHP, _PRM, _vp, _I64x4, _vp, _vp, _vp]),
+    'hopk_gwnet_backward': (_i, [_SHP, _PRM, _vp, _I64x4, _vp, _vp, _vp, _GRD, _vp, _vp]),
+    'hopk_nconv_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'hopk_nconv_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'hopk_linear_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'hopk_linear_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'hopk_conv1x1_nchw_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'hopk_conv1x1_nchw_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'hopk_xattn_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp]),
+    'hopk_xattn_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the CDLL; raises if libhopk.so has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python __graft_entry__.py build` '
+                '(nvcc, sm_100a). hop_b200 has no CPU / eager fallback.')
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)          # AttributeError here == header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(lib().hopk_last_error().decode() + f' (code {rc})')
+
+
+def stream_ptr():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL); refuses host tensors so nothing can run on the CPU."""
+    if t is None:
+        return _vp(0)
+    if not t.is_cuda:
+        raise RuntimeError('hop_b200 kernels need CUDA tensors (no CPU fallback)')
+    return _vp(t.data_ptr())
+
+
+def f32c(t):
+    """fp32 + contiguous view/copy of a CUDA tensor."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

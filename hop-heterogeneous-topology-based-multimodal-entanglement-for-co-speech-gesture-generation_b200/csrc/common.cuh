@@ -1,0 +1,29 @@
+// common.cuh -- error plumbing shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace hopk {
+
+char* err_buf();                    // thread-local message buffer (api.cu)
+constexpr int ERR_BUF = 512;
+
+inline int fail(int code, const char* what, const char* detail = "")
+{
+    snprintf(err_buf(), ERR_BUF, "hopk: %s %s", what, detail);
+    return code;
+}
+
+#define HOPK_REQUIRE(cond, msg) \
+    do { if (!(cond)) return hopk::fail(2, "bad argument:", msg " [" #cond "]"); } while (0)
+
+#define HOPK_CUDA(expr) \
+    do { cudaError_t _e = (expr); if (_e != cudaSuccess) return hopk::fail(3, #expr, cudaGetErrorString(_e)); } while (0)
+
+#define HOPK_LAUNCH_CHECK(name) \
+    do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return hopk::fail(4, "launch failed: " name, cudaGetErrorString(_e)); } while (0)
+
+inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace hopk

@@ -1,0 +1,120 @@
+// functors.cuh -- tile loaders and epilogues plugged into hopk::gemm_kernel (see gemm_core.cuh).
+//
+// Activation layout used by every gwnet kernel ("rows" layout): a tensor that the reference keeps
+// as NCHW (B, C, V, T) is stored as rows r = (b*T + t)*V + v with the C channels contiguous.
+// Time-major rows make a dilated tap a constant row offset (d*V) and let HOP.Model's glue hand
+// its (B, 16, V, 173) buffer to the kernels without a permute copy.
+#pragma once
+#include "gemm_core.cuh"
+
+namespace hopk {
+
+// ---------------------------------------------------------------- generic 2-D operand loaders
+// MODE 0: plain, 1: relu(value), 2: value masked by aux > 0
+template <bool KFAST, int MODE>
+struct Ld2D {
+    static constexpr bool kFast = KFAST;
+    const float* p; const float* aux; long ld;
+    __device__ __forceinline__ float operator()(int i, int k) const {
+        long idx = KFAST ? (long)i * ld + k : (long)k * ld + i;
+        float v = __ldg(p + idx);
+        if (MODE == 1) v = fmaxf(v, 0.f);
+        if (MODE == 2) v = (__ldg(aux + idx) > 0.f) ? v : 0.f;
+        return v;
+    }
+};
+
+// same, plus one virtual all-ones *output* column at index `ones_at`
+// (used by weight-gradient GEMMs so the bias gradient falls out as an extra column for free).
+template <bool KFAST>
+struct Ld2DOnes {
+    static constexpr bool kFast = KFAST;
+    const float* p; long ld; int ones_at;
+    __device__ __forceinline__ float operator()(int i, int k) const {
+        if (i == ones_at) return 1.f;
+        long idx = KFAST ? (long)i * ld + k : (long)k * ld + i;
+        return __ldg(p + idx);
+    }
+};
+
+// rows-layout <-> (b,t,v) decomposition with arbitrary element strides (NCHW views etc.)
+struct RowMap {
+    int T, V; long sB, sT, sV, sC;
+    __device__ __forceinline__ long off(int m, int c) const {
+        int v = m % V; int bt = m / V; int t = bt % T; int b = bt / T;
+        return (long)b * sB + (long)t * sT + (long)v * sV + (long)c * sC;
+    }
+};
+template <bool KFAST>
+struct LdStrided {          // A(m, k) = x[rowmap(m), k]
+    static constexpr bool kFast = KFAST;
+    const float* p; RowMap rm;
+    __device__ __forceinline__ float operator()(int m, int k) const { return __ldg(p + rm.off(m, k)); }
+};
+template <bool KFAST>
+struct LdStridedT {         // B'(kout, m) = x[rowmap(m), kout], with a virtual ones column at kout == ones_at
+    static constexpr bool kFast = KFAST;
+    const float* p; RowMap rm; int ones_at;
+    __device__ __forceinline__ float operator()(int kout, int m) const {
+        if (kout == ones_at) return 1.f;
+        return __ldg(p + rm.off(m, kout));
+    }
+};
+
+// ---------------------------------------------------------------- generic epilogues
+// flags: 1 = relu on output, 2 = atomicAdd (split-K partials into a zeroed buffer), 4 = mask by aux>0
+template <int NG>
+struct EpiStore {
+    float* out; long ld; const float* bias; const float* aux; int N; int flags;
+    __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[4 * NG]) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = nb + 64 * g + j;
+                if (n < N) {
+                    float x = v[4 * g + j];
+                    if (bias) x += __ldg(bias + n);
+                    if (flags & 1) x = fmaxf(x, 0.f);
+                    long idx = (long)m * ld + n;
+                    if (flags & 4) x = (__ldg(aux + idx) > 0.f) ? x : 0.f;
+                    if (flags & 2) atomicAdd(out + idx, x); else out[idx] = x;
+                }
+            }
+    }
+    __device__ __forceinline__ void flush(int) {}
+};
+
+template <int NG>
+struct EpiStoreStrided {    // out[rowmap(m), n] = v + bias[n]
+    float* out; RowMap rm; const float* bias; int N;
+    __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[4 * NG]) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = nb + 64 * g + j;
+                if (n < N) out[rm.off(m, n)] = v[4 * g + j] + (bias ? __ldg(bias + n) : 0.f);
+            }
+    }
+    __device__ __forceinline__ void flush(int) {}
+};
+
+// weight-gradient epilogue: rows n of dW (ld = K) plus the bias gradient in virtual column K.
+template <int NG>
+struct EpiWgrad {
+    float* dw; long ld; float* db; int K; int Nrows;
+    __device__ __forceinline__ void operator()(int n, int kb, const float (&v)[4 * NG]) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int k = kb + 64 * g + j;
+                if (k < K) atomicAdd(dw + (long)n * ld + k, v[4 * g + j]);
+                else if (k == K && db) atomicAdd(db + n, v[4 * g + j]);
+            }
+    }
+    __device__ __forceinline__ void flush(int) {}
+};
+
+}  // namespace hopk

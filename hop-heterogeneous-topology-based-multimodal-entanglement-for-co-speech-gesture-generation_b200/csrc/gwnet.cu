@@ -1,0 +1,978 @@
+// gwnet.cu -- Graph-WaveNet block of HOP, forward and backward, fp32-exact path (dtype 0).
+//
+// Replaces the ATen/cuDNN/cuBLAS sequence behind gwnet.forward (reference model/gwnet.py:143-249)
+// and its autograd backward.  Maths: SURVEY.md Appendix A.  All activations live in the "rows"
+// layout (see functors.cuh); per layer i with dilation d, T_out = T_in - d:
+//
+//   forward   gate GEMM      [x_t | x_{t+d}] (K = 2C)  ->  tanh(f) * sigmoid(g)      (BN_{i-1} folded into the load,
+//                                                                                     skip slice written to ycat)
+//             node mix       x1 = A^T y, x2 = (A^2)^T y                               (V x V support in smem)
+//             mlp GEMM       [y | x1 | x2] (K = 3C) + bias + residual x_{t+d} -> u    (+ per-channel sum / sum^2)
+//             bn finalize    mean/rstd, scale/shift for the next load, running stats
+//   head      one concat GEMM over the last T_l steps of all layers' y -> relu -> end1 -> relu -> end2
+//
+//   backward  per layer, reverse: BN-backward elementwise (du), node mix with A, A^2 (P1, P2),
+//             mlp weight-grad GEMM (+bias column), dA Gram accumulation (M1, M2), dy GEMM fused with the
+//             gate derivative, gate weight-grad GEMM (+bias columns), dx GEMM (4C contraction over taps x {f,g})
+//             fused with the residual gradient and the BatchNorm-backward sums of the previous layer.
+//   dA = M1 + A^T M2 + M2 A^T is finished once, then pushed through softmax(relu(E1 E2)).
+#include "functors.cuh"
+#include "common.cuh"
+#include "../../include/hopk.h"
+
+namespace hopk {
+
+constexpr float BN_EPS = 1e-5f;
+constexpr float BN_MOM = 0.1f;
+
+// ============================================================================ layouts
+struct GwLayout {
+    int Tlen[HOPK_MAX_LAYERS + 1];
+    int Tp, pad, Tl;
+    size_t x0, u[HOPK_MAX_LAYERS], tf[HOPK_MAX_LAYERS], sg[HOPK_MAX_LAYERS], y[HOPK_MAX_LAYERS],
+        x1[HOPK_MAX_LAYERS], x2[HOPK_MAX_LAYERS];
+    size_t ycat, r0, r1, orow, ss, mr, A, A2, At, A2t, Z, stats, total;
+    // scratch (backward)
+    size_t s_du, s_p1, s_p2, s_g, s_df, s_dg, s_dxa, s_dxb, s_dorow, s_de1, s_dskip, s_dycat, s_bnsum, s_m12, s_dA,
+        s_total;
+};
+
+static int receptive_field(const HopkGwnetShape* s)
+{
+    int rf = 1;
+    for (int i = 0; i < s->L; ++i) rf += s->dil[i];
+    return rf;
+}
+
+static size_t bump(size_t& cur, size_t bytes)
+{
+    size_t at = cur;
+    cur += (bytes + 255) & ~size_t(255);
+    return at;
+}
+
+static GwLayout make_layout(const HopkGwnetShape* s)
+{
+    GwLayout g;
+    memset(&g, 0, sizeof(g));
+    int rf = receptive_field(s);
+    g.Tp = s->T < rf ? rf : s->T;
+    g.pad = g.Tp - s->T;
+    g.Tlen[0] = g.Tp;
+    for (int i = 0; i < s->L; ++i) g.Tlen[i + 1] = g.Tlen[i] - s->dil[i];
+    g.Tl = g.Tlen[s->L];
+    const size_t f = sizeof(float);
+    const size_t BV = (size_t)s->B * s->V;
+    size_t cur = 0;
+    g.x0 = bump(cur, BV * g.Tp * s->C * f);
+    for (int i = 0; i < s->L; ++i) {
+        size_t n = BV * g.Tlen[i + 1] * s->C * f;
+        g.u[i] = bump(cur, n); g.tf[i] = bump(cur, n); g.sg[i] = bump(cur, n);
+        g.y[i] = bump(cur, n); g.x1[i] = bump(cur, n); g.x2[i] = bump(cur, n);
+    }
+    g.ycat = bump(cur, BV * g.Tl * s->L * s->C * f);
+    g.r0 = bump(cur, BV * g.Tl * s->S * f);
+    g.r1 = bump(cur, BV * g.Tl * s->E * f);
+    g.orow = bump(cur, BV * g.Tl * s->out_dim * f);
+    g.ss = bump(cur, (size_t)(s->L + 1) * 2 * s->C * f);
+    g.mr = bump(cur, (size_t)s->L * 2 * s->C * f);
+    size_t vv = (size_t)s->V * s->V * f;
+    g.A = bump(cur, vv); g.A2 = bump(cur, vv); g.At = bump(cur, vv); g.A2t = bump(cur, vv); g.Z = bump(cur, vv);
+    g.stats = bump(cur, (size_t)s->L * 2 * s->C * sizeof(double));
+    g.total = cur;
+
+    cur = 0;
+    size_t nmax = BV * g.Tlen[0] * s->C * f;
+    g.s_du = bump(cur, nmax); g.s_p1 = bump(cur, nmax); g.s_p2 = bump(cur, nmax);
+    g.s_g = bump(cur, 2 * nmax);
+    g.s_df = bump(cur, nmax); g.s_dg = bump(cur, nmax);
+    g.s_dxa = bump(cur, nmax); g.s_dxb = bump(cur, nmax);
+    g.s_dorow = bump(cur, BV * g.Tl * s->out_dim * f);
+    g.s_de1 = bump(cur, BV * g.Tl * s->E * f);
+    g.s_dskip = bump(cur, BV * g.Tl * s->S * f);
+    g.s_dycat = bump(cur, BV * g.Tl * s->L * s->C * f);
+    g.s_bnsum = bump(cur, (size_t)s->L * 2 * s->C * sizeof(double));
+    g.s_m12 = bump(cur, 2 * vv);
+    g.s_dA = bump(cur, vv);
+    g.s_total = cur;
+    return g;
+}
+
+// ============================================================================ small kernels
+// A = softmax(relu(E1 E2), dim=1); also A^2, transposes and Z = E1 E2 (gwnet.py:163)
+__global__ void adp_fwd_kernel(const float* __restrict__ e1, const float* __restrict__ e2, int V, int R,
+                               float* A, float* A2, float* At, float* A2t, float* Z)
+{
+    extern __shared__ float sm[];
+    float* sA = sm;                       // V*V
+    for (int idx = threadIdx.x; idx < V * V; idx += blockDim.x) {
+        int v = idx / V, w = idx % V;
+        float z = 0.f;
+        for (int r = 0; r < R; ++r) z = fmaf(e1[v * R + r], e2[r * V + w], z);
+        Z[idx] = z;
+        sA[idx] = fmaxf(z, 0.f);
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        float mx = -INFINITY;
+        for (int w = 0; w < V; ++w) mx = fmaxf(mx, sA[v * V + w]);
+        float sum = 0.f;
+        for (int w = 0; w < V; ++w) { float e = expf(sA[v * V + w] - mx); sA[v * V + w] = e; sum += e; }
+        float inv = 1.f / sum;
+        for (int w = 0; w < V; ++w) sA[v * V + w] *= inv;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < V * V; idx += blockDim.x) {
+        int v = idx / V, w = idx % V;
+        float a2 = 0.f;
+        for (int k = 0; k < V; ++k) a2 = fmaf(sA[v * V + k], sA[k * V + w], a2);
+        A[idx] = sA[idx];
+        At[w * V + v] = sA[idx];
+        A2[idx] = a2;
+        A2t[w * V + v] = a2;
+    }
+}
+
+// dA = M1 + A^T M2 + M2 A^T ; dR = A*(dA - rowsum(dA*A)) ; dZ = dR*[Z>0] ; dE1 = dZ E2^T ; dE2 = E1^T dZ
+// If M2 == nullptr, M1 already holds dA (standalone nconv use).
+__global__ void adp_bwd_kernel(const float* __restrict__ e1, const float* __restrict__ e2, const float* __restrict__ A,
+                               const float* __restrict__ Z, const float* __restrict__ M1, const float* __restrict__ M2,
+                               int V, int R, float* de1, float* de2)
+{
+    extern __shared__ float sm[];
+    float* dA = sm;               // V*V, becomes dZ
+    for (int idx = threadIdx.x; idx < V * V; idx += blockDim.x) {
+        int v = idx / V, w = idx % V;
+        float acc = M1[idx];
+        if (M2) {
+            for (int k = 0; k < V; ++k) acc += A[k * V + v] * M2[k * V + w] + M2[v * V + k] * A[w * V + k];
+        }
+        dA[idx] = acc;
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        float dot = 0.f;
+        for (int w = 0; w < V; ++w) dot += dA[v * V + w] * A[v * V + w];
+        for (int w = 0; w < V; ++w) {
+            float dr = A[v * V + w] * (dA[v * V + w] - dot);
+            dA[v * V + w] = Z[v * V + w] > 0.f ? dr : 0.f;
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < V * R; idx += blockDim.x) {
+        int v = idx / R, r = idx % R;
+        float a = 0.f;
+        for (int w = 0; w < V; ++w) a += dA[v * V + w] * e2[r * V + w];
+        de1[idx] = a;                              // (V, R)
+        int r2 = idx / V, w2 = idx % V;            // reuse the same index space for (R, V)
+        float b = 0.f;
+        for (int k = 0; k < V; ++k) b += e1[k * R + r2] * dA[k * V + w2];
+        de2[idx] = b;
+    }
+}
+
+__global__ void fill_identity_kernel(float* ss, int C)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) { ss[c] = 1.f; ss[C + c] = 0.f; }
+}
+
+// BatchNorm2d finalize (gwnet.py:120,237): statistics -> mean/rstd, folded scale/shift, running stats
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* rmean, float* rvar, long long* nbt,
+                                   float* mr, float* ss, int C, int training)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mean, rstd;
+    if (training) {
+        double m = stats[c] / count;
+        double var = stats[C + c] / count - m * m;
+        if (var < 0) var = 0;
+        mean = (float)m;
+        rstd = (float)(1.0 / sqrt(var + (double)BN_EPS));
+        double unb = count > 1 ? var * count / (count - 1) : var;
+        rmean[c] = (1.f - BN_MOM) * rmean[c] + BN_MOM * mean;
+        rvar[c] = (1.f - BN_MOM) * rvar[c] + BN_MOM * (float)unb;
+        if (c == 0 && nbt) *nbt += 1;
+    } else {
+        mean = rmean[c];
+        rstd = 1.f / sqrtf(rvar[c] + BN_EPS);
+    }
+    mr[c] = mean; mr[C + c] = rstd;
+    float sc = gamma[c] * rstd;
+    ss[c] = sc; ss[C + c] = beta[c] - mean * sc;
+}
+
+// node mix: out1[(g,w)] = sum_v M1[v][w] in[(g,v)], out2 likewise with M2 (gwnet.py:12-14 applied on rows layout)
+__global__ void node_mix_kernel(const float* __restrict__ in, const float* __restrict__ M1, const float* __restrict__ M2,
+                                float* __restrict__ out1, float* __restrict__ out2, int groups, int V, int C, int gpb)
+{
+    extern __shared__ float sm[];
+    const int vv4 = (V * V + 3) & ~3;                                      // keep sx 16-byte aligned
+    float* s1 = sm; float* s2 = s1 + vv4; float* sx = s2 + vv4;            // sx: gpb*V*C
+    for (int i = threadIdx.x; i < V * V; i += blockDim.x) { s1[i] = M1[i]; s2[i] = M2[i]; }
+    int g0 = blockIdx.x * gpb;
+    int ng = min(gpb, groups - g0);
+    int C4 = C >> 2;
+    const float4* in4 = reinterpret_cast<const float4*>(in + (size_t)g0 * V * C);
+    float4* sx4 = reinterpret_cast<float4*>(sx);
+    for (int i = threadIdx.x; i < ng * V * C4; i += blockDim.x) sx4[i] = in4[i];
+    __syncthreads();
+    float4* o1 = reinterpret_cast<float4*>(out1 + (size_t)g0 * V * C);
+    float4* o2 = reinterpret_cast<float4*>(out2 + (size_t)g0 * V * C);
+    for (int i = threadIdx.x; i < ng * V * C4; i += blockDim.x) {
+        int c4 = i % C4; int gw = i / C4; int w = gw % V; int g = gw / V;
+        float4 a = make_float4(0, 0, 0, 0), b = a;
+        const float4* row = sx4 + (size_t)g * V * C4 + c4;
+        for (int v = 0; v < V; ++v) {
+            float4 x = row[(size_t)v * C4];
+            float m1 = s1[v * V + w], m2 = s2[v * V + w];
+            a.x = fmaf(m1, x.x, a.x); a.y = fmaf(m1, x.y, a.y); a.z = fmaf(m1, x.z, a.z); a.w = fmaf(m1, x.w, a.w);
+            b.x = fmaf(m2, x.x, b.x); b.y = fmaf(m2, x.y, b.y); b.z = fmaf(m2, x.z, b.z); b.w = fmaf(m2, x.w, b.w);
+        }
+        o1[i] = a; o2[i] = b;
+    }
+}
+
+// dA Gram accumulation: M1[v][w] += sum_{g,c} Y[(g,v)][c] G[(g,w)][c], M2 with G[..][C + c]   (G has ld 2C)
+__global__ void gram_kernel(const float* __restrict__ Y, const float* __restrict__ G, float* __restrict__ M12,
+                            int groups, int V, int C, int gpb)
+{
+    extern __shared__ float sm[];
+    float* sy = sm;                 // V * (C+1)
+    float* sg = sy + V * (C + 1);   // V * (2C+1)
+    constexpr int MAXP = 8;         // pairs per thread: V*V <= 8*256  (V <= 45)
+    float a1[MAXP], a2[MAXP];
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p) { a1[p] = 0.f; a2[p] = 0.f; }
+    int g0 = blockIdx.x * gpb;
+    int ng = min(gpb, groups - g0);
+    for (int g = 0; g < ng; ++g) {
+        const float* yp = Y + (size_t)(g0 + g) * V * C;
+        const float* gp = G + (size_t)(g0 + g) * V * 2 * C;
+        __syncthreads();
+        for (int i = threadIdx.x; i < V * C; i += blockDim.x) sy[(i / C) * (C + 1) + i % C] = yp[i];
+        for (int i = threadIdx.x; i < V * 2 * C; i += blockDim.x) sg[(i / (2 * C)) * (2 * C + 1) + i % (2 * C)] = gp[i];
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < MAXP; ++p) {
+            int pair = threadIdx.x + p * blockDim.x;
+            if (pair < V * V) {
+                int v = pair / V, w = pair % V;
+                const float* yr = sy + v * (C + 1);
+                const float* gr = sg + w * (2 * C + 1);
+                float s1 = 0.f, s2 = 0.f;
+                for (int c = 0; c < C; ++c) { s1 = fmaf(yr[c], gr[c], s1); s2 = fmaf(yr[c], gr[C + c], s2); }
+                a1[p] += s1; a2[p] += s2;
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p) {
+        int pair = threadIdx.x + p * blockDim.x;
+        if (pair < V * V) { atomicAdd(M12 + pair, a1[p]); atomicAdd(M12 + V * V + pair, a2[p]); }
+    }
+}
+
+// BatchNorm backward, elementwise part: du = gamma*rstd*(dxn - mean(dxn) - xhat*mean(dxn*xhat))
+__global__ void bn_bwd_kernel(const float* __restrict__ dxn, const float* __restrict__ u, const float* __restrict__ mr,
+                              const float* __restrict__ gamma, const double* __restrict__ sums, double count,
+                              float* __restrict__ du, float* dgamma, float* dbeta, size_t rows, int C, int training)
+{
+    extern __shared__ float sm[];
+    float* k1 = sm; float* m1 = k1 + C; float* m2 = m1 + C; float* mu = m2 + C; float* rs = mu + C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float rstd = mr[C + c];
+        k1[c] = gamma[c] * rstd; mu[c] = mr[c]; rs[c] = rstd;
+        m1[c] = training ? (float)(sums[c] / count) : 0.f;
+        m2[c] = training ? (float)(sums[C + c] / count) : 0.f;
+        if (blockIdx.x == 0) {
+            if (dbeta) dbeta[c] = (float)sums[c];
+            if (dgamma) dgamma[c] = (float)sums[C + c];
+        }
+    }
+    __syncthreads();
+    size_t n4 = rows * C / 4;
+    const float4* d4 = reinterpret_cast<const float4*>(dxn);
+    const float4* u4 = reinterpret_cast<const float4*>(u);
+    float4* o4 = reinterpret_cast<float4*>(du);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        int c = (int)((i * 4) % C);
+        float4 d = d4[i], x = u4[i], o;
+        o.x = k1[c] * (d.x - m1[c] - (x.x - mu[c]) * rs[c] * m2[c]);
+        o.y = k1[c + 1] * (d.y - m1[c + 1] - (x.y - mu[c + 1]) * rs[c + 1] * m2[c + 1]);
+        o.z = k1[c + 2] * (d.z - m1[c + 2] - (x.z - mu[c + 2]) * rs[c + 2] * m2[c + 2]);
+        o.w = k1[c + 3] * (d.w - m1[c + 3] - (x.w - mu[c + 3]) * rs[c + 3] * m2[c + 3]);
+        o4[i] = o;
+    }
+}
+
+// (B, O, V, T) contiguous <-> rows layout (B, T, V, O); tiny tensors (head in/out)
+__global__ void nchw_to_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int O, int V, int T)
+{
+    size_t n = (size_t)B * O * V * T;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int o = (int)(i % O); size_t r = i / O; int v = (int)(r % V); size_t bt = r / V; int t = (int)(bt % T); size_t b = bt / T;
+        dst[i] = src[((b * O + o) * V + v) * T + t];
+    }
+}
+__global__ void rows_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int O, int V, int T)
+{
+    size_t n = (size_t)B * O * V * T;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int t = (int)(i % T); size_t r = i / T; int v = (int)(r % V); size_t bo = r / V; int o = (int)(bo % O); size_t b = bo / O;
+        dst[i] = src[((b * T + t) * V + v) * O + o];
+    }
+}
+
+// ============================================================================ gwnet-specific functors
+struct LayerGeom {           // rows bookkeeping of one layer
+    int V, C, Ti, To, d;
+    __device__ __forceinline__ long in_row(int m_out) const {      // out row -> row of the layer input at the same (b,t,v)
+        int per = To * V; int b = m_out / per;
+        return (long)m_out + (long)b * d * V;
+    }
+};
+
+struct StartA {              // A(m, k) = x[b, k, v, t - pad] (0 in the left padding), arbitrary strides
+    static constexpr bool kFast = true;
+    const float* x; int Tp, V, pad; long sB, sC, sV, sT;
+    __device__ __forceinline__ float operator()(int m, int k) const {
+        int v = m % V; int bt = m / V; int t = bt % Tp - pad; int b = bt / Tp;
+        if (t < 0) return 0.f;
+        return __ldg(x + b * sB + k * sC + v * sV + t * sT);
+    }
+};
+struct StartAT {             // B'(kout, m) for the weight gradient, ones column at kout == K
+    static constexpr bool kFast = false;
+    const float* x; int Tp, V, pad, K; long sB, sC, sV, sT;
+    __device__ __forceinline__ float operator()(int kout, int m) const {
+        if (kout == K) return 1.f;
+        int v = m % V; int bt = m / V; int t = bt % Tp - pad; int b = bt / Tp;
+        if (t < 0) return 0.f;
+        return __ldg(x + b * sB + kout * sC + v * sV + t * sT);
+    }
+};
+struct StartDxEpi {          // dIn rows layout over the un-padded T
+    float* dx; int Tp, T, V, pad, K;
+    __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[8]) {
+        int vv = m % V; int bt = m / V; int t = bt % Tp - pad; int b = bt / Tp;
+        if (t < 0) return;
+        float* row = dx + ((size_t)(b * T + t) * V + vv) * K;
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { int n = nb + 64 * g + j; if (n < K) row[n] = v[4 * g + j]; }
+    }
+    __device__ __forceinline__ void flush(int) {}
+};
+
+struct GateA {               // k = tap*C + c ; value = BN_{i-1}(u_prev)[b, t + tap*d, v, c]
+    static constexpr bool kFast = true;
+    const float* up; const float* ss; LayerGeom g;
+    __device__ __forceinline__ float operator()(int m, int k) const {
+        int tap = k >= g.C; int c = k - tap * g.C;
+        long r = g.in_row(m) + (long)tap * g.d * g.V;
+        return fmaf(__ldg(up + r * g.C + c), __ldg(ss + c), __ldg(ss + g.C + c));
+    }
+};
+struct GateB {               // logical column n: block of 128 = [64 filter channels | the same 64 gate channels]
+    static constexpr bool kFast = true;
+    const float* wf; const float* wg; int C;
+    __device__ __forceinline__ float operator()(int n, int k) const {
+        int blk = n >> 7, w = n & 127; int fg = w >> 6; int o = blk * 64 + (w & 63);
+        if (o >= C) return 0.f;
+        int tap = k >= C; int c = k - tap * C;
+        return __ldg((fg ? wg : wf) + (size_t)o * 2 * C + 2 * c + tap);
+    }
+};
+struct GateEpi {             // tanh(f)*sigmoid(g) (gwnet.py:186-200); keeps tf, sg, y; writes the skip slice
+    const float* bf; const float* bg; float* TF; float* SG; float* Y; float* ycat;
+    LayerGeom g; int layer, L, Tl;
+    __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[8]) {
+        int c0 = (nb >> 7) * 64 + (nb & 127);
+        if (c0 >= g.C) return;
+        float tf[4], sg[4], y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            tf[j] = tanhf(v[j] + __ldg(bf + c0 + j));
+            sg[j] = sigmoidf_acc(v[4 + j] + __ldg(bg + c0 + j));
+            y[j] = tf[j] * sg[j];
+        }
+        size_t o = (size_t)m * g.C + c0;
+        *reinterpret_cast<float4*>(TF + o) = make_float4(tf[0], tf[1], tf[2], tf[3]);
+        *reinterpret_cast<float4*>(SG + o) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+        *reinterpret_cast<float4*>(Y + o) = make_float4(y[0], y[1], y[2], y[3]);
+        int vv = m % g.V; int bt = m / g.V; int t = bt % g.To; int b = bt / g.To;
+        int tt = t - (g.To - Tl);
+        if (tt >= 0) {
+            size_t q = ((size_t)(b * Tl + tt) * g.V + vv) * ((size_t)L * g.C) + (size_t)layer * g.C + c0;
+            *reinterpret_cast<float4*>(ycat + q) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+    }
+    __device__ __forceinline__ void flush(int) {}
+};
+
+struct Seg3A {               // A(m, k): k = seg*C + c over three row-layout sources
+    static constexpr bool kFast = true;
+    const float* p0; const float* p1; const float* p2; int C;
+    __device__ __forceinline__ float operator()(int m, int k) const {
+        int seg = k / C; int c = k - seg * C;
+        const float* p = seg == 0 ? p0 : (seg == 1 ? p1 : p2);
+        return __ldg(p + (size_t)m * C + c);
+    }
+};
+struct Seg3AT {              // B'(kout, m): same sources, transposed role, ones column at 3C
+    static constexpr bool kFast = false;
+    const float* p0; const float* p1; const float* p2; int C;
+    __device__ __forceinline__ float operator()(int kout, int m) const {
+        if (kout == 3 * C) return 1.f;
+        int seg = kout / C; int c = kout - seg * C;
+        const float* p = seg == 0 ? p0 : (seg == 1 ? p1 : p2);
+        return __ldg(p + (size_t)m * C + c);
+    }
+};
+template <int NG>
+struct MlpEpi {              // u = h + bias + residual (gwnet.py:43-45, 233) and BatchNorm statistics
+    const float* bm; const float* up; const float* ss; float* U; double* stats; LayerGeom g;
+    float s1[4 * NG], s2[4 * NG];
+    __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[4 * NG]) {
+        long rr = g.in_row(m) + (long)g.d * g.V;
+#pragma unroll
+        for (int gg = 0; gg < NG; ++gg)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = nb + 64 * gg + j;
+                if (n < g.C) {
+                    float x = fmaf(__ldg(up + rr * g.C + n), __ldg(ss + n), __ldg(ss + g.C + n));
+                    float u = v[4 * gg + j] + __ldg(bm + n) + x;
+                    U[(size_t)m * g.C + n] = u;
+                    s1[4 * gg + j] += u; s2[4 * gg + j] += u * u;
+                }
+            }
+    }
+    __device__ __forceinline__ void flush(int nb) {
+#pragma unroll
+        for (int q = 0; q < 4 * NG; ++q) {
+            float a = s1[q] + __shfl_xor_sync(0xffffffffu, s1[q], 16);
+            float b = s2[q] + __shfl_xor_sync(0xffffffffu, s2[q], 16);
+            int n = nb + 64 * (q >> 2) + (q & 3);
+            if ((threadIdx.x & 31) < 16 && n < g.C && stats) {
+                atomicAdd(stats + n, (double)a);
+                atomicAdd(stats + g.C + n, (double)b);
+            }
+        }
+    }
+};
+
+struct SkipW {               // B(n, k): concatenated skip weights, k = layer*C + c  
+    static constexpr bool kFast = true;
+    const float* w[HOPK_MAX_LAYERS]; int C;
+    __device__ __forceinline__ float operator()(int n, int k) const {
+        int l = k / C; int c = k - l * C;
+        return __ldg(w[l] + (size_t)n * C + c);
+    }
+};
+struct SkipWT {              // B(n = layer*C + c, k = s) = w[layer][s][c]   (dgrad through the concat GEMM)
+    static constexpr bool kFast = false;
+    const float* w[HOPK_MAX_LAYERS]; int C;
+    __device__ __forceinline__ float operator()(int n, int k) const {
+        int l = n / C; int c = n - l * C;
+        return __ldg(w[l] + (size_t)k * C + c);
+    }
+};
+template <int NG>
+struct SkipEpi {             // relu(sum + sum_l bias_l)
+    float* out; const float* b[HOPK_MAX_LAYERS]; int L, N;
+    __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[4 * NG]) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = nb + 64 * g + j;
+                if (n < N) {
+                    float x = v[4 * g + j];
+                    for (int l = 0; l < L; ++l) x += __ldg(b[l] + n);
+                    out[(size_t)m * N + n] = fmaxf(x, 0.f);
+                }
+            }
+    }
+    __device__ __forceinline__ void flush(int) {}
+};
+template <int NG>
+struct SkipWgradEpi {        // out row n = s, col k = layer*C + c (+ bias column at L*C, written to every layer's bias)
+    float* dw[HOPK_MAX_LAYERS]; float* db[HOPK_MAX_LAYERS]; int C, L;
+    __device__ __forceinline__ void operator()(int n, int kb, const float (&v)[4 * NG]) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int k = kb + 64 * g + j;
+                if (k < L * C) { int l = k / C; atomicAdd(dw[l] + (size_t)n * C + (k - l * C), v[4 * g + j]); }
+                else if (k == L * C) { for (int l = 0; l < L; ++l) atomicAdd(db[l] + n, v[4 * g + j]); }
+            }
+    }
+    __device__ __forceinline__ void flush(int) {}
+};
+
+struct DyB {                 // B(n = c, k = seg*C + o) = Wm[o][seg*C + c]
+    static constexpr bool kFast = false;
+    const float* wm; int C;
+    __device__ __forceinline__ float operator()(int n, int k) const {
+        int seg = k / C; int o = k - seg * C;
+        return __ldg(wm + (size_t)o * 3 * C + seg * C + n);
+    }
+};
+template <int NG>
+struct DyEpi {               // dy (+ skip-path gradient) -> df, dg   (Appendix A, gated TCN backward)
+    const float* TF; const float* SG; const float* dycat; float* DF; float* DG; LayerGeom g; int layer, L, Tl;
+    __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[4 * NG]) {
+        int vv = m % g.V; int bt = m / g.V; int t = bt % g.To; int b = bt / g.To;
+        int tt = t - (g.To - Tl);
+        const float* dyc = tt >= 0 ? dycat + ((size_t)(b * Tl + tt) * g.V + vv) * ((size_t)L * g.C) + (size_t)layer * g.C : nullptr;
+#pragma unroll
+        for (int gg = 0; gg < NG; ++gg)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = nb + 64 * gg + j;
+                if (n < g.C) {
+                    float dy = v[4 * gg + j] + (dyc ? __ldg(dyc + n) : 0.f);
+                    size_t o = (size_t)m * g.C + n;
+                    float tf = __ldg(TF + o), sg = __ldg(SG + o);
+                    DF[o] = dy * sg * (1.f - tf * tf);
+                    DG[o] = dy * tf * sg * (1.f - sg);
+                }
+            }
+    }
+    __device__ __forceinline__ void flush(int) {}
+};
+
+struct GateWgA {             // A'(n = fg*C + o, m) = (fg ? DG : DF)[m][o]
+    static constexpr bool kFast = false;
+    const float* DF; const float* DG; int C;
+    __device__ __forceinline__ float operator()(int n, int m) const {
+        int fg = n >= C; int o = n - fg * C;
+        return __ldg((fg ? DG : DF) + (size_t)m * C + o);
+    }
+};
+struct GateWgB {             // B'(kout = 2c + tap, m) = x[in_row(m) + tap*d*V][c] ; ones column at 2C
+    static constexpr bool kFast = false;
+    const float* up; const float* ss; LayerGeom g;
+    __device__ __forceinline__ float operator()(int kout, int m) const {
+        if (kout == 2 * g.C) return 1.f;
+        int c = kout >> 1, tap = kout & 1;
+        long r = g.in_row(m) + (long)tap * g.d * g.V;
+        return fmaf(__ldg(up + r * g.C + c), __ldg(ss + c), __ldg(ss + g.C + c));
+    }
+};
+template <int NG>
+struct GateWgEpi {
+    float* dwf; float* dwg; float* dbf; float* dbg; int C;
+    __device__ __forceinline__ void operator()(int n, int kb, const float (&v)[4 * NG]) {
+        int fg = n >= C; int o = n - fg * C;
+        float* dw = fg ? dwg : dwf; float* db = fg ? dbg : dbf;
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int k = kb + 64 * g + j;
+                if (k < 2 * C) atomicAdd(dw + (size_t)o * 2 * C + k, v[4 * g + j]);
+                else if (k == 2 * C) atomicAdd(db + o, v[4 * g + j]);
+            }
+    }
+    __device__ __forceinline__ void flush(int) {}
+};
+
+struct DxA {                 // A(m_in, k = (tap*2 + fg)*C + o) = (fg?DG:DF)[(b, t - tap*d, v)][o], 0 outside [0, To)
+    static constexpr bool kFast = true;
+    const float* DF; const float* DG; LayerGeom g;
+    __device__ __forceinline__ float operator()(int m, int k) const {
+        int q = k / g.C; int o = k - q * g.C; int tap = q >> 1, fg = q & 1;
+        int vv = m % g.V; int bt = m / g.V; int t = bt % g.Ti - tap * g.d; int b = bt / g.Ti;
+        if (t < 0 || t >= g.To) return 0.f;
+        return __ldg((fg ? DG : DF) + ((size_t)(b * g.To + t) * g.V + vv) * g.C + o);
+    }
+};
+struct DxB {                 // B(n = c, k) = W_fg[o][c][tap]
+    static constexpr bool kFast = false;
+    const float* wf; const float* wg; int C;
+    __device__ __forceinline__ float operator()(int n, int k) const {
+        int q = k / C; int o = k - q * C; int tap = q >> 1, fg = q & 1;
+        return __ldg((fg ? wg : wf) + (size_t)o * 2 * C + 2 * n + tap);
+    }
+};
+template <int NG>
+struct DxEpi {               // + residual gradient du[t-d]; BatchNorm-backward sums for the previous layer
+    const float* DU; float* DX; const float* uprev; const float* mr_prev; double* sums_prev; LayerGeom g;
+    float s1[4 * NG], s2[4 * NG];
+    __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[4 * NG]) {
+        int vv = m % g.V; int bt = m / g.V; int t = bt % g.Ti; int b = bt / g.Ti;
+        const float* du = (DU && t >= g.d) ? DU + ((size_t)(b * g.To + t - g.d) * g.V + vv) * g.C : nullptr;
+#pragma unroll
+        for (int gg = 0; gg < NG; ++gg)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = nb + 64 * gg + j;
+                if (n < g.C) {
+                    float dx = v[4 * gg + j] + (du ? __ldg(du + n) : 0.f);
+                    DX[(size_t)m * g.C + n] = dx;
+                    if (sums_prev) {
+                        float xh = (__ldg(uprev + (size_t)m * g.C + n) - __ldg(mr_prev + n)) * __ldg(mr_prev + g.C + n);
+                        s1[4 * gg + j] += dx; s2[4 * gg + j] += dx * xh;
+                    }
+                }
+            }
+    }
+    __device__ __forceinline__ void flush(int nb) {
+        if (!sums_prev) return;
+#pragma unroll
+        for (int q = 0; q < 4 * NG; ++q) {
+            float a = s1[q] + __shfl_xor_sync(0xffffffffu, s1[q], 16);
+            float b = s2[q] + __shfl_xor_sync(0xffffffffu, s2[q], 16);
+            int n = nb + 64 * (q >> 2) + (q & 3);
+            if ((threadIdx.x & 31) < 16 && n < g.C) {
+                atomicAdd(sums_prev + n, (double)a);
+                atomicAdd(sums_prev + g.C + n, (double)b);
+            }
+        }
+    }
+};
+
+// ============================================================================ launch helpers
+template <int MG, int NG, class AL, class BL, class EP>
+static void launch_gemm(int M, int N, int K, int splits, AL a, BL b, EP e, cudaStream_t st)
+{
+    int kper = K;
+    if (splits > 1) { kper = ((cdiv(K, splits) + GEMM_BK - 1) / GEMM_BK) * GEMM_BK; splits = cdiv(K, kper); }
+    if (splits < 1) splits = 1;
+    dim3 grid(cdiv(N, 64 * NG), cdiv(M, 64 * MG), splits);
+    gemm_kernel<MG, NG, AL, BL, EP><<<grid, GEMM_THREADS, 0, st>>>(M, N, K, kper, a, b, e);
+}
+
+static int pick_splits(int M, int N, int K, int mg, int ng)
+{
+    long tiles = (long)cdiv(M, 64 * mg) * cdiv(N, 64 * ng);
+    long want = (2 * 148 + tiles - 1) / tiles;
+    long maxs = K / 256 > 0 ? K / 256 : 1;
+    return (int)(want < maxs ? want : maxs);
+}
+
+static size_t node_mix_smem(int V, int C, int gpb) { return (2 * (size_t)((V * V + 3) & ~3) + (size_t)gpb * V * C) * sizeof(float); }
+
+static int launch_node_mix(const float* in, const float* M1, const float* M2, float* o1, float* o2, int groups, int V, int C,
+                           cudaStream_t st)
+{
+    int gpb = 48 / V > 0 ? 48 / V : 1;
+    size_t smem = node_mix_smem(V, C, gpb);
+    if (smem > 48 * 1024) HOPK_CUDA(cudaFuncSetAttribute(node_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    node_mix_kernel<<<cdiv(groups, gpb), 256, smem, st>>>(in, M1, M2, o1, o2, groups, V, C, gpb);
+    HOPK_LAUNCH_CHECK("node_mix");
+    return 0;
+}
+
+}  // namespace hopk
+
+using namespace hopk;
+
+// ============================================================================ C ABI
+extern "C" size_t hopk_gwnet_workspace_bytes(const HopkGwnetShape* s) { return make_layout(s).total; }
+extern "C" size_t hopk_gwnet_scratch_bytes(const HopkGwnetShape* s) { return make_layout(s).s_total; }
+extern "C" int hopk_gwnet_out_steps(const HopkGwnetShape* s) { return make_layout(s).Tl; }
+
+static int check_shape(const HopkGwnetShape* s)
+{
+    HOPK_REQUIRE(s->dtype == 0, "gwnet: only dtype 0 (fp32) is implemented in this entry point");
+    HOPK_REQUIRE(s->L >= 1 && s->L <= HOPK_MAX_LAYERS, "layer count");
+    HOPK_REQUIRE(s->C % 4 == 0 && s->C >= 4 && s->C <= 256, "C must be a multiple of 4, <= 256");
+    HOPK_REQUIRE(s->V >= 1 && s->V <= 45, "V must be <= 45");
+    HOPK_REQUIRE(s->B >= 1 && s->T >= 1 && s->in_dim >= 1 && s->out_dim >= 1 && s->S >= 1 && s->E >= 1, "sizes");
+    HOPK_REQUIRE((long)s->B * s->V * 64 * 256 < (1L << 31), "tensor too large for 32-bit row indices");
+    return 0;
+}
+
+extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams* p, const float* x, const int64_t xs[4],
+                                  float* out, void* ws_, void* stream)
+{
+    if (int rc = check_shape(s)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    GwLayout g = make_layout(s);
+    char* ws = (char*)ws_;
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    const int C = s->C, V = s->V, B = s->B, L = s->L;
+    double* stats = reinterpret_cast<double*>(ws + g.stats);
+    HOPK_CUDA(cudaMemsetAsync(stats, 0, (size_t)L * 2 * C * sizeof(double), st));
+
+    adp_fwd_kernel<<<1, 256, V * V * sizeof(float), st>>>(p->nodevec1, p->nodevec2, V, s->rank, F(g.A), F(g.A2), F(g.At),
+                                                           F(g.A2t), F(g.Z));
+    HOPK_LAUNCH_CHECK("adp_fwd");
+    fill_identity_kernel<<<cdiv(C, 128), 128, 0, st>>>(F(g.ss), C);
+
+    // start conv (gwnet.py:144-149)
+    {
+        int M = B * g.Tp * V;
+        StartA a{x, g.Tp, V, g.pad, (long)xs[0], (long)xs[1], (long)xs[2], (long)xs[3]};
+        Ld2D<true, 0> b{p->start_w, nullptr, s->in_dim};
+        EpiStore<1> e{F(g.x0), C, p->start_b, nullptr, C, 0};
+        if (C <= 64) launch_gemm<2, 1>(M, C, s->in_dim, 1, a, b, e, st);
+        else {
+            EpiStore<2> e2{F(g.x0), C, p->start_b, nullptr, C, 0};
+            launch_gemm<2, 2>(M, C, s->in_dim, 1, a, b, e2, st);
+        }
+        HOPK_LAUNCH_CHECK("start_conv");
+    }
+
+    const float* uprev = F(g.x0);
+    for (int i = 0; i < L; ++i) {
+        LayerGeom lg{V, C, g.Tlen[i], g.Tlen[i + 1], s->dil[i]};
+        int M = B * lg.To * V;
+        const float* ss = F(g.ss) + (size_t)i * 2 * C;
+        // gated dilated conv (gwnet.py:186-200) + skip slice
+        {
+            GateA a{uprev, ss, lg};
+            GateB b{p->filter_w[i], p->gate_w[i], C};
+            GateEpi e{p->filter_b[i], p->gate_b[i], F(g.tf[i]), F(g.sg[i]), F(g.y[i]), F(g.ycat), lg, i, L, g.Tl};
+            int Nlog = cdiv(C, 64) * 128;
+            launch_gemm<2, 2>(M, Nlog, 2 * C, 1, a, b, e, st);
+            HOPK_LAUNCH_CHECK("gate");
+        }
+        // diffusion (gwnet.py:12-14, 35-41)
+        if (int rc = launch_node_mix(F(g.y[i]), F(g.A), F(g.A2), F(g.x1[i]), F(g.x2[i]), B * lg.To, V, C, st)) return rc;
+        // gcn mlp + residual + BN statistics (gwnet.py:43-45, 233, 237)
+        {
+            Seg3A a{F(g.y[i]), F(g.x1[i]), F(g.x2[i]), C};
+            Ld2D<true, 0> b{p->mlp_w[i], nullptr, 3 * C};
+            double* st_i = stats + (size_t)i * 2 * C;
+            if (C <= 64) {
+                MlpEpi<1> e; memset(&e, 0, sizeof(e));
+                e.bm = p->mlp_b[i]; e.up = uprev; e.ss = ss; e.U = F(g.u[i]); e.stats = st_i; e.g = lg;
+                launch_gemm<2, 1>(M, C, 3 * C, 1, a, b, e, st);
+            } else {
+                MlpEpi<2> e; memset(&e, 0, sizeof(e));
+                e.bm = p->mlp_b[i]; e.up = uprev; e.ss = ss; e.U = F(g.u[i]); e.stats = st_i; e.g = lg;
+                launch_gemm<2, 2>(M, C, 3 * C, 1, a, b, e, st);
+            }
+            HOPK_LAUNCH_CHECK("mlp");
+        }
+        bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats + (size_t)i * 2 * C, (double)M, p->bn_w[i], p->bn_b[i],
+                                                          p->bn_mean[i], p->bn_var[i], (long long*)p->bn_nbt[i],
+                                                          F(g.mr) + (size_t)i * 2 * C, F(g.ss) + (size_t)(i + 1) * 2 * C, C,
+                                                          s->training);
+        HOPK_LAUNCH_CHECK("bn_finalize");
+        uprev = F(g.u[i]);
+    }
+
+    // head (gwnet.py:240-246) on the last Tl steps only
+    {
+        int M = B * g.Tl * V;
+        Ld2D<true, 0> a{F(g.ycat), nullptr, (long)L * C};
+        SkipW b; b.C = C; for (int l = 0; l < L; ++l) b.w[l] = p->skip_w[l];
+        SkipEpi<2> e; e.out = F(g.r0); e.L = L; e.N = s->S; for (int l = 0; l < L; ++l) e.b[l] = p->skip_b[l];
+        launch_gemm<1, 2>(M, s->S, L * C, 1, a, b, e, st);
+        HOPK_LAUNCH_CHECK("skip");
+        Ld2D<true, 0> a1{F(g.r0), nullptr, s->S};
+        Ld2D<true, 0> b1{p->end1_w, nullptr, s->S};
+        EpiStore<2> e1{F(g.r1), s->E, p->end1_b, nullptr, s->E, 1};
+        launch_gemm<1, 2>(M, s->E, s->S, 1, a1, b1, e1, st);
+        HOPK_LAUNCH_CHECK("end1");
+        Ld2D<true, 0> a2{F(g.r1), nullptr, s->E};
+        Ld2D<true, 0> b2{p->end2_w, nullptr, s->E};
+        RowMap rm{g.Tl, V, (long)s->out_dim * V * g.Tl, 1, g.Tl, (long)V * g.Tl};
+        EpiStoreStrided<2> e2{out, rm, p->end2_b, s->out_dim};
+        launch_gemm<1, 2>(M, s->out_dim, s->E, 1, a2, b2, e2, st);
+        HOPK_LAUNCH_CHECK("end2");
+    }
+    return 0;
+}
+
+extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParams* p, const float* x, const int64_t xs[4],
+                                   const float* dout, void* ws_, void* scratch_, const HopkGwnetGrads* gr, float* dx,
+                                   void* stream)
+{
+    if (int rc = check_shape(s)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    GwLayout g = make_layout(s);
+    char* ws = (char*)ws_; char* sc = (char*)scratch_;
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    auto S = [&](size_t off) { return reinterpret_cast<float*>(sc + off); };
+    const int C = s->C, V = s->V, B = s->B, L = s->L, Sk = s->S, E = s->E, O = s->out_dim;
+    double* bnsum = reinterpret_cast<double*>(sc + g.s_bnsum);
+    HOPK_CUDA(cudaMemsetAsync(bnsum, 0, (size_t)L * 2 * C * sizeof(double), st));
+    HOPK_CUDA(cudaMemsetAsync(S(g.s_m12), 0, 2 * (size_t)V * V * sizeof(float), st));
+
+    // ---- head backward
+    const int M4 = B * g.Tl * V;
+    {
+        nchw_to_rows_kernel<<<cdiv((long)M4 * O, 256), 256, 0, st>>>(dout, S(g.s_dorow), B, O, V, g.Tl);
+        HOPK_LAUNCH_CHECK("dout_rows");
+        // end_conv_2
+        HOPK_CUDA(cudaMemsetAsync(gr->end2_w, 0, (size_t)O * E * sizeof(float), st));
+        HOPK_CUDA(cudaMemsetAsync(gr->end2_b, 0, (size_t)O * sizeof(float), st));
+        {
+            Ld2D<false, 0> a{S(g.s_dorow), nullptr, O};
+            Ld2DOnes<false> b{F(g.r1), E, E};
+            EpiWgrad<2> e{gr->end2_w, E, gr->end2_b, E, O};
+            launch_gemm<1, 2>(O, E + 1, M4, pick_splits(O, E + 1, M4, 1, 2), a, b, e, st);
+            HOPK_LAUNCH_CHECK("end2_wgrad");
+            Ld2D<true, 0> a2{S(g.s_dorow), nullptr, O};
+            Ld2D<false, 0> b2{p->end2_w, nullptr, E};
+            EpiStore<2> e2{S(g.s_de1), E, nullptr, F(g.r1), E, 4};
+            launch_gemm<1, 2>(M4, E, O, 1, a2, b2, e2, st);
+            HOPK_LAUNCH_CHECK("end2_dgrad");
+        }
+        // end_conv_1
+        HOPK_CUDA(cudaMemsetAsync(gr->end1_w, 0, (size_t)E * Sk * sizeof(float), st));
+        HOPK_CUDA(cudaMemsetAsync(gr->end1_b, 0, (size_t)E * sizeof(float), st));
+        {
+            Ld2D<false, 0> a{S(g.s_de1), nullptr, E};
+            Ld2DOnes<false> b{F(g.r0), Sk, Sk};
+            EpiWgrad<2> e{gr->end1_w, Sk, gr->end1_b, Sk, E};
+            launch_gemm<1, 2>(E, Sk + 1, M4, pick_splits(E, Sk + 1, M4, 1, 2), a, b, e, st);
+            HOPK_LAUNCH_CHECK("end1_wgrad");
+            Ld2D<true, 0> a2{S(g.s_de1), nullptr, E};
+            Ld2D<false, 0> b2{p->end1_w, nullptr, Sk};
+            EpiStore<2> e2{S(g.s_dskip), Sk, nullptr, F(g.r0), Sk, 4};
+            launch_gemm<1, 2>(M4, Sk, E, 1, a2, b2, e2, st);
+            HOPK_LAUNCH_CHECK("end1_dgrad");
+        }
+        // skip convs: one concat GEMM each way
+        for (int l = 0; l < L; ++l) {
+            HOPK_CUDA(cudaMemsetAsync(gr->skip_w[l], 0, (size_t)Sk * C * sizeof(float), st));
+            HOPK_CUDA(cudaMemsetAsync(gr->skip_b[l], 0, (size_t)Sk * sizeof(float), st));
+        }
+        {
+            Ld2D<false, 0> a{S(g.s_dskip), nullptr, Sk};
+            Ld2DOnes<false> b{F(g.ycat), (long)L * C, L * C};
+            SkipWgradEpi<2> e; e.C = C; e.L = L;
+            for (int l = 0; l < L; ++l) { e.dw[l] = gr->skip_w[l]; e.db[l] = gr->skip_b[l]; }
+            launch_gemm<1, 2>(Sk, L * C + 1, M4, pick_splits(Sk, L * C + 1, M4, 1, 2), a, b, e, st);
+            HOPK_LAUNCH_CHECK("skip_wgrad");
+            Ld2D<true, 0> a2{S(g.s_dskip), nullptr, Sk};
+            SkipWT b2; b2.C = C; for (int l = 0; l < L; ++l) b2.w[l] = p->skip_w[l];
+            EpiStore<2> e2{S(g.s_dycat), (long)L * C, nullptr, nullptr, L * C, 0};
+            launch_gemm<1, 2>(M4, L * C, Sk, 1, a2, b2, e2, st);
+            HOPK_LAUNCH_CHECK("skip_dgrad");
+        }
+    }
+
+    // ---- layers, last to first
+    float* dxn = nullptr;                 // gradient w.r.t. BN_i output (= layer i+1 input)
+    float* dx_buf[2] = {S(g.s_dxa), S(g.s_dxb)};
+    int flip = 0;
+    for (int i = L - 1; i >= 0; --i) {
+        LayerGeom lg{V, C, g.Tlen[i], g.Tlen[i + 1], s->dil[i]};
+        const int M = B * lg.To * V;
+        const int Min = B * lg.Ti * V;
+        const float* uprev = i == 0 ? F(g.x0) : F(g.u[i - 1]);
+        const float* ss = F(g.ss) + (size_t)i * 2 * C;
+        const bool has_du = dxn != nullptr;
+        float* DU = S(g.s_du);
+        if (has_du) {
+            size_t smem = 5 * C * sizeof(float);
+            long n4 = (long)M * C / 4;
+            int blocks = (int)((n4 + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+            bn_bwd_kernel<<<blocks, 256, smem, st>>>(dxn, F(g.u[i]), F(g.mr) + (size_t)i * 2 * C, p->bn_w[i],
+                                                     bnsum + (size_t)i * 2 * C, (double)M, DU, gr->bn_w[i], gr->bn_b[i],
+                                                     (size_t)M, C, s->training);
+            HOPK_LAUNCH_CHECK("bn_bwd");
+            // P1 = A du, P2 = A^2 du  (node mix with the transposed supports)
+            int groups = B * lg.To;
+            if (int rc = launch_node_mix(DU, F(g.At), F(g.A2t), S(g.s_p1), S(g.s_p2), groups, V, C, st)) return rc;
+            // mlp weight + bias gradient
+            HOPK_CUDA(cudaMemsetAsync(gr->mlp_w[i], 0, (size_t)C * 3 * C * sizeof(float), st));
+            HOPK_CUDA(cudaMemsetAsync(gr->mlp_b[i], 0, (size_t)C * sizeof(float), st));
+            {
+                Ld2D<false, 0> a{DU, nullptr, C};
+                Seg3AT b{F(g.y[i]), F(g.x1[i]), F(g.x2[i]), C};
+                EpiWgrad<2> e{gr->mlp_w[i], (long)3 * C, gr->mlp_b[i], 3 * C, C};
+                if (C <= 64) launch_gemm<1, 2>(C, 3 * C + 1, M, pick_splits(C, 3 * C + 1, M, 1, 2), a, b, e, st);
+                else launch_gemm<2, 2>(C, 3 * C + 1, M, pick_splits(C, 3 * C + 1, M, 2, 2), a, b, e, st);
+                HOPK_LAUNCH_CHECK("mlp_wgrad");
+            }
+            // G = du [Wm1 | Wm2]  and the Gram products for dA
+            {
+                Ld2D<true, 0> a{DU, nullptr, C};
+                Ld2D<false, 0> b{p->mlp_w[i] + C, nullptr, (long)3 * C};
+                EpiStore<2> e{S(g.s_g), (long)2 * C, nullptr, nullptr, 2 * C, 0};
+                launch_gemm<2, 2>(M, 2 * C, C, 1, a, b, e, st);
+                HOPK_LAUNCH_CHECK("g_gemm");
+                int gpb2 = 8;
+                size_t smem3 = ((size_t)V * (C + 1) + (size_t)V * (2 * C + 1)) * sizeof(float);
+                if (smem3 > 48 * 1024) HOPK_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                gram_kernel<<<cdiv(groups, gpb2), 256, smem3, st>>>(F(g.y[i]), S(g.s_g), S(g.s_m12), groups, V, C, gpb2);
+                HOPK_LAUNCH_CHECK("gram");
+            }
+        }
+        // dy (+ skip path) -> df, dg
+        {
+            Seg3A a{DU, S(g.s_p1), S(g.s_p2), C};
+            DyB b{p->mlp_w[i], C};
+            int K = has_du ? 3 * C : 0;
+            if (C <= 64) {
+                DyEpi<1> e{F(g.tf[i]), F(g.sg[i]), S(g.s_dycat), S(g.s_df), S(g.s_dg), lg, i, L, g.Tl};
+                launch_gemm<2, 1>(M, C, K, 1, a, b, e, st);
+            } else {
+                DyEpi<2> e{F(g.tf[i]), F(g.sg[i]), S(g.s_dycat), S(g.s_df), S(g.s_dg), lg, i, L, g.Tl};
+                launch_gemm<2, 2>(M, C, K, 1, a, b, e, st);
+            }
+            HOPK_LAUNCH_CHECK("dy_gemm");
+        }
+        // gate conv weight + bias gradients
+        HOPK_CUDA(cudaMemsetAsync(gr->filter_w[i], 0, (size_t)C * 2 * C * sizeof(float), st));
+        HOPK_CUDA(cudaMemsetAsync(gr->gate_w[i], 0, (size_t)C * 2 * C * sizeof(float), st));
+        HOPK_CUDA(cudaMemsetAsync(gr->filter_b[i], 0, (size_t)C * sizeof(float), st));
+        HOPK_CUDA(cudaMemsetAsync(gr->gate_b[i], 0, (size_t)C * sizeof(float), st));
+        {
+            GateWgA a{S(g.s_df), S(g.s_dg), C};
+            GateWgB b{uprev, ss, lg};
+            GateWgEpi<2> e{gr->filter_w[i], gr->gate_w[i], gr->filter_b[i], gr->gate_b[i], C};
+            launch_gemm<2, 2>(2 * C, 2 * C + 1, M, pick_splits(2 * C, 2 * C + 1, M, 2, 2), a, b, e, st);
+            HOPK_LAUNCH_CHECK("gate_wgrad");
+        }
+        // dx of the layer input (+ residual gradient) and BN-backward sums of layer i-1
+        {
+            DxA a{S(g.s_df), S(g.s_dg), lg};
+            DxB b{p->filter_w[i], p->gate_w[i], C};
+            float* DX = dx_buf[flip];
+            if (C <= 64) {
+                DxEpi<1> e; memset(&e, 0, sizeof(e));
+                e.DU = has_du ? DU : nullptr; e.DX = DX; e.uprev = uprev; e.g = lg;
+                e.mr_prev = i > 0 ? F(g.mr) + (size_t)(i - 1) * 2 * C : nullptr;
+                e.sums_prev = i > 0 ? bnsum + (size_t)(i - 1) * 2 * C : nullptr;
+                launch_gemm<2, 1>(Min, C, 4 * C, 1, a, b, e, st);
+            } else {
+                DxEpi<2> e; memset(&e, 0, sizeof(e));
+                e.DU = has_du ? DU : nullptr; e.DX = DX; e.uprev = uprev; e.g = lg;
+                e.mr_prev = i > 0 ? F(g.mr) + (size_t)(i - 1) * 2 * C : nullptr;
+                e.sums_prev = i > 0 ? bnsum + (size_t)(i - 1) * 2 * C : nullptr;
+                launch_gemm<2, 2>(Min, C, 4 * C, 1, a, b, e, st);
+            }
+            HOPK_LAUNCH_CHECK("dx_gemm");
+            dxn = DX; flip ^= 1;
+        }
+    }
+
+    // ---- adaptive adjacency and start conv
+    adp_bwd_kernel<<<1, 256, V * V * sizeof(float), st>>>(p->nodevec1, p->nodevec2, F(g.A), F(g.Z), S(g.s_m12),
+                                                           S(g.s_m12) + V * V, V, s->rank, gr->nodevec1, gr->nodevec2);
+    HOPK_LAUNCH_CHECK("adp_bwd");
+    {
+        int M = B * g.Tp * V;
+        HOPK_CUDA(cudaMemsetAsync(gr->start_w, 0, (size_t)C * s->in_dim * sizeof(float), st));
+        HOPK_CUDA(cudaMemsetAsync(gr->start_b, 0, (size_t)C * sizeof(float), st));
+        Ld2D<false, 0> a{dxn, nullptr, C};
+        StartAT b{x, g.Tp, V, g.pad, s->in_dim, (long)xs[0], (long)xs[1], (long)xs[2], (long)xs[3]};
+        EpiWgrad<2> e{gr->start_w, s->in_dim, gr->start_b, s->in_dim, C};
+        if (C <= 64) launch_gemm<1, 2>(C, s->in_dim + 1, M, pick_splits(C, s->in_dim + 1, M, 1, 2), a, b, e, st);
+        else launch_gemm<2, 2>(C, s->in_dim + 1, M, pick_splits(C, s->in_dim + 1, M, 2, 2), a, b, e, st);
+        HOPK_LAUNCH_CHECK("start_wgrad");
+        if (dx) {
+            Ld2D<true, 0> a2{dxn, nullptr, C};
+            Ld2D<false, 0> b2{p->start_w, nullptr, s->in_dim};
+            StartDxEpi e2{dx, g.Tp, s->T, V, g.pad, s->in_dim};
+            launch_gemm<2, 2>(M, s->in_dim, C, 1, a2, b2, e2, st);
+            HOPK_LAUNCH_CHECK("start_dgrad");
+        }
+    }
+    return 0;
+}

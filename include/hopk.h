@@ -1,0 +1,135 @@
+/* hopk.h -- C ABI of libhopk.so: the sm_100a kernels behind HOP's training hot path.
+ *
+ * The reference (Chenghyyy/HOP-...) has no native code and no plugin/FFI registry: its
+ * "operator interface" for this path is the Python class surface
+ *     model/gwnet.py:8-46    nconv / linear / gcn
+ *     model/gwnet.py:49-249  gwnet.__init__ / gwnet.forward
+ *     model/HOP.py:255-299   ReprogrammingLayer.__init__ / forward / reprogramming
+ * and autograd's backward of each.  Every entry point below replaces the ATen/cuDNN/cuBLAS call
+ * sequence behind one of those methods (file:line cited per function).  The host-side mirror in
+ * hop_b200/{gwnet,HOP}.py binds these symbols with ctypes (see INTEGRATION.md for the stub a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers + sizes only; no torch types; all pointers are DEVICE pointers unless noted.
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises the host, never allocates: outputs and workspaces are caller-owned.
+ *   - return 0 on success; non-zero = error, message via hopk_last_error() (thread-local).
+ *   - dtype: 0 = fp32 storage + fp32 FFMA math (1e-5 parity mode),
+ *            1 = bf16 storage / tensor-core math with fp32 accumulation (2e-2 mode).
+ *   - "rows layout": an NCHW tensor (B, C, V, T) of the reference stored as rows
+ *     r = (b*T + t)*V + v with the C channels contiguous (i.e. the contiguous (B, T, V, C) array).
+ */
+#ifndef HOPK_H
+#define HOPK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOPK_MAX_LAYERS 16
+
+const char* hopk_last_error(void);
+int hopk_version(void);
+
+/* ------------------------------------------------------------------ Graph-WaveNet block */
+typedef struct HopkGwnetShape {
+    int B, V, T;                 /* batch, nodes (bones), input time steps (before left-padding) */
+    int in_dim, out_dim;         /* 173 / 173 in HOP (model/HOP.py:141-143) */
+    int C;                       /* residual_channels == dilation_channels (64) */
+    int S, E;                    /* skip_channels (256), end_channels (512) */
+    int L;                       /* blocks*layers (8) */
+    int dil[HOPK_MAX_LAYERS];    /* dilation of each gated conv (1,2,1,2,...), gwnet.py:98-123 */
+    int rank;                    /* adaptive-adjacency embedding width (10), gwnet.py:82-83 */
+    int training;                /* 1: BatchNorm batch statistics + running-stat update */
+    int dtype;                   /* see above */
+} HopkGwnetShape;
+
+/* Parameter / buffer pointers, named after the reference's state_dict keys (gwnet.py:50-139).
+ * All fp32 in their native PyTorch layouts: conv weights (out, in, 1, k) contiguous. */
+typedef struct HopkGwnetParams {
+    const float *nodevec1, *nodevec2;                    /* (V, rank), (rank, V) */
+    const float *start_w, *start_b;                      /* (C, in_dim, 1, 1), (C) */
+    const float *filter_w[HOPK_MAX_LAYERS], *filter_b[HOPK_MAX_LAYERS];   /* (C, C, 1, 2) */
+    const float *gate_w[HOPK_MAX_LAYERS], *gate_b[HOPK_MAX_LAYERS];       /* (C, C, 1, 2) */
+    const float *skip_w[HOPK_MAX_LAYERS], *skip_b[HOPK_MAX_LAYERS];       /* (S, C, 1, 1) */
+    const float *mlp_w[HOPK_MAX_LAYERS], *mlp_b[HOPK_MAX_LAYERS];         /* gconv.i.mlp.mlp (C, 3C, 1, 1) */
+    const float *bn_w[HOPK_MAX_LAYERS], *bn_b[HOPK_MAX_LAYERS];           /* (C) */
+    float *bn_mean[HOPK_MAX_LAYERS], *bn_var[HOPK_MAX_LAYERS];            /* running stats, updated in place */
+    int64_t *bn_nbt[HOPK_MAX_LAYERS];                                     /* num_batches_tracked */
+    const float *end1_w, *end1_b;                        /* (E, S, 1, 1) */
+    const float *end2_w, *end2_b;                        /* (out_dim, E, 1, 1) */
+} HopkGwnetParams;
+
+/* Gradient destinations (fp32, same shapes as the parameters, OVERWRITTEN not accumulated).
+ * Entries may be NULL for tensors the reference never reaches (last layer's mlp / bn affine). */
+typedef struct HopkGwnetGrads {
+    float *nodevec1, *nodevec2;
+    float *start_w, *start_b;
+    float *filter_w[HOPK_MAX_LAYERS], *filter_b[HOPK_MAX_LAYERS];
+    float *gate_w[HOPK_MAX_LAYERS], *gate_b[HOPK_MAX_LAYERS];
+    float *skip_w[HOPK_MAX_LAYERS], *skip_b[HOPK_MAX_LAYERS];
+    float *mlp_w[HOPK_MAX_LAYERS], *mlp_b[HOPK_MAX_LAYERS];
+    float *bn_w[HOPK_MAX_LAYERS], *bn_b[HOPK_MAX_LAYERS];
+    float *end1_w, *end1_b, *end2_w, *end2_b;
+} HopkGwnetGrads;
+
+/* bytes of the forward workspace (holds everything backward re-reads) and of backward's scratch */
+size_t hopk_gwnet_workspace_bytes(const HopkGwnetShape* s);
+size_t hopk_gwnet_scratch_bytes(const HopkGwnetShape* s);
+int hopk_gwnet_out_steps(const HopkGwnetShape* s);       /* max(T, receptive_field) - rf + 1 */
+
+/* gwnet.forward (model/gwnet.py:143-249).
+ *   x: input viewed as (B, in_dim, V, T) through element strides xs = {sB, sC, sV, sT}
+ *      (so both an NCHW tensor and HOP.Model's permuted (B,T,V,C) buffer are read in place).
+ *   out: (B, out_dim, V, T_out) contiguous NCHW, fp32.
+ *   ws: hopk_gwnet_workspace_bytes() bytes; must be kept untouched until backward.           */
+int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams* p,
+                       const float* x, const int64_t xs[4], float* out, void* ws, void* stream);
+
+/* autograd backward of the call above.
+ *   dout: (B, out_dim, V, T_out) contiguous.   dx: (B, T, V, in_dim) contiguous ("rows layout"),
+ *   may be NULL when the input needs no gradient.                                             */
+int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParams* p,
+                        const float* x, const int64_t xs[4], const float* dout,
+                        void* ws, void* scratch, const HopkGwnetGrads* g, float* dx, void* stream);
+
+/* nconv.forward (model/gwnet.py:12-14): out[n,c,w,l] = sum_v x[n,c,v,l] * A[v,w], contiguous NCHW.
+ * hopk_nconv_bwd: dx (same layout) and dA (V x V, overwritten). */
+int hopk_nconv_fwd(const float* x, const float* A, float* out, int N, int C, int V, int T, void* stream);
+int hopk_nconv_bwd(const float* x, const float* A, const float* dout, float* dx, float* dA,
+                   int N, int C, int V, int T, void* stream);
+
+/* ------------------------------------------------------------------ dense layers
+ * y[M,N] = act_in(x[M,K]) * w[N,K]^T + b ; flags: 1 = ReLU on the input (HOP.py:284-285 fuses the
+ * activation before out_projection), 2 = ReLU on the output.  gwnet's `linear` (gwnet.py:16-22),
+ * the reprogramming Q/K/V/O projections (HOP.py:262-265, 276-278, 285). */
+int hopk_linear_fwd(const float* x, const float* w, const float* b, float* y,
+                    int M, int N, int K, int flags, void* stream);
+/* dx (nullable), dw, db (nullable) overwritten.  `y` is needed only with flag 2. */
+int hopk_linear_bwd(const float* x, const float* w, const float* y, const float* dy,
+                    float* dx, float* dw, float* db, int M, int N, int K, int flags, void* stream);
+/* 1x1 Conv2d on NCHW (gwnet.py:16-22 `linear`, standalone use): x (B,K,V,T) -> y (B,N,V,T) */
+int hopk_conv1x1_nchw_fwd(const float* x, const float* w, const float* b, float* y,
+                          int B, int K, int N, int V, int T, void* stream);
+int hopk_conv1x1_nchw_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
+                          int B, int K, int N, int V, int T, void* stream);
+
+/* ------------------------------------------------------------------ reprogramming cross-attention
+ * ReprogrammingLayer.reprogramming (model/HOP.py:289-299):
+ *   O[b,l,h,:] = dropout(softmax_s(Q[b,l,h,:].K[s,h,:] / sqrt(E))) . V[s,h,:]
+ * q,o: (B, L, H, E)   k,v: (S, H, E)   lse: (B, H, L) log-sum-exp saved for backward.
+ * Dropout uses the counter-based mask documented in oracle/reprog_np.py (seed, flat index). */
+int hopk_xattn_fwd(const float* q, const float* k, const float* v, float* o, float* lse,
+                   int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
+/* dq (B,L,H,E), dk, dv (S,H,E): overwritten.  delta: caller-owned scratch of B*H*L floats. */
+int hopk_xattn_bwd(const float* q, const float* k, const float* v, const float* o, const float* lse,
+                   const float* dout, float* dq, float* dk, float* dv, float* delta,
+                   int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOPK_H */

@@ -1,0 +1,125 @@
+"""GPU parity of hop_b200.gwnet (libhopk.so through the C ABI) against the numpy oracle and the
+reference-generated golden fixtures.  fp32 mode: every tensor within 1e-5 of its scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gwnet_np
+from tests.golden.make_golden import GW_CASES, gw_inputs
+from tests.util import GOLDEN, TOL_FP32, Report, golden_compare, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def build_module(P, V, cfg, dev, training=True):
+    from hop_b200 import gwnet as G
+    m = G.gwnet(dev, V, dropout=0, supports=None, gcn_bool=True, addaptadj=True, aptinit=None, in_dim=cfg['in_dim'],
+                out_dim=cfg['out_dim'], residual_channels=cfg['residual'], dilation_channels=cfg['dilation'],
+                skip_channels=cfg['skip'], end_channels=cfg['end']).to(dev)
+    sd = {k: torch.from_numpy(np.asarray(v)).to(torch.float32 if np.asarray(v).dtype.kind == 'f' else torch.int64)
+          for k, v in P.items()}
+    m.load_state_dict(sd, strict=True)          # state_dict key parity with the reference's names
+    m.train(training)
+    return m
+
+
+def run_case(name, dev, channels_last):
+    seed, B, V, T, cfg = GW_CASES[name]
+    training = not name.endswith('_eval')
+    P, x, dout = gw_inputs(seed, B, V, T, cfg)
+    m = build_module(P, V, cfg, dev, training)
+    xt = torch.from_numpy(x).float().to(dev)
+    if channels_last:                             # HOP.Model hands gwnet a permuted (B,T,V,C) buffer
+        xt = xt.permute(0, 3, 2, 1).contiguous().permute(0, 3, 2, 1)
+    xt.requires_grad_(True)
+    out = m(xt)
+    out.backward(torch.from_numpy(dout).float().to(dev))
+    torch.cuda.synchronize()
+    return m, out, xt, (P, x, dout, training, cfg)
+
+
+@pytest.mark.parametrize('channels_last', [False, True])
+@pytest.mark.parametrize('name', list(GW_CASES))
+def test_gwnet_vs_oracle_and_golden(name, channels_last, cuda):
+    m, out, xt, (P, x, dout, training, cfg) = run_case(name, cuda, channels_last)
+    o_out, o_bufs, cache = gwnet_np.forward(P, x, training=training, keep=True)
+    o_dx, o_G = gwnet_np.backward(P, cache, dout)
+    fix = np.load(os.path.join(GOLDEN, name + '.npz'))
+    rep = Report(f'{name}_{"cl" if channels_last else "nchw"}', TOL_FP32)
+    rep.add('out', relerr(out.detach().cpu().numpy(), o_out))
+    rep.add('out(golden)', relerr(out.detach().cpu().numpy(), fix['out']))
+    rep.add('dx', relerr(xt.grad.cpu().numpy(), o_dx))
+    rep.add('dx(golden)', golden_compare(fix, 'dx', xt.grad.cpu().numpy()))
+    gscale = max(float(np.abs(v).max()) for v in o_G.values())
+    none_grads = set(fix['none_grads'].tolist())
+    for k, p_ in m.named_parameters():
+        if k in none_grads:
+            assert p_.grad is None, f'{k} must not receive a gradient (reference: grad None)'
+            continue
+        assert p_.grad is not None, k
+        g = p_.grad.cpu().numpy()
+        ref = o_G[k].reshape(g.shape)
+        if np.abs(ref).max() < 1e-9 * gscale:      # analytically zero (bias in front of train-mode BN)
+            rep.add('grad0:' + k, float(np.abs(g).max()) / gscale)
+        else:
+            rep.add('grad:' + k, relerr(g, ref))
+            rep.add('grad(golden):' + k, golden_compare(fix, k, g, zero_scale=gscale))
+    sd = m.state_dict()
+    for k in sd:
+        if 'running_' in k or 'num_batches' in k:
+            rep.add('buf:' + k, relerr(sd[k].cpu().numpy(), fix['buf:' + k]), tol=1e-6)
+    rep.finish()
+
+
+def test_gwnet_repeat_forward_updates_running_stats(cuda):
+    """BN running stats / num_batches_tracked advance on every forward (2-3 per training step)."""
+    seed, B, V, T, cfg = GW_CASES['gwnet_tiny']
+    P, x, _ = gw_inputs(seed, B, V, T, cfg)
+    m = build_module(P, V, cfg, cuda, True)
+    xt = torch.from_numpy(x).float().to(cuda)
+    with torch.no_grad():
+        m(xt); m(xt)
+    _, bufs1, _ = gwnet_np.forward(P, x, training=True)
+    P2 = dict(P); P2.update(bufs1)
+    _, bufs2, _ = gwnet_np.forward(P2, x, training=True)
+    sd = m.state_dict()
+    for k, v in bufs2.items():
+        assert relerr(sd[k].cpu().numpy(), v) < 1e-6, k
+
+
+def test_gwnet_batch128_properties(cuda):
+    """Full BASELINE size (B=128, TED): size-independent properties instead of an oracle run.
+    (1) batch-permutation equivariance of the train-mode block, (2) gradient linearity in dout."""
+    torch.manual_seed(0)
+    from hop_b200 import gwnet as G
+    m = G.gwnet(cuda, 9, dropout=0, in_dim=173, out_dim=173, residual_channels=64, dilation_channels=64,
+                skip_channels=256, end_channels=512).to(cuda)
+    x = torch.randn(128, 173, 9, 16, device=cuda)
+    perm = torch.randperm(128, device=cuda)
+    with torch.no_grad():
+        y = m(x)
+        yp = m(x[perm])
+    assert y.shape == (128, 173, 9, 4)
+    assert relerr(yp.cpu().numpy(), y[perm].cpu().numpy()) < 1e-5
+    d1 = torch.randn_like(y); d2 = torch.randn_like(y)
+
+    def grads(d):
+        m.zero_grad(set_to_none=True)
+        xx = x.clone().requires_grad_(True)
+        m(xx).backward(d)
+        return xx.grad.clone(), m.start_conv.weight.grad.clone(), m.nodevec1.grad.clone()
+    a, b, c = grads(d1), grads(d2), grads(d1 + 2 * d2)
+    for u, v, w in zip(a, b, c):
+        assert relerr(w.cpu().numpy(), (u + 2 * v).cpu().numpy()) < 2e-5
+
+
+def test_gwnet_unsupported_config_raises(cuda):
+    from hop_b200 import gwnet as G
+    m = G.gwnet(cuda, 5, dropout=0, gcn_bool=False, in_dim=4, out_dim=4).to(cuda)
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(2, 4, 5, 16, device=cuda))
+    m2 = G.gwnet(cuda, 5, dropout=0, in_dim=4, out_dim=4).to(cuda)
+    with pytest.raises(RuntimeError):
+        m2(torch.randn(2, 4, 5, 16))          # CPU tensor: no fallback

@@ -1,0 +1,122 @@
+"""GPU parity of hop_b200.HOP.ReprogrammingLayer against the numpy oracle / golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reprog_np
+from tests.golden.make_golden import RP_CASES, rp_inputs
+from tests.util import GOLDEN, TOL_FP32, Report, golden_compare, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def build(P, cfg, dev):
+    from hop_b200.HOP import ReprogrammingLayer
+    m = ReprogrammingLayer(cfg['d_model'], cfg['n_heads'], cfg['d_keys'], cfg['d_llm']).to(dev)
+    m.load_state_dict({k: torch.from_numpy(v).float() for k, v in P.items()}, strict=True)
+    return m
+
+
+@pytest.mark.parametrize('name', list(RP_CASES))
+def test_reprog_vs_oracle_and_golden(name, cuda):
+    seed, B, L, S, cfg = RP_CASES[name]
+    P, x, src, dY = rp_inputs(seed, B, L, S, cfg)
+    m = build(P, cfg, cuda).eval()               # p = 0: comparable with the reference itself
+    xt = torch.from_numpy(x).float().to(cuda).requires_grad_(True)
+    st = torch.from_numpy(src).float().to(cuda).requires_grad_(True)
+    y = m(xt, st, st)
+    y.backward(torch.from_numpy(dY).float().to(cuda))
+    o_y, cache = reprog_np.forward(P, x, src, src, cfg['n_heads'], keep=True)
+    o_dx, o_ds, o_dv, o_G = reprog_np.backward(P, cache, dY, cfg['n_heads'])
+    fix = np.load(os.path.join(GOLDEN, name + '.npz'))
+    rep = Report(name, TOL_FP32)
+    rep.add('out', relerr(y.detach().cpu().numpy(), o_y))
+    rep.add('out(golden)', relerr(y.detach().cpu().numpy(), fix['out']))
+    rep.add('dx', relerr(xt.grad.cpu().numpy(), o_dx))
+    rep.add('dsource', relerr(st.grad.cpu().numpy(), o_ds + o_dv))
+    rep.add('dsource(golden)', golden_compare(fix, 'dsource', st.grad.cpu().numpy()))
+    gscale = max(float(np.abs(v).max()) for v in o_G.values())
+    for k, p_ in m.named_parameters():
+        g = p_.grad.cpu().numpy()
+        if np.abs(o_G[k]).max() < 1e-9 * gscale:
+            rep.add('grad0:' + k, float(np.abs(g).max()) / gscale)
+        else:
+            rep.add('grad:' + k, relerr(g, o_G[k].reshape(g.shape)))
+            rep.add('grad(golden):' + k, golden_compare(fix, k, g, zero_scale=gscale))
+    rep.finish()
+
+
+@pytest.mark.parametrize('name', list(RP_CASES))
+def test_reprog_dropout_matches_oracle_mask(name, cuda):
+    """Train mode, p = 0.1: the kernel's counter-based mask is restated bit-for-bit by the oracle."""
+    seed, B, L, S, cfg = RP_CASES[name]
+    P, x, src, dY = rp_inputs(seed, B, L, S, cfg)
+    from hop_b200.HOP import _XattnFn
+    rs = np.random.RandomState(5)
+    H, E = cfg['n_heads'], cfg['d_keys']
+    q = rs.standard_normal((B, L, H, E)); k = rs.standard_normal((S, H, E)); v = rs.standard_normal((S, H, E))
+    do = rs.standard_normal((B, L, H, E))
+    drop_seed, p = 0x1234_5678_9ABC, 0.1
+    qt, kt, vt = [torch.from_numpy(a).float().to(cuda).requires_grad_(True) for a in (q, k, v)]
+    o = _XattnFn.apply(qt, kt, vt, p, drop_seed)
+    o.backward(torch.from_numpy(do).float().to(cuda))
+    # oracle with the same mask
+    sc = np.einsum('blhe,she->bhls', q, k) / np.sqrt(E)
+    pr = np.exp(sc - sc.max(-1, keepdims=True)); pr /= pr.sum(-1, keepdims=True)
+    idx = np.arange(B * H * L * S, dtype=np.uint64).reshape(B, H, L, S)
+    mask = reprog_np.dropout_keep(drop_seed, idx, p) / (1 - p)
+    o_ref = np.einsum('bhls,she->blhe', pr * mask, v)
+    dpd = np.einsum('blhe,she->bhls', do, v)
+    dv_ref = np.einsum('bhls,blhe->she', pr * mask, do)
+    dpr = dpd * mask
+    dsc = pr * (dpr - (dpr * pr).sum(-1, keepdims=True))
+    dq_ref = np.einsum('bhls,she->blhe', dsc, k) / np.sqrt(E)
+    dk_ref = np.einsum('bhls,blhe->she', dsc, q) / np.sqrt(E)
+    rep = Report(name + '_dropout', TOL_FP32)
+    rep.add('o', relerr(o.detach().cpu().numpy(), o_ref))
+    rep.add('dq', relerr(qt.grad.cpu().numpy(), dq_ref))
+    rep.add('dk', relerr(kt.grad.cpu().numpy(), dk_ref))
+    rep.add('dv', relerr(vt.grad.cpu().numpy(), dv_ref))
+    rep.finish()
+
+
+def test_reprog_train_mode_dropout_statistics(cuda):
+    """Module-level: train mode drops ~10% of attention weights and rescales by 1/(1-p) (unbiased in expectation)."""
+    seed, B, L, S, cfg = RP_CASES['reprog_hop']
+    P, x, src, _ = rp_inputs(seed, B, L, S, cfg)
+    m = build(P, cfg, cuda)
+    xt = torch.from_numpy(x).float().to(cuda); st = torch.from_numpy(src).float().to(cuda)
+    torch.manual_seed(3)
+    m.train()
+    q = torch.randn(B, L, 8, 128, device=cuda); k = torch.randn(S, 8, 128, device=cuda) * 0.05
+    v = torch.ones(S, 8, 128, device=cuda)
+    o = m.reprogramming(q, k, v)                 # V = 1 -> each output = sum of kept, rescaled probabilities
+    mean = float(o.mean())
+    assert abs(mean - 1.0) < 5e-3, mean
+    assert float(o.std()) > 1e-3                 # dropout really is active
+    m.eval()
+    o2 = m.reprogramming(q, k, v)
+    assert float((o2 - 1).abs().max()) < 1e-4
+    y1 = m.train()(xt, st, st); y2 = m(xt, st, st)
+    assert float((y1 - y2).abs().max()) > 0      # fresh seed per call
+
+
+def test_xattn_full_size_properties(cuda):
+    """BASELINE size (B=128, L=34, H=8, E=128, S=1500): rows of softmax sum to one (V = 1 -> O = 1) and
+    the output is invariant to a permutation of the S prototypes."""
+    from hop_b200.HOP import _XattnFn
+    torch.manual_seed(0)
+    B, L, H, E, S = 128, 34, 8, 128, 1500
+    q = torch.randn(B, L, H, E, device=cuda); k = torch.randn(S, H, E, device=cuda); v = torch.randn(S, H, E, device=cuda)
+    o1 = _XattnFn.apply(q, k, torch.ones_like(v), 0.0, 0)
+    assert float((o1 - 1).abs().max()) < 1e-5
+    perm = torch.randperm(S, device=cuda)
+    o2 = _XattnFn.apply(q, k, v, 0.0, 0); o3 = _XattnFn.apply(q, k[perm], v[perm], 0.0, 0)
+    assert relerr(o3.cpu().numpy(), o2.cpu().numpy()) < 1e-5
+    # against torch on the same device for one batch slice (fp32, TF32 off)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sc = torch.einsum('blhe,she->bhls', q[:4], k) / E ** 0.5
+    ref = torch.einsum('bhls,she->blhe', torch.softmax(sc, -1), v)
+    assert relerr(o2[:4].cpu().numpy(), ref.cpu().numpy()) < 1e-5
