@@ -17,7 +17,7 @@ from math import sqrt
 import torch
 import torch.nn as nn
 
-from . import gwnet
+from . import gwnet, profiler
 from ._lib import check, f32c, lib, ptr, stream_ptr
 
 
@@ -33,7 +33,8 @@ class _LinearFn(torch.autograd.Function):
         M, K = x2.shape
         N = w.shape[0]
         y = torch.empty((M, N), device=x.device, dtype=torch.float32)
-        check(lib().hopk_linear_fwd(ptr(x2), ptr(w), ptr(b), ptr(y), M, N, K, flags, stream_ptr()))
+        with profiler.span('linear_fwd'):
+            check(lib().hopk_linear_fwd(ptr(x2), ptr(w), ptr(b), ptr(y), M, N, K, flags, stream_ptr()))
         ctx.save_for_backward(x2, w, y if flags & 2 else None)
         ctx.flags, ctx.shp, ctx.has_bias = flags, shp, b is not None
         return y.view(*shp[:-1], N)
@@ -47,8 +48,9 @@ class _LinearFn(torch.autograd.Function):
         dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
         dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
         db = torch.empty(N, device=w.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        check(lib().hopk_linear_bwd(ptr(x2), ptr(w), ptr(y), ptr(dy2), ptr(dx), ptr(dw), ptr(db), M, N, K, ctx.flags,
-                                    stream_ptr()))
+        with profiler.span('linear_bwd'):
+            check(lib().hopk_linear_bwd(ptr(x2), ptr(w), ptr(y), ptr(dy2), ptr(dx), ptr(dw), ptr(db), M, N, K, ctx.flags,
+                                        stream_ptr()))
         return (dx.view(ctx.shp) if dx is not None else None), dw, db, None
 
 
@@ -62,8 +64,9 @@ class _XattnFn(torch.autograd.Function):
         S = k.shape[0]
         o = torch.empty_like(q)
         lse = torch.empty((B, H, L), device=q.device, dtype=torch.float32)
-        check(lib().hopk_xattn_fwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, L, H, E, S, float(p_drop), int(seed),
-                                   stream_ptr()))
+        with profiler.span('xattn_fwd'):
+            check(lib().hopk_xattn_fwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, L, H, E, S, float(p_drop), int(seed),
+                                       stream_ptr()))
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.p_drop, ctx.seed = float(p_drop), int(seed)
         return o
@@ -76,9 +79,34 @@ class _XattnFn(torch.autograd.Function):
         do = f32c(do)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         delta = torch.empty_like(lse)
-        check(lib().hopk_xattn_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv), ptr(delta),
-                                   B, L, H, E, S, ctx.p_drop, ctx.seed, stream_ptr()))
+        with profiler.span('xattn_bwd'):
+            check(lib().hopk_xattn_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
+                                       ptr(delta), B, L, H, E, S, ctx.p_drop, ctx.seed, stream_ptr()))
         return dq, dk, dv, None, None
+
+
+class _SourceFn(torch.autograd.Function):
+    """Text prototypes source = W_map @ WE + b[:, None]  (== mapping_layer(WE^T)^T, reference HOP.py:200).
+
+    WE (the frozen BERT word embeddings) is identical on every data-parallel rank and ``source`` is linear
+    in W_map, so backward first all-reduces the small upstream gradient (1500 x 768) through ``reducer`` and
+    then forms the full, already-averaged dW_map = dSource @ WE^T locally: the 183 MB weight-gradient
+    all-reduce disappears.  ``reducer`` is None on a single GPU.
+    """
+
+    @staticmethod
+    def forward(ctx, w_map, b_map, we, reducer):
+        ctx.save_for_backward(we)
+        ctx.reducer = reducer
+        return torch.addmm(b_map.unsqueeze(1), w_map, we)
+
+    @staticmethod
+    def backward(ctx, dsrc):
+        (we,) = ctx.saved_tensors
+        dsrc = dsrc.contiguous()
+        if ctx.reducer is not None:
+            dsrc = ctx.reducer(dsrc.clone())
+        return dsrc @ we.t(), dsrc.sum(1), None, None
 
 
 def _draw_seed():
@@ -197,6 +225,11 @@ class Model(nn.Module):
         self.out = nn.Sequential(nn.Linear(self.hidden_size, self.hidden_size // 2), nn.Dropout(0), nn.LeakyReLU(True),
                                  nn.Linear(self.hidden_size // 2, self.pred_g_len))
         self._win_idx = {}
+        self._source_reducer = None
+
+    def set_source_grad_reducer(self, fn):
+        """hop_b200.dp installs its all-reduce here (see :class:`_SourceFn`)."""
+        self._source_reducer = fn
 
     def forward(self, in_audio, x_enc, text, pre_seq, vid_indices=None):
         return self.forecast(in_audio, x_enc, text, pre_seq, vid_indices)
@@ -210,7 +243,8 @@ class Model(nn.Module):
 
     def source_embeddings(self):
         """Text prototypes (1500, d_llm) = mapping_layer(word_embeddings^T)^T  (HOP.py:200); batch independent."""
-        return self.mapping_layer(self.word_embeddings.permute(1, 0)).permute(1, 0)
+        return _SourceFn.apply(self.mapping_layer.weight, self.mapping_layer.bias, self.word_embeddings,
+                               self._source_reducer)
 
     def forecast(self, in_audio, x_enc, text, pre_seq, vid_indices, source=None):
         B = pre_seq.shape[0]
@@ -220,7 +254,7 @@ class Model(nn.Module):
             z_context = self.speaker_embedding(vid_indices)
             z_mu = self.speaker_mu(z_context)
             z_logvar = self.speaker_logvar(z_context)
-            z_context = reparameterize(z_mu, z_logvar)
+            z_context = reparameterize(z_mu, z_logvar)       # module-level so tests can share the noise
         else:
             z_mu = z_logvar = z_context = None
 

@@ -46,6 +46,7 @@ _I64x4 = C.c_int64 * 4
 SIGNATURES = {
     'hopk_last_error': (C.c_char_p, []),
     'hopk_version': (_i, []),
+    'hopk_launch_count': (C.c_longlong, []),
     'hopk_gwnet_workspace_bytes': (_sz, [_SHP]),
     'hopk_gwnet_scratch_bytes': (_sz, [_SHP]),
     'hopk_gwnet_out_steps': (_i, [_SHP]),

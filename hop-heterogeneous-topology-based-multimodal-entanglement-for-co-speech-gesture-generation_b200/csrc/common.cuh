@@ -21,8 +21,11 @@ inline int fail(int code, const char* what, const char* detail = "")
 #define HOPK_CUDA(expr) \
     do { cudaError_t _e = (expr); if (_e != cudaSuccess) return hopk::fail(3, #expr, cudaGetErrorString(_e)); } while (0)
 
+long long& launch_counter();        // kernels launched by this library since load (api.cu)
+
 #define HOPK_LAUNCH_CHECK(name) \
-    do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return hopk::fail(4, "launch failed: " name, cudaGetErrorString(_e)); } while (0)
+    do { hopk::launch_counter() += 1; cudaError_t _e = cudaGetLastError(); \
+         if (_e != cudaSuccess) return hopk::fail(4, "launch failed: " name, cudaGetErrorString(_e)); } while (0)
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 

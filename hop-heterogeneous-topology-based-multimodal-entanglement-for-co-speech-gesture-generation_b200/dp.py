@@ -1,0 +1,176 @@
+"""Batch-sharded data parallelism for the HOP step: one process per GPU, NCCL over NVLink/NVSwitch.
+
+Replaces what the reference gets implicitly from HF Accelerate + DeepSpeed/DDP
+(run_ted.py:110-112, 363-364):
+
+* replicas start identical (rank-0 broadcast of parameters and buffers); BatchNorm statistics stay
+  per rank, like the reference (no SyncBatchNorm);
+* gradients are all-reduced in ~25 MB buckets on a side stream *while backward is still running*:
+  each parameter's post-accumulate hook drops the gradient into its bucket's flat buffer and the
+  bucket is launched as soon as its last member arrives;
+* tensors the reference never gives a gradient (audio_encoder.*) are discovered on the
+  first step and skipped afterwards;
+* ``mapping_layer`` (183 MB of the 263 MB of gradients, produced last) is never all-reduced: its upstream
+  gradient ``dSource`` (1500x768, 4.6 MB) is all-reduced instead and every rank forms the identical
+  ``dW = dSource @ WE^T`` locally (valid because ``source`` is linear in ``W_map`` and WE is frozen and
+  replicated) -- see ``Model.source_embeddings``.
+
+``DataParallel.backward(loss)`` is the only call the training step needs (the reference's
+``accelerator.backward``).  With world_size 1 (or no process group) it degrades to ``loss.backward()``.
+"""
+import torch
+import torch.distributed as dist
+
+
+class _Bucket:
+    def __init__(self, params, device):
+        self.params = params
+        self.numel = sum(p.numel() for p in params)
+        self.flat = torch.zeros(self.numel, device=device, dtype=torch.float32)
+        self.views, off = [], 0
+        for p in params:
+            self.views.append(self.flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        self.pending = len(params)
+        self.work = None
+        self.event = None
+
+
+class _ModuleDP:
+    """Hooks + buckets of one module (generator and discriminator get one each, so a backward that only
+    touches one of them only reduces that one)."""
+
+    def __init__(self, module, owner):
+        self.module, self.o = module, owner
+        self.buckets = None
+        self._seen, self._order, self._where = set(), [], {}
+        self.fired = False
+        self.pre_reduced = set()
+        if hasattr(module, 'set_source_grad_reducer'):          # the dSource trick (see module docstring)
+            module.set_source_grad_reducer(owner._reduce_now)
+            self.pre_reduced = set(id(p) for p in module.mapping_layer.parameters())
+        seen = set()
+        for p in module.parameters():
+            if p.requires_grad and id(p) not in seen and id(p) not in self.pre_reduced:
+                seen.add(id(p))
+                p.register_post_accumulate_grad_hook(self._on_grad)
+
+    def _build_buckets(self, used):
+        device = used[0].device
+        cur, size = [], 0
+        self.buckets = []
+        for p in used:
+            cur.append(p); size += p.numel() * 4
+            if size >= self.o.bucket_bytes:
+                self.buckets.append(_Bucket(cur, device)); cur, size = [], 0
+        if cur:
+            self.buckets.append(_Bucket(cur, device))
+        for bi, b in enumerate(self.buckets):
+            for pi, p in enumerate(b.params):
+                self._where[id(p)] = (bi, pi)
+
+    def _on_grad(self, p):
+        self.fired = True
+        if self.buckets is None:                                # discovery step: record readiness order
+            if id(p) not in self._seen:
+                self._seen.add(id(p)); self._order.append(p)
+            return
+        where = self._where.get(id(p))
+        if where is None:
+            return
+        b = self.buckets[where[0]]
+        b.views[where[1]].copy_(p.grad)
+        b.pending -= 1
+        if b.pending == 0:
+            self.o._launch(b)
+
+    def begin(self):
+        self.fired = False
+        if self.buckets is not None:
+            for b in self.buckets:
+                b.pending = len(b.params)
+                b.work = None
+
+    def end(self):
+        if not self.fired:
+            return
+        if self.buckets is None:
+            # first active step: the backward was a plain one; bucket in readiness order and reduce now
+            used = [p for p in self._order if p.grad is not None]
+            self._build_buckets(used)
+            for b in self.buckets:
+                for v, p in zip(b.views, b.params):
+                    v.copy_(p.grad)
+                self.o._launch(b)
+        else:
+            for b in self.buckets:                              # members that got no gradient this step count as zero
+                if b.work is None:
+                    for (v, p) in zip(b.views, b.params):
+                        if self._where[id(p)] and p.grad is None:
+                            v.zero_()
+                    self.o._launch(b)
+        for b in self.buckets:
+            b.work.wait()                                       # orders the current stream after the collective
+        if self.o.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.o.comm_stream)
+        inv = 1.0 / self.o.world
+        for b in self.buckets:
+            b.flat.mul_(inv)
+            for v, p in zip(b.views, b.params):
+                if p.grad is not None:
+                    p.grad = v                                  # hand the averaged view to the optimiser (no copy back)
+
+
+class DataParallel:
+    def __init__(self, modules, bucket_mb=25, process_group=None, broadcast=True):
+        self.modules = list(modules) if isinstance(modules, (list, tuple)) else [modules]
+        self.group = process_group
+        self.world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        self.bucket_bytes = int(bucket_mb * (1 << 20))
+        self.stats = dict(allreduce_bytes=0, buckets=0)
+        self.comm_stream = None
+        self.parts = []
+        if self.world > 1:
+            dev = next(self.modules[0].parameters()).device
+            if dev.type == 'cuda':
+                self.comm_stream = torch.cuda.Stream(device=dev)
+            if broadcast:
+                for m in self.modules:
+                    for t in list(m.parameters()) + list(m.buffers()):
+                        dist.broadcast(t.data, src=0, group=self.group)
+            self.parts = [_ModuleDP(m, self) for m in self.modules]
+
+    def _reduce_now(self, t):
+        """Stream-ordered mean all-reduce used inside autograd for the small dSource tensor."""
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+            t.div_(self.world)
+            self.stats['allreduce_bytes'] += t.numel() * t.element_size()
+        return t
+
+    def _launch(self, b):
+        if self.comm_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record()                                         # gradients of this bucket are complete here
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                b.work = dist.all_reduce(b.flat, group=self.group, async_op=True)
+        else:
+            b.work = dist.all_reduce(b.flat, group=self.group, async_op=True)
+        self.stats['allreduce_bytes'] += b.numel * 4
+        self.stats['buckets'] += 1
+
+    def backward(self, loss):
+        """The reference's ``accelerator.backward(loss)``: backward + averaged gradients on every rank."""
+        for part in self.parts:
+            part.begin()
+        loss.backward()
+        for part in self.parts:
+            part.end()
+
+    def broadcast_buffers(self, src=0):
+        """Checkpoint-time buffer sync (BatchNorm running stats are per rank during training)."""
+        if self.world > 1:
+            for m in self.modules:
+                for t in m.buffers():
+                    dist.broadcast(t.data, src=src, group=self.group)

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib
+from . import _lib, profiler
 from ._lib import GwnetGrads, GwnetParams, GwnetShape, check, f32c, lib, ptr, stream_ptr
 
 
@@ -132,7 +132,8 @@ class _GwnetFn(torch.autograd.Function):
         out = torch.empty((B, shape.out_dim, V, t_out), device=x.device, dtype=torch.float32)
         ws = torch.empty(l.hopk_gwnet_workspace_bytes(shape), device=x.device, dtype=torch.uint8)
         xs = _lib._I64x4(*x.stride())
-        check(l.hopk_gwnet_forward(shape, pstruct, ptr(x), xs, ptr(out), ptr(ws), stream_ptr()))
+        with profiler.span('gwnet_fwd'):
+            check(l.hopk_gwnet_forward(shape, pstruct, ptr(x), xs, ptr(out), ptr(ws), stream_ptr()))
         ctx.mod, ctx.shape, ctx.ws, ctx.x, ctx.params, ctx.keep = mod, shape, ws, x, params, keep
         return out
 
@@ -164,8 +165,9 @@ class _GwnetFn(torch.autograd.Function):
             dx = torch.empty((shape.B, shape.T, shape.V, shape.in_dim), device=x.device, dtype=torch.float32)
         scratch = torch.empty(l.hopk_gwnet_scratch_bytes(shape), device=x.device, dtype=torch.uint8)
         xs = _lib._I64x4(*x.stride())
-        check(l.hopk_gwnet_backward(shape, pstruct, ptr(x), xs, ptr(dout), ptr(ctx.ws), ptr(scratch), g, ptr(dx),
-                                    stream_ptr()))
+        with profiler.span('gwnet_bwd'):
+            check(l.hopk_gwnet_backward(shape, pstruct, ptr(x), xs, ptr(dout), ptr(ctx.ws), ptr(scratch), g, ptr(dx),
+                                        stream_ptr()))
         ctx.ws = None
         if dx is not None:
             dx = dx.permute(0, 3, 2, 1)          # (B, T, V, C) rows layout -> (B, C, V, T) view

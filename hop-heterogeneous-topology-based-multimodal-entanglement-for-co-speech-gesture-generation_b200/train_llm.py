@@ -1,0 +1,95 @@
+"""Mirror of the reference's training step ``train_eval/train_llm.py::train_llm`` (lines 9-98).
+
+Same signature, same losses, same optimiser calls, same returned dict -- so the epoch loops of
+run_ted.py:399-402 / run_expressive.py:446-449 can call it unchanged.  Differences that do not
+change the arithmetic:
+  * the batch-independent text prototypes (``mapping_layer(word_embeddings)``, 70 GFLOP) are computed
+    once per step and shared by the 2-3 generator forwards (the reference recomputes them);
+  * the random-speaker pass, whose outputs the reference only uses ``.detach()``-ed, runs under
+    ``torch.no_grad()`` (its BatchNorm running-stat updates and dropout draws still happen);
+  * the 2-5 ``.item()`` host syncs are folded into one device->host read at the end.
+``accelerator`` only needs ``.backward(loss)`` (hop_b200.dp.DataParallel provides it; so does HF Accelerate).
+"""
+import torch
+import torch.nn.functional as F
+
+
+def add_noise(data):
+    return data + torch.randn_like(data) * 0.1
+
+
+def _forward(model, in_audio, log_melspec, text, pre_seq, vids, source):
+    if source is not None:
+        return model.forecast(in_audio, log_melspec, text, pre_seq, vids, source=source)
+    return model(in_audio, log_melspec, text, pre_seq, vids)
+
+
+def train_llm(args, epoch, in_audio, log_melspec, text_token_padded, target_dir_vec, vid_indices,
+              model, discriminator, model_optim, dis_optimizer, accelerator):
+    pre_seq = target_dir_vec[:, 0:16]
+    dis_error = None
+    core = getattr(model, 'module', model)
+    source = core.source_embeddings() if hasattr(core, 'source_embeddings') else None
+    gan = epoch > 10 and args.loss_gan_weight > 0.0
+
+    if gan:                                                     # discriminator step (train_llm.py:15-36)
+        dis_optimizer.zero_grad()
+        with torch.no_grad():
+            outputs, *_ = _forward(core, in_audio, log_melspec, text_token_padded, pre_seq, vid_indices,
+                                   None if source is None else source.detach())
+        dis_real = discriminator(add_noise(target_dir_vec), text_token_padded)
+        dis_fake = discriminator(add_noise(outputs.detach()), text_token_padded)
+        dis_error = torch.sum(-torch.mean(torch.log(dis_real + 1e-8) + torch.log(1 - dis_fake + 1e-8)))
+        accelerator.backward(dis_error)
+        dis_optimizer.step()
+
+    model_optim.zero_grad()                                     # generator step (train_llm.py:38-86)
+    outputs, z_context, z_mu, z_logvar = _forward(core, in_audio, log_melspec, text_token_padded, pre_seq,
+                                                   vid_indices, source)
+    dis_output = discriminator(outputs, text_token_padded)      # computed every step, like train_llm.py:43-44
+    gen_error = -torch.mean(torch.log(dis_output + 1e-8))
+    huber_loss = F.smooth_l1_loss(outputs / 0.1, target_dir_vec / 0.1) * 0.1
+    kld = div_reg = None
+    if (args.z_type == 'speaker' or args.z_type == 'random') and args.loss_reg_weight > 0.0:
+        if args.z_type == 'speaker':
+            rand_idx = torch.randperm(vid_indices.shape[0], device=vid_indices.device)
+            rand_vids = vid_indices[rand_idx]
+        else:
+            rand_vids = None
+        with torch.no_grad():
+            out_dir_vec_rand_vid, z_rand_vid, _, _ = _forward(core, in_audio, log_melspec, text_token_padded, pre_seq,
+                                                              rand_vids, None if source is None else source.detach())
+        beta = 0.05
+        pose_l1 = F.smooth_l1_loss(outputs / beta, out_dir_vec_rand_vid.detach() / beta, reduction='none') * beta
+        pose_l1 = pose_l1.sum(dim=1).sum(dim=1)
+        pose_l1 = pose_l1.view(pose_l1.shape[0], -1).mean(1)
+        z_l1 = F.l1_loss(z_context.detach(), z_rand_vid.detach(), reduction='none')
+        z_l1 = z_l1.view(z_l1.shape[0], -1).mean(1)
+        div_reg = torch.clamp(-(pose_l1 / (z_l1 + 1.0e-5)), min=-1000).mean()
+        if args.z_type == 'speaker':
+            kld = -0.5 * torch.mean(1 + z_logvar - z_mu.pow(2) - z_logvar.exp())
+            loss = huber_loss * args.loss_regression_weight + div_reg * args.loss_reg_weight + kld * args.loss_kld_weight
+        else:
+            loss = huber_loss * args.loss_regression_weight + div_reg * args.loss_reg_weight
+    else:
+        loss = huber_loss * args.loss_regression_weight
+    if gan:
+        loss = loss + gen_error * args.loss_gan_weight
+
+    accelerator.backward(loss)
+    model_optim.step()
+
+    # one device->host read for all reported scalars
+    names, vals = ['loss'], [args.loss_regression_weight * huber_loss.detach()]
+    if kld is not None:
+        names.append('KLD'); vals.append(args.loss_kld_weight * kld.detach())
+    if div_reg is not None:
+        names.append('DIV_REG'); vals.append(args.loss_reg_weight * div_reg.detach())
+    if gan:
+        names += ['gen', 'dis']; vals += [args.loss_gan_weight * gen_error.detach(), dis_error.detach()]
+    host = torch.stack([v.float().reshape(()) for v in vals]).tolist()
+    ret = dict(zip(names, host))
+    for k in ('KLD', 'DIV_REG'):                                # the reference drops falsy entries (`if kld:`)
+        if k in ret and not ret[k]:
+            del ret[k]
+    return ret

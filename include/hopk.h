@@ -33,6 +33,7 @@ extern "C" {
 
 const char* hopk_last_error(void);
 int hopk_version(void);
+long long hopk_launch_count(void);   /* kernels this library has launched in this process (host-side counter) */
 
 /* ------------------------------------------------------------------ Graph-WaveNet block */
 typedef struct HopkGwnetShape {

@@ -122,3 +122,40 @@ def generator_loss(out, out_rand, z, z_rand, z_mu, z_logvar, target, w_reg=600.0
     div = torch.clamp(-(pose_l1 / (z_l1 + 1.0e-5)), min=-1000).mean()
     kld = -0.5 * torch.mean(1 + z_logvar - z_mu.pow(2) - z_logvar.exp())
     return huber * w_reg + div * w_div + kld * w_kld, huber, div, kld
+
+
+class OracleTrainer:
+    """The reference's generator step (epoch <= 10 semantics: 2 forwards + backward + Adam(0.5, 0.999), lr const)
+    on the functional oracle.  Used as the CPU baseline / ``--impl reference`` arm of bench.py (kind "port")."""
+
+    def __init__(self, state_dict, bert, lr=4e-4, p_drop=0.1, datasets='TED'):
+        self.bert = bert
+        self.sd = {}
+        self.params = []
+        frozen = ('llm_model.', 'word_embeddings')
+        for k, v in state_dict.items():
+            t = v.detach().clone()
+            if t.is_floating_point() and not k.startswith(frozen) and 'running_' not in k:
+                t.requires_grad_(True)
+                self.params.append(t)
+            self.sd[k] = t
+        for p in bert.parameters():
+            p.requires_grad_(False)
+        self.opt = torch.optim.Adam(self.params, lr=lr, betas=(0.5, 0.999))
+        self.p_drop = p_drop
+        self.w = (600.0, 0.4, 0.6) if datasets == 'TED' else (2100.0, 0.5, 0.8)
+
+    def step(self, in_audio, x_enc, text, target, vid):
+        pre_seq = target[:, :16]
+        self.opt.zero_grad(set_to_none=True)
+        noise = torch.randn(target.shape[0], 16)
+        out, z, z_mu, z_lv = model_forward(self.sd, self.bert, in_audio, x_enc, text, pre_seq, vid, noise,
+                                           p_drop=self.p_drop)
+        rand_vid = vid[torch.randperm(vid.shape[0])]
+        with torch.no_grad():
+            out_r, z_r, _, _ = model_forward(self.sd, self.bert, in_audio, x_enc, text, pre_seq, rand_vid,
+                                             torch.randn(target.shape[0], 16), p_drop=self.p_drop)
+        loss, huber, div, kld = generator_loss(out, out_r, z, z_r, z_mu, z_lv, target, *self.w)
+        loss.backward()
+        self.opt.step()
+        return float(loss.detach())

@@ -167,6 +167,87 @@ def make_reprog(ref_hop, name):
     print(name, 'ok; out', y.shape)
 
 
+# ---------------------------------------------------------------------------------------------- full model
+class DummyTok:
+    eos_token = None
+    pad_token = None
+
+    def add_special_tokens(self, d):
+        return None
+
+
+class DummySpk:
+    n_words = 1370
+
+
+MODEL_SEED = 2021
+CHECK_PARAMS = ['gwnet.nodevec1', 'gwnet.start_conv.weight', 'gwnet.filter_convs.3.weight', 'gwnet.gconv.5.mlp.mlp.weight',
+                'gwnet.end_conv_2.bias', 'reprogramming_layer.query_projection.weight',
+                'reprogramming_layer.out_projection.bias', 'mapping_layer.bias', 'align_layer.weight', 'beat.0.weight',
+                'beat.2.bias', 'gru.weight_ih_l0', 'gru.weight_hh_l3_reverse', 'out.3.weight', 'speaker_mu.weight',
+                'speaker_embedding.0.weight', 'llm_model.encoder.layer.5.output.dense.weight', 'word_embeddings',
+                'audio_encoder.feat_extractor.0.weight']
+GRAD_PARAMS = ['gwnet.nodevec1', 'gwnet.nodevec2', 'gwnet.start_conv.weight', 'gwnet.filter_convs.0.weight',
+               'gwnet.gate_convs.7.weight', 'gwnet.skip_convs.2.weight', 'gwnet.gconv.3.mlp.mlp.weight', 'gwnet.bn.4.weight',
+               'gwnet.end_conv_1.weight', 'gwnet.end_conv_2.bias', 'reprogramming_layer.query_projection.weight',
+               'reprogramming_layer.key_projection.weight', 'reprogramming_layer.value_projection.bias',
+               'reprogramming_layer.out_projection.weight', 'mapping_layer.bias', 'mapping_layer.weight',
+               'align_layer.weight', 'beat.0.weight', 'beat.2.bias', 'gru.weight_ih_l0', 'out.3.weight',
+               'speaker_mu.weight']
+
+
+def model_inputs(datasets='TED', B=2, seed=31):
+    rs = np.random.RandomState(seed)
+    pose = 27 if datasets == 'TED' else 126
+    return dict(in_audio=(0.1 * rs.standard_normal((B, 36267))).astype(np.float32),
+                x_enc=(-80 * rs.rand(B, 34, 128)).astype(np.float32),
+                text=(rs.randint(0, 30522, (B, 34)) * (rs.rand(B, 34) > 0.7)).astype(np.int64),
+                pre_seq=np.clip(0.3 * rs.standard_normal((B, 16, pose)), -1, 1).astype(np.float32),
+                vid=rs.randint(0, 1370, (B,)).astype(np.int64),
+                noise=rs.standard_normal((B, 16)).astype(np.float32),
+                d_out=rs.standard_normal((B, 34, pose)).astype(np.float32),
+                d_mu=rs.standard_normal((B, 16)).astype(np.float32),
+                d_lv=rs.standard_normal((B, 16)).astype(np.float32))
+
+
+def model_configs(datasets='TED'):
+    return types.SimpleNamespace(d_ff=128, llm_dim=768, use_gwnet=True, use_reprograme=True, d_model=128, n_heads=8,
+                                 datasets=datasets)
+
+
+def build_bert():
+    from transformers import BertConfig, BertModel
+    return BertModel(BertConfig(num_hidden_layers=6)).eval()
+
+
+def make_model(ref_hop, datasets='TED'):
+    """Reference HOP.Model, fp32 (the reference's own precision), seed 2021, dropout p=0, shared reparameterize noise."""
+    from model import embedding_net
+    inp = model_inputs(datasets)
+    torch.manual_seed(MODEL_SEED)
+    bert = build_bert()
+    m = ref_hop.Model(model_configs(datasets), bert, DummyTok(), DummySpk()).float()
+    m.reprogramming_layer.dropout.p = 0.0
+    noise = torch.from_numpy(inp['noise'])
+    embedding_net.reparameterize = lambda mu, logvar: mu + noise * torch.exp(0.5 * logvar)
+    sd = m.state_dict()
+    fix = {'wsum:' + k: np.array([float(sd[k].double().sum()), float(sd[k].double().abs().sum())]) for k in CHECK_PARAMS}
+    fix['n_keys'] = np.array(len(sd))
+    fix['keys'] = np.array(sorted(sd.keys()))
+    t = lambda k: torch.from_numpy(inp[k])
+    out, z, z_mu, z_lv = m(t('in_audio'), t('x_enc'), t('text'), t('pre_seq'), t('vid'))
+    loss = (out * t('d_out')).sum() + (z_mu * t('d_mu')).sum() + (z_lv * t('d_lv')).sum()
+    loss.backward()
+    fix.update(out=out.detach().numpy(), z=z.detach().numpy(), z_mu=z_mu.detach().numpy(), z_logvar=z_lv.detach().numpy())
+    params = dict(m.named_parameters())
+    for k in GRAD_PARAMS:
+        pack_grad(fix, k, params[k].grad.numpy())
+    fix['none_grads'] = np.array(sorted(k for k, p_ in params.items() if p_.requires_grad and p_.grad is None))
+    name = 'hop_model_' + ('ted' if datasets == 'TED' else 'expr')
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **fix)
+    print(name, 'ok; keys', len(sd), 'out', out.shape, 'none_grads', len(fix['none_grads']))
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     ref_gwnet, ref_hop = import_reference()
@@ -174,3 +255,5 @@ if __name__ == '__main__':
         make_gwnet(ref_gwnet, n)
     for n in RP_CASES:
         make_reprog(ref_hop, n)
+    make_model(ref_hop, 'TED')
+    make_model(ref_hop, 'TED_expressive')
