@@ -177,7 +177,7 @@ def run_ours(a):
 
     torch.manual_seed(SEED)
     bert = build_bert()
-    model = Model(model_cfg(a.datasets), bert, _Tok(), _Spk()).float().to(dev)
+    model = Model(model_cfg(a.datasets), bert, _Tok(), _Spk()).float().to(dev).set_precision(a.precision)
     pose = 27 if a.datasets == 'TED' else 126
     disc = ConvDiscriminator(pose).to(dev)
     lr = 4e-4 if a.datasets == 'TED' else 2e-4                # OneCycleLR start value, never stepped
@@ -238,8 +238,11 @@ def run_ours(a):
         h2d = sum(t.numel() * t.element_size() for t in host)
         line = {'metric': 'HOP train samples/s', 'value': samples / (ms * 1e-3), 'unit': 'samples/s', 'n_gpus': world,
                 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-                'config': workload_config(a, world) | {'tf32_library_gemms': bool(a.tf32), 'gan_phase': bool(a.gan)},
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32' if a.precision == 'fp32' else 'bf16+fp32', 'data': 'synthetic',
+                'config': workload_config(a, world) | {'tf32_library_gemms': bool(a.tf32), 'gan_phase': bool(a.gan),
+                                                       'precision': a.precision + (' autocast for the stock BERT/GRU/MLP parts; '
+                                                                                   'gwnet + reprogramming kernels fp32 FFMA (this round)'
+                                                                                   if a.precision == 'bf16' else '')},
                 'clocks': clocks,
                 'e2e': {'value': samples / (e2e_ms * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': 4 * len(out)},
@@ -310,6 +313,8 @@ def main():
     ap.add_argument('--gan', action='store_true', help='epoch > 10 variant (adds the discriminator step)')
     ap.add_argument('--tf32', type=int, default=0, help='allow TF32 in the stock cuBLAS/cuDNN parts (off = fp32 like the reference)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
+                    help='bf16 (BASELINE configs[1]): stock cuBLAS/cuDNN parts under bf16 autocast; fp32: reference numerics')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)

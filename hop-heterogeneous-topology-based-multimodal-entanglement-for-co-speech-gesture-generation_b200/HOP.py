@@ -95,18 +95,21 @@ class _SourceFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, w_map, b_map, we, reducer):
+    def forward(ctx, w_map, b_map, we, reducer, dt):
+        # ``we`` arrives already in the GEMM dtype ``dt`` (cached cast of the frozen embeddings)
         ctx.save_for_backward(we)
-        ctx.reducer = reducer
-        return torch.addmm(b_map.unsqueeze(1), w_map, we)
+        ctx.reducer, ctx.dt = reducer, dt
+        with torch.autocast('cuda', enabled=False):
+            src = torch.addmm(b_map.to(dt).unsqueeze(1), w_map.to(dt), we)
+        return src.float()
 
     @staticmethod
     def backward(ctx, dsrc):
         (we,) = ctx.saved_tensors
-        dsrc = dsrc.contiguous()
+        dsrc = dsrc.contiguous().float()
         if ctx.reducer is not None:
             dsrc = ctx.reducer(dsrc.clone())
-        return dsrc @ we.t(), dsrc.sum(1), None, None
+        return (dsrc.to(ctx.dt) @ we.t()).float(), dsrc.sum(1), None, None, None
 
 
 def _draw_seed():
@@ -226,10 +229,19 @@ class Model(nn.Module):
                                  nn.Linear(self.hidden_size // 2, self.pred_g_len))
         self._win_idx = {}
         self._source_reducer = None
+        self.amp_dtype = None          # None: everything fp32 like the reference; torch.bfloat16: see set_precision
+        self._we_cast = None
 
     def set_source_grad_reducer(self, fn):
         """hop_b200.dp installs its all-reduce here (see :class:`_SourceFn`)."""
         self._source_reducer = fn
+
+    def set_precision(self, name):
+        """'fp32' (reference numerics, default) or 'bf16': the stock-PyTorch parts that are not on the
+        hand-written path (mapping GEMM, align, frozen BERT, beat MLP, GRU, out MLP) run under bf16 autocast."""
+        self.amp_dtype = {'fp32': None, 'bf16': torch.bfloat16}[name]
+        self._we_cast = None
+        return self
 
     def forward(self, in_audio, x_enc, text, pre_seq, vid_indices=None):
         return self.forecast(in_audio, x_enc, text, pre_seq, vid_indices)
@@ -243,10 +255,19 @@ class Model(nn.Module):
 
     def source_embeddings(self):
         """Text prototypes (1500, d_llm) = mapping_layer(word_embeddings^T)^T  (HOP.py:200); batch independent."""
-        return _SourceFn.apply(self.mapping_layer.weight, self.mapping_layer.bias, self.word_embeddings,
-                               self._source_reducer)
+        dt = self.amp_dtype or torch.float32
+        we = self.word_embeddings
+        if dt != we.dtype:
+            if self._we_cast is None or self._we_cast.device != we.device:
+                self._we_cast = we.detach().to(dt)          # frozen: cast once
+            we = self._we_cast
+        return _SourceFn.apply(self.mapping_layer.weight, self.mapping_layer.bias, we, self._source_reducer, dt)
 
     def forecast(self, in_audio, x_enc, text, pre_seq, vid_indices, source=None):
+        with torch.autocast('cuda', dtype=self.amp_dtype or torch.bfloat16, enabled=self.amp_dtype is not None):
+            return self._forecast(in_audio, x_enc, text, pre_seq, vid_indices, source)
+
+    def _forecast(self, in_audio, x_enc, text, pre_seq, vid_indices, source=None):
         B = pre_seq.shape[0]
         J = int(pre_seq.shape[2] / 3)
         if self.z_obj:
@@ -270,7 +291,7 @@ class Model(nn.Module):
         windows = in_audio.unfold(1, 3400, 2191)                         # (B, 16, 3400)
         feat = self.beat(windows)                                        # (B, 16, 170)
         feat = feat[:, self._window_index(J, feat.device)]               # (B, 16, J, 170)
-        seq_audio = torch.cat([pre_seq.view(B, 16, -1, 3), feat], dim=3)  # (B, 16, J, 173) == rows layout
+        seq_audio = torch.cat([pre_seq.view(B, 16, -1, 3), feat.float()], dim=3)  # (B, 16, J, 173) == rows layout
         feature = self.gwnet(seq_audio.permute(0, 3, 2, 1))               # strided view, read in place
 
         g_seq = feature[:, :3, :, :]

@@ -28,7 +28,7 @@ class Toy(nn.Module):
 
     def forward(self, x):
         from hop_b200.HOP import _SourceFn
-        src = _SourceFn.apply(self.mapping_layer.weight, self.mapping_layer.bias, self.we, self._red)   # (7, 4)
+        src = _SourceFn.apply(self.mapping_layer.weight, self.mapping_layer.bias, self.we, self._red, torch.float32)   # (7, 4)
         return self.b(torch.tanh(self.a(x))).sum(1) + self.c(src).sum() * x.mean(1)
 
 
