@@ -265,7 +265,8 @@ class Model(nn.Module):
 
     def forecast(self, in_audio, x_enc, text, pre_seq, vid_indices, source=None):
         with torch.autocast('cuda', dtype=self.amp_dtype or torch.bfloat16, enabled=self.amp_dtype is not None):
-            return self._forecast(in_audio, x_enc, text, pre_seq, vid_indices, source)
+            out = self._forecast(in_audio, x_enc, text, pre_seq, vid_indices, source)
+        return tuple(t.float() if t is not None else None for t in out)     # callers (losses, discriminator) see fp32
 
     def _forecast(self, in_audio, x_enc, text, pre_seq, vid_indices, source=None):
         B = pre_seq.shape[0]

@@ -3,6 +3,7 @@
 //   * hopk_conv1x1_nchw_{fwd,bwd}: gwnet's `linear` module used stand-alone (model/gwnet.py:16-22)
 //   * hopk_nconv_{fwd,bwd}: gwnet's `nconv` module used stand-alone (model/gwnet.py:8-14)
 #include "functors.cuh"
+#include "gemm_tc.cuh"
 #include "common.cuh"
 #include "../../include/hopk.h"
 
@@ -129,6 +130,13 @@ extern "C" int hopk_linear_fwd(const float* x, const float* w, const float* b, f
     cudaStream_t st = (cudaStream_t)stream;
     Ld2D<true, 0> wl{w, nullptr, K};
     int oflags = (flags & 2) ? 1 : 0;
+    if (flags & 0x100) {                      // bf16 tensor-core math (tcgen05), fp32 accumulate / output
+        EpiStoreTC e{y, N, b, nullptr, N, oflags};
+        if (flags & 1) { Ld2D<true, 1> a{x, nullptr, K}; HOPK_CUDA(launch_gemm_tc(M, N, K, a, wl, e, st)); }
+        else { Ld2D<true, 0> a{x, nullptr, K}; HOPK_CUDA(launch_gemm_tc(M, N, K, a, wl, e, st)); }
+        hopk::launch_counter() += 1;
+        return 0;
+    }
     if (flags & 1) {
         Ld2D<true, 1> a{x, nullptr, K};
         EpiStore<2> e{y, N, b, nullptr, N, oflags};

@@ -75,3 +75,24 @@ def test_linear_fn_flags(cuda):
         rep.add(f'dw[{flags}]', relerr(wg.grad.cpu().numpy(), wr.grad.numpy()))
         rep.add(f'db[{flags}]', relerr(bg.grad.cpu().numpy(), br.grad.numpy()))
     rep.finish()
+
+
+@pytest.mark.parametrize('M,K,N', [(128, 64, 128), (300, 128, 1024), (1500, 768, 1024), (70, 37, 45), (4352, 1024, 768)])
+def test_linear_tcgen05_forward(M, K, N, cuda):
+    """bf16 tensor-core path (tcgen05, flag 0x100): with inputs already representable in bf16 the only
+    error left is fp32 accumulation order, so the UMMA plumbing is checked at 1e-5."""
+    from hop_b200.HOP import _LinearFn
+    torch.manual_seed(M + K)
+    x = torch.randn(M, K).bfloat16().double()
+    w = (torch.randn(N, K) * 0.1).bfloat16().double()
+    b = torch.randn(N, dtype=torch.float64)
+    rep = Report(f'linear_tc_{M}_{K}_{N}', TOL_FP32)
+    for flags in (0, 1, 2):
+        xin = torch.relu(x) if flags & 1 else x
+        ref = xin @ w.T + b
+        if flags & 2:
+            ref = torch.relu(ref)
+        with torch.no_grad():
+            y = _LinearFn.apply(x.float().to(cuda), w.float().to(cuda), b.float().to(cuda), flags | 0x100)
+        rep.add(f'y[{flags}]', relerr(y.cpu().numpy(), ref.numpy()))
+    rep.finish()
