@@ -131,17 +131,24 @@ class ReprogrammingLayer(nn.Module):
         self.n_heads = n_heads
         self.activation = nn.ReLU()
         self.dropout = nn.Dropout(attention_dropout)
+        self.precision = 'fp32'       # 'bf16': projections on tcgen05 (bf16 operands, fp32 accumulate)
+
+    def set_precision(self, name):
+        assert name in ('fp32', 'bf16')
+        self.precision = name
+        return self
 
     def forward(self, target_embedding, source_embedding, value_embedding):
         B, L, _ = target_embedding.shape
         S, _ = source_embedding.shape
         H = self.n_heads
-        q = _LinearFn.apply(target_embedding, self.query_projection.weight, self.query_projection.bias, 0).view(B, L, H, -1)
-        k = _LinearFn.apply(source_embedding, self.key_projection.weight, self.key_projection.bias, 0).view(S, H, -1)
-        v = _LinearFn.apply(value_embedding, self.value_projection.weight, self.value_projection.bias, 0).view(S, H, -1)
+        tc = 0x100 if self.precision == 'bf16' else 0
+        q = _LinearFn.apply(target_embedding, self.query_projection.weight, self.query_projection.bias, tc).view(B, L, H, -1)
+        k = _LinearFn.apply(source_embedding, self.key_projection.weight, self.key_projection.bias, tc).view(S, H, -1)
+        v = _LinearFn.apply(value_embedding, self.value_projection.weight, self.value_projection.bias, tc).view(S, H, -1)
         out = self.reprogramming(q, k, v).reshape(B, L, -1)
         # ReLU (HOP.py:284) is fused into the out-projection's operand load (flag 1)
-        return _LinearFn.apply(out, self.out_projection.weight, self.out_projection.bias, 1)
+        return _LinearFn.apply(out, self.out_projection.weight, self.out_projection.bias, 1 | tc)
 
     def reprogramming(self, target_embedding, source_embedding, value_embedding):
         p = self.dropout.p if self.training else 0.0
@@ -241,6 +248,8 @@ class Model(nn.Module):
         hand-written path (mapping GEMM, align, frozen BERT, beat MLP, GRU, out MLP) run under bf16 autocast."""
         self.amp_dtype = {'fp32': None, 'bf16': torch.bfloat16}[name]
         self._we_cast = None
+        self.gwnet.set_precision(name)
+        self.reprogramming_layer.set_precision(name)
         return self
 
     def forward(self, in_audio, x_enc, text, pre_seq, vid_indices=None):

@@ -6,6 +6,7 @@
 // its (B, 16, V, 173) buffer to the kernels without a permute copy.
 #pragma once
 #include "gemm_core.cuh"
+#include "gemm_tc.cuh"
 
 namespace hopk {
 
@@ -83,6 +84,23 @@ struct EpiStore {
             }
     }
     __device__ __forceinline__ void flush(int) {}
+    // tensor-core skeleton (gemm_tc.cuh): 32 consecutive columns of one row
+    __device__ __forceinline__ void row32(int m, bool valid, int n0, float (&v)[32], float*) {
+        if (!valid) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int n = n0 + j;
+            if (n < N) {
+                float x = v[j];
+                if (bias) x += __ldg(bias + n);
+                if (flags & 1) x = fmaxf(x, 0.f);
+                long idx = (long)m * ld + n;
+                if (flags & 4) x = (__ldg(aux + idx) > 0.f) ? x : 0.f;
+                if (flags & 2) atomicAdd(out + idx, x); else out[idx] = x;
+            }
+        }
+    }
+    __device__ __forceinline__ void finish(float*) {}
 };
 
 template <int NG>
@@ -98,6 +116,15 @@ struct EpiStoreStrided {    // out[rowmap(m), n] = v + bias[n]
             }
     }
     __device__ __forceinline__ void flush(int) {}
+    __device__ __forceinline__ void row32(int m, bool valid, int n0, float (&v)[32], float*) {
+        if (!valid) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int n = n0 + j;
+            if (n < N) out[rm.off(m, n)] = v[j] + (bias ? __ldg(bias + n) : 0.f);
+        }
+    }
+    __device__ __forceinline__ void finish(float*) {}
 };
 
 // weight-gradient epilogue: rows n of dW (ld = K) plus the bias gradient in virtual column K.
@@ -115,6 +142,16 @@ struct EpiWgrad {
             }
     }
     __device__ __forceinline__ void flush(int) {}
+    __device__ __forceinline__ void row32(int n, bool valid, int k0, float (&v)[32], float*) {
+        if (!valid) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int k = k0 + j;
+            if (k < K) atomicAdd(dw + (long)n * ld + k, v[j]);
+            else if (k == K && db) atomicAdd(db + n, v[j]);
+        }
+    }
+    __device__ __forceinline__ void finish(float*) {}
 };
 
 }  // namespace hopk

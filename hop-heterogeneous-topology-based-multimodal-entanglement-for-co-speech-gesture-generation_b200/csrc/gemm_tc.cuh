@@ -1,32 +1,35 @@
 // gemm_tc.cuh -- tcgen05 GEMM skeleton: C[m][n] = sum_k A(m,k) * B(n,k) with bf16 operands and fp32 TMEM accumulators.
 //
-// Same functor contracts as the FFMA skeleton (gemm_core.cuh): loaders return fp32 elements (so gathers, BatchNorm
+// Same loader contract as the FFMA skeleton (gemm_core.cuh): loaders return fp32 elements (so gathers, BatchNorm
 // folding, dilated taps and concatenations fuse into the tile load exactly as on the fp32 path); the conversion to bf16
-// happens on the way into shared memory.  One CTA = one 128 x 128 output tile; K is consumed in slabs of 64:
+// happens on the way into shared memory.  One CTA = one 128 x BN output tile (BN = 64 or 128) over one K split;
+// K is consumed in slabs of 64:
 //   all 256 threads stage slab k+1 (global -> regs -> bf16 -> swizzled smem) while the tensor core works on slab k
 //   (two smem stages, one mbarrier per stage armed by tcgen05.commit); one elected thread issues the UMMAs;
 //   the epilogue reads the accumulator row-per-thread with tcgen05.ld (warps 0-3 = TMEM lane quarters).
-// Epilogue contract:  void row32(int m, int n0, const float (&v)[32]);   // 32 consecutive columns of row m
-//                     void finish();                                       // once per thread (column reductions)
+// Epilogue contract (thread-private copy, like the FFMA skeleton):
+//   void row32(int m, bool valid, int n0, float (&v)[32], float* red);  // 32 consecutive columns of row m; called by
+//                                                                       // every lane of warps 0-3 (valid = m < M)
+//   void finish(float* red);        // by all 256 threads after a __syncthreads; red = 256 zero-initialised smem floats
 #pragma once
 #include "tc_core.cuh"
 
 namespace hopk {
 
 constexpr int TC_THREADS = 256;
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
-// dynamic smem: 2 stages x (A slab + B slab) + 1024 B alignment slack
-constexpr size_t TC_SMEM_BYTES = 2 * (tc::slab_bytes(TC_BM) + tc::slab_bytes(TC_BN)) + 1024;
+constexpr int TC_BM = 128, TC_BK = 64;
+template <int BN>
+constexpr size_t tc_smem_bytes() { return 2 * (tc::slab_bytes(TC_BM) + tc::slab_bytes(BN)) + 1024; }
 
-template <class L>
+template <int ROWS, class L>
 __device__ __forceinline__ void tc_stage_slab(uint8_t* slab, const L& ld, int row0, int nrows_valid, int k0, int kmax)
 {
-    // 128 rows x 8 chunks; lane order follows the loader's contiguous index so global reads coalesce
+    // ROWS rows x 8 chunks; lane order follows the loader's contiguous index so global reads coalesce
 #pragma unroll
-    for (int it = 0; it < (128 * 8) / TC_THREADS; ++it) {
+    for (int it = 0; it < (ROWS * 8) / TC_THREADS; ++it) {
         int idx = threadIdx.x + it * TC_THREADS;
         int row, ch;
-        if (L::kFast) { ch = idx & 7; row = idx >> 3; } else { row = idx & 127; ch = idx >> 7; }
+        if (L::kFast) { ch = idx & 7; row = idx >> 3; } else { row = idx % ROWS; ch = idx / ROWS; }
         float f[8];
         int i = row0 + row;
 #pragma unroll
@@ -38,38 +41,60 @@ __device__ __forceinline__ void tc_stage_slab(uint8_t* slab, const L& ld, int ro
     }
 }
 
-template <class ALoad, class BLoad, class Epi>
+// sum over the 32 lanes of v[j], result for column j = lane delivered to that lane (31 shuffles)
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32])
+{
+    const int lane = threadIdx.x & 31;
+#define HOPK_TS_STEP(OFF)                                                          \
+    {                                                                              \
+        const bool upper = lane & OFF;                                             \
+        _Pragma("unroll") for (int j = 0; j < OFF; ++j) {                          \
+            float send = upper ? v[j] : v[j + OFF];                                \
+            float keep = upper ? v[j + OFF] : v[j];                                \
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);                 \
+        }                                                                          \
+    }
+    HOPK_TS_STEP(16) HOPK_TS_STEP(8) HOPK_TS_STEP(4) HOPK_TS_STEP(2) HOPK_TS_STEP(1)
+#undef HOPK_TS_STEP
+    return v[0];
+}
+
+template <int BN, class ALoad, class BLoad, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(int M, int N, int K, ALoad aload, BLoad bload, Epi epi)
+gemm_tc_kernel(int M, int N, int K, int k_per_split, ALoad aload, BLoad bload, Epi epi)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float red[256];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr uint32_t A_BYTES = tc::slab_bytes(TC_BM), B_BYTES = tc::slab_bytes(TC_BN), STAGE = A_BYTES + B_BYTES;
+    constexpr uint32_t A_BYTES = tc::slab_bytes(TC_BM), B_BYTES = tc::slab_bytes(BN), STAGE = A_BYTES + B_BYTES;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    const int k_begin = blockIdx.z * k_per_split;
+    const int k_end = min(K, k_begin + k_per_split);
 
     if (tid == 0) {
         tc::mbar_init(&bars[0], 1);
         tc::mbar_init(&bars[1], 1);
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 128);
+    red[tid] = 0.f;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, BN);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_smem;
-    constexpr uint32_t idesc = tc::idesc_bf16(TC_BM, TC_BN, 0, 0);
+    constexpr uint32_t idesc = tc::idesc_bf16(TC_BM, BN, 0, 0);
 
-    const int nslabs = (K + TC_BK - 1) / TC_BK;
+    const int nslabs = k_end > k_begin ? (k_end - k_begin + TC_BK - 1) / TC_BK : 0;
     for (int ks = 0; ks < nslabs; ++ks) {
         const int buf = ks & 1;
         if (ks >= 2) tc::mbar_wait(&bars[buf], ((ks >> 1) - 1) & 1);      // UMMAs that read this stage are done
         uint8_t* sa = smem + buf * STAGE;
         uint8_t* sb = sa + A_BYTES;
-        tc_stage_slab(sa, aload, m0, M, ks * TC_BK, K);
-        tc_stage_slab(sb, bload, n0, N, ks * TC_BK, K);
+        tc_stage_slab<TC_BM>(sa, aload, m0, M, k_begin + ks * TC_BK, k_end);
+        tc_stage_slab<BN>(sb, bload, n0, N, k_begin + ks * TC_BK, k_end);
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
@@ -92,51 +117,37 @@ gemm_tc_kernel(int M, int N, int K, ALoad aload, BLoad bload, Epi epi)
         const int m = m0 + warp * 32 + (tid & 31);
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < TC_BN / 32; ++c) {
+        for (int c = 0; c < BN / 32; ++c) {
             float v[32];
             if (nslabs > 0) tc::tmem_ld32(lane_addr + c * 32, v);
             else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
             }
-            if (m < M) e.row32(m, n0 + c * 32, v);
+            e.row32(m, m < M, n0 + c * 32, v, red);
         }
     }
-    e.finish();
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 128);
+    e.finish(red);
+    if (warp == 0) tc::tmem_dealloc(tmem, BN);
 }
 
-// ---------------------------------------------------------------- epilogues for the tensor-core skeleton
-// flags: 1 = relu on output, 4 = mask by aux > 0
-struct EpiStoreTC {
-    float* out; long ld; const float* bias; const float* aux; int N; int flags;
-    __device__ __forceinline__ void row32(int m, int n0, const float (&v)[32]) {
-        float* row = out + (size_t)m * ld;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            int n = n0 + j;
-            if (n < N) {
-                float x = v[j];
-                if (bias) x += __ldg(bias + n);
-                if (flags & 1) x = fmaxf(x, 0.f);
-                if (flags & 4) x = (__ldg(aux + (size_t)m * ld + n) > 0.f) ? x : 0.f;
-                row[n] = x;
-            }
-        }
-    }
-    __device__ __forceinline__ void finish() {}
-};
-
-template <class AL, class BL, class EP>
-static cudaError_t launch_gemm_tc(int M, int N, int K, AL a, BL b, EP e, cudaStream_t st)
+template <int BN, class AL, class BL, class EP>
+static cudaError_t launch_gemm_tc(int M, int N, int K, int splits, AL a, BL b, EP e, cudaStream_t st)
 {
-    auto kern = gemm_tc_kernel<AL, BL, EP>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-    if (err != cudaSuccess) return err;
-    dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
-    kern<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(M, N, K, a, b, e);
+    auto kern = gemm_tc_kernel<BN, AL, BL, EP>;
+    static bool configured = false;             // per instantiation
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<BN>());
+        if (err != cudaSuccess) return err;
+        configured = true;
+    }
+    int kper = K;
+    if (splits > 1) { kper = (((K + splits - 1) / splits + TC_BK - 1) / TC_BK) * TC_BK; splits = (K + kper - 1) / kper; }
+    if (splits < 1) splits = 1;
+    dim3 grid((N + BN - 1) / BN, (M + TC_BM - 1) / TC_BM, splits);
+    kern<<<grid, TC_THREADS, tc_smem_bytes<BN>(), st>>>(M, N, K, kper, a, b, e);
     return cudaGetLastError();
 }
 

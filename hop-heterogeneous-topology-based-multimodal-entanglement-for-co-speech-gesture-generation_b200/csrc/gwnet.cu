@@ -366,6 +366,15 @@ struct StartDxEpi {          // dIn rows layout over the un-padded T
             for (int j = 0; j < 4; ++j) { int n = nb + 64 * g + j; if (n < K) row[n] = v[4 * g + j]; }
     }
     __device__ __forceinline__ void flush(int) {}
+    __device__ __forceinline__ void row32(int m, bool valid, int n0, float (&v)[32], float*) {
+        if (!valid) return;
+        int vv = m % V; int bt = m / V; int t = bt % Tp - pad; int b = bt / Tp;
+        if (t < 0) return;
+        float* row = dx + ((size_t)(b * T + t) * V + vv) * K;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { int n = n0 + j; if (n < K) row[n] = v[j]; }
+    }
+    __device__ __forceinline__ void finish(float*) {}
 };
 
 struct GateA {               // k = tap*C + c ; value = BN_{i-1}(u_prev)[b, t + tap*d, v, c]
@@ -379,9 +388,11 @@ struct GateA {               // k = tap*C + c ; value = BN_{i-1}(u_prev)[b, t + 
 };
 struct GateB {               // logical column n: block of 128 = [64 filter channels | the same 64 gate channels]
     static constexpr bool kFast = true;
-    const float* wf; const float* wg; int C;
+    const float* wf; const float* wg; int C; int tcmap;     // tcmap: blocks of 32 = [16 filter | the same 16 gate]
     __device__ __forceinline__ float operator()(int n, int k) const {
-        int blk = n >> 7, w = n & 127; int fg = w >> 6; int o = blk * 64 + (w & 63);
+        int fg, o;
+        if (tcmap) { fg = (n >> 4) & 1; o = (n >> 5) * 16 + (n & 15); }
+        else { int blk = n >> 7, w = n & 127; fg = w >> 6; o = blk * 64 + (w & 63); }
         if (o >= C) return 0.f;
         int tap = k >= C; int c = k - tap * C;
         return __ldg((fg ? wg : wf) + (size_t)o * 2 * C + 2 * c + tap);
@@ -412,6 +423,31 @@ struct GateEpi {             // tanh(f)*sigmoid(g) (gwnet.py:186-200); keeps tf,
         }
     }
     __device__ __forceinline__ void flush(int) {}
+    // tensor-core column map: v[0..15] = filter channels c0.., v[16..31] = gate channels c0..
+    __device__ __forceinline__ void row32(int m, bool valid, int n0, float (&v)[32], float*) {
+        int c0 = (n0 >> 5) * 16;
+        if (!valid || c0 >= g.C) return;
+        int vv = m % g.V; int bt = m / g.V; int t = bt % g.To; int b = bt / g.To;
+        int tt = t - (g.To - Tl);
+        size_t o = (size_t)m * g.C + c0;
+        size_t q = tt >= 0 ? ((size_t)(b * Tl + tt) * g.V + vv) * ((size_t)L * g.C) + (size_t)layer * g.C + c0 : 0;
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+            if (c0 + j4 >= g.C) break;
+            float tf[4], sg[4], y[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                tf[j] = tanhf(v[j4 + j] + __ldg(bf + c0 + j4 + j));
+                sg[j] = sigmoidf_acc(v[16 + j4 + j] + __ldg(bg + c0 + j4 + j));
+                y[j] = tf[j] * sg[j];
+            }
+            *reinterpret_cast<float4*>(TF + o + j4) = make_float4(tf[0], tf[1], tf[2], tf[3]);
+            *reinterpret_cast<float4*>(SG + o + j4) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+            *reinterpret_cast<float4*>(Y + o + j4) = make_float4(y[0], y[1], y[2], y[3]);
+            if (tt >= 0) *reinterpret_cast<float4*>(ycat + q + j4) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+    }
+    __device__ __forceinline__ void finish(float*) {}
 };
 
 struct Seg3A {               // A(m, k): k = seg*C + c over three row-layout sources
@@ -435,8 +471,33 @@ struct Seg3AT {              // B'(kout, m): same sources, transposed role, ones
 };
 template <int NG>
 struct MlpEpi {              // u = h + bias + residual (gwnet.py:43-45, 233) and BatchNorm statistics
-    const float* bm; const float* up; const float* ss; float* U; double* stats; LayerGeom g;
+    const float* bm; const float* up; const float* ss; float* U; double* stats; LayerGeom g; int tc_bn;
     float s1[4 * NG], s2[4 * NG];
+    __device__ __forceinline__ void row32(int m, bool valid, int n0, float (&v)[32], float* red) {
+        float sq[32];
+        long rr = valid ? g.in_row(m) + (long)g.d * g.V : 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int n = n0 + j;
+            float u = 0.f;
+            if (valid && n < g.C) {
+                float x = fmaf(__ldg(up + rr * g.C + n), __ldg(ss + n), __ldg(ss + g.C + n));
+                u = v[j] + __ldg(bm + n) + x;
+                U[(size_t)m * g.C + n] = u;
+            }
+            v[j] = u; sq[j] = u * u;
+        }
+        float a = warp_transpose_sum(v), b = warp_transpose_sum(sq);
+        int slot = (n0 + (threadIdx.x & 31)) & 127;
+        atomicAdd(red + slot, a); atomicAdd(red + 128 + slot, b);
+    }
+    __device__ __forceinline__ void finish(float* red) {
+        int n = blockIdx.x * tc_bn + threadIdx.x;
+        if ((int)threadIdx.x < tc_bn && n < g.C && stats) {
+            atomicAdd(stats + n, (double)red[n & 127]);
+            atomicAdd(stats + g.C + n, (double)red[128 + (n & 127)]);
+        }
+    }
     __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[4 * NG]) {
         long rr = g.in_row(m) + (long)g.d * g.V;
 #pragma unroll
@@ -499,6 +560,19 @@ struct SkipEpi {             // relu(sum + sum_l bias_l)
             }
     }
     __device__ __forceinline__ void flush(int) {}
+    __device__ __forceinline__ void row32(int m, bool valid, int n0, float (&v)[32], float*) {
+        if (!valid) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int n = n0 + j;
+            if (n < N) {
+                float x = v[j];
+                for (int l = 0; l < L; ++l) x += __ldg(b[l] + n);
+                out[(size_t)m * N + n] = fmaxf(x, 0.f);
+            }
+        }
+    }
+    __device__ __forceinline__ void finish(float*) {}
 };
 template <int NG>
 struct SkipWgradEpi {        // out row n = s, col k = layer*C + c (+ bias column at L*C, written to every layer's bias)
@@ -514,6 +588,16 @@ struct SkipWgradEpi {        // out row n = s, col k = layer*C + c (+ bias colum
             }
     }
     __device__ __forceinline__ void flush(int) {}
+    __device__ __forceinline__ void row32(int n, bool valid, int k0, float (&v)[32], float*) {
+        if (!valid) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int k = k0 + j;
+            if (k < L * C) { int l = k / C; atomicAdd(dw[l] + (size_t)n * C + (k - l * C), v[j]); }
+            else if (k == L * C) { for (int l = 0; l < L; ++l) atomicAdd(db[l] + n, v[j]); }
+        }
+    }
+    __device__ __forceinline__ void finish(float*) {}
 };
 
 struct DyB {                 // B(n = c, k = seg*C + o) = Wm[o][seg*C + c]
@@ -546,6 +630,24 @@ struct DyEpi {               // dy (+ skip-path gradient) -> df, dg   (Appendix 
             }
     }
     __device__ __forceinline__ void flush(int) {}
+    __device__ __forceinline__ void row32(int m, bool valid, int n0, float (&v)[32], float*) {
+        if (!valid) return;
+        int vv = m % g.V; int bt = m / g.V; int t = bt % g.To; int b = bt / g.To;
+        int tt = t - (g.To - Tl);
+        const float* dyc = tt >= 0 ? dycat + ((size_t)(b * Tl + tt) * g.V + vv) * ((size_t)L * g.C) + (size_t)layer * g.C : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int n = n0 + j;
+            if (n < g.C) {
+                float dy = v[j] + (dyc ? __ldg(dyc + n) : 0.f);
+                size_t o = (size_t)m * g.C + n;
+                float tf = __ldg(TF + o), sg = __ldg(SG + o);
+                DF[o] = dy * sg * (1.f - tf * tf);
+                DG[o] = dy * tf * sg * (1.f - sg);
+            }
+        }
+    }
+    __device__ __forceinline__ void finish(float*) {}
 };
 
 struct GateWgA {             // A'(n = fg*C + o, m) = (fg ? DG : DF)[m][o]
@@ -582,6 +684,18 @@ struct GateWgEpi {
             }
     }
     __device__ __forceinline__ void flush(int) {}
+    __device__ __forceinline__ void row32(int n, bool valid, int k0, float (&v)[32], float*) {
+        if (!valid) return;
+        int fg = n >= C; int o = n - fg * C;
+        float* dw = fg ? dwg : dwf; float* db = fg ? dbg : dbf;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int k = k0 + j;
+            if (k < 2 * C) atomicAdd(dw + (size_t)o * 2 * C + k, v[j]);
+            else if (k == 2 * C) atomicAdd(db + o, v[j]);
+        }
+    }
+    __device__ __forceinline__ void finish(float*) {}
 };
 
 struct DxA {                 // A(m_in, k = (tap*2 + fg)*C + o) = (fg?DG:DF)[(b, t - tap*d, v)][o], 0 outside [0, To)
@@ -604,8 +718,37 @@ struct DxB {                 // B(n = c, k) = W_fg[o][c][tap]
 };
 template <int NG>
 struct DxEpi {               // + residual gradient du[t-d]; BatchNorm-backward sums for the previous layer
-    const float* DU; float* DX; const float* uprev; const float* mr_prev; double* sums_prev; LayerGeom g;
+    const float* DU; float* DX; const float* uprev; const float* mr_prev; double* sums_prev; LayerGeom g; int tc_bn;
     float s1[4 * NG], s2[4 * NG];
+    __device__ __forceinline__ void row32(int m, bool valid, int n0, float (&v)[32], float* red) {
+        float w[32];
+        int vv = 0, t = 0, b = 0;
+        if (valid) { vv = m % g.V; int bt = m / g.V; t = bt % g.Ti; b = bt / g.Ti; }
+        const float* du = (valid && DU && t >= g.d) ? DU + ((size_t)(b * g.To + t - g.d) * g.V + vv) * g.C : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int n = n0 + j;
+            float dx = 0.f, xh = 0.f;
+            if (valid && n < g.C) {
+                dx = v[j] + (du ? __ldg(du + n) : 0.f);
+                DX[(size_t)m * g.C + n] = dx;
+                if (sums_prev) xh = (__ldg(uprev + (size_t)m * g.C + n) - __ldg(mr_prev + n)) * __ldg(mr_prev + g.C + n);
+            }
+            v[j] = dx; w[j] = dx * xh;
+        }
+        if (sums_prev) {
+            float a = warp_transpose_sum(v), c = warp_transpose_sum(w);
+            int slot = (n0 + (threadIdx.x & 31)) & 127;
+            atomicAdd(red + slot, a); atomicAdd(red + 128 + slot, c);
+        }
+    }
+    __device__ __forceinline__ void finish(float* red) {
+        int n = blockIdx.x * tc_bn + threadIdx.x;
+        if (sums_prev && (int)threadIdx.x < tc_bn && n < g.C) {
+            atomicAdd(sums_prev + n, (double)red[n & 127]);
+            atomicAdd(sums_prev + g.C + n, (double)red[128 + (n & 127)]);
+        }
+    }
     __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[4 * NG]) {
         int vv = m % g.V; int bt = m / g.V; int t = bt % g.Ti; int b = bt / g.Ti;
         const float* du = (DU && t >= g.d) ? DU + ((size_t)(b * g.To + t - g.d) * g.V + vv) * g.C : nullptr;
@@ -641,8 +784,13 @@ struct DxEpi {               // + residual gradient du[t-d]; BatchNorm-backward 
 
 // ============================================================================ launch helpers
 template <int MG, int NG, class AL, class BL, class EP>
-static void launch_gemm(int M, int N, int K, int splits, AL a, BL b, EP e, cudaStream_t st)
+static void launch_gemm(bool tc, int M, int N, int K, int splits, AL a, BL b, EP e, cudaStream_t st)
 {
+    if (tc) {                     // dtype 1: bf16 operands on tcgen05, fp32 accumulate (gemm_tc.cuh)
+        if (N <= 64) launch_gemm_tc<64>(M, N, K, splits, a, b, e, st);
+        else launch_gemm_tc<128>(M, N, K, splits, a, b, e, st);
+        return;
+    }
     int kper = K;
     if (splits > 1) { kper = ((cdiv(K, splits) + GEMM_BK - 1) / GEMM_BK) * GEMM_BK; splits = cdiv(K, kper); }
     if (splits < 1) splits = 1;
@@ -650,11 +798,12 @@ static void launch_gemm(int M, int N, int K, int splits, AL a, BL b, EP e, cudaS
     gemm_kernel<MG, NG, AL, BL, EP><<<grid, GEMM_THREADS, 0, st>>>(M, N, K, kper, a, b, e);
 }
 
-static int pick_splits(int M, int N, int K, int mg, int ng)
+static int pick_splits(bool tc, int M, int N, int K, int mg, int ng)
 {
+    if (tc) { mg = 2; ng = N <= 64 ? 1 : 2; }
     long tiles = (long)cdiv(M, 64 * mg) * cdiv(N, 64 * ng);
     long want = (2 * 148 + tiles - 1) / tiles;
-    long maxs = K / 256 > 0 ? K / 256 : 1;
+    long maxs = K / (tc ? 512 : 256) > 0 ? K / (tc ? 512 : 256) : 1;
     return (int)(want < maxs ? want : maxs);
 }
 
@@ -682,7 +831,7 @@ extern "C" int hopk_gwnet_out_steps(const HopkGwnetShape* s) { return make_layou
 
 static int check_shape(const HopkGwnetShape* s)
 {
-    HOPK_REQUIRE(s->dtype == 0, "gwnet: only dtype 0 (fp32) is implemented in this entry point");
+    HOPK_REQUIRE(s->dtype == 0 || s->dtype == 1, "gwnet: dtype must be 0 (fp32 FFMA) or 1 (bf16 tensor-core math)");
     HOPK_REQUIRE(s->L >= 1 && s->L <= HOPK_MAX_LAYERS, "layer count");
     HOPK_REQUIRE(s->C % 4 == 0 && s->C >= 4 && s->C <= 256, "C must be a multiple of 4, <= 256");
     HOPK_REQUIRE(s->V >= 1 && s->V <= 45, "V must be <= 45");
@@ -700,6 +849,8 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
     char* ws = (char*)ws_;
     auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
     const int C = s->C, V = s->V, B = s->B, L = s->L;
+    const bool tc = s->dtype == 1;
+    const int tcbn = C <= 64 ? 64 : 128;
     double* stats = reinterpret_cast<double*>(ws + g.stats);
     HOPK_CUDA(cudaMemsetAsync(stats, 0, (size_t)L * 2 * C * sizeof(double), st));
 
@@ -714,10 +865,10 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
         StartA a{x, g.Tp, V, g.pad, (long)xs[0], (long)xs[1], (long)xs[2], (long)xs[3]};
         Ld2D<true, 0> b{p->start_w, nullptr, s->in_dim};
         EpiStore<1> e{F(g.x0), C, p->start_b, nullptr, C, 0};
-        if (C <= 64) launch_gemm<2, 1>(M, C, s->in_dim, 1, a, b, e, st);
+        if (C <= 64) launch_gemm<2, 1>(tc, M, C, s->in_dim, 1, a, b, e, st);
         else {
             EpiStore<2> e2{F(g.x0), C, p->start_b, nullptr, C, 0};
-            launch_gemm<2, 2>(M, C, s->in_dim, 1, a, b, e2, st);
+            launch_gemm<2, 2>(tc, M, C, s->in_dim, 1, a, b, e2, st);
         }
         HOPK_LAUNCH_CHECK("start_conv");
     }
@@ -730,10 +881,10 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
         // gated dilated conv (gwnet.py:186-200) + skip slice
         {
             GateA a{uprev, ss, lg};
-            GateB b{p->filter_w[i], p->gate_w[i], C};
+            GateB b{p->filter_w[i], p->gate_w[i], C, tc ? 1 : 0};
             GateEpi e{p->filter_b[i], p->gate_b[i], F(g.tf[i]), F(g.sg[i]), F(g.y[i]), F(g.ycat), lg, i, L, g.Tl};
-            int Nlog = cdiv(C, 64) * 128;
-            launch_gemm<2, 2>(M, Nlog, 2 * C, 1, a, b, e, st);
+            int Nlog = tc ? cdiv(C, 16) * 32 : cdiv(C, 64) * 128;
+            launch_gemm<2, 2>(tc, M, Nlog, 2 * C, 1, a, b, e, st);
             HOPK_LAUNCH_CHECK("gate");
         }
         // diffusion (gwnet.py:12-14, 35-41)
@@ -745,12 +896,12 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
             double* st_i = stats + (size_t)i * 2 * C;
             if (C <= 64) {
                 MlpEpi<1> e; memset(&e, 0, sizeof(e));
-                e.bm = p->mlp_b[i]; e.up = uprev; e.ss = ss; e.U = F(g.u[i]); e.stats = st_i; e.g = lg;
-                launch_gemm<2, 1>(M, C, 3 * C, 1, a, b, e, st);
+                e.bm = p->mlp_b[i]; e.up = uprev; e.ss = ss; e.U = F(g.u[i]); e.stats = st_i; e.g = lg; e.tc_bn = tcbn;
+                launch_gemm<2, 1>(tc, M, C, 3 * C, 1, a, b, e, st);
             } else {
                 MlpEpi<2> e; memset(&e, 0, sizeof(e));
-                e.bm = p->mlp_b[i]; e.up = uprev; e.ss = ss; e.U = F(g.u[i]); e.stats = st_i; e.g = lg;
-                launch_gemm<2, 2>(M, C, 3 * C, 1, a, b, e, st);
+                e.bm = p->mlp_b[i]; e.up = uprev; e.ss = ss; e.U = F(g.u[i]); e.stats = st_i; e.g = lg; e.tc_bn = tcbn;
+                launch_gemm<2, 2>(tc, M, C, 3 * C, 1, a, b, e, st);
             }
             HOPK_LAUNCH_CHECK("mlp");
         }
@@ -768,18 +919,18 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
         Ld2D<true, 0> a{F(g.ycat), nullptr, (long)L * C};
         SkipW b; b.C = C; for (int l = 0; l < L; ++l) b.w[l] = p->skip_w[l];
         SkipEpi<2> e; e.out = F(g.r0); e.L = L; e.N = s->S; for (int l = 0; l < L; ++l) e.b[l] = p->skip_b[l];
-        launch_gemm<1, 2>(M, s->S, L * C, 1, a, b, e, st);
+        launch_gemm<1, 2>(tc, M, s->S, L * C, 1, a, b, e, st);
         HOPK_LAUNCH_CHECK("skip");
         Ld2D<true, 0> a1{F(g.r0), nullptr, s->S};
         Ld2D<true, 0> b1{p->end1_w, nullptr, s->S};
         EpiStore<2> e1{F(g.r1), s->E, p->end1_b, nullptr, s->E, 1};
-        launch_gemm<1, 2>(M, s->E, s->S, 1, a1, b1, e1, st);
+        launch_gemm<1, 2>(tc, M, s->E, s->S, 1, a1, b1, e1, st);
         HOPK_LAUNCH_CHECK("end1");
         Ld2D<true, 0> a2{F(g.r1), nullptr, s->E};
         Ld2D<true, 0> b2{p->end2_w, nullptr, s->E};
         RowMap rm{g.Tl, V, (long)s->out_dim * V * g.Tl, 1, g.Tl, (long)V * g.Tl};
         EpiStoreStrided<2> e2{out, rm, p->end2_b, s->out_dim};
-        launch_gemm<1, 2>(M, s->out_dim, s->E, 1, a2, b2, e2, st);
+        launch_gemm<1, 2>(tc, M, s->out_dim, s->E, 1, a2, b2, e2, st);
         HOPK_LAUNCH_CHECK("end2");
     }
     return 0;
@@ -796,6 +947,8 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
     auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
     auto S = [&](size_t off) { return reinterpret_cast<float*>(sc + off); };
     const int C = s->C, V = s->V, B = s->B, L = s->L, Sk = s->S, E = s->E, O = s->out_dim;
+    const bool tc = s->dtype == 1;
+    const int tcbn = C <= 64 ? 64 : 128;
     double* bnsum = reinterpret_cast<double*>(sc + g.s_bnsum);
     HOPK_CUDA(cudaMemsetAsync(bnsum, 0, (size_t)L * 2 * C * sizeof(double), st));
     HOPK_CUDA(cudaMemsetAsync(S(g.s_m12), 0, 2 * (size_t)V * V * sizeof(float), st));
@@ -812,12 +965,12 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             Ld2D<false, 0> a{S(g.s_dorow), nullptr, O};
             Ld2DOnes<false> b{F(g.r1), E, E};
             EpiWgrad<2> e{gr->end2_w, E, gr->end2_b, E, O};
-            launch_gemm<1, 2>(O, E + 1, M4, pick_splits(O, E + 1, M4, 1, 2), a, b, e, st);
+            launch_gemm<1, 2>(tc, O, E + 1, M4, pick_splits(tc, O, E + 1, M4, 1, 2), a, b, e, st);
             HOPK_LAUNCH_CHECK("end2_wgrad");
             Ld2D<true, 0> a2{S(g.s_dorow), nullptr, O};
             Ld2D<false, 0> b2{p->end2_w, nullptr, E};
             EpiStore<2> e2{S(g.s_de1), E, nullptr, F(g.r1), E, 4};
-            launch_gemm<1, 2>(M4, E, O, 1, a2, b2, e2, st);
+            launch_gemm<1, 2>(tc, M4, E, O, 1, a2, b2, e2, st);
             HOPK_LAUNCH_CHECK("end2_dgrad");
         }
         // end_conv_1
@@ -827,12 +980,12 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             Ld2D<false, 0> a{S(g.s_de1), nullptr, E};
             Ld2DOnes<false> b{F(g.r0), Sk, Sk};
             EpiWgrad<2> e{gr->end1_w, Sk, gr->end1_b, Sk, E};
-            launch_gemm<1, 2>(E, Sk + 1, M4, pick_splits(E, Sk + 1, M4, 1, 2), a, b, e, st);
+            launch_gemm<1, 2>(tc, E, Sk + 1, M4, pick_splits(tc, E, Sk + 1, M4, 1, 2), a, b, e, st);
             HOPK_LAUNCH_CHECK("end1_wgrad");
             Ld2D<true, 0> a2{S(g.s_de1), nullptr, E};
             Ld2D<false, 0> b2{p->end1_w, nullptr, Sk};
             EpiStore<2> e2{S(g.s_dskip), Sk, nullptr, F(g.r0), Sk, 4};
-            launch_gemm<1, 2>(M4, Sk, E, 1, a2, b2, e2, st);
+            launch_gemm<1, 2>(tc, M4, Sk, E, 1, a2, b2, e2, st);
             HOPK_LAUNCH_CHECK("end1_dgrad");
         }
         // skip convs: one concat GEMM each way
@@ -845,12 +998,12 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             Ld2DOnes<false> b{F(g.ycat), (long)L * C, L * C};
             SkipWgradEpi<2> e; e.C = C; e.L = L;
             for (int l = 0; l < L; ++l) { e.dw[l] = gr->skip_w[l]; e.db[l] = gr->skip_b[l]; }
-            launch_gemm<1, 2>(Sk, L * C + 1, M4, pick_splits(Sk, L * C + 1, M4, 1, 2), a, b, e, st);
+            launch_gemm<1, 2>(tc, Sk, L * C + 1, M4, pick_splits(tc, Sk, L * C + 1, M4, 1, 2), a, b, e, st);
             HOPK_LAUNCH_CHECK("skip_wgrad");
             Ld2D<true, 0> a2{S(g.s_dskip), nullptr, Sk};
             SkipWT b2; b2.C = C; for (int l = 0; l < L; ++l) b2.w[l] = p->skip_w[l];
             EpiStore<2> e2{S(g.s_dycat), (long)L * C, nullptr, nullptr, L * C, 0};
-            launch_gemm<1, 2>(M4, L * C, Sk, 1, a2, b2, e2, st);
+            launch_gemm<1, 2>(tc, M4, L * C, Sk, 1, a2, b2, e2, st);
             HOPK_LAUNCH_CHECK("skip_dgrad");
         }
     }
@@ -885,8 +1038,8 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
                 Ld2D<false, 0> a{DU, nullptr, C};
                 Seg3AT b{F(g.y[i]), F(g.x1[i]), F(g.x2[i]), C};
                 EpiWgrad<2> e{gr->mlp_w[i], (long)3 * C, gr->mlp_b[i], 3 * C, C};
-                if (C <= 64) launch_gemm<1, 2>(C, 3 * C + 1, M, pick_splits(C, 3 * C + 1, M, 1, 2), a, b, e, st);
-                else launch_gemm<2, 2>(C, 3 * C + 1, M, pick_splits(C, 3 * C + 1, M, 2, 2), a, b, e, st);
+                if (C <= 64) launch_gemm<1, 2>(tc, C, 3 * C + 1, M, pick_splits(tc, C, 3 * C + 1, M, 1, 2), a, b, e, st);
+                else launch_gemm<2, 2>(tc, C, 3 * C + 1, M, pick_splits(tc, C, 3 * C + 1, M, 2, 2), a, b, e, st);
                 HOPK_LAUNCH_CHECK("mlp_wgrad");
             }
             // G = du [Wm1 | Wm2]  and the Gram products for dA
@@ -894,7 +1047,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
                 Ld2D<true, 0> a{DU, nullptr, C};
                 Ld2D<false, 0> b{p->mlp_w[i] + C, nullptr, (long)3 * C};
                 EpiStore<2> e{S(g.s_g), (long)2 * C, nullptr, nullptr, 2 * C, 0};
-                launch_gemm<2, 2>(M, 2 * C, C, 1, a, b, e, st);
+                launch_gemm<2, 2>(tc, M, 2 * C, C, 1, a, b, e, st);
                 HOPK_LAUNCH_CHECK("g_gemm");
                 int gpb2 = 8;
                 size_t smem3 = ((size_t)V * (C + 1) + (size_t)V * (2 * C + 1)) * sizeof(float);
@@ -910,10 +1063,10 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             int K = has_du ? 3 * C : 0;
             if (C <= 64) {
                 DyEpi<1> e{F(g.tf[i]), F(g.sg[i]), S(g.s_dycat), S(g.s_df), S(g.s_dg), lg, i, L, g.Tl};
-                launch_gemm<2, 1>(M, C, K, 1, a, b, e, st);
+                launch_gemm<2, 1>(tc, M, C, K, 1, a, b, e, st);
             } else {
                 DyEpi<2> e{F(g.tf[i]), F(g.sg[i]), S(g.s_dycat), S(g.s_df), S(g.s_dg), lg, i, L, g.Tl};
-                launch_gemm<2, 2>(M, C, K, 1, a, b, e, st);
+                launch_gemm<2, 2>(tc, M, C, K, 1, a, b, e, st);
             }
             HOPK_LAUNCH_CHECK("dy_gemm");
         }
@@ -926,7 +1079,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             GateWgA a{S(g.s_df), S(g.s_dg), C};
             GateWgB b{uprev, ss, lg};
             GateWgEpi<2> e{gr->filter_w[i], gr->gate_w[i], gr->filter_b[i], gr->gate_b[i], C};
-            launch_gemm<2, 2>(2 * C, 2 * C + 1, M, pick_splits(2 * C, 2 * C + 1, M, 2, 2), a, b, e, st);
+            launch_gemm<2, 2>(tc, 2 * C, 2 * C + 1, M, pick_splits(tc, 2 * C, 2 * C + 1, M, 2, 2), a, b, e, st);
             HOPK_LAUNCH_CHECK("gate_wgrad");
         }
         // dx of the layer input (+ residual gradient) and BN-backward sums of layer i-1
@@ -936,16 +1089,16 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             float* DX = dx_buf[flip];
             if (C <= 64) {
                 DxEpi<1> e; memset(&e, 0, sizeof(e));
-                e.DU = has_du ? DU : nullptr; e.DX = DX; e.uprev = uprev; e.g = lg;
+                e.DU = has_du ? DU : nullptr; e.DX = DX; e.uprev = uprev; e.g = lg; e.tc_bn = tcbn;
                 e.mr_prev = i > 0 ? F(g.mr) + (size_t)(i - 1) * 2 * C : nullptr;
                 e.sums_prev = i > 0 ? bnsum + (size_t)(i - 1) * 2 * C : nullptr;
-                launch_gemm<2, 1>(Min, C, 4 * C, 1, a, b, e, st);
+                launch_gemm<2, 1>(tc, Min, C, 4 * C, 1, a, b, e, st);
             } else {
                 DxEpi<2> e; memset(&e, 0, sizeof(e));
-                e.DU = has_du ? DU : nullptr; e.DX = DX; e.uprev = uprev; e.g = lg;
+                e.DU = has_du ? DU : nullptr; e.DX = DX; e.uprev = uprev; e.g = lg; e.tc_bn = tcbn;
                 e.mr_prev = i > 0 ? F(g.mr) + (size_t)(i - 1) * 2 * C : nullptr;
                 e.sums_prev = i > 0 ? bnsum + (size_t)(i - 1) * 2 * C : nullptr;
-                launch_gemm<2, 2>(Min, C, 4 * C, 1, a, b, e, st);
+                launch_gemm<2, 2>(tc, Min, C, 4 * C, 1, a, b, e, st);
             }
             HOPK_LAUNCH_CHECK("dx_gemm");
             dxn = DX; flip ^= 1;
@@ -963,14 +1116,14 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
         Ld2D<false, 0> a{dxn, nullptr, C};
         StartAT b{x, g.Tp, V, g.pad, s->in_dim, (long)xs[0], (long)xs[1], (long)xs[2], (long)xs[3]};
         EpiWgrad<2> e{gr->start_w, s->in_dim, gr->start_b, s->in_dim, C};
-        if (C <= 64) launch_gemm<1, 2>(C, s->in_dim + 1, M, pick_splits(C, s->in_dim + 1, M, 1, 2), a, b, e, st);
-        else launch_gemm<2, 2>(C, s->in_dim + 1, M, pick_splits(C, s->in_dim + 1, M, 2, 2), a, b, e, st);
+        if (C <= 64) launch_gemm<1, 2>(tc, C, s->in_dim + 1, M, pick_splits(tc, C, s->in_dim + 1, M, 1, 2), a, b, e, st);
+        else launch_gemm<2, 2>(tc, C, s->in_dim + 1, M, pick_splits(tc, C, s->in_dim + 1, M, 2, 2), a, b, e, st);
         HOPK_LAUNCH_CHECK("start_wgrad");
         if (dx) {
             Ld2D<true, 0> a2{dxn, nullptr, C};
             Ld2D<false, 0> b2{p->start_w, nullptr, s->in_dim};
             StartDxEpi e2{dx, g.Tp, s->T, V, g.pad, s->in_dim};
-            launch_gemm<2, 2>(M, s->in_dim, C, 1, a2, b2, e2, st);
+            launch_gemm<2, 2>(tc, M, s->in_dim, C, 1, a2, b2, e2, st);
             HOPK_LAUNCH_CHECK("start_dgrad");
         }
     }

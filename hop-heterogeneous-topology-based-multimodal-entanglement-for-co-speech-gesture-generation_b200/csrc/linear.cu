@@ -2,6 +2,7 @@
 //   * hopk_linear_{fwd,bwd}: the reprogramming Q/K/V/O projections (reference model/HOP.py:262-265,276-285)
 //   * hopk_conv1x1_nchw_{fwd,bwd}: gwnet's `linear` module used stand-alone (model/gwnet.py:16-22)
 //   * hopk_nconv_{fwd,bwd}: gwnet's `nconv` module used stand-alone (model/gwnet.py:8-14)
+#include <type_traits>
 #include "functors.cuh"
 #include "gemm_tc.cuh"
 #include "common.cuh"
@@ -9,9 +10,21 @@
 
 namespace hopk {
 
+template <class T, class = void> struct has_row32 : std::false_type {};
+template <class T> struct has_row32<T, std::void_t<decltype(&T::row32)>> : std::true_type {};
+
+static thread_local bool g_tc = false;     // set per call from flag 0x100: bf16 tensor-core math (tcgen05)
+
 template <int MG, int NG, class AL, class BL, class EP>
 static void launch_gemm2(int M, int N, int K, int splits, AL a, BL b, EP e, cudaStream_t st)
 {
+    if constexpr (has_row32<EP>::value) {
+        if (g_tc) {
+            if (N <= 64) launch_gemm_tc<64>(M, N, K, splits, a, b, e, st);
+            else launch_gemm_tc<128>(M, N, K, splits, a, b, e, st);
+            return;
+        }
+    }
     int kper = K;
     if (splits > 1) { kper = ((cdiv(K, splits) + GEMM_BK - 1) / GEMM_BK) * GEMM_BK; splits = cdiv(K, kper); }
     if (splits < 1) splits = 1;
@@ -21,6 +34,7 @@ static void launch_gemm2(int M, int N, int K, int splits, AL a, BL b, EP e, cuda
 
 static int splits_for(int M, int N, int K, int mg, int ng)
 {
+    if (g_tc) { mg = 2; ng = N <= 64 ? 1 : 2; }
     long tiles = (long)cdiv(M, 64 * mg) * cdiv(N, 64 * ng);
     long want = (2 * 148 + tiles - 1) / tiles;
     long maxs = K / 256 > 0 ? K / 256 : 1;
@@ -128,15 +142,9 @@ extern "C" int hopk_linear_fwd(const float* x, const float* w, const float* b, f
 {
     HOPK_REQUIRE(M > 0 && N > 0 && K > 0, "linear sizes");
     cudaStream_t st = (cudaStream_t)stream;
+    g_tc = (flags & 0x100) != 0;
     Ld2D<true, 0> wl{w, nullptr, K};
     int oflags = (flags & 2) ? 1 : 0;
-    if (flags & 0x100) {                      // bf16 tensor-core math (tcgen05), fp32 accumulate / output
-        EpiStoreTC e{y, N, b, nullptr, N, oflags};
-        if (flags & 1) { Ld2D<true, 1> a{x, nullptr, K}; HOPK_CUDA(launch_gemm_tc(M, N, K, a, wl, e, st)); }
-        else { Ld2D<true, 0> a{x, nullptr, K}; HOPK_CUDA(launch_gemm_tc(M, N, K, a, wl, e, st)); }
-        hopk::launch_counter() += 1;
-        return 0;
-    }
     if (flags & 1) {
         Ld2D<true, 1> a{x, nullptr, K};
         EpiStore<2> e{y, N, b, nullptr, N, oflags};
@@ -156,6 +164,7 @@ extern "C" int hopk_linear_bwd(const float* x, const float* w, const float* y, c
     HOPK_REQUIRE(M > 0 && N > 0 && K > 0, "linear sizes");
     HOPK_REQUIRE(!(flags & 2) || y != nullptr, "relu-out backward needs y");
     cudaStream_t st = (cudaStream_t)stream;
+    g_tc = (flags & 0x100) != 0;
     const bool relu_in = flags & 1, relu_out = flags & 2;
     // dw[n][k] = sum_m dy_eff[m][n] * x_eff[m][k]  (+ bias gradient as virtual column K)
     if (dw) {
@@ -190,6 +199,7 @@ extern "C" int hopk_conv1x1_nchw_fwd(const float* x, const float* w, const float
 {
     HOPK_REQUIRE(B > 0 && K > 0 && N > 0 && V > 0 && T > 0, "conv1x1 sizes");
     cudaStream_t st = (cudaStream_t)stream;
+    g_tc = false;
     int VT = V * T, M = B * VT;
     NchwA a{x, K, VT};
     Ld2D<true, 0> wl{w, nullptr, K};
@@ -204,6 +214,7 @@ extern "C" int hopk_conv1x1_nchw_bwd(const float* x, const float* w, const float
 {
     HOPK_REQUIRE(B > 0 && K > 0 && N > 0 && V > 0 && T > 0, "conv1x1 sizes");
     cudaStream_t st = (cudaStream_t)stream;
+    g_tc = false;
     int VT = V * T, M = B * VT;
     if (dw) {
         HOPK_CUDA(cudaMemsetAsync(dw, 0, (size_t)N * K * sizeof(float), st));

@@ -243,6 +243,12 @@ class gwnet(nn.Module):
         self._cfg = dict(in_dim=in_dim, out_dim=out_dim, C=residual_channels, D=dilation_channels, S=skip_channels,
                          E=end_channels)
         self._names = None
+        self.precision = 'fp32'       # 'fp32': FFMA, 1e-5 parity mode; 'bf16': tcgen05 bf16 operands, fp32 accumulate
+
+    def set_precision(self, name):
+        assert name in ('fp32', 'bf16')
+        self.precision = name
+        return self
 
     # ---- kernel plumbing ---------------------------------------------------------------------
     def _check_supported(self):
@@ -298,7 +304,7 @@ class gwnet(nn.Module):
             s.dil[i] = d
         s.rank = self.nodevec1.shape[1]
         s.training = 1 if self.training else 0
-        s.dtype = 0
+        s.dtype = 1 if self.precision == 'bf16' else 0
         return s
 
     def _param_struct(self, params):

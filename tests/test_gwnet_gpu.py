@@ -8,7 +8,7 @@ import torch
 
 from oracle import gwnet_np
 from tests.golden.make_golden import GW_CASES, gw_inputs
-from tests.util import GOLDEN, TOL_FP32, Report, golden_compare, relerr
+from tests.util import GOLDEN, TOL_BF16, TOL_FP32, Report, golden_compare, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -25,11 +25,11 @@ def build_module(P, V, cfg, dev, training=True):
     return m
 
 
-def run_case(name, dev, channels_last):
+def run_case(name, dev, channels_last, precision='fp32'):
     seed, B, V, T, cfg = GW_CASES[name]
     training = not name.endswith('_eval')
     P, x, dout = gw_inputs(seed, B, V, T, cfg)
-    m = build_module(P, V, cfg, dev, training)
+    m = build_module(P, V, cfg, dev, training).set_precision(precision)
     xt = torch.from_numpy(x).float().to(dev)
     if channels_last:                             # HOP.Model hands gwnet a permuted (B,T,V,C) buffer
         xt = xt.permute(0, 3, 2, 1).contiguous().permute(0, 3, 2, 1)
@@ -40,14 +40,16 @@ def run_case(name, dev, channels_last):
     return m, out, xt, (P, x, dout, training, cfg)
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 @pytest.mark.parametrize('channels_last', [False, True])
 @pytest.mark.parametrize('name', list(GW_CASES))
-def test_gwnet_vs_oracle_and_golden(name, channels_last, cuda):
-    m, out, xt, (P, x, dout, training, cfg) = run_case(name, cuda, channels_last)
+def test_gwnet_vs_oracle_and_golden(name, channels_last, precision, cuda):
+    tol = TOL_FP32 if precision == 'fp32' else TOL_BF16
+    m, out, xt, (P, x, dout, training, cfg) = run_case(name, cuda, channels_last, precision)
     o_out, o_bufs, cache = gwnet_np.forward(P, x, training=training, keep=True)
     o_dx, o_G = gwnet_np.backward(P, cache, dout)
     fix = np.load(os.path.join(GOLDEN, name + '.npz'))
-    rep = Report(f'{name}_{"cl" if channels_last else "nchw"}', TOL_FP32)
+    rep = Report(f'{name}_{"cl" if channels_last else "nchw"}_{precision}', tol)
     rep.add('out', relerr(out.detach().cpu().numpy(), o_out))
     rep.add('out(golden)', relerr(out.detach().cpu().numpy(), fix['out']))
     rep.add('dx', relerr(xt.grad.cpu().numpy(), o_dx))
@@ -69,7 +71,7 @@ def test_gwnet_vs_oracle_and_golden(name, channels_last, cuda):
     sd = m.state_dict()
     for k in sd:
         if 'running_' in k or 'num_batches' in k:
-            rep.add('buf:' + k, relerr(sd[k].cpu().numpy(), fix['buf:' + k]), tol=1e-6)
+            rep.add('buf:' + k, relerr(sd[k].cpu().numpy(), fix['buf:' + k]), tol=1e-6 if precision == 'fp32' else tol)
     rep.finish()
 
 

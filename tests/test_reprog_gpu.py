@@ -7,7 +7,7 @@ import torch
 
 from oracle import reprog_np
 from tests.golden.make_golden import RP_CASES, rp_inputs
-from tests.util import GOLDEN, TOL_FP32, Report, golden_compare, relerr
+from tests.util import GOLDEN, TOL_BF16, TOL_FP32, Report, golden_compare, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -19,11 +19,12 @@ def build(P, cfg, dev):
     return m
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 @pytest.mark.parametrize('name', list(RP_CASES))
-def test_reprog_vs_oracle_and_golden(name, cuda):
+def test_reprog_vs_oracle_and_golden(name, precision, cuda):
     seed, B, L, S, cfg = RP_CASES[name]
     P, x, src, dY = rp_inputs(seed, B, L, S, cfg)
-    m = build(P, cfg, cuda).eval()               # p = 0: comparable with the reference itself
+    m = build(P, cfg, cuda).eval().set_precision(precision)   # p = 0: comparable with the reference itself
     xt = torch.from_numpy(x).float().to(cuda).requires_grad_(True)
     st = torch.from_numpy(src).float().to(cuda).requires_grad_(True)
     y = m(xt, st, st)
@@ -31,7 +32,7 @@ def test_reprog_vs_oracle_and_golden(name, cuda):
     o_y, cache = reprog_np.forward(P, x, src, src, cfg['n_heads'], keep=True)
     o_dx, o_ds, o_dv, o_G = reprog_np.backward(P, cache, dY, cfg['n_heads'])
     fix = np.load(os.path.join(GOLDEN, name + '.npz'))
-    rep = Report(name, TOL_FP32)
+    rep = Report(name + '_' + precision, TOL_FP32 if precision == 'fp32' else TOL_BF16)
     rep.add('out', relerr(y.detach().cpu().numpy(), o_y))
     rep.add('out(golden)', relerr(y.detach().cpu().numpy(), fix['out']))
     rep.add('dx', relerr(xt.grad.cpu().numpy(), o_dx))
