@@ -51,9 +51,21 @@ def receptive_field(blocks=4, layers=2, kernel_size=2):
     return rf
 
 
-def _pw(x, w, b):
-    """1x1 conv: w is (O, C, 1, 1)."""
-    return np.einsum('oc,bcvt->bovt', w[:, :, 0, 0], x) + b[None, :, None, None]
+def _id(a):
+    return a
+
+
+def bf16_round(a):
+    """Round-to-nearest-even to bfloat16 (returned as float64): the operand quantiser of the tensor-core path."""
+    a32 = np.ascontiguousarray(a, dtype=np.float32)
+    u = a32.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).astype(np.float64).reshape(a32.shape)
+
+
+def _pw(x, w, b, q=_id):
+    """1x1 conv: w is (O, C, 1, 1).  ``q`` quantises the two GEMM operands (identity = exact reference)."""
+    return np.einsum('oc,bcvt->bovt', q(w[:, :, 0, 0]), q(x)) + b[None, :, None, None]
 
 
 def adaptive_adjacency(e1, e2):
@@ -69,12 +81,16 @@ def _sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
 
 
-def forward(params, x_in, blocks=4, layers=2, training=True, keep=False):
+def forward(params, x_in, blocks=4, layers=2, training=True, keep=False, q=_id):
     """gwnet.forward (gwnet.py:143-249).
 
     Returns (out, new_buffers, cache).  ``new_buffers`` holds the updated
     ``bn.i.running_mean / running_var / num_batches_tracked`` (train mode).
     ``cache`` is what :func:`backward` needs (only when keep=True).
+
+    ``q`` (default identity) is applied to both operands of every dense contraction -- start/gate/mlp/skip/end
+    convs -- and nowhere else; with ``q=bf16_round`` this is the quantisation-aware reference of the bf16
+    tensor-core mode (dtype 1: bf16 operands, fp32 accumulation, everything else fp32).
     """
     p = {k: np.asarray(v, dtype=np.float64) for k, v in params.items()}
     x = np.asarray(x_in, dtype=np.float64)
@@ -85,7 +101,7 @@ def forward(params, x_in, blocks=4, layers=2, training=True, keep=False):
         pad = rf - x.shape[3]
         x = np.pad(x, ((0, 0), (0, 0), (0, 0), (pad, 0)))
     x0 = x
-    x = _pw(x, p['start_conv.weight'], p['start_conv.bias'])
+    x = _pw(x, p['start_conv.weight'], p['start_conv.bias'], q)
     A, Z = adaptive_adjacency(p['nodevec1'], p['nodevec2'])
     skip = None
     bufs = {}
@@ -94,20 +110,21 @@ def forward(params, x_in, blocks=4, layers=2, training=True, keep=False):
         T = x.shape[3]
         To = T - d
         wf, wg = p[f'filter_convs.{i}.weight'], p[f'gate_convs.{i}.weight']
-        f = (np.einsum('oc,bcvt->bovt', wf[:, :, 0, 0], x[..., :To]) +
-             np.einsum('oc,bcvt->bovt', wf[:, :, 0, 1], x[..., d:]) +
+        xq, wfq, wgq = q(x), q(wf), q(wg)
+        f = (np.einsum('oc,bcvt->bovt', wfq[:, :, 0, 0], xq[..., :To]) +
+             np.einsum('oc,bcvt->bovt', wfq[:, :, 0, 1], xq[..., d:]) +
              p[f'filter_convs.{i}.bias'][None, :, None, None])
-        g = (np.einsum('oc,bcvt->bovt', wg[:, :, 0, 0], x[..., :To]) +
-             np.einsum('oc,bcvt->bovt', wg[:, :, 0, 1], x[..., d:]) +
+        g = (np.einsum('oc,bcvt->bovt', wgq[:, :, 0, 0], xq[..., :To]) +
+             np.einsum('oc,bcvt->bovt', wgq[:, :, 0, 1], xq[..., d:]) +
              p[f'gate_convs.{i}.bias'][None, :, None, None])
         tf, sg = np.tanh(f), _sigmoid(g)
         y = tf * sg
-        s = _pw(y, p[f'skip_convs.{i}.weight'], p[f'skip_convs.{i}.bias'])
+        s = _pw(y, p[f'skip_convs.{i}.weight'], p[f'skip_convs.{i}.bias'], q)
         skip = s if skip is None else s + skip[..., -To:]
         x1 = np.einsum('ncvl,vw->ncwl', y, A)
         x2 = np.einsum('ncvl,vw->ncwl', x1, A)
         hcat = np.concatenate([y, x1, x2], axis=1)
-        h = _pw(hcat, p[f'gconv.{i}.mlp.mlp.weight'], p[f'gconv.{i}.mlp.mlp.bias'])
+        h = _pw(hcat, p[f'gconv.{i}.mlp.mlp.weight'], p[f'gconv.{i}.mlp.mlp.bias'], q)
         u = h + x[..., -To:]
         gam, bet = p[f'bn.{i}.weight'], p[f'bn.{i}.bias']
         if training:
@@ -127,23 +144,25 @@ def forward(params, x_in, blocks=4, layers=2, training=True, keep=False):
             cache['layers'].append(dict(x=x, tf=tf, sg=sg, y=y, x1=x1, x2=x2, xhat=xhat, rstd=rstd, d=d))
         x = xn
     r0 = np.maximum(skip, 0.0)
-    e1 = _pw(r0, p['end_conv_1.weight'], p['end_conv_1.bias'])
+    e1 = _pw(r0, p['end_conv_1.weight'], p['end_conv_1.bias'], q)
     r1 = np.maximum(e1, 0.0)
-    out = _pw(r1, p['end_conv_2.weight'], p['end_conv_2.bias'])
+    out = _pw(r1, p['end_conv_2.weight'], p['end_conv_2.bias'], q)
     if keep:
         cache.update(skip=skip, r0=r0, e1=e1, r1=r1, training=training)
     return out, bufs, cache
 
 
-def _pw_bwd(x, w, dy):
-    """Backward of a 1x1 conv: returns (dx, dw(O,C,1,1), db)."""
-    dx = np.einsum('oc,bovt->bcvt', w[:, :, 0, 0], dy)
-    dw = np.einsum('bovt,bcvt->oc', dy, x)[:, :, None, None]
-    db = dy.sum(axis=(0, 2, 3))
+def _pw_bwd(x, w, dy, q=_id):
+    """Backward of a 1x1 conv: returns (dx, dw(O,C,1,1), db).  The bias gradient rides the weight-gradient GEMM as
+    an all-ones column in the kernels, so it sums the *quantised* dy."""
+    dyq = q(dy)
+    dx = np.einsum('oc,bovt->bcvt', q(w[:, :, 0, 0]), dyq)
+    dw = np.einsum('bovt,bcvt->oc', dyq, q(x))[:, :, None, None]
+    db = dyq.sum(axis=(0, 2, 3))
     return dx, dw, db
 
 
-def backward(params, cache, dout, blocks=4, layers=2):
+def backward(params, cache, dout, blocks=4, layers=2, q=_id):
     """Gradient of sum(out*dout) w.r.t. every parameter and the input.
 
     Returns (dx_in, grads) with grads keyed like the state_dict; tensors the
@@ -155,13 +174,14 @@ def backward(params, cache, dout, blocks=4, layers=2):
     L = len(dil)
     G = {}
     dout = np.asarray(dout, dtype=np.float64)
-    dr1, G['end_conv_2.weight'], G['end_conv_2.bias'] = _pw_bwd(cache['r1'], p['end_conv_2.weight'], dout)
+    dr1, G['end_conv_2.weight'], G['end_conv_2.bias'] = _pw_bwd(cache['r1'], p['end_conv_2.weight'], dout, q)
     de1 = dr1 * (cache['e1'] > 0)
-    dr0, G['end_conv_1.weight'], G['end_conv_1.bias'] = _pw_bwd(cache['r0'], p['end_conv_1.weight'], de1)
+    dr0, G['end_conv_1.weight'], G['end_conv_1.bias'] = _pw_bwd(cache['r0'], p['end_conv_1.weight'], de1, q)
     dskip = dr0 * (cache['skip'] > 0)            # (B, S, V, T_last)
     Tl = dskip.shape[3]
     A = cache['A']
-    dA = np.zeros_like(A)
+    M1 = np.zeros_like(A)
+    M2 = np.zeros_like(A)
     dxn = None                                    # grad w.r.t. BN output of layer i (= input of layer i+1)
     for i in reversed(range(L)):
         c = cache['layers'][i]
@@ -185,30 +205,35 @@ def backward(params, cache, dout, blocks=4, layers=2):
                 du = (gam * rstd)[None, :, None, None] * dxn
             # residual x[..., -To:]
             dx[..., -To:] += du
-            # gcn mlp on cat[y, x1, x2]
-            wm = p[f'gconv.{i}.mlp.mlp.weight']
+            # gcn mlp on cat[y, x1, x2] and the two diffusion hops, in the form the kernels use
+            # (mathematically identical to back-propagating hop by hop):
+            #   P1 = A du, P2 = A P1 (node mixing with A, not A^T);  dy = [du|P1|P2] . Wm
+            #   dWm = du^T [y|x1|x2];   dA = M1 + A^T M2 + M2 A^T  with  M_k = sum y (x) (du . Wm_k)
+            wm = p[f'gconv.{i}.mlp.mlp.weight'][:, :, 0, 0]
+            P1 = np.einsum('ncwl,vw->ncvl', du, A)
+            P2 = np.einsum('ncwl,vw->ncvl', P1, A)
+            duq, wmq = q(du), q(wm)
             hcat = np.concatenate([y, x1, x2], axis=1)
-            dcat, G[f'gconv.{i}.mlp.mlp.weight'], G[f'gconv.{i}.mlp.mlp.bias'] = _pw_bwd(hcat, wm, du)
-            dy += dcat[:, :C]
-            dx1 = dcat[:, C:2 * C]
-            dx2 = dcat[:, 2 * C:]
-            # x2 = nconv(x1, A)
-            dA += np.einsum('ncvl,ncwl->vw', x1, dx2)
-            dx1 = dx1 + np.einsum('ncwl,vw->ncvl', dx2, A)
-            # x1 = nconv(y, A)
-            dA += np.einsum('ncvl,ncwl->vw', y, dx1)
-            dy += np.einsum('ncwl,vw->ncvl', dx1, A)
+            G[f'gconv.{i}.mlp.mlp.weight'] = np.einsum('bovt,bcvt->oc', duq, q(hcat))[:, :, None, None]
+            G[f'gconv.{i}.mlp.mlp.bias'] = duq.sum(axis=(0, 2, 3))
+            dy += (np.einsum('oc,bovt->bcvt', wmq[:, :C], duq) +
+                   np.einsum('oc,bovt->bcvt', wmq[:, C:2 * C], q(P1)) +
+                   np.einsum('oc,bovt->bcvt', wmq[:, 2 * C:], q(P2)))
+            M1 += np.einsum('ncvl,ncwl->vw', y, np.einsum('oc,bovt->bcvt', wmq[:, C:2 * C], duq))
+            M2 += np.einsum('ncvl,ncwl->vw', y, np.einsum('oc,bovt->bcvt', wmq[:, 2 * C:], duq))
         # skip path: only the last Tl time steps of s_i reach the head
         ws = p[f'skip_convs.{i}.weight']
         ds = np.zeros((y.shape[0], ws.shape[0], y.shape[2], To))
         ds[..., -Tl:] = dskip
-        dys, G[f'skip_convs.{i}.weight'], G[f'skip_convs.{i}.bias'] = _pw_bwd(y, ws, ds)
+        dys, G[f'skip_convs.{i}.weight'], G[f'skip_convs.{i}.bias'] = _pw_bwd(y, ws, ds, q)
         dy += dys
         # gate
         df = dy * sg * (1 - tf * tf)
         dg = dy * tf * sg * (1 - sg)
         wf, wg = p[f'filter_convs.{i}.weight'], p[f'gate_convs.{i}.weight']
-        xa, xb = x[..., :To], x[..., d:]
+        xq = q(x)
+        xa, xb = xq[..., :To], xq[..., d:]
+        df, dg, wf, wg = q(df), q(dg), q(wf), q(wg)
         G[f'filter_convs.{i}.weight'] = np.stack([np.einsum('bovt,bcvt->oc', df, xa),
                                                    np.einsum('bovt,bcvt->oc', df, xb)], axis=-1)[:, :, None, :]
         G[f'gate_convs.{i}.weight'] = np.stack([np.einsum('bovt,bcvt->oc', dg, xa),
@@ -221,11 +246,12 @@ def backward(params, cache, dout, blocks=4, layers=2):
                         np.einsum('oc,bovt->bcvt', wg[:, :, 0, 1], dg))
         dxn = dx
     # adaptive adjacency backward: A = softmax_row(relu(E1 E2))
+    dA = M1 + A.T @ M2 + M2 @ A.T
     dR = A * (dA - (dA * A).sum(axis=1, keepdims=True))
     dZ = dR * (cache['Z'] > 0)
     G['nodevec1'] = dZ @ p['nodevec2'].T
     G['nodevec2'] = p['nodevec1'].T @ dZ
-    dx0, G['start_conv.weight'], G['start_conv.bias'] = _pw_bwd(cache['x0'], p['start_conv.weight'], dxn)
+    dx0, G['start_conv.weight'], G['start_conv.bias'] = _pw_bwd(cache['x0'], p['start_conv.weight'], dxn, q)
     if cache['pad']:
         dx0 = dx0[..., cache['pad']:]
     return dx0, G

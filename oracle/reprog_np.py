@@ -46,8 +46,15 @@ def dropout_keep(seed, idx, p):
     return (h >> np.uint64(8)) >= thr
 
 
-def forward(P, target, source, value, n_heads, p_drop=0.0, seed=0, keep=False):
-    """ReprogrammingLayer.forward.  target (B,L,dm); source,value (S,dllm).  Returns (B,L,dllm)."""
+def _id(a):
+    return a
+
+
+def forward(P, target, source, value, n_heads, p_drop=0.0, seed=0, keep=False, q=_id):
+    """ReprogrammingLayer.forward.  target (B,L,dm); source,value (S,dllm).  Returns (B,L,dllm).
+
+    ``q`` quantises both operands of the four projection GEMMs (identity = exact reference;
+    oracle.gwnet_np.bf16_round = quantisation-aware reference of the bf16 tensor-core mode)."""
     P = {k: np.asarray(v, dtype=np.float64) for k, v in P.items()}
     x = np.asarray(target, np.float64)
     src = np.asarray(source, np.float64)
@@ -55,9 +62,9 @@ def forward(P, target, source, value, n_heads, p_drop=0.0, seed=0, keep=False):
     B, L, _ = x.shape
     S = src.shape[0]
     H = n_heads
-    Q = (x @ P['query_projection.weight'].T + P['query_projection.bias']).reshape(B, L, H, -1)
-    K = (src @ P['key_projection.weight'].T + P['key_projection.bias']).reshape(S, H, -1)
-    V = (val @ P['value_projection.weight'].T + P['value_projection.bias']).reshape(S, H, -1)
+    Q = (q(x) @ q(P['query_projection.weight']).T + P['query_projection.bias']).reshape(B, L, H, -1)
+    K = (q(src) @ q(P['key_projection.weight']).T + P['key_projection.bias']).reshape(S, H, -1)
+    V = (q(val) @ q(P['value_projection.weight']).T + P['value_projection.bias']).reshape(S, H, -1)
     E = Q.shape[-1]
     scale = 1.0 / np.sqrt(E)
     sc = np.einsum('blhe,she->bhls', Q, K) * scale
@@ -72,12 +79,12 @@ def forward(P, target, source, value, n_heads, p_drop=0.0, seed=0, keep=False):
     pd = pr * mask
     O = np.einsum('bhls,she->blhe', pd, V).reshape(B, L, H * E)
     R = np.maximum(O, 0.0)
-    Y = R @ P['out_projection.weight'].T + P['out_projection.bias']
+    Y = q(R) @ q(P['out_projection.weight']).T + P['out_projection.bias']
     cache = dict(x=x, src=src, val=val, Q=Q, K=K, V=V, pr=pr, mask=mask, O=O, R=R, scale=scale) if keep else None
     return Y, cache
 
 
-def backward(P, cache, dY, n_heads):
+def backward(P, cache, dY, n_heads, q=_id):
     """Returns (dtarget, dsource, dvalue, grads-by-state_dict-name)."""
     P = {k: np.asarray(v, dtype=np.float64) for k, v in P.items()}
     c = cache
@@ -85,9 +92,10 @@ def backward(P, cache, dY, n_heads):
     B, L, _ = dY.shape
     H = n_heads
     G = {}
-    G['out_projection.weight'] = np.einsum('blo,bli->oi', dY, c['R'])
-    G['out_projection.bias'] = dY.sum(axis=(0, 1))
-    dR = dY @ P['out_projection.weight']
+    dYq = q(dY)
+    G['out_projection.weight'] = np.einsum('blo,bli->oi', dYq, q(c['R']))
+    G['out_projection.bias'] = dYq.sum(axis=(0, 1))      # bias gradient = all-ones column of the weight-gradient GEMM
+    dR = dYq @ q(P['out_projection.weight'])
     dO = (dR * (c['O'] > 0)).reshape(B, L, H, -1)
     dpd = np.einsum('blhe,she->bhls', dO, c['V'])
     dV = np.einsum('bhls,blhe->she', c['pr'] * c['mask'], dO)
@@ -96,17 +104,17 @@ def backward(P, cache, dY, n_heads):
     dQ = np.einsum('bhls,she->blhe', dsc, c['K']) * c['scale']
     dK = np.einsum('bhls,blhe->she', dsc, c['Q']) * c['scale']
     S = dK.shape[0]
-    dQf, dKf, dVf = dQ.reshape(B * L, -1), dK.reshape(S, -1), dV.reshape(S, -1)
+    dQf, dKf, dVf = q(dQ.reshape(B * L, -1)), q(dK.reshape(S, -1)), q(dV.reshape(S, -1))
     xf = c['x'].reshape(B * L, -1)
-    G['query_projection.weight'] = dQf.T @ xf
+    G['query_projection.weight'] = dQf.T @ q(xf)
     G['query_projection.bias'] = dQf.sum(0)
-    G['key_projection.weight'] = dKf.T @ c['src']
+    G['key_projection.weight'] = dKf.T @ q(c['src'])
     G['key_projection.bias'] = dKf.sum(0)
-    G['value_projection.weight'] = dVf.T @ c['val']
+    G['value_projection.weight'] = dVf.T @ q(c['val'])
     G['value_projection.bias'] = dVf.sum(0)
-    dx = (dQf @ P['query_projection.weight']).reshape(c['x'].shape)
-    dsrc = dKf @ P['key_projection.weight']
-    dval = dVf @ P['value_projection.weight']
+    dx = (dQf @ q(P['query_projection.weight'])).reshape(c['x'].shape)
+    dsrc = dKf @ q(P['key_projection.weight'])
+    dval = dVf @ q(P['value_projection.weight'])
     return dx, dsrc, dval, G
 
 

@@ -96,3 +96,25 @@ def test_linear_tcgen05_forward(M, K, N, cuda):
             y = _LinearFn.apply(x.float().to(cuda), w.float().to(cuda), b.float().to(cuda), flags | 0x100)
         rep.add(f'y[{flags}]', relerr(y.cpu().numpy(), ref.numpy()))
     rep.finish()
+
+
+@pytest.mark.parametrize('M,K,N', [(128, 64, 128), (68, 128, 1024), (1500, 768, 1024), (70, 37, 45), (4352, 1024, 768),
+                                   (68, 1024, 768), (20000, 64, 64)])
+def test_linear_tcgen05_backward_exact(M, K, N, cuda):
+    """dgrad / wgrad / bias-grad on tcgen05 with bf16-representable x, w, dy: only fp32 accumulation error remains."""
+    from hop_b200.HOP import _LinearFn
+    torch.manual_seed(M + K + N)
+    x = torch.randn(M, K).bfloat16().double()
+    w = (torch.randn(N, K) * 0.1).bfloat16().double()
+    b = torch.randn(N, dtype=torch.float64)
+    dy = torch.randn(M, N).bfloat16().double()
+    rep = Report(f'linear_tc_bwd_{M}_{K}_{N}', 2e-5)
+    for flags in (0, 1):
+        xr, wr, br = [t.clone().requires_grad_(True) for t in (x, w, b)]
+        ((torch.relu(xr) if flags & 1 else xr) @ wr.T + br).backward(dy)
+        xg, wg, bg = [t.float().to(cuda).requires_grad_(True) for t in (x, w, b)]
+        _LinearFn.apply(xg, wg, bg, flags | 0x100).backward(dy.float().to(cuda))
+        rep.add(f'dx[{flags}]', relerr(xg.grad.cpu().numpy(), xr.grad.numpy()))
+        rep.add(f'dw[{flags}]', relerr(wg.grad.cpu().numpy(), wr.grad.numpy()))
+        rep.add(f'db[{flags}]', relerr(bg.grad.cpu().numpy(), br.grad.numpy()))
+    rep.finish()

@@ -22,6 +22,16 @@ def relerr(a, ref):
     return float(np.abs(a - ref).max() / (np.abs(ref).max() + 1e-30))
 
 
+def l2err(a, ref):
+    """Relative Frobenius error ||a - ref|| / ||ref||: the bf16-mode metric.  A single ReLU-mask flip (an activation
+    within rounding distance of zero) changes one gradient element completely; max-norm over a tensor built from a
+    handful of rows is dominated by such flips for ANY reduced-precision implementation, the 2-norm is not."""
+    a = np.asarray(a, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    return float(np.linalg.norm(a - ref) / (np.linalg.norm(ref) + 1e-30))
+
+
 def hash_name(name):
     h = 2166136261
     for ch in name.encode():
