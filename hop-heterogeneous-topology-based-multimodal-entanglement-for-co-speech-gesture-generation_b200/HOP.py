@@ -58,14 +58,15 @@ class _XattnFn(torch.autograd.Function):
     """softmax(Q K^T / sqrt(E)) -> dropout -> . V without materialising the (B,H,L,S) scores."""
 
     @staticmethod
-    def forward(ctx, q, k, v, p_drop, seed):
+    def forward(ctx, q, k, v, p_drop, seed, tc=False):
         q, k, v = f32c(q), f32c(k), f32c(v)
         B, L, H, E = q.shape
         S = k.shape[0]
         o = torch.empty_like(q)
         lse = torch.empty((B, H, L), device=q.device, dtype=torch.float32)
+        fwd = lib().hopk_xattn_fwd_tc if (tc and E == 128) else lib().hopk_xattn_fwd
         with profiler.span('xattn_fwd'):
-            check(lib().hopk_xattn_fwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, L, H, E, S, float(p_drop), int(seed),
+            check(fwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, L, H, E, S, float(p_drop), int(seed),
                                        stream_ptr()))
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.p_drop, ctx.seed = float(p_drop), int(seed)
@@ -82,7 +83,7 @@ class _XattnFn(torch.autograd.Function):
         with profiler.span('xattn_bwd'):
             check(lib().hopk_xattn_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
                                        ptr(delta), B, L, H, E, S, ctx.p_drop, ctx.seed, stream_ptr()))
-        return dq, dk, dv, None, None
+        return dq, dk, dv, None, None, None
 
 
 class _SourceFn(torch.autograd.Function):
@@ -153,7 +154,7 @@ class ReprogrammingLayer(nn.Module):
     def reprogramming(self, target_embedding, source_embedding, value_embedding):
         p = self.dropout.p if self.training else 0.0
         seed = _draw_seed() if p > 0 else 0
-        return _XattnFn.apply(target_embedding, source_embedding, value_embedding, p, seed)
+        return _XattnFn.apply(target_embedding, source_embedding, value_embedding, p, seed, self.precision == 'bf16')
 
 
 # ------------------------------------------------------------------------------------ Model

@@ -47,6 +47,7 @@ SIGNATURES = {
     'hopk_last_error': (C.c_char_p, []),
     'hopk_version': (_i, []),
     'hopk_launch_count': (C.c_longlong, []),
+    'hopk_debug_set': (_i, [_vp]),
     'hopk_gwnet_workspace_bytes': (_sz, [_SHP]),
     'hopk_gwnet_scratch_bytes': (_sz, [_SHP]),
     'hopk_gwnet_out_steps': (_i, [_SHP]),
@@ -59,6 +60,7 @@ SIGNATURES = {
     'hopk_conv1x1_nchw_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'hopk_conv1x1_nchw_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'hopk_xattn_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp]),
+    'hopk_xattn_fwd_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp]),
     'hopk_xattn_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp]),
 }
 

@@ -1,0 +1,228 @@
+// xattn_tc.cu -- reprogramming cross-attention on the 5th-generation tensor cores (tcgen05 + TMEM), dtype 1.
+//
+// Same contract as csrc/xattn.cu (reference model/HOP.py:289-299 and its backward) with bf16 operands and fp32
+// accumulation.  Head dim E = 128 (HOP: d_keys = d_ff = 128).  A CTA owns 128 query rows of one head (the flattened
+// (b, l) axis) and streams the S text prototypes in tiles of 128:
+//     S_j  = Q K_j^T              UMMA 128x128x128, both operands K-major slabs, accumulator in TMEM cols [0,128)
+//     P_j  = online softmax       one thread per row: tcgen05.ld of its own TMEM lane, no shuffles; dropout hash
+//     O   += P_j V_j              P_j written back to smem as bf16 (K-major A), V_j read MN-major (its natural layout)
+// The running output lives in TMEM cols [128,256) and is rescaled in place (tcgen05.ld/st) only when a row's maximum
+// moved.  Backward = two passes that recompute P from the saved log-sum-exp (dQ: loop over S; dK/dV: loop over rows),
+// every transposed operand being just an MN-major *view* of a row-major slab, so nothing is physically transposed.
+#include "tc_core.cuh"
+#include "common.cuh"
+#include "../../include/hopk.h"
+
+namespace hopk {
+
+__device__ volatile int* g_dbg = nullptr;      // optional progress markers in mapped host memory (debug builds of tests)
+#define DBG(slot, val) do { if (g_dbg && blockIdx.x == 0 && blockIdx.y == 0) { g_dbg[slot] = (val); __threadfence_system(); } } while (0)
+
+constexpr int AT = 128;                       // tile edge: query rows, prototypes per tile, head dim
+constexpr uint32_t AT_SLAB = tc::slab_bytes(AT);        // 16 KB: [128 rows][64 bf16]
+
+__device__ __forceinline__ uint32_t lowbias32_tc(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ bool keep_mask_tc(uint64_t seed, uint64_t idx, uint32_t thr)
+{
+    uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
+    uint32_t i_lo = (uint32_t)idx, i_hi = (uint32_t)(idx >> 32);
+    uint32_t h = lowbias32_tc((i_lo + lowbias32_tc(i_hi ^ s_hi)) ^ s_lo);
+    return (h >> 8) >= thr;
+}
+
+// stage a [128 rows][128 cols] fp32 tile of a (rows, H, E=128) tensor (head h) as two bf16 slabs (cols 0-63 | 64-127)
+__device__ __forceinline__ void stage_rows_f32(uint8_t* slabs, const float* __restrict__ src, int row0, int nrows, int H, int h)
+{
+#pragma unroll
+    for (int it = 0; it < (AT * 16) / 256; ++it) {
+        int idx = threadIdx.x + it * 256;
+        int ch16 = idx & 15, row = idx >> 4;              // 16 chunks of 8 floats per row
+        float f[8];
+        if (row0 + row < nrows) {
+            const float4* p = reinterpret_cast<const float4*>(src + ((size_t)(row0 + row) * H + h) * AT + ch16 * 8);
+            float4 a = __ldg(p), b = __ldg(p + 1);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        }
+        tc::slab_store8(slabs + (ch16 >> 3) * AT_SLAB, row, ch16 & 7, f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(256, 1)
+xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                    float* __restrict__ O, float* __restrict__ LSE, int M, int L, int H, int S, float scale,
+                    float inv_keep, uint32_t thr, uint64_t seed)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_s, bar_o;
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* Qs = smem; uint8_t* Ks = Qs + 2 * AT_SLAB; uint8_t* Vs = Ks + 2 * AT_SLAB; uint8_t* Ps = Vs + 2 * AT_SLAB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.y, m0 = blockIdx.x * AT;
+
+    if (tid == 0) { tc::mbar_init(&bar_s, 1); tc::mbar_init(&bar_o, 1); tc::fence_barrier_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 256);
+    stage_rows_f32(Qs, Q, m0, M, H, h);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_s = tmem_base_smem, tmem_o = tmem_base_smem + 128;
+    if (tid == 0) DBG(0, 1 + (int)tmem_base_smem);
+    constexpr uint32_t idesc_qk = tc::idesc_bf16(AT, AT, 0, 0);
+    constexpr uint32_t idesc_pv = tc::idesc_bf16(AT, AT, 0, 1);
+
+    const int row = warp * 32 + lane;                       // softmax threads (warps 0-3): one query row each
+    const int m = m0 + row;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint64_t drop_base = (warp < 4 && m < M) ? (((uint64_t)(m / L) * H + h) * (uint64_t)L + (uint64_t)(m % L)) * (uint64_t)S : 0;
+    float mrow = -INFINITY, lrow = 0.f;
+    const int ntiles = (S + AT - 1) / AT;
+
+    for (int j = 0; j < ntiles; ++j) {
+        const int s0 = j * AT;
+        if (j > 0) tc::mbar_wait(&bar_o, (j - 1) & 1);      // P V of the previous tile done: K/V/P smem and O are free
+        stage_rows_f32(Ks, K, s0, S, H, h);
+        stage_rows_f32(Vs, V, s0, S, H, h);
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t qa = tc::smem_u32(Qs), ka = tc::smem_u32(Ks);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    tc::mma_bf16(tmem_s, tc::desc_kmajor(qa + c * AT_SLAB, t), tc::desc_kmajor(ka + c * AT_SLAB, t), idesc_qk,
+                                 (c | t) != 0);
+            tc::mma_commit(&bar_s);
+            DBG(1, j + 1);
+        }
+        if (warp < 4) {
+            tc::mbar_wait(&bar_s, j & 1);
+            tc::fence_after_sync();
+            if (tid == 0) DBG(2, j + 1);
+            // pass 1: row maximum of this tile
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                tc::tmem_ld32(tmem_s + lane_off + c * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (s0 + c * 32 + i < S) mx = fmaxf(mx, v[i] * scale);
+            }
+            const float mnew = fmaxf(mrow, mx);
+            const float corr = __expf(mrow - mnew);
+            // rescale the running output in TMEM only if some row of this warp moved its maximum
+            if (j > 0 && __any_sync(0xffffffffu, mnew > mrow)) {
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    float v[32];
+                    tc::tmem_ld32(tmem_o + lane_off + c * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= corr;
+                    tc::tmem_st32(tmem_o + lane_off + c * 32, v);
+                }
+            }
+            // pass 2: probabilities -> bf16 P tile (K-major A operand of P V), row sum
+            float rs = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                tc::tmem_ld32(tmem_s + lane_off + c * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    int s = s0 + c * 32 + i;
+                    float p = s < S ? __expf(v[i] * scale - mnew) : 0.f;
+                    rs += p;
+                    if (thr) p = keep_mask_tc(seed, drop_base + (uint64_t)s, thr) ? p * inv_keep : 0.f;
+                    v[i] = p;
+                }
+#pragma unroll
+                for (int q8 = 0; q8 < 4; ++q8) {
+                    float f[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = v[q8 * 8 + i];
+                    int col = c * 32 + q8 * 8;                   // s offset inside the tile
+                    tc::slab_store8(Ps + (col >> 6) * AT_SLAB, row, (col & 63) >> 3, f);
+                }
+            }
+            lrow = lrow * corr + rs;
+            mrow = mnew;
+            if (tid == 0) DBG(3, j + 1);
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t pa = tc::smem_u32(Ps), va = tc::smem_u32(Vs);
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                tc::mma_bf16(tmem_o, tc::desc_kmajor(pa + (t >> 2) * AT_SLAB, t & 3), tc::desc_mnmajor(va, AT_SLAB, t), idesc_pv,
+                             (j | t) != 0);
+            tc::mma_commit(&bar_o);
+            DBG(5, j + 1);
+        }
+    }
+    tc::mbar_wait(&bar_o, (ntiles - 1) & 1);
+    tc::fence_after_sync();
+    if (tid == 0) DBG(6, 1);
+    if (warp < 4) {                                          // tcgen05.ld is warp-collective: no per-lane guard around it
+        const float inv = 1.f / lrow;
+        float* orow = O + ((size_t)(m < M ? m : 0) * H + h) * AT;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float v[32];
+            tc::tmem_ld32(tmem_o + lane_off + c * 32, v);
+            if (m < M) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(orow + c * 32 + i) = make_float4(v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
+            }
+        }
+        if (m < M) LSE[((size_t)(m / L) * H + h) * L + (m % L)] = mrow + logf(lrow);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);
+}
+
+}  // namespace hopk
+using namespace hopk;
+
+extern "C" int hopk_debug_set(void* mapped_host_ints)
+{
+    int* p = (int*)mapped_host_ints;
+    return cudaMemcpyToSymbol(hopk::g_dbg, &p, sizeof(p)) == cudaSuccess ? 0 : 1;
+}
+
+extern "C" int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v, float* o, float* lse, int B, int L, int H,
+                                 int E, int S, float p_drop, uint64_t seed, void* stream)
+{
+    HOPK_REQUIRE(B > 0 && L > 0 && H > 0 && S > 0, "xattn sizes");
+    HOPK_REQUIRE(E == 128, "tensor-core attention is specialised for head dim 128");
+    HOPK_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "dropout p in [0,1)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = B * L;
+    const size_t smem = 8 * AT_SLAB + 1024;
+    static bool configured = false;
+    if (!configured) {
+        HOPK_CUDA(cudaFuncSetAttribute(xattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    uint32_t thr = (uint32_t)lrintf(p_drop * 16777216.f);
+    xattn_fwd_tc_kernel<<<dim3(cdiv(M, AT), H), 256, smem, st>>>(q, k, v, o, lse, M, L, H, S, 1.f / sqrtf((float)E),
+                                                                 1.f / (1.f - p_drop), thr, seed);
+    HOPK_LAUNCH_CHECK("xattn_fwd_tc");
+    return 0;
+}

@@ -33,7 +33,8 @@ extern "C" {
 
 const char* hopk_last_error(void);
 int hopk_version(void);
-long long hopk_launch_count(void);   /* kernels this library has launched in this process (host-side counter) */
+long long hopk_launch_count(void);
+int hopk_debug_set(void* mapped_host_ints);   /* debugging aid: progress markers of the tensor-core kernels (NULL = off) */   /* kernels this library has launched in this process (host-side counter) */
 
 /* ------------------------------------------------------------------ Graph-WaveNet block */
 typedef struct HopkGwnetShape {
@@ -129,6 +130,11 @@ int hopk_xattn_fwd(const float* q, const float* k, const float* v, float* o, flo
 int hopk_xattn_bwd(const float* q, const float* k, const float* v, const float* o, const float* lse,
                    const float* dout, float* dq, float* dk, float* dv, float* delta,
                    int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
+
+/* dtype-1 variants of the two calls above: bf16 operands on tcgen05 (UMMA 128x128, TMEM accumulators), fp32
+ * accumulation and fp32 I/O; head dim must be 128.  Same arguments and semantics. */
+int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v, float* o, float* lse,
+                      int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
 
 #ifdef __cplusplus
 }
