@@ -69,7 +69,7 @@ class _XattnFn(torch.autograd.Function):
             check(fwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, L, H, E, S, float(p_drop), int(seed),
                                        stream_ptr()))
         ctx.save_for_backward(q, k, v, o, lse)
-        ctx.p_drop, ctx.seed = float(p_drop), int(seed)
+        ctx.p_drop, ctx.seed, ctx.tc = float(p_drop), int(seed), bool(tc and E == 128)
         return o
 
     @staticmethod
@@ -80,8 +80,9 @@ class _XattnFn(torch.autograd.Function):
         do = f32c(do)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         delta = torch.empty_like(lse)
+        bwd = lib().hopk_xattn_bwd_tc if ctx.tc else lib().hopk_xattn_bwd
         with profiler.span('xattn_bwd'):
-            check(lib().hopk_xattn_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
+            check(bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
                                        ptr(delta), B, L, H, E, S, ctx.p_drop, ctx.seed, stream_ptr()))
         return dq, dk, dv, None, None, None
 

@@ -197,6 +197,277 @@ xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
     if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);
 }
 
+
+// ------------------------------------------------------------------------------------------------ backward: dQ (+ delta)
+// TMEM: S [0,128)  dP [128,256)  dQ [256,384).  smem slabs: Q, dO, K_j, V_j, dS (2 each).
+__global__ void __launch_bounds__(256, 1)
+xattn_bwd_dq_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                       const float* __restrict__ O, const float* __restrict__ LSE, const float* __restrict__ dO,
+                       float* __restrict__ dQ, float* __restrict__ delta, int M, int L, int H, int S, float scale,
+                       float inv_keep, uint32_t thr, uint64_t seed)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_s, bar_q;
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* Qs = smem; uint8_t* dOs = Qs + 2 * AT_SLAB; uint8_t* Ks = dOs + 2 * AT_SLAB; uint8_t* Vs = Ks + 2 * AT_SLAB;
+    uint8_t* dSs = Vs + 2 * AT_SLAB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.y, m0 = blockIdx.x * AT;
+
+    if (tid == 0) { tc::mbar_init(&bar_s, 1); tc::mbar_init(&bar_q, 1); tc::fence_barrier_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 512);
+    stage_rows_f32(Qs, Q, m0, M, H, h);
+    stage_rows_f32(dOs, dO, m0, M, H, h);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_s = tmem_base_smem, tmem_dp = tmem_base_smem + 128, tmem_dq = tmem_base_smem + 256;
+    constexpr uint32_t idesc_kk = tc::idesc_bf16(AT, AT, 0, 0);
+    constexpr uint32_t idesc_kmn = tc::idesc_bf16(AT, AT, 0, 1);
+
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+    const bool rvalid = warp < 4 && m < M;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const size_t li = rvalid ? ((size_t)(m / L) * H + h) * L + (m % L) : 0;
+    const uint64_t drop_base = (uint64_t)li * (uint64_t)S;
+    float lse = 0.f, dl = 0.f;
+    if (rvalid) {                                            // delta = rowsum(dO * O) in fp32 from global
+        lse = __ldg(LSE + li);
+        const float4* o4 = reinterpret_cast<const float4*>(O + ((size_t)m * H + h) * AT);
+        const float4* d4 = reinterpret_cast<const float4*>(dO + ((size_t)m * H + h) * AT);
+#pragma unroll 4
+        for (int i = 0; i < AT / 4; ++i) {
+            float4 a = __ldg(o4 + i), b = __ldg(d4 + i);
+            dl += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+        delta[li] = dl;
+    }
+    const int ntiles = (S + AT - 1) / AT;
+    for (int j = 0; j < ntiles; ++j) {
+        const int s0 = j * AT;
+        if (j > 0) tc::mbar_wait(&bar_q, (j - 1) & 1);      // dQ UMMAs of the previous tile done: K_j / dS smem free
+        stage_rows_f32(Ks, K, s0, S, H, h);
+        stage_rows_f32(Vs, V, s0, S, H, h);
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t qa = tc::smem_u32(Qs), ka = tc::smem_u32(Ks), da = tc::smem_u32(dOs), va = tc::smem_u32(Vs);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    tc::mma_bf16(tmem_s, tc::desc_kmajor(qa + c * AT_SLAB, t), tc::desc_kmajor(ka + c * AT_SLAB, t), idesc_kk, (c | t) != 0);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    tc::mma_bf16(tmem_dp, tc::desc_kmajor(da + c * AT_SLAB, t), tc::desc_kmajor(va + c * AT_SLAB, t), idesc_kk, (c | t) != 0);
+            tc::mma_commit(&bar_s);
+        }
+        if (warp < 4) {
+            tc::mbar_wait(&bar_s, j & 1);
+            tc::fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float sv[32], dv[32];
+                tc::tmem_ld32(tmem_s + lane_off + c * 32, sv);
+                tc::tmem_ld32(tmem_dp + lane_off + c * 32, dv);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    int s = s0 + c * 32 + i;
+                    float ds = 0.f;
+                    if (rvalid && s < S) {
+                        float p = __expf(sv[i] * scale - lse);
+                        float d = dv[i];
+                        if (thr) d = keep_mask_tc(seed, drop_base + (uint64_t)s, thr) ? d * inv_keep : 0.f;
+                        ds = p * (d - dl) * scale;
+                    }
+                    sv[i] = ds;
+                }
+#pragma unroll
+                for (int q8 = 0; q8 < 4; ++q8) {
+                    float f[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = sv[q8 * 8 + i];
+                    int col = c * 32 + q8 * 8;
+                    tc::slab_store8(dSs + (col >> 6) * AT_SLAB, row, (col & 63) >> 3, f);
+                }
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t sa = tc::smem_u32(dSs), ka = tc::smem_u32(Ks);
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                tc::mma_bf16(tmem_dq, tc::desc_kmajor(sa + (t >> 2) * AT_SLAB, t & 3), tc::desc_mnmajor(ka, AT_SLAB, t), idesc_kmn,
+                             (j | t) != 0);
+            tc::mma_commit(&bar_q);
+        }
+    }
+    tc::mbar_wait(&bar_q, (ntiles - 1) & 1);
+    tc::fence_after_sync();
+    if (warp < 4) {
+        float* qrow = dQ + ((size_t)(m < M ? m : 0) * H + h) * AT;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float v[32];
+            tc::tmem_ld32(tmem_dq + lane_off + c * 32, v);
+            if (m < M) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(qrow + c * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dK, dV
+// One CTA per (128 prototypes, head); loops over the query-row tiles.  TMEM: S [0,128) dP [128,256) dK [256,384) dV [384,512).
+// P~ and dS are written row-major [row][s]; the dV / dK UMMAs read them (and dO / Q) through MN-major views.
+__global__ void __launch_bounds__(256, 1)
+xattn_bwd_dkv_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                        const float* __restrict__ LSE, const float* __restrict__ delta, const float* __restrict__ dO,
+                        float* __restrict__ dK, float* __restrict__ dV, int M, int L, int H, int S, float scale,
+                        float inv_keep, uint32_t thr, uint64_t seed)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_s, bar_kv;
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* Ks = smem; uint8_t* Vs = Ks + 2 * AT_SLAB; uint8_t* Qs = Vs + 2 * AT_SLAB; uint8_t* dOs = Qs + 2 * AT_SLAB;
+    uint8_t* Ps = dOs + 2 * AT_SLAB; uint8_t* dSs = Ps + 2 * AT_SLAB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.y, s0 = blockIdx.x * AT;
+
+    if (tid == 0) { tc::mbar_init(&bar_s, 1); tc::mbar_init(&bar_kv, 1); tc::fence_barrier_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 512);
+    stage_rows_f32(Ks, K, s0, S, H, h);
+    stage_rows_f32(Vs, V, s0, S, H, h);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_s = tmem_base_smem, tmem_dp = tmem_base_smem + 128, tmem_dk = tmem_base_smem + 256,
+                   tmem_dv = tmem_base_smem + 384;
+    constexpr uint32_t idesc_kk = tc::idesc_bf16(AT, AT, 0, 0);
+    constexpr uint32_t idesc_mm = tc::idesc_bf16(AT, AT, 1, 1);
+    const int row = warp * 32 + lane;                       // a query row inside the current row tile (softmax threads)
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int ntiles = (M + AT - 1) / AT;
+    for (int i = 0; i < ntiles; ++i) {
+        const int m0 = i * AT;
+        if (i > 0) tc::mbar_wait(&bar_kv, (i - 1) & 1);     // dK/dV UMMAs of the previous row tile done
+        stage_rows_f32(Qs, Q, m0, M, H, h);
+        stage_rows_f32(dOs, dO, m0, M, H, h);
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t qa = tc::smem_u32(Qs), ka = tc::smem_u32(Ks), da = tc::smem_u32(dOs), va = tc::smem_u32(Vs);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    tc::mma_bf16(tmem_s, tc::desc_kmajor(qa + c * AT_SLAB, t), tc::desc_kmajor(ka + c * AT_SLAB, t), idesc_kk, (c | t) != 0);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    tc::mma_bf16(tmem_dp, tc::desc_kmajor(da + c * AT_SLAB, t), tc::desc_kmajor(va + c * AT_SLAB, t), idesc_kk, (c | t) != 0);
+            tc::mma_commit(&bar_s);
+        }
+        if (warp < 4) {
+            const int m = m0 + row;
+            const bool rvalid = m < M;
+            const size_t li = rvalid ? ((size_t)(m / L) * H + h) * L + (m % L) : 0;
+            const float lse = rvalid ? __ldg(LSE + li) : 0.f;
+            const float dl = rvalid ? __ldg(delta + li) : 0.f;
+            const uint64_t drop_base = (uint64_t)li * (uint64_t)S;
+            tc::mbar_wait(&bar_s, i & 1);
+            tc::fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float sv[32], dv[32];
+                tc::tmem_ld32(tmem_s + lane_off + c * 32, sv);
+                tc::tmem_ld32(tmem_dp + lane_off + c * 32, dv);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    int s = s0 + c * 32 + k;
+                    float pt = 0.f, ds = 0.f;
+                    if (rvalid && s < S) {
+                        float p = __expf(sv[k] * scale - lse);
+                        float d = dv[k];
+                        pt = p;
+                        if (thr) {
+                            bool kp = keep_mask_tc(seed, drop_base + (uint64_t)s, thr);
+                            pt = kp ? p * inv_keep : 0.f;
+                            d = kp ? d * inv_keep : 0.f;
+                        }
+                        ds = p * (d - dl) * scale;
+                    }
+                    sv[k] = pt; dv[k] = ds;
+                }
+#pragma unroll
+                for (int q8 = 0; q8 < 4; ++q8) {
+                    float f[8], g[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { f[k] = sv[q8 * 8 + k]; g[k] = dv[q8 * 8 + k]; }
+                    int col = c * 32 + q8 * 8;
+                    tc::slab_store8(Ps + (col >> 6) * AT_SLAB, row, (col & 63) >> 3, f);
+                    tc::slab_store8(dSs + (col >> 6) * AT_SLAB, row, (col & 63) >> 3, g);
+                }
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t pa = tc::smem_u32(Ps), sa = tc::smem_u32(dSs), da = tc::smem_u32(dOs), qa = tc::smem_u32(Qs);
+#pragma unroll
+            for (int t = 0; t < 8; ++t)       // dV[s][e] += sum_row P~[row][s] dO[row][e]
+                tc::mma_bf16(tmem_dv, tc::desc_mnmajor(pa, AT_SLAB, t), tc::desc_mnmajor(da, AT_SLAB, t), idesc_mm, (i | t) != 0);
+#pragma unroll
+            for (int t = 0; t < 8; ++t)       // dK[s][e] += sum_row dS[row][s] Q[row][e]
+                tc::mma_bf16(tmem_dk, tc::desc_mnmajor(sa, AT_SLAB, t), tc::desc_mnmajor(qa, AT_SLAB, t), idesc_mm, (i | t) != 0);
+            tc::mma_commit(&bar_kv);
+        }
+    }
+    tc::mbar_wait(&bar_kv, (ntiles - 1) & 1);
+    tc::fence_after_sync();
+    if (warp < 4) {
+        const int s = s0 + row;
+        float* kr = dK + ((size_t)(s < S ? s : 0) * H + h) * AT;
+        float* vr = dV + ((size_t)(s < S ? s : 0) * H + h) * AT;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float a[32], b[32];
+            tc::tmem_ld32(tmem_dk + lane_off + c * 32, a);
+            tc::tmem_ld32(tmem_dv + lane_off + c * 32, b);
+            if (s < S) {
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    *reinterpret_cast<float4*>(kr + c * 32 + k) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
+                    *reinterpret_cast<float4*>(vr + c * 32 + k) = make_float4(b[k], b[k + 1], b[k + 2], b[k + 3]);
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 512);
+}
+
 }  // namespace hopk
 using namespace hopk;
 
@@ -224,5 +495,33 @@ extern "C" int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v,
     xattn_fwd_tc_kernel<<<dim3(cdiv(M, AT), H), 256, smem, st>>>(q, k, v, o, lse, M, L, H, S, 1.f / sqrtf((float)E),
                                                                  1.f / (1.f - p_drop), thr, seed);
     HOPK_LAUNCH_CHECK("xattn_fwd_tc");
+    return 0;
+}
+
+extern "C" int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v, const float* o, const float* lse,
+                                 const float* dout, float* dq, float* dk, float* dv, float* delta, int B, int L, int H, int E,
+                                 int S, float p_drop, uint64_t seed, void* stream)
+{
+    HOPK_REQUIRE(B > 0 && L > 0 && H > 0 && S > 0, "xattn sizes");
+    HOPK_REQUIRE(E == 128, "tensor-core attention is specialised for head dim 128");
+    HOPK_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "dropout p in [0,1)");
+    HOPK_REQUIRE(delta != nullptr, "delta scratch (B*H*L floats) required");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = B * L;
+    uint32_t thr = (uint32_t)lrintf(p_drop * 16777216.f);
+    const float inv_keep = 1.f / (1.f - p_drop), scale = 1.f / sqrtf((float)E);
+    const size_t smem1 = 10 * AT_SLAB + 1024, smem2 = 12 * AT_SLAB + 1024;
+    static bool configured = false;
+    if (!configured) {
+        HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        configured = true;
+    }
+    xattn_bwd_dq_tc_kernel<<<dim3(cdiv(M, AT), H), 256, smem1, st>>>(q, k, v, o, lse, dout, dq, delta, M, L, H, S, scale,
+                                                                     inv_keep, thr, seed);
+    HOPK_LAUNCH_CHECK("xattn_bwd_dq_tc");
+    xattn_bwd_dkv_tc_kernel<<<dim3(cdiv(S, AT), H), 256, smem2, st>>>(q, k, v, lse, delta, dout, dk, dv, M, L, H, S, scale,
+                                                                      inv_keep, thr, seed);
+    HOPK_LAUNCH_CHECK("xattn_bwd_dkv_tc");
     return 0;
 }

@@ -135,6 +135,9 @@ int hopk_xattn_bwd(const float* q, const float* k, const float* v, const float* 
  * accumulation and fp32 I/O; head dim must be 128.  Same arguments and semantics. */
 int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v, float* o, float* lse,
                       int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
+int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v, const float* o, const float* lse,
+                      const float* dout, float* dq, float* dk, float* dv, float* delta,
+                      int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
 
 #ifdef __cplusplus
 }

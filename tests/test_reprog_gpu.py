@@ -168,3 +168,28 @@ def test_xattn_tcgen05_forward_exact(cuda):
         a = _XattnFn.apply(q, k, torch.ones_like(v), 0.1, 77, True)
         b = _XattnFn.apply(q, k, torch.ones_like(v), 0.1, 77, False)
     assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.parametrize('B,L,H,S,p', [(2, 34, 8, 1500, 0.0), (3, 7, 1, 300, 0.0), (5, 34, 2, 128, 0.1)])
+def test_xattn_tcgen05_backward(B, L, H, S, p, cuda):
+    """Tensor-core attention backward (dQ and dK/dV passes) against float64 on bf16-representable inputs.
+    Remaining error: bf16 rounding of P~ and dS (2^-9 relative per element) -> 5e-3 in relative 2-norm."""
+    from hop_b200.HOP import _XattnFn
+    torch.manual_seed(B + S)
+    q = torch.randn(B, L, H, 128).bfloat16().double().requires_grad_(True)
+    k = torch.randn(S, H, 128).bfloat16().double().requires_grad_(True)
+    v = torch.randn(S, H, 128).bfloat16().double().requires_grad_(True)
+    do = torch.randn(B, L, H, 128).bfloat16().double()
+    sc = torch.einsum('blhe,she->bhls', q, k) / 128 ** 0.5
+    pr = torch.softmax(sc, -1)
+    if p > 0:
+        idx = np.arange(B * H * L * S, dtype=np.uint64).reshape(B, H, L, S)
+        pr = pr * torch.from_numpy(reprog_np.dropout_keep(99, idx, p) / (1 - p))
+    torch.einsum('bhls,she->blhe', pr, v).backward(do)
+    qg, kg, vg = [t.detach().float().to(cuda).requires_grad_(True) for t in (q, k, v)]
+    _XattnFn.apply(qg, kg, vg, p, 99, True).backward(do.float().to(cuda))
+    rep = Report(f'xattn_tc_bwd_{B}_{S}', 5e-3)
+    rep.add('dq', l2err(qg.grad.cpu().numpy(), q.grad.numpy()))
+    rep.add('dk', l2err(kg.grad.cpu().numpy(), k.grad.numpy()))
+    rep.add('dv', l2err(vg.grad.cpu().numpy(), v.grad.numpy()))
+    rep.finish()
