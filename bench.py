@@ -142,7 +142,7 @@ def run_reference(a):
                              'sample': f'{max(1, a.steps)} training step(s) at batch {batch} of the same synthetic workload '
                                        '(oracle/hop_torch.py: functional PyTorch-CPU port of the reference step)'},
             'e2e': {'value': rate, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(a, world):
@@ -256,7 +256,7 @@ def run_ours(a):
             line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
                                     'sample': f'1 training step at batch {a.cpu_batch} (after 1 warm-up) of the same '
                                               'synthetic workload, oracle/hop_torch.py on the host cores'}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -301,7 +301,25 @@ def roofline(spans, a, world):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Library chatter (e.g. the 'NCCL version' banner) must not pollute the one-JSON-line contract: everything that
+    writes to fd 1 during the run goes to stderr; emit() writes the JSON line to the real stdout at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + '\n')
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)

@@ -248,9 +248,88 @@ def make_model(ref_hop, datasets='TED'):
     print(name, 'ok; keys', len(sd), 'out', out.shape, 'none_grads', len(fix['none_grads']))
 
 
+# ---------------------------------------------------------------------------------------------- 200-step loss curve
+CURVE_STEPS, CURVE_B = 200, 4
+
+
+def curve_batch(step, datasets='TED', B=CURVE_B):
+    """Synthetic batch of training step ``step`` (SURVEY 8(d) shapes), reproducible from numpy alone."""
+    rs = np.random.RandomState(10_000 + step)
+    pose = 27 if datasets == 'TED' else 126
+    return dict(in_audio=(0.1 * rs.standard_normal((B, 36267))).astype(np.float32),
+                melspec=(-80 * rs.rand(B, 34, 128)).astype(np.float32),
+                text=(rs.randint(0, 30522, (B, 34)) * (rs.rand(B, 34) > 0.7)).astype(np.int64),
+                target=np.clip(0.3 * rs.standard_normal((B, 34, pose)), -1, 1).astype(np.float32),
+                vid=rs.randint(0, 1370, (B,)).astype(np.int64))
+
+
+class NoiseSource:
+    """Shared randomness of the step: reparameterize noise and the speaker permutation, in call order."""
+
+    def __init__(self, B=CURVE_B):
+        self.rs, self.B = np.random.RandomState(4242), B
+
+    def noise(self):
+        return torch.from_numpy(self.rs.standard_normal((self.B, 16)).astype(np.float32))
+
+    def perm(self):
+        return torch.from_numpy(self.rs.permutation(self.B).astype(np.int64))
+
+
+def curve_args(datasets='TED'):
+    ted = datasets == 'TED'
+    return types.SimpleNamespace(z_type='speaker', loss_regression_weight=600.0 if ted else 2100.0, loss_gan_weight=5.0,
+                                 loss_kld_weight=0.6 if ted else 0.8, loss_reg_weight=0.4 if ted else 0.5)
+
+
+class PlainAccelerator:
+    def backward(self, loss):
+        loss.backward()
+
+
+def make_loss_curve(ref_hop):
+    """Run the REFERENCE train_llm (train_eval/train_llm.py) for 200 generator steps on the CPU, fp32."""
+    import importlib.machinery
+    torch.manual_seed(MODEL_SEED)
+    bert = build_bert()
+    for name in ['soundfile', 'librosa', 'lmdb']:            # data-loader imports pulled in by train_llm.py:2
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            mod.__spec__ = importlib.machinery.ModuleSpec(name, None)
+            sys.modules[name] = mod
+    from model import embedding_net
+    from model.multimodal_context_net import ConvDiscriminator
+    from train_eval import train_llm as ref_step
+    m = ref_hop.Model(model_configs('TED'), bert, DummyTok(), DummySpk()).float()
+    m.reprogramming_layer.dropout.p = 0.0
+    disc = ConvDiscriminator(27)
+    opt = torch.optim.Adam([p_ for p_ in m.parameters() if p_.requires_grad], lr=4e-4, betas=(0.5, 0.999))
+    dopt = torch.optim.Adam(disc.parameters(), lr=4e-4, betas=(0.5, 0.999))
+    src = NoiseSource()
+    embedding_net.reparameterize = lambda mu, logvar: mu + src.noise() * torch.exp(0.5 * logvar)
+    real_randperm = torch.randperm
+    torch.randperm = lambda n, **kw: src.perm()
+    rows = []
+    try:
+        for step in range(CURVE_STEPS):
+            b = {k: torch.from_numpy(v) for k, v in curve_batch(step).items()}
+            ret = ref_step.train_llm(curve_args(), 1, b['in_audio'], b['melspec'], b['text'], b['target'], b['vid'], m, disc,
+                                     opt, dopt, PlainAccelerator())
+            rows.append([ret.get('loss', 0.0), ret.get('KLD', 0.0), ret.get('DIV_REG', 0.0)])
+            if step % 20 == 0:
+                print('step', step, rows[-1], flush=True)
+    finally:
+        torch.randperm = real_randperm
+    np.savez_compressed(os.path.join(HERE, 'loss_curve_ted.npz'), curve=np.array(rows, np.float64))
+    print('loss_curve_ted ok')
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     ref_gwnet, ref_hop = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == 'curve':
+        make_loss_curve(ref_hop)
+        sys.exit(0)
     for n in GW_CASES:
         make_gwnet(ref_gwnet, n)
     for n in RP_CASES:
