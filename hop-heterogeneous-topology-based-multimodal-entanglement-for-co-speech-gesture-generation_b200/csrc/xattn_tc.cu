@@ -55,7 +55,41 @@ __device__ __forceinline__ void stage_rows_f32(uint8_t* slabs, const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(256, 1)
+// v2: prototypes streamed in tiles of 64 so that one CTA needs 81 KB of shared memory and 256 TMEM columns ->
+// TWO CTAs per SM, whose stage / UMMA / softmax phases overlap each other.  Two threads per query row (warps w and
+// w+4 share TMEM lane quarter w&3 and split the 64 score columns), log2-domain softmax (one FFMA + one MUFU.EX2 per
+// element), dropout hash with the per-row high word hoisted.
+constexpr int FS = 64;                                   // prototypes per tile
+constexpr uint32_t FS_SLAB = tc::slab_bytes(FS);         // 8 KB: [64 rows][64 bf16]
+
+__device__ __forceinline__ float ex2f(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// stage a [64 rows][128 cols] fp32 tile as two bf16 slabs of 64 rows
+__device__ __forceinline__ void stage_rows64_f32(uint8_t* slabs, const float* __restrict__ src, int row0, int nrows, int H, int h)
+{
+#pragma unroll
+    for (int it = 0; it < (FS * 16) / 256; ++it) {
+        int idx = threadIdx.x + it * 256;
+        int ch16 = idx & 15, row = idx >> 4;
+        float f[8];
+        if (row0 + row < nrows) {
+            const float4* p = reinterpret_cast<const float4*>(src + ((size_t)(row0 + row) * H + h) * AT + ch16 * 8);
+            float4 a = __ldg(p), b = __ldg(p + 1);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        }
+        tc::slab_store8(slabs + (ch16 >> 3) * FS_SLAB, row, ch16 & 7, f);
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
 xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                     float* __restrict__ O, float* __restrict__ LSE, int M, int L, int H, int S, float scale,
                     float inv_keep, uint32_t thr, uint64_t seed)
@@ -63,8 +97,9 @@ xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_s, bar_o;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float xch[2][AT];                             // partial row maxima / sums of the two column halves
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* Qs = smem; uint8_t* Ks = Qs + 2 * AT_SLAB; uint8_t* Vs = Ks + 2 * AT_SLAB; uint8_t* Ps = Vs + 2 * AT_SLAB;
+    uint8_t* Qs = smem; uint8_t* Ks = Qs + 2 * AT_SLAB; uint8_t* Vs = Ks + 2 * FS_SLAB; uint8_t* Ps = Vs + 2 * FS_SLAB;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int h = blockIdx.y, m0 = blockIdx.x * AT;
 
@@ -74,23 +109,25 @@ xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem_s = tmem_base_smem, tmem_o = tmem_base_smem + 128;
-    if (tid == 0) DBG(0, 1 + (int)tmem_base_smem);
-    constexpr uint32_t idesc_qk = tc::idesc_bf16(AT, AT, 0, 0);
+    const uint32_t tmem_s = tmem_base_smem, tmem_o = tmem_base_smem + 64;
+    constexpr uint32_t idesc_qk = tc::idesc_bf16(AT, FS, 0, 0);
     constexpr uint32_t idesc_pv = tc::idesc_bf16(AT, AT, 0, 1);
 
-    const int row = warp * 32 + lane;                       // softmax threads (warps 0-3): one query row each
+    const int row = (warp & 3) * 32 + lane;                 // query row inside the tile; two threads per row
+    const int half = warp >> 2;                             // which 32 of the 64 score columns / which 64 of the 128 outputs
     const int m = m0 + row;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint64_t drop_base = (warp < 4 && m < M) ? (((uint64_t)(m / L) * H + h) * (uint64_t)L + (uint64_t)(m % L)) * (uint64_t)S : 0;
-    float mrow = -INFINITY, lrow = 0.f;
-    const int ntiles = (S + AT - 1) / AT;
+    const uint64_t drop_base = m < M ? (((uint64_t)(m / L) * H + h) * (uint64_t)L + (uint64_t)(m % L)) * (uint64_t)S : 0;
+    const uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
+    const float sc2 = scale * 1.4426950408889634f;           // scores are tracked in the log2 domain
+    float mrow = -INFINITY, lrow = 0.f;                      // lrow: partial sum over this thread's columns
+    const int ntiles = (S + FS - 1) / FS;
 
     for (int j = 0; j < ntiles; ++j) {
-        const int s0 = j * AT;
+        const int s0 = j * FS;
         if (j > 0) tc::mbar_wait(&bar_o, (j - 1) & 1);      // P V of the previous tile done: K/V/P smem and O are free
-        stage_rows_f32(Ks, K, s0, S, H, h);
-        stage_rows_f32(Vs, V, s0, S, H, h);
+        stage_rows64_f32(Ks, K, s0, S, H, h);
+        stage_rows64_f32(Vs, V, s0, S, H, h);
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
@@ -101,65 +138,59 @@ xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
-                    tc::mma_bf16(tmem_s, tc::desc_kmajor(qa + c * AT_SLAB, t), tc::desc_kmajor(ka + c * AT_SLAB, t), idesc_qk,
+                    tc::mma_bf16(tmem_s, tc::desc_kmajor(qa + c * AT_SLAB, t), tc::desc_kmajor(ka + c * FS_SLAB, t), idesc_qk,
                                  (c | t) != 0);
             tc::mma_commit(&bar_s);
-            DBG(1, j + 1);
         }
-        if (warp < 4) {
-            tc::mbar_wait(&bar_s, j & 1);
-            tc::fence_after_sync();
-            if (tid == 0) DBG(2, j + 1);
-            // pass 1: row maximum of this tile
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float v[32];
-                tc::tmem_ld32(tmem_s + lane_off + c * 32, v);
+        tc::mbar_wait(&bar_s, j & 1);
+        tc::fence_after_sync();
+        float v[32];
+        tc::tmem_ld32(tmem_s + lane_off + half * 32, v);
+        const int sb = s0 + half * 32;                       // first prototype of this thread's columns
+        float mx = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (s0 + c * 32 + i < S) mx = fmaxf(mx, v[i] * scale);
-            }
-            const float mnew = fmaxf(mrow, mx);
-            const float corr = __expf(mrow - mnew);
-            // rescale the running output in TMEM only if some row of this warp moved its maximum
-            if (j > 0 && __any_sync(0xffffffffu, mnew > mrow)) {
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    float v[32];
-                    tc::tmem_ld32(tmem_o + lane_off + c * 32, v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= corr;
-                    tc::tmem_st32(tmem_o + lane_off + c * 32, v);
-                }
-            }
-            // pass 2: probabilities -> bf16 P tile (K-major A operand of P V), row sum
-            float rs = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float v[32];
-                tc::tmem_ld32(tmem_s + lane_off + c * 32, v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    int s = s0 + c * 32 + i;
-                    float p = s < S ? __expf(v[i] * scale - mnew) : 0.f;
-                    rs += p;
-                    if (thr) p = keep_mask_tc(seed, drop_base + (uint64_t)s, thr) ? p * inv_keep : 0.f;
-                    v[i] = p;
-                }
-#pragma unroll
-                for (int q8 = 0; q8 < 4; ++q8) {
-                    float f[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = v[q8 * 8 + i];
-                    int col = c * 32 + q8 * 8;                   // s offset inside the tile
-                    tc::slab_store8(Ps + (col >> 6) * AT_SLAB, row, (col & 63) >> 3, f);
-                }
-            }
-            lrow = lrow * corr + rs;
-            mrow = mnew;
-            if (tid == 0) DBG(3, j + 1);
+        for (int i = 0; i < 32; ++i) {
+            v[i] = sb + i < S ? v[i] * sc2 : -INFINITY;
+            mx = fmaxf(mx, v[i]);
         }
+        xch[half][row] = mx;
+        __syncthreads();
+        const float mnew = fmaxf(mrow, fmaxf(mx, xch[half ^ 1][row]));
+        const float corr = ex2f(mrow - mnew);
+        if (j > 0 && __any_sync(0xffffffffu, mnew > mrow)) {   // rescale this thread's 64 output columns in TMEM
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                float o[32];
+                tc::tmem_ld32(tmem_o + lane_off + half * 64 + c * 32, o);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] *= corr;
+                tc::tmem_st32(tmem_o + lane_off + half * 64 + c * 32, o);
+            }
+        }
+        float rs = 0.f;
+        const uint64_t idx0 = drop_base + (uint64_t)sb;
+        const uint32_t lo0 = (uint32_t)idx0, hi0 = (uint32_t)(idx0 >> 32);
+        const uint32_t in0 = lowbias32_tc(hi0 ^ s_hi), in1 = lowbias32_tc((hi0 + 1) ^ s_hi);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float p = ex2f(v[i] - mnew);
+            rs += p;
+            if (thr) {
+                uint32_t lo = lo0 + (uint32_t)i;
+                uint32_t hsh = lowbias32_tc((lo + (lo < lo0 ? in1 : in0)) ^ s_lo);
+                p = (hsh >> 8) >= thr ? p * inv_keep : 0.f;
+            }
+            v[i] = p;
+        }
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = v[q8 * 8 + i];
+            tc::slab_store8(Ps, row, half * 4 + q8, f);
+        }
+        lrow = lrow * corr + rs;
+        mrow = mnew;
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
@@ -167,36 +198,35 @@ xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             tc::fence_after_sync();
             const uint32_t pa = tc::smem_u32(Ps), va = tc::smem_u32(Vs);
 #pragma unroll
-            for (int t = 0; t < 8; ++t)
-                tc::mma_bf16(tmem_o, tc::desc_kmajor(pa + (t >> 2) * AT_SLAB, t & 3), tc::desc_mnmajor(va, AT_SLAB, t), idesc_pv,
-                             (j | t) != 0);
+            for (int t = 0; t < 4; ++t)
+                tc::mma_bf16(tmem_o, tc::desc_kmajor(pa, t), tc::desc_mnmajor(va, FS_SLAB, t), idesc_pv, (j | t) != 0);
             tc::mma_commit(&bar_o);
-            DBG(5, j + 1);
         }
     }
     tc::mbar_wait(&bar_o, (ntiles - 1) & 1);
     tc::fence_after_sync();
-    if (tid == 0) DBG(6, 1);
-    if (warp < 4) {                                          // tcgen05.ld is warp-collective: no per-lane guard around it
-        const float inv = 1.f / lrow;
-        float* orow = O + ((size_t)(m < M ? m : 0) * H + h) * AT;
+    xch[half][row] = lrow;
+    __syncthreads();
+    const float ltot = lrow + xch[half ^ 1][row];
+    {                                                        // tcgen05.ld is warp-collective: no per-lane guard around it
+        const float inv = 1.f / ltot;
+        float* orow = O + ((size_t)(m < M ? m : 0) * H + h) * AT + half * 64;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            float v[32];
-            tc::tmem_ld32(tmem_o + lane_off + c * 32, v);
+        for (int c = 0; c < 2; ++c) {
+            float o[32];
+            tc::tmem_ld32(tmem_o + lane_off + half * 64 + c * 32, o);
             if (m < M) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(orow + c * 32 + i) = make_float4(v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
+                    *reinterpret_cast<float4*>(orow + c * 32 + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
             }
         }
-        if (m < M) LSE[((size_t)(m / L) * H + h) * L + (m % L)] = mrow + logf(lrow);
+        if (m < M && half == 0) LSE[((size_t)(m / L) * H + h) * L + (m % L)] = (mrow + log2f(ltot)) * 0.6931471805599453f;
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);
 }
-
 
 // ------------------------------------------------------------------------------------------------ backward: dQ (+ delta)
 // TMEM: S [0,128)  dP [128,256)  dQ [256,384).  smem slabs: Q, dO, K_j, V_j, dS (2 each).
@@ -485,7 +515,7 @@ extern "C" int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v,
     HOPK_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "dropout p in [0,1)");
     cudaStream_t st = (cudaStream_t)stream;
     const int M = B * L;
-    const size_t smem = 8 * AT_SLAB + 1024;
+    const size_t smem = 2 * AT_SLAB + 4 * FS_SLAB + AT_SLAB + 1024;       // Q + K + V + P = 80 KB (+ alignment): 2 CTAs / SM
     static bool configured = false;
     if (!configured) {
         HOPK_CUDA(cudaFuncSetAttribute(xattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
