@@ -7,6 +7,7 @@
 #pragma once
 #include "gemm_core.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc_wgrad.cuh"
 
 namespace hopk {
 
@@ -152,6 +153,7 @@ struct EpiWgrad {
         }
     }
     __device__ __forceinline__ void finish(float*) {}
+    __device__ __forceinline__ void bias(int n, float v) { if (db) atomicAdd(db + n, v); }   // gemm_tc_wgrad.cuh
 };
 
 }  // namespace hopk

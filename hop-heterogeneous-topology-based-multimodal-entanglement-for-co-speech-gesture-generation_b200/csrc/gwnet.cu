@@ -698,6 +698,54 @@ struct GateWgEpi {
     __device__ __forceinline__ void finish(float*) {}
 };
 
+// ---- operands / epilogue of the MN-major weight-gradient skeleton (gemm_tc_wgrad.cuh) ----
+struct W8Seg3 {              // [p0 | p1 | p2], C columns each (C % 8 == 0)
+    const float* p0; const float* p1; const float* p2; int C; int ncols;
+    __device__ __forceinline__ void ld8(int r, int c0, float (&f)[8]) const {
+        if (c0 >= ncols) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            return;
+        }
+        int seg = c0 / C; int c = c0 - seg * C;
+        const float* p = (seg == 0 ? p0 : (seg == 1 ? p1 : p2)) + (size_t)r * C + c;
+        float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+};
+struct W8GateX {             // columns j = tap*C + c : BN_{i-1}-folded layer input at (b, t + tap*d, v)
+    const float* up; const float* ss; LayerGeom g; int ncols;
+    __device__ __forceinline__ void ld8(int r, int c0, float (&f)[8]) const {
+        if (c0 >= ncols) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            return;
+        }
+        int tap = c0 >= g.C; int c = c0 - tap * g.C;
+        const float* p = up + (size_t)(g.in_row(r) + (long)tap * g.d * g.V) * g.C + c;
+        float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+        float4 s0 = __ldg(reinterpret_cast<const float4*>(ss + c)), s1 = __ldg(reinterpret_cast<const float4*>(ss + c + 4));
+        float4 h0 = __ldg(reinterpret_cast<const float4*>(ss + g.C + c)), h1 = __ldg(reinterpret_cast<const float4*>(ss + g.C + c + 4));
+        f[0] = fmaf(a.x, s0.x, h0.x); f[1] = fmaf(a.y, s0.y, h0.y); f[2] = fmaf(a.z, s0.z, h0.z); f[3] = fmaf(a.w, s0.w, h0.w);
+        f[4] = fmaf(b.x, s1.x, h1.x); f[5] = fmaf(b.y, s1.y, h1.y); f[6] = fmaf(b.z, s1.z, h1.z); f[7] = fmaf(b.w, s1.w, h1.w);
+    }
+};
+struct GateWgEpi2 {          // out[i = fg*C + o][j = tap*C + c] -> d(filter|gate)_w[o][c][tap]; bias = column sums of [DF|DG]
+    float* dwf; float* dwg; float* dbf; float* dbg; int C;
+    __device__ __forceinline__ void row32(int i, bool valid, int j0, float (&v)[32], float*) {
+        if (!valid) return;
+        int fg = i >= C; int o = i - fg * C;
+        float* dw = (fg ? dwg : dwf) + (size_t)o * 2 * C;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+            int j = j0 + jj;
+            if (j < 2 * C) { int tap = j >= C; int c = j - tap * C; atomicAdd(dw + 2 * c + tap, v[jj]); }
+        }
+    }
+    __device__ __forceinline__ void finish(float*) {}
+    __device__ __forceinline__ void bias(int i, float v) { int fg = i >= C; atomicAdd((fg ? dbg : dbf) + (i - fg * C), v); }
+};
+
 struct DxA {                 // A(m_in, k = (tap*2 + fg)*C + o) = (fg?DG:DF)[(b, t - tap*d, v)][o], 0 outside [0, To)
     static constexpr bool kFast = true;
     const float* DF; const float* DG; LayerGeom g;
@@ -1034,7 +1082,13 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             // mlp weight + bias gradient
             HOPK_CUDA(cudaMemsetAsync(gr->mlp_w[i], 0, (size_t)C * 3 * C * sizeof(float), st));
             HOPK_CUDA(cudaMemsetAsync(gr->mlp_b[i], 0, (size_t)C * sizeof(float), st));
-            {
+            if (tc && C % 8 == 0) {          // MN-major tensor-core weight gradient: dWm[o][k] = sum_r du[r][o] [y|x1|x2][r][k]
+                W8Plain a{DU, nullptr, C, C, 0};
+                W8Seg3 b{F(g.y[i]), F(g.x1[i]), F(g.x2[i]), C, 3 * C};
+                EpiWgrad<2> e{gr->mlp_w[i], (long)3 * C, gr->mlp_b[i], 3 * C, C};
+                HOPK_CUDA(launch_gemm_tc_wgrad<128>(M, C, 3 * C, a, b, e, true, st));
+                HOPK_LAUNCH_CHECK("mlp_wgrad_tc");
+            } else {
                 Ld2D<false, 0> a{DU, nullptr, C};
                 Seg3AT b{F(g.y[i]), F(g.x1[i]), F(g.x2[i]), C};
                 EpiWgrad<2> e{gr->mlp_w[i], (long)3 * C, gr->mlp_b[i], 3 * C, C};
@@ -1075,7 +1129,13 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
         HOPK_CUDA(cudaMemsetAsync(gr->gate_w[i], 0, (size_t)C * 2 * C * sizeof(float), st));
         HOPK_CUDA(cudaMemsetAsync(gr->filter_b[i], 0, (size_t)C * sizeof(float), st));
         HOPK_CUDA(cudaMemsetAsync(gr->gate_b[i], 0, (size_t)C * sizeof(float), st));
-        {
+        if (tc && C % 8 == 0) {
+            W8Seg3 a{S(g.s_df), S(g.s_dg), S(g.s_dg), C, 2 * C};
+            W8GateX b{uprev, ss, lg, 2 * C};
+            GateWgEpi2 e{gr->filter_w[i], gr->gate_w[i], gr->filter_b[i], gr->gate_b[i], C};
+            HOPK_CUDA(launch_gemm_tc_wgrad<128>(M, 2 * C, 2 * C, a, b, e, true, st));
+            HOPK_LAUNCH_CHECK("gate_wgrad_tc");
+        } else {
             GateWgA a{S(g.s_df), S(g.s_dg), C};
             GateWgB b{uprev, ss, lg};
             GateWgEpi<2> e{gr->filter_w[i], gr->gate_w[i], gr->filter_b[i], gr->gate_b[i], C};

@@ -172,7 +172,12 @@ extern "C" int hopk_linear_bwd(const float* x, const float* w, const float* y, c
         if (db) HOPK_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
         EpiWgrad<2> e{dw, K, db, K, N};
         int sp = splits_for(N, K + 1, M, 2, 2);
-        if (relu_in) {
+        if (g_tc) {                          // MN-major tensor-core weight gradient (gemm_tc_wgrad.cuh)
+            W8Plain a{dy, y, N, N, relu_out ? 2 : 0};
+            W8Plain bl{x, nullptr, K, K, relu_in ? 1 : 0};
+            if (K <= 64) HOPK_CUDA(launch_gemm_tc_wgrad<64>(M, N, K, a, bl, e, db != nullptr, st));
+            else HOPK_CUDA(launch_gemm_tc_wgrad<128>(M, N, K, a, bl, e, db != nullptr, st));
+        } else if (relu_in) {
             XRelu bl{x, K, K};
             if (relu_out) { Ld2D<false, 2> a{dy, y, N}; launch_gemm2<2, 2>(N, K + 1, M, sp, a, bl, e, st); }
             else { Ld2D<false, 0> a{dy, nullptr, N}; launch_gemm2<2, 2>(N, K + 1, M, sp, a, bl, e, st); }
