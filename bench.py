@@ -240,9 +240,9 @@ def run_ours(a):
                 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32' if a.precision == 'fp32' else 'bf16+fp32', 'data': 'synthetic',
                 'config': workload_config(a, world) | {'tf32_library_gemms': bool(a.tf32), 'gan_phase': bool(a.gan),
-                                                       'precision': a.precision + (' autocast for the stock BERT/GRU/MLP parts; '
-                                                                                   'gwnet + reprogramming kernels fp32 FFMA (this round)'
-                                                                                   if a.precision == 'bf16' else '')},
+                                                       'precision': a.precision + (' (gwnet + reprogramming on tcgen05 bf16 UMMA kernels, fp32 accumulate; '
+                                                                                   'stock BERT/GRU/MLP parts under bf16 autocast)'
+                                                                                   if a.precision == 'bf16' else ' (FFMA kernels, reference numerics)')},
                 'clocks': clocks,
                 'e2e': {'value': samples / (e2e_ms * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': 4 * len(out)},
@@ -274,8 +274,8 @@ def roofline(spans, a, world):
     """Dominant hand-written kernel group of the step: the cross-attention backward (dQ + dK/dV kernels).
 
     Algorithmic FLOPs per launch group: forward 4*B*L*S*H*E; backward recomputes QK^T and dO V^T in both
-    passes: (2+2+1+2)*2*B*L*S*H*E = 14*B*L*S*H*E.  Arithmetic is fp32 FFMA in this round, reported against the
-    measured dense-bf16 tensor peak the kernel is headed for (so the fraction is honest about the gap)."""
+    passes: (2+2+1+2)*2*B*L*S*H*E = 14*B*L*S*H*E.  bf16 precision: tcgen05 UMMA kernels (csrc/xattn_tc.cu); fp32
+    precision: FFMA kernels, still reported against the measured dense-bf16 tensor peak (honest about the gap)."""
     B, L, S, H, E = a.batch, 34, 1500, 8, 128
     hbm, tf, which = peaks()
     out = {}
@@ -288,7 +288,8 @@ def roofline(spans, a, world):
     achieved = flops / (total_ms / calls * 1e-3) / 1e12
     out = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': tf, 'unit': 'TFLOP/s', 'frac': achieved / tf,
            'traffic': None, 'peak_source': which + ' (bf16_tflops_sustained)', 'launches_timed': calls,
-           'avg_ms': total_ms / calls, 'arithmetic': 'fp32 FFMA'}
+           'avg_ms': total_ms / calls,
+           'arithmetic': 'bf16 tcgen05 UMMA, fp32 accumulate in TMEM' if a.precision == 'bf16' else 'fp32 FFMA'}
     # the memory-bound side: whole gwnet block vs its fused-floor traffic; informational
     V, s = (9, 4) if a.datasets == 'TED' else (42, 4)
     floor_fwd = s * B * V * (173 * 16 + 64 * 16 + 64 * (88 + 76) + 2 * 8 * 64 * 4 + 173 * 4)

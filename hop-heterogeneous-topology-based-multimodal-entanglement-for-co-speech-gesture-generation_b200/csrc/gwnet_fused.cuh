@@ -1,0 +1,260 @@
+// gwnet_fused.cuh -- one kernel per Graph-WaveNet layer (forward, dtype 1, C = 64).
+//
+// A CTA owns a tile of G = floor(128 / V) complete (b, t) node groups (126 rows for V = 9 and for V = 42) and runs the
+// whole layer on it without leaving the SM:
+//   1. stage [x_t | x_{t+d}] (BatchNorm_{i-1} folded into the load) as bf16 slabs; copy the pre-packed gate weights
+//   2. UMMA 128x128x128  ->  TMEM (filter | gate pre-activations)
+//   3. tanh * sigmoid (two threads per row), y kept in shared memory (fp32) and written out with tanh/sigmoid
+//      (backward needs them) + the skip slice
+//   4. diffusion x1 = A^T y, x2 = A^T x1 per node group, entirely in shared memory (fp32), re-quantised into slabs
+//   5. UMMA 128x64x192 on [y | x1 | x2]  ->  TMEM
+//   6. + bias + residual (BN-folded), u written out, per-channel sum / sum^2 (shuffle transpose-reduce -> smem -> fp64 atomics)
+// Reference lines fused: model/gwnet.py:186-200 (gated conv), :209-220 (skip slice), :12-14,:35-46 (gcn), :233 (residual),
+// and the statistics half of :237 (BatchNorm).
+#pragma once
+#include "functors.cuh"
+
+namespace hopk {
+
+constexpr int FZ_C = 64;
+constexpr uint32_t FZ_WG_BYTES = 2 * tc::slab_bytes(128);            // gate weights [128 n][128 k]: 32 KB
+constexpr uint32_t FZ_WM_BYTES = 3 * tc::slab_bytes(64);             // mlp weights  [64 n][192 k]: 24 KB
+constexpr uint32_t FZ_PACK_BYTES = FZ_WG_BYTES + FZ_WM_BYTES;        // per layer
+constexpr int FZ_LDF = FZ_C + 4;                                     // fp32 row pitch of the y / x1 tiles in smem
+
+// bf16 slab images of one layer's weights, byte-for-byte what the kernel copies into 1024-aligned shared memory
+__global__ void fz_pack_weights_kernel(const HopkGwnetParams p, int L, uint8_t* __restrict__ pack)
+{
+    const int l = blockIdx.x;
+    if (l >= L) return;
+    uint8_t* img = pack + (size_t)l * FZ_PACK_BYTES;
+    const float* wf = p.filter_w[l]; const float* wg = p.gate_w[l]; const float* wm = p.mlp_w[l];
+    constexpr int C = FZ_C;
+    for (int idx = threadIdx.x; idx < 128 * 128; idx += blockDim.x) {      // gate: n -> (fg, o) in blocks [16 f | 16 g], k = tap*C + c
+        int n = idx >> 7, k = idx & 127;
+        int fg = (n >> 4) & 1, o = (n >> 5) * 16 + (n & 15);
+        int tap = k >= C, c = k - tap * C;
+        float v = (fg ? wg : wf)[(size_t)o * 2 * C + 2 * c + tap];
+        int slab = k >> 6, col = k & 63;
+        uint32_t off = slab * tc::slab_bytes(128) + tc::slab_chunk_off(n, col >> 3) + (col & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v);
+    }
+    for (int idx = threadIdx.x; idx < 64 * 192; idx += blockDim.x) {       // mlp: [o][k], k = seg*C + c (native order)
+        int n = idx / 192, k = idx - n * 192;
+        float v = wm[(size_t)n * 192 + k];
+        int slab = k >> 6, col = k & 63;
+        uint32_t off = FZ_WG_BYTES + slab * tc::slab_bytes(64) + tc::slab_chunk_off(n, col >> 3) + (col & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v);
+    }
+}
+
+struct FzArgs {
+    const float* up; const float* ss;                 // layer input (pre-BN of the previous layer or start conv) + folded scale/shift
+    const uint8_t* pack;                              // this layer's packed weights
+    const float* bf; const float* bg; const float* bm;
+    const float* A;                                   // adaptive adjacency (V x V)
+    float* TF; float* SG; float* Y; float* X1; float* X2; float* U; float* ycat; double* stats;
+    LayerGeom g; int layer, L, Tl, groups, gpt;       // groups = B*To, gpt = groups per tile
+};
+
+constexpr size_t fz_smem_bytes(int V) { return 73728 + 2 * 128 * FZ_LDF * 4 + (size_t)((V * V + 3) & ~3) * 4 + 1024; }
+
+__global__ void __launch_bounds__(256, 1) fz_layer_fwd_kernel(const FzArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float red[256];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int C = FZ_C;
+    constexpr uint32_t SL128 = tc::slab_bytes(128), SL64 = tc::slab_bytes(64);
+    uint8_t* A1 = smem;                       // phase 1: [x_t | x_{t+d}] 2 slabs        phase 2: [y | x1 | x2] 3 slabs
+    uint8_t* Wg = smem + 2 * SL128;           // phase 1: gate weights 2 slabs (32 KB)
+    uint8_t* A2 = smem;                       // 48 KB
+    uint8_t* Wm = smem + 3 * SL128;           // phase 2: mlp weights 3 x 8 KB (ends at 72 KB)
+    float* Yf = reinterpret_cast<float*>(smem + 73728);
+    float* X1f = Yf + 128 * FZ_LDF;
+    float* As = X1f + 128 * FZ_LDF;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = a.g.V;
+    const int g0 = blockIdx.x * a.gpt;
+    const int ng = min(a.gpt, a.groups - g0);
+    const int r0 = g0 * V, nrows = ng * V;               // rows of this tile in the layer's output rows layout
+
+    if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_barrier_init(); }
+    red[tid] = 0.f;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 256);
+    for (int i = tid; i < V * V; i += 256) As[i] = __ldg(a.A + i);
+    // ---- 1. stage the gate operands
+    {
+        W8GateX ld{a.up, a.ss, a.g, 2 * C};
+#pragma unroll
+        for (int it = 0; it < (128 * 16) / 256; ++it) {
+            int idx = tid + it * 256;
+            int ch = idx & 15, row = idx >> 4;
+            float f[8];
+            if (row < nrows) ld.ld8(r0 + row, ch * 8, f);
+            else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            }
+            tc::slab_store8(A1 + (ch >> 3) * SL128, row, ch & 7, f);
+        }
+        const uint4* src = reinterpret_cast<const uint4*>(a.pack);
+        uint4* dst = reinterpret_cast<uint4*>(Wg);
+        for (int i = tid; i < (int)(FZ_WG_BYTES / 16); i += 256) dst[i] = __ldg(src + i);
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_g = tmem_base_smem, tmem_h = tmem_base_smem + 128;
+    // ---- 2. gate UMMA
+    if (tid == 0) {
+        constexpr uint32_t idesc = tc::idesc_bf16(128, 128, 0, 0);
+        const uint32_t aa = tc::smem_u32(A1), wa = tc::smem_u32(Wg);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                tc::mma_bf16(tmem_g, tc::desc_kmajor(aa + c * SL128, t), tc::desc_kmajor(wa + c * SL128, t), idesc, (c | t) != 0);
+        tc::mma_commit(&bars[0]);
+    }
+    tc::mbar_wait(&bars[0], 0);
+    tc::fence_after_sync();
+    // ---- 3. gating epilogue: two threads per row, each 32 channels (two [16 f | 16 g] column blocks)
+    const int row = (warp & 3) * 32 + lane;
+    const int half = warp >> 2;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const bool rvalid = row < nrows;
+    const int m = r0 + row;                                   // global output row
+    int tt = -1; size_t ycat_off = 0;
+    if (rvalid) {
+        int vv = m % V; int bt = m / V; int t = bt % a.g.To; int b = bt / a.g.To;
+        tt = t - (a.g.To - a.Tl);
+        if (tt >= 0) ycat_off = ((size_t)(b * a.Tl + tt) * V + vv) * ((size_t)a.L * C) + (size_t)a.layer * C;
+    }
+    // mlp weights arrive while the gate epilogue runs (their smem region was the gate's B operand: UMMA 1 is complete)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.pack + FZ_WG_BYTES);
+        uint4* dst = reinterpret_cast<uint4*>(Wm);
+        for (int i = tid; i < (int)(FZ_WM_BYTES / 16); i += 256) dst[i] = __ldg(src + i);
+    }
+#pragma unroll 1
+    for (int blk = 0; blk < 2; ++blk) {
+        const int c0 = (half * 2 + blk) * 16;                 // first channel of this 32-column block
+        float v[32];
+        tc::tmem_ld32(tmem_g + lane_off + (half * 2 + blk) * 32, v);
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float tf = tanhf(v[j] + __ldg(a.bf + c0 + j));
+            float sg = sigmoidf_acc(v[16 + j] + __ldg(a.bg + c0 + j));
+            y[j] = rvalid ? tf * sg : 0.f;
+            v[j] = tf; v[16 + j] = sg;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(Yf + row * FZ_LDF + c0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+        if (rvalid) {
+            size_t o = (size_t)m * C + c0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                *reinterpret_cast<float4*>(a.TF + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                *reinterpret_cast<float4*>(a.SG + o + j) = make_float4(v[16 + j], v[17 + j], v[18 + j], v[19 + j]);
+                *reinterpret_cast<float4*>(a.Y + o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                if (tt >= 0) *reinterpret_cast<float4*>(a.ycat + ycat_off + c0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            }
+        }
+#pragma unroll
+        for (int q8 = 0; q8 < 2; ++q8) {                      // y as bf16 into slab 0 of the mlp A operand
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = y[q8 * 8 + j];
+            tc::slab_store8(A2, row, (c0 >> 3) + q8, f);
+        }
+    }
+    __syncthreads();
+    // ---- 4. diffusion in shared memory: items = (row, 8 channels)
+#pragma unroll 1
+    for (int hop = 0; hop < 2; ++hop) {
+        const float* src = hop == 0 ? Yf : X1f;
+        float* gout = hop == 0 ? a.X1 : a.X2;
+#pragma unroll 1
+        for (int it = 0; it < (128 * 8) / 256; ++it) {
+            int idx = tid + it * 256;
+            int c8 = idx & 7, rr = idx >> 3;                  // rr = (group, w)
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            if (rr < nrows) {
+                int gidx = rr / V, w = rr - gidx * V;
+                const float* base = src + (size_t)gidx * V * FZ_LDF + c8 * 8;
+                for (int v = 0; v < V; ++v) {
+                    float av = As[v * V + w];
+                    float4 x0 = *reinterpret_cast<const float4*>(base + v * FZ_LDF);
+                    float4 x1 = *reinterpret_cast<const float4*>(base + v * FZ_LDF + 4);
+                    acc[0] = fmaf(av, x0.x, acc[0]); acc[1] = fmaf(av, x0.y, acc[1]); acc[2] = fmaf(av, x0.z, acc[2]); acc[3] = fmaf(av, x0.w, acc[3]);
+                    acc[4] = fmaf(av, x1.x, acc[4]); acc[5] = fmaf(av, x1.y, acc[5]); acc[6] = fmaf(av, x1.z, acc[6]); acc[7] = fmaf(av, x1.w, acc[7]);
+                }
+                float* go = gout + (size_t)(r0 + rr) * C + c8 * 8;
+                *reinterpret_cast<float4*>(go) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                *reinterpret_cast<float4*>(go + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+            if (hop == 0) {
+                *reinterpret_cast<float4*>(X1f + rr * FZ_LDF + c8 * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                *reinterpret_cast<float4*>(X1f + rr * FZ_LDF + c8 * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+            tc::slab_store8(A2 + (1 + hop) * SL128, rr, c8, acc);
+        }
+        __syncthreads();
+    }
+    // ---- 5. mlp UMMA: [y | x1 | x2] (K = 192) x Wm^T (N = 64)
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        tc::fence_after_sync();
+        constexpr uint32_t idesc = tc::idesc_bf16(128, 64, 0, 0);
+        const uint32_t aa = tc::smem_u32(A2), wa = tc::smem_u32(Wm);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                tc::mma_bf16(tmem_h, tc::desc_kmajor(aa + s * SL128, t), tc::desc_kmajor(wa + s * SL64, t), idesc, (s | t) != 0);
+        tc::mma_commit(&bars[1]);
+    }
+    tc::mbar_wait(&bars[1], 0);
+    tc::fence_after_sync();
+    // ---- 6. bias + residual + statistics: thread = (row, 32 output channels)
+    {
+        float v[32], sq[32];
+        tc::tmem_ld32(tmem_h + lane_off + half * 32, v);
+        const long rr = rvalid ? a.g.in_row(m) + (long)a.g.d * V : 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int n = half * 32 + j;
+            float u = 0.f;
+            if (rvalid) {
+                float x = fmaf(__ldg(a.up + rr * C + n), __ldg(a.ss + n), __ldg(a.ss + C + n));
+                u = v[j] + __ldg(a.bm + n) + x;
+            }
+            v[j] = u; sq[j] = u * u;
+        }
+        if (rvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(a.U + (size_t)m * C + half * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        float s1 = warp_transpose_sum(v), s2 = warp_transpose_sum(sq);
+        atomicAdd(red + half * 32 + lane, s1);
+        atomicAdd(red + 128 + half * 32 + lane, s2);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid < C && a.stats) {
+        atomicAdd(a.stats + tid, (double)red[tid]);
+        atomicAdd(a.stats + C + tid, (double)red[128 + tid]);
+    }
+    if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);
+}
+
+}  // namespace hopk

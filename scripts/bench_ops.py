@@ -75,6 +75,8 @@ def main():
             t_f = timeit(lambda: m(x), a.iters, flush)
 
         def fb():
+            m.zero_grad(set_to_none=True)
+            x.grad = None
             y = m(x)
             y.backward(dy)
         t_fb = timeit(fb, a.iters, flush)
