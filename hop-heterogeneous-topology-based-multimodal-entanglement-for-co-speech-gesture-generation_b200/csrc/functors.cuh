@@ -5,6 +5,7 @@
 // Time-major rows make a dilated tap a constant row offset (d*V) and let HOP.Model's glue hand
 // its (B, 16, V, 173) buffer to the kernels without a permute copy.
 #pragma once
+#include <type_traits>
 #include "gemm_core.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc_wgrad.cuh"
@@ -24,6 +25,28 @@ struct Ld2D {
         if (MODE == 2) v = (__ldg(aux + idx) > 0.f) ? v : 0.f;
         return v;
     }
+    // vector interfaces for the tensor-core skeleton (see gemm_tc.cuh): 8 elements along the contiguous index
+    __device__ __forceinline__ void vec8(long base, int c, int cmax, float (&f)[8]) const {
+        if (c + 8 <= cmax && ((base | ld | c) & 3) == 0) {
+            float4 a = __ldg(reinterpret_cast<const float4*>(p + base + c)), b = __ldg(reinterpret_cast<const float4*>(p + base + c + 4));
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = c + q < cmax ? __ldg(p + base + c + q) : 0.f;
+        }
+        if (MODE == 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = fmaxf(f[q], 0.f);
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = (c + q < cmax && __ldg(aux + base + c + q) > 0.f) ? f[q] : 0.f;
+        }
+    }
+    template <bool KF = KFAST, typename std::enable_if<KF, int>::type = 0>
+    __device__ __forceinline__ void ld8(int i, int k, int kmax, float (&f)[8]) const { vec8((long)i * ld, k, kmax, f); }
+    template <bool KF = KFAST, typename std::enable_if<!KF, int>::type = 0>
+    __device__ __forceinline__ void ld8mn(int k, int i, int imax, float (&f)[8]) const { vec8((long)k * ld, i, imax, f); }
 };
 
 // same, plus one virtual all-ones *output* column at index `ones_at`

@@ -12,6 +12,8 @@
 //                                                                       // every lane of warps 0-3 (valid = m < M)
 //   void finish(float* red);        // by all 256 threads after a __syncthreads; red = 256 zero-initialised smem floats
 #pragma once
+#include <type_traits>
+#include <utility>
 #include "tc_core.cuh"
 
 namespace hopk {
@@ -21,9 +23,52 @@ constexpr int TC_BM = 128, TC_BK = 64;
 template <int BN>
 constexpr size_t tc_smem_bytes() { return 2 * (tc::slab_bytes(TC_BM) + tc::slab_bytes(BN)) + 1024; }
 
+// optional vector interfaces of a loader:
+//   void ld8(int i, int k, int kmax, float (&f)[8]) const;     K-contiguous operand: elements (i, k .. k+7), 0 for k >= kmax
+//   void ld8mn(int k, int i, int imax, float (&f)[8]) const;   M/N-contiguous operand: elements (i .. i+7, k), 0 for i >= imax
+template <class T, class = void> struct has_ld8 : std::false_type {};
+template <class T>
+struct has_ld8<T, std::void_t<decltype(std::declval<const T&>().ld8(0, 0, 0, std::declval<float (&)[8]>()))>> : std::true_type {};
+template <class T, class = void> struct has_ld8mn : std::false_type {};
+template <class T>
+struct has_ld8mn<T, std::void_t<decltype(std::declval<const T&>().ld8mn(0, 0, 0, std::declval<float (&)[8]>()))>> : std::true_type {};
+
+// B operand whose N index is contiguous in memory: staged as [64 K-rows][BN columns] slabs and read MN-major
+template <int BN, class L>
+__device__ __forceinline__ void tc_stage_slab_mn(uint8_t* slabs, const L& ld, int n0, int N, int k0, int kmax)
+{
+#pragma unroll
+    for (int it = 0; it < (TC_BK * (BN / 8)) / TC_THREADS; ++it) {
+        int idx = threadIdx.x + it * TC_THREADS;
+        int ch = idx % (BN / 8), krow = idx / (BN / 8);
+        float f[8];
+        if (k0 + krow < kmax) ld.ld8mn(k0 + krow, n0 + ch * 8, N, f);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        }
+        tc::slab_store8(slabs + (ch >> 3) * tc::slab_bytes(TC_BK), krow, ch & 7, f);
+    }
+}
+
 template <int ROWS, class L>
 __device__ __forceinline__ void tc_stage_slab(uint8_t* slab, const L& ld, int row0, int nrows_valid, int k0, int kmax)
 {
+    if constexpr (has_ld8<L>::value) {
+#pragma unroll
+        for (int it = 0; it < (ROWS * 8) / TC_THREADS; ++it) {
+            int idx = threadIdx.x + it * TC_THREADS;
+            int ch = idx & 7, row = idx >> 3;
+            float f[8];
+            if (row0 + row < nrows_valid) ld.ld8(row0 + row, k0 + ch * 8, kmax, f);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.f;
+            }
+            tc::slab_store8(slab, row, ch, f);
+        }
+        return;
+    }
     // ROWS rows x 8 chunks; lane order follows the loader's contiguous index so global reads coalesce
 #pragma unroll
     for (int it = 0; it < (ROWS * 8) / TC_THREADS; ++it) {
@@ -85,7 +130,8 @@ gemm_tc_kernel(int M, int N, int K, int k_per_split, ALoad aload, BLoad bload, E
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_smem;
-    constexpr uint32_t idesc = tc::idesc_bf16(TC_BM, BN, 0, 0);
+    constexpr bool B_MN = !BLoad::kFast && has_ld8mn<BLoad>::value;       // N-contiguous B: no transpose, MN-major view
+    constexpr uint32_t idesc = tc::idesc_bf16(TC_BM, BN, 0, B_MN ? 1 : 0);
 
     const int nslabs = k_end > k_begin ? (k_end - k_begin + TC_BK - 1) / TC_BK : 0;
     for (int ks = 0; ks < nslabs; ++ks) {
@@ -94,7 +140,8 @@ gemm_tc_kernel(int M, int N, int K, int k_per_split, ALoad aload, BLoad bload, E
         uint8_t* sa = smem + buf * STAGE;
         uint8_t* sb = sa + A_BYTES;
         tc_stage_slab<TC_BM>(sa, aload, m0, M, k_begin + ks * TC_BK, k_end);
-        tc_stage_slab<BN>(sb, bload, n0, N, k_begin + ks * TC_BK, k_end);
+        if constexpr (B_MN) tc_stage_slab_mn<BN>(sb, bload, n0, N, k_begin + ks * TC_BK, k_end);
+        else tc_stage_slab<BN>(sb, bload, n0, N, k_begin + ks * TC_BK, k_end);
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
@@ -102,7 +149,8 @@ gemm_tc_kernel(int M, int N, int K, int k_per_split, ALoad aload, BLoad bload, E
             const uint32_t a_addr = tc::smem_u32(sa), b_addr = tc::smem_u32(sb);
 #pragma unroll
             for (int j = 0; j < TC_BK / 16; ++j)
-                tc::mma_bf16(tmem, tc::desc_kmajor(a_addr, j), tc::desc_kmajor(b_addr, j), idesc, (ks | j) != 0);
+                tc::mma_bf16(tmem, tc::desc_kmajor(a_addr, j),
+                             B_MN ? tc::desc_mnmajor(b_addr, tc::slab_bytes(TC_BK), j) : tc::desc_kmajor(b_addr, j), idesc, (ks | j) != 0);
             tc::mma_commit(&bars[buf]);
         }
     }

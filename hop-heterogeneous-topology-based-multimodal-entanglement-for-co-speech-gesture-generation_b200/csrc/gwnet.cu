@@ -459,6 +459,17 @@ struct Seg3A {               // A(m, k): k = seg*C + c over three row-layout sou
         const float* p = seg == 0 ? p0 : (seg == 1 ? p1 : p2);
         return __ldg(p + (size_t)m * C + c);
     }
+    __device__ __forceinline__ void ld8(int m, int k, int kmax, float (&f)[8]) const {      // C % 8 == 0
+        if (k >= kmax) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            return;
+        }
+        int seg = k / C; int c = k - seg * C;
+        const float* p = (seg == 0 ? p0 : (seg == 1 ? p1 : p2)) + (size_t)m * C + c;
+        float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
 };
 struct Seg3AT {              // B'(kout, m): same sources, transposed role, ones column at 3C
     static constexpr bool kFast = false;
@@ -535,6 +546,17 @@ struct SkipW {               // B(n, k): concatenated skip weights, k = layer*C 
         int l = k / C; int c = k - l * C;
         return __ldg(w[l] + (size_t)n * C + c);
     }
+    __device__ __forceinline__ void ld8(int n, int k, int kmax, float (&f)[8]) const {      // C % 8 == 0
+        if (k >= kmax) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            return;
+        }
+        int l = k / C; int c = k - l * C;
+        const float* p = w[l] + (size_t)n * C + c;
+        float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
 };
 struct SkipWT {              // B(n = layer*C + c, k = s) = w[layer][s][c]   (dgrad through the concat GEMM)
     static constexpr bool kFast = false;
@@ -542,6 +564,17 @@ struct SkipWT {              // B(n = layer*C + c, k = s) = w[layer][s][c]   (dg
     __device__ __forceinline__ float operator()(int n, int k) const {
         int l = n / C; int c = n - l * C;
         return __ldg(w[l] + (size_t)k * C + c);
+    }
+    __device__ __forceinline__ void ld8mn(int k, int n, int nmax, float (&f)[8]) const {    // C % 8 == 0
+        if (n >= nmax) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            return;
+        }
+        int l = n / C; int c = n - l * C;
+        const float* p = w[l] + (size_t)k * C + c;
+        float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
     }
 };
 template <int NG>
@@ -607,6 +640,17 @@ struct DyB {                 // B(n = c, k = seg*C + o) = Wm[o][seg*C + c]
     __device__ __forceinline__ float operator()(int n, int k) const {
         int seg = k / C; int o = k - seg * C;
         return __ldg(wm + (size_t)o * 3 * C + seg * C + n);
+    }
+    __device__ __forceinline__ void ld8mn(int k, int n, int nmax, float (&f)[8]) const {    // C % 8 == 0
+        if (n >= nmax) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            return;
+        }
+        int seg = k / C; int o = k - seg * C;
+        const float* p = wm + (size_t)o * 3 * C + seg * C + n;
+        float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
     }
 };
 template <int NG>
@@ -755,6 +799,17 @@ struct DxA {                 // A(m_in, k = (tap*2 + fg)*C + o) = (fg?DG:DF)[(b,
         int vv = m % g.V; int bt = m / g.V; int t = bt % g.Ti - tap * g.d; int b = bt / g.Ti;
         if (t < 0 || t >= g.To) return 0.f;
         return __ldg((fg ? DG : DF) + ((size_t)(b * g.To + t) * g.V + vv) * g.C + o);
+    }
+    __device__ __forceinline__ void ld8(int m, int k, int kmax, float (&f)[8]) const {      // C % 8 == 0
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] = 0.f;
+        if (k >= kmax) return;
+        int q4 = k / g.C; int o = k - q4 * g.C; int tap = q4 >> 1, fg = q4 & 1;
+        int vv = m % g.V; int bt = m / g.V; int t = bt % g.Ti - tap * g.d; int b = bt / g.Ti;
+        if (t < 0 || t >= g.To) return;
+        const float* p = (fg ? DG : DF) + ((size_t)(b * g.To + t) * g.V + vv) * g.C + o;
+        float4 x = __ldg(reinterpret_cast<const float4*>(p)), y = __ldg(reinterpret_cast<const float4*>(p + 4));
+        f[0] = x.x; f[1] = x.y; f[2] = x.z; f[3] = x.w; f[4] = y.x; f[5] = y.y; f[6] = y.z; f[7] = y.w;
     }
 };
 struct DxB {                 // B(n = c, k) = W_fg[o][c][tap]

@@ -57,9 +57,24 @@ struct FzArgs {
     LayerGeom g; int layer, L, Tl, groups, gpt;       // groups = B*To, gpt = groups per tile
 };
 
-constexpr size_t fz_smem_bytes(int V) { return 73728 + 2 * 128 * FZ_LDF * 4 + (size_t)((V * V + 3) & ~3) * 4 + 1024; }
+constexpr size_t fz_smem_bytes(int V) { return 73728 + (size_t)((V * V + 3) & ~3) * 4 + 1024; }   // 3 CTAs / SM
 
-__global__ void __launch_bounds__(256, 1) fz_layer_fwd_kernel(const FzArgs a)
+__device__ __forceinline__ float tanh_fast(float x)
+{
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 8 bf16 channels of one slab row -> fp32
+__device__ __forceinline__ void slab_load8(const uint8_t* slab, int row, int ch, float (&f)[8])
+{
+    uint4 v = *reinterpret_cast<const uint4*>(slab + tc::slab_chunk_off(row, ch));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { float2 t = __bfloat1622float2(h[q]); f[2 * q] = t.x; f[2 * q + 1] = t.y; }
+}
+
+__global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[2];
@@ -72,9 +87,7 @@ __global__ void __launch_bounds__(256, 1) fz_layer_fwd_kernel(const FzArgs a)
     uint8_t* Wg = smem + 2 * SL128;           // phase 1: gate weights 2 slabs (32 KB)
     uint8_t* A2 = smem;                       // 48 KB
     uint8_t* Wm = smem + 3 * SL128;           // phase 2: mlp weights 3 x 8 KB (ends at 72 KB)
-    float* Yf = reinterpret_cast<float*>(smem + 73728);
-    float* X1f = Yf + 128 * FZ_LDF;
-    float* As = X1f + 128 * FZ_LDF;
+    float* As = reinterpret_cast<float*>(smem + 73728);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = a.g.V;
     const int g0 = blockIdx.x * a.gpt;
@@ -148,13 +161,11 @@ __global__ void __launch_bounds__(256, 1) fz_layer_fwd_kernel(const FzArgs a)
         float y[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            float tf = tanhf(v[j] + __ldg(a.bf + c0 + j));
-            float sg = sigmoidf_acc(v[16 + j] + __ldg(a.bg + c0 + j));
+            float tf = tanh_fast(v[j] + __ldg(a.bf + c0 + j));                       // MUFU.TANH (2^-11 rel. error << bf16)
+            float sg = fmaf(0.5f, tanh_fast(0.5f * (v[16 + j] + __ldg(a.bg + c0 + j))), 0.5f);   // sigmoid(x) = (1 + tanh(x/2)) / 2
             y[j] = rvalid ? tf * sg : 0.f;
             v[j] = tf; v[16 + j] = sg;
         }
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(Yf + row * FZ_LDF + c0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
         if (rvalid) {
             size_t o = (size_t)m * C + c0;
 #pragma unroll
@@ -174,10 +185,10 @@ __global__ void __launch_bounds__(256, 1) fz_layer_fwd_kernel(const FzArgs a)
         }
     }
     __syncthreads();
-    // ---- 4. diffusion in shared memory: items = (row, 8 channels)
+    // ---- 4. diffusion in shared memory on the bf16 slabs (fp32 accumulate): items = (row, 8 channels)
 #pragma unroll 1
     for (int hop = 0; hop < 2; ++hop) {
-        const float* src = hop == 0 ? Yf : X1f;
+        const uint8_t* src = A2 + hop * SL128;                // hop 0 reads y (slab 0), hop 1 reads x1 (slab 1)
         float* gout = hop == 0 ? a.X1 : a.X2;
 #pragma unroll 1
         for (int it = 0; it < (128 * 8) / 256; ++it) {
@@ -188,21 +199,16 @@ __global__ void __launch_bounds__(256, 1) fz_layer_fwd_kernel(const FzArgs a)
             for (int j = 0; j < 8; ++j) acc[j] = 0.f;
             if (rr < nrows) {
                 int gidx = rr / V, w = rr - gidx * V;
-                const float* base = src + (size_t)gidx * V * FZ_LDF + c8 * 8;
                 for (int v = 0; v < V; ++v) {
                     float av = As[v * V + w];
-                    float4 x0 = *reinterpret_cast<const float4*>(base + v * FZ_LDF);
-                    float4 x1 = *reinterpret_cast<const float4*>(base + v * FZ_LDF + 4);
-                    acc[0] = fmaf(av, x0.x, acc[0]); acc[1] = fmaf(av, x0.y, acc[1]); acc[2] = fmaf(av, x0.z, acc[2]); acc[3] = fmaf(av, x0.w, acc[3]);
-                    acc[4] = fmaf(av, x1.x, acc[4]); acc[5] = fmaf(av, x1.y, acc[5]); acc[6] = fmaf(av, x1.z, acc[6]); acc[7] = fmaf(av, x1.w, acc[7]);
+                    float x[8];
+                    slab_load8(src, gidx * V + v, c8, x);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(av, x[j], acc[j]);
                 }
                 float* go = gout + (size_t)(r0 + rr) * C + c8 * 8;
                 *reinterpret_cast<float4*>(go) = make_float4(acc[0], acc[1], acc[2], acc[3]);
                 *reinterpret_cast<float4*>(go + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            }
-            if (hop == 0) {
-                *reinterpret_cast<float4*>(X1f + rr * FZ_LDF + c8 * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                *reinterpret_cast<float4*>(X1f + rr * FZ_LDF + c8 * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
             }
             tc::slab_store8(A2 + (1 + hop) * SL128, rr, c8, acc);
         }
