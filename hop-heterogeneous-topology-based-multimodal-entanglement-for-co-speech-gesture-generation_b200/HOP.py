@@ -64,10 +64,14 @@ class _XattnFn(torch.autograd.Function):
         S = k.shape[0]
         o = torch.empty_like(q)
         lse = torch.empty((B, H, L), device=q.device, dtype=torch.float32)
-        fwd = lib().hopk_xattn_fwd_tc if (tc and E == 128) else lib().hopk_xattn_fwd
         with profiler.span('xattn_fwd'):
-            check(fwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, L, H, E, S, float(p_drop), int(seed),
-                                       stream_ptr()))
+            if tc and E == 128:
+                pack = torch.empty(lib().hopk_xattn_pack_bytes(S, H), device=q.device, dtype=torch.uint8)
+                check(lib().hopk_xattn_fwd_tc(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(pack), B, L, H, E, S,
+                                              float(p_drop), int(seed), stream_ptr()))
+            else:
+                check(lib().hopk_xattn_fwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, L, H, E, S, float(p_drop), int(seed),
+                                           stream_ptr()))
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.p_drop, ctx.seed, ctx.tc = float(p_drop), int(seed), bool(tc and E == 128)
         return o

@@ -23,13 +23,16 @@ __device__ __forceinline__ uint32_t lowbias32(uint32_t x)
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
     return x;
 }
-// keep iff top-24-bit hash >= p * 2^24   (oracle/reprog_np.py::dropout_keep)
+// one hash per element pair (idx >> 1); element uses its low / high 16 bits; keep iff field >= round(p * 65536)
+// (oracle/reprog_np.py::dropout_keep)
 __device__ __forceinline__ bool keep_mask(uint64_t seed, uint64_t idx, uint32_t thr)
 {
     uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
-    uint32_t i_lo = (uint32_t)idx, i_hi = (uint32_t)(idx >> 32);
-    uint32_t h = lowbias32((i_lo + lowbias32(i_hi ^ s_hi)) ^ s_lo);
-    return (h >> 8) >= thr;
+    uint64_t q = idx >> 1;
+    uint32_t q_lo = (uint32_t)q, q_hi = (uint32_t)(q >> 32);
+    uint32_t h = lowbias32((q_lo + lowbias32(q_hi ^ s_hi)) ^ s_lo);
+    uint32_t field = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+    return field >= thr;
 }
 
 // acc[i][j] += sum_k A[r0+i][k] * B[c0 + 16 j][k]        (both row-major with k contiguous)
@@ -382,8 +385,8 @@ extern "C" int hopk_xattn_fwd(const float* q, const float* k, const float* v, fl
     int M = B * L;
     size_t smem = ((size_t)3 * XT * (E + 4) + XT * XLDP) * sizeof(float);
     HOPK_CUDA(cudaFuncSetAttribute(xattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t thr = (uint32_t)lrintf(p_drop * 16777216.f);
-    float inv_keep = 1.f / (1.f - p_drop);
+    uint32_t thr = (uint32_t)lrintf(p_drop * 65536.f);
+    float inv_keep = 65536.f / (65536.f - (float)thr);
     dim3 grid(cdiv(M, XT), H);
     xattn_fwd_kernel<<<grid, 256, smem, st>>>(q, k, v, o, lse, M, L, H, E, S, 1.f / sqrtf((float)E), inv_keep, thr, seed);
     HOPK_LAUNCH_CHECK("xattn_fwd");
@@ -398,8 +401,8 @@ extern "C" int hopk_xattn_bwd(const float* q, const float* k, const float* v, co
     HOPK_REQUIRE(delta != nullptr, "delta scratch (B*H*L floats) required");
     cudaStream_t st = (cudaStream_t)stream;
     int M = B * L;
-    uint32_t thr = (uint32_t)lrintf(p_drop * 16777216.f);
-    float inv_keep = 1.f / (1.f - p_drop);
+    uint32_t thr = (uint32_t)lrintf(p_drop * 65536.f);
+    float inv_keep = 65536.f / (65536.f - (float)thr);
     float scale = 1.f / sqrtf((float)E);
     size_t smem1 = ((size_t)4 * XT * (E + 4) + XT * XLDP) * sizeof(float);
     HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));

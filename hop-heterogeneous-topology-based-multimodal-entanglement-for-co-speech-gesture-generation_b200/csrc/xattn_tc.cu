@@ -29,9 +29,27 @@ __device__ __forceinline__ uint32_t lowbias32_tc(uint32_t x)
 __device__ __forceinline__ bool keep_mask_tc(uint64_t seed, uint64_t idx, uint32_t thr)
 {
     uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
-    uint32_t i_lo = (uint32_t)idx, i_hi = (uint32_t)(idx >> 32);
-    uint32_t h = lowbias32_tc((i_lo + lowbias32_tc(i_hi ^ s_hi)) ^ s_lo);
-    return (h >> 8) >= thr;
+    uint64_t q = idx >> 1;
+    uint32_t q_lo = (uint32_t)q, q_hi = (uint32_t)(q >> 32);
+    uint32_t h = lowbias32_tc((q_lo + lowbias32_tc(q_hi ^ s_hi)) ^ s_lo);
+    uint32_t field = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+    return field >= thr;
+}
+// dropout on N consecutive elements starting at an EVEN flat index idx0: one hash per pair
+template <int N>
+__device__ __forceinline__ void dropout_run_even(float (&p)[N], uint64_t idx0, uint64_t seed, uint32_t thr, float inv_keep)
+{
+    const uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
+    const uint64_t q0 = idx0 >> 1;
+    const uint32_t lo0 = (uint32_t)q0, hi0 = (uint32_t)(q0 >> 32);
+    const uint32_t in0 = lowbias32_tc(hi0 ^ s_hi), in1 = lowbias32_tc((hi0 + 1) ^ s_hi);
+#pragma unroll
+    for (int t = 0; t < N / 2; ++t) {
+        uint32_t lo = lo0 + (uint32_t)t;
+        uint32_t h = lowbias32_tc((lo + (lo < lo0 ? in1 : in0)) ^ s_lo);
+        p[2 * t] = (h & 0xFFFFu) >= thr ? p[2 * t] * inv_keep : 0.f;
+        p[2 * t + 1] = (h >> 16) >= thr ? p[2 * t + 1] * inv_keep : 0.f;
+    }
 }
 
 // stage a [128 rows][128 cols] fp32 tile of a (rows, H, E=128) tensor (head h) as two bf16 slabs (cols 0-63 | 64-127)
@@ -169,18 +187,17 @@ xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
         }
         float rs = 0.f;
         const uint64_t idx0 = drop_base + (uint64_t)sb;
-        const uint32_t lo0 = (uint32_t)idx0, hi0 = (uint32_t)(idx0 >> 32);
-        const uint32_t in0 = lowbias32_tc(hi0 ^ s_hi), in1 = lowbias32_tc((hi0 + 1) ^ s_hi);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            float p = ex2f(v[i] - mnew);
-            rs += p;
-            if (thr) {
-                uint32_t lo = lo0 + (uint32_t)i;
-                uint32_t hsh = lowbias32_tc((lo + (lo < lo0 ? in1 : in0)) ^ s_lo);
-                p = (hsh >> 8) >= thr ? p * inv_keep : 0.f;
+            v[i] = ex2f(v[i] - mnew);
+            rs += v[i];
+        }
+        if (thr) {
+            if ((idx0 & 1) == 0) dropout_run_even<32>(v, idx0, seed, thr, inv_keep);
+            else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = keep_mask_tc(seed, idx0 + (uint64_t)i, thr) ? v[i] * inv_keep : 0.f;
             }
-            v[i] = p;
         }
 #pragma unroll
         for (int q8 = 0; q8 < 4; ++q8) {
@@ -222,6 +239,224 @@ xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
             }
         }
         if (m < M && half == 0) LSE[((size_t)(m / L) * H + h) * L + (m % L)] = (mrow + log2f(ltot)) * 0.6931471805599453f;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ forward v3
+// K / V are packed ONCE per call into bf16 slab images, one contiguous 32 KB record per (head, 64-prototype tile):
+// [K e<64 | K e>=64 | V e<64 | V e>=64], byte-for-byte what the UMMA descriptors expect in shared memory.  The main
+// kernel then never touches K / V with its threads: one elected thread streams the records with cp.async.bulk
+// (TMA bulk copy, completion on an mbarrier via complete_tx) into a 3-stage ring, and S is double-buffered in TMEM so
+// that the QK^T UMMA of tile j+1 runs while the 256 threads do the softmax of tile j.
+constexpr int KV_STAGES = 3;
+constexpr uint32_t KV_REC = 4 * FS_SLAB;                 // 32 KB per (head, tile)
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__global__ void xattn_pack_kv_kernel(const float* __restrict__ K, const float* __restrict__ V, uint8_t* __restrict__ pack,
+                                     int S, int H, int ntiles)
+{
+    const int j = blockIdx.x, h = blockIdx.y;
+    uint8_t* rec = pack + ((size_t)h * ntiles + j) * KV_REC;
+    const int s0 = j * FS;
+    for (int idx = threadIdx.x; idx < 2 * FS * 16; idx += blockDim.x) {       // 2 tensors x 64 rows x 16 chunks of 8
+        int which = idx / (FS * 16), r = idx - which * FS * 16;
+        int ch16 = r & 15, row = r >> 4;
+        const float* src = which ? V : K;
+        float f[8];
+        if (s0 + row < S) {
+            const float4* p4 = reinterpret_cast<const float4*>(src + ((size_t)(s0 + row) * H + h) * AT + ch16 * 8);
+            float4 a = __ldg(p4), b = __ldg(p4 + 1);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+        }
+        tc::slab_store8(rec + (which * 2 + (ch16 >> 3)) * FS_SLAB, row, ch16 & 7, f);
+    }
+}
+
+// Warp-specialised: 16 softmax warps (four threads per query row: warps w, w+4, w+8, w+12 share TMEM lane quarter
+// w & 3 and take 16 score columns each) + 1 control warp whose lane 0 streams the K/V records (cp.async.bulk) and
+// issues every UMMA.  The only synchronisation inside the loop is mbarriers (S ready, P ready, PV done) and a
+// 128-thread named barrier per lane quarter for the row-maximum exchange.
+constexpr int FWD3_THREADS = 512 + 32;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(FWD3_THREADS, 1)
+xattn_fwd_tc3_kernel(const float* __restrict__ Q, const uint8_t* __restrict__ kvpack, float* __restrict__ O,
+                     float* __restrict__ LSE, int M, int L, int H, int S, float scale, float inv_keep, uint32_t thr,
+                     uint64_t seed)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[KV_STAGES], bar_s[2], bar_p[2], bar_o[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float xch[2][4][AT];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* Qs = smem; uint8_t* Ps = Qs + 2 * AT_SLAB; uint8_t* ring = Ps + 2 * AT_SLAB;      // P is double-buffered
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.y, m0 = blockIdx.x * AT;
+    const int ntiles = (S + FS - 1) / FS;
+    const uint8_t* recs = kvpack + (size_t)h * ntiles * KV_REC;
+
+    if (tid == 512) {
+#pragma unroll
+        for (int i = 0; i < KV_STAGES; ++i) tc::mbar_init(&bar_full[i], 1);
+        tc::mbar_init(&bar_s[0], 1); tc::mbar_init(&bar_s[1], 1);
+        tc::mbar_init(&bar_p[0], 512); tc::mbar_init(&bar_p[1], 512); tc::mbar_init(&bar_o[0], 1); tc::mbar_init(&bar_o[1], 1);
+        tc::fence_barrier_init();
+        for (int t = 0; t < KV_STAGES && t < ntiles; ++t) {            // fill the ring
+            mbar_expect_tx(&bar_full[t], KV_REC);
+            bulk_g2s(ring + t * KV_REC, recs + (size_t)t * KV_REC, KV_REC, &bar_full[t]);
+        }
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 256);
+    if (tid < 256) stage_rows_f32(Qs, Q, m0, M, H, h);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_s0 = tmem_base_smem, tmem_o = tmem_base_smem + 128;     // S buffers at columns 0 and 64
+
+    if (warp == 16) {
+        // ------------------------------------------------------------------ control warp
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = tc::idesc_bf16(AT, FS, 0, 0);
+            constexpr uint32_t idesc_pv = tc::idesc_bf16(AT, AT, 0, 1);
+            const uint32_t qa = tc::smem_u32(Qs), pa = tc::smem_u32(Ps);
+            auto issue_s = [&](int t) {                                  // S_t = Q K_t^T into TMEM buffer t & 1
+                tc::mbar_wait(&bar_full[t % KV_STAGES], (t / KV_STAGES) & 1);
+                tc::fence_after_sync();
+                const uint32_t ka = tc::smem_u32(ring + (t % KV_STAGES) * KV_REC);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::mma_bf16(tmem_s0 + (t & 1) * 64, tc::desc_kmajor(qa + c * AT_SLAB, k), tc::desc_kmajor(ka + c * FS_SLAB, k),
+                                     idesc_qk, (c | k) != 0);
+                tc::mma_commit(&bar_s[t & 1]);
+            };
+            issue_s(0);
+            for (int j = 0; j < ntiles; ++j) {
+                if (j + 1 < ntiles) issue_s(j + 1);                      // runs while the softmax warps work on tile j
+                if (j > 0 && j + 2 < ntiles) {                           // P V_{j-1} done -> ring stage (j-1) % 3 is free: refill
+                    tc::mbar_wait(&bar_o[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    const int t = j + 2;
+                    mbar_expect_tx(&bar_full[t % KV_STAGES], KV_REC);
+                    bulk_g2s(ring + (t % KV_STAGES) * KV_REC, recs + (size_t)t * KV_REC, KV_REC, &bar_full[t % KV_STAGES]);
+                }
+                tc::mbar_wait(&bar_p[j & 1], (j >> 1) & 1);              // P_j written (and O rescaled) by all softmax threads
+                tc::fence_after_sync();
+                const uint32_t va = tc::smem_u32(ring + (j % KV_STAGES) * KV_REC + 2 * FS_SLAB);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    tc::mma_bf16(tmem_o, tc::desc_kmajor(pa + (j & 1) * AT_SLAB, t), tc::desc_mnmajor(va, FS_SLAB, t), idesc_pv,
+                                 (j | t) != 0);
+                tc::mma_commit(&bar_o[j & 1]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps
+        const int row = (warp & 3) * 32 + lane;
+        const int quad = warp >> 2;                              // which 16 of the 64 score columns / which 32 of the 128 outputs
+        const int m = m0 + row;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const uint64_t drop_base = m < M ? (((uint64_t)(m / L) * H + h) * (uint64_t)L + (uint64_t)(m % L)) * (uint64_t)S : 0;
+        const uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
+        const float sc2 = scale * 1.4426950408889634f;
+        float mrow = -INFINITY, lrow = 0.f;
+        for (int j = 0; j < ntiles; ++j) {
+            const int s0 = j * FS;
+            tc::mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
+            tc::fence_after_sync();
+            float v[16];
+            tc::tmem_ld16(tmem_s0 + (j & 1) * 64 + lane_off + quad * 16, v);
+            const int sb = s0 + quad * 16;
+            if (s0 + FS > S) {                                   // ragged last tile: mask the missing prototypes
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = sb + i < S ? v[i] : -INFINITY;
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+            mx *= sc2;                                           // log2-domain maximum (sc2 > 0 commutes with max)
+            float (*x)[AT] = xch[j & 1];
+            x[quad][row] = mx;
+            named_bar_sync(1 + (warp & 3), 128);                 // the four warps that share this lane quarter
+            const float mnew = fmaxf(fmaxf(mrow, mx), fmaxf(fmaxf(x[quad ^ 1][row], x[quad ^ 2][row]), x[quad ^ 3][row]));
+            const float corr = ex2f(mrow - mnew);
+            if (j >= 2) tc::mbar_wait(&bar_o[j & 1], ((j >> 1) - 1) & 1);    // P V_{j-2} done: P buffer j & 1 is free
+            if (j > 0 && __any_sync(0xffffffffu, mnew > mrow)) {     // a row of this warp moved its maximum: rescale O
+                tc::mbar_wait(&bar_o[(j - 1) & 1], ((j - 1) >> 1) & 1);      // needs P V_{j-1} complete
+                tc::fence_after_sync();
+                {
+                    float o[32];
+                    tc::tmem_ld32(tmem_o + lane_off + quad * 32, o);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] *= corr;
+                    tc::tmem_st32(tmem_o + lane_off + quad * 32, o);
+                }
+            }
+            float rs = 0.f;
+            const uint64_t idx0 = drop_base + (uint64_t)sb;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] = ex2f(fmaf(v[i], sc2, -mnew));
+                rs += v[i];
+            }
+            if (thr) {
+                if ((idx0 & 1) == 0) dropout_run_even<16>(v, idx0, seed, thr, inv_keep);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = keep_mask_tc(seed, idx0 + (uint64_t)i, thr) ? v[i] * inv_keep : 0.f;
+                }
+            }
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = v[q8 * 8 + i];
+                tc::slab_store8(Ps + (j & 1) * AT_SLAB, row, quad * 2 + q8, f);
+            }
+            lrow = lrow * corr + rs;
+            mrow = mnew;
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            tc::mbar_arrive(&bar_p[j & 1]);
+        }
+        if (ntiles >= 2) tc::mbar_wait(&bar_o[(ntiles - 2) & 1], ((ntiles - 2) >> 1) & 1);
+        tc::mbar_wait(&bar_o[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+        tc::fence_after_sync();
+        float (*x)[AT] = xch[ntiles & 1];
+        x[quad][row] = lrow;
+        named_bar_sync(1 + (warp & 3), 128);
+        const float ltot = x[0][row] + x[1][row] + x[2][row] + x[3][row];
+        const float inv = 1.f / ltot;
+        float* orow = O + ((size_t)(m < M ? m : 0) * H + h) * AT + quad * 32;
+        float o[32];
+        tc::tmem_ld32(tmem_o + lane_off + quad * 32, o);
+        if (m < M) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(orow + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+        }
+        if (m < M && quad == 0) LSE[((size_t)(m / L) * H + h) * L + (m % L)] = (mrow + log2f(ltot)) * 0.6931471805599453f;
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -507,8 +742,10 @@ extern "C" int hopk_debug_set(void* mapped_host_ints)
     return cudaMemcpyToSymbol(hopk::g_dbg, &p, sizeof(p)) == cudaSuccess ? 0 : 1;
 }
 
-extern "C" int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v, float* o, float* lse, int B, int L, int H,
-                                 int E, int S, float p_drop, uint64_t seed, void* stream)
+extern "C" size_t hopk_xattn_pack_bytes(int S, int H) { return (size_t)H * ((S + FS - 1) / FS) * KV_REC + 1024; }
+
+extern "C" int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v, float* o, float* lse, void* kv_pack, int B,
+                                 int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream)
 {
     HOPK_REQUIRE(B > 0 && L > 0 && H > 0 && S > 0, "xattn sizes");
     HOPK_REQUIRE(E == 128, "tensor-core attention is specialised for head dim 128");
@@ -521,9 +758,26 @@ extern "C" int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v,
         HOPK_CUDA(cudaFuncSetAttribute(xattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    uint32_t thr = (uint32_t)lrintf(p_drop * 16777216.f);
+    uint32_t thr = (uint32_t)lrintf(p_drop * 65536.f);
+    const float inv_keep_h = 65536.f / (65536.f - (float)thr);
+    if (kv_pack) {                              // v3: packed bf16 K/V + bulk-copy ring + double-buffered S
+        const size_t smem3 = 4 * AT_SLAB + KV_STAGES * KV_REC + 1024;
+        static bool configured3 = false;
+        if (!configured3) {
+            HOPK_CUDA(cudaFuncSetAttribute(xattn_fwd_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            configured3 = true;
+        }
+        uint8_t* pack = reinterpret_cast<uint8_t*>(((uintptr_t)kv_pack + 1023) & ~uintptr_t(1023));
+        const int ntiles = cdiv(S, FS);
+        xattn_pack_kv_kernel<<<dim3(ntiles, H), 256, 0, st>>>(k, v, pack, S, H, ntiles);
+        HOPK_LAUNCH_CHECK("xattn_pack_kv");
+        xattn_fwd_tc3_kernel<<<dim3(cdiv(M, AT), H), FWD3_THREADS, smem3, st>>>(q, pack, o, lse, M, L, H, S, 1.f / sqrtf((float)E),
+                                                                       inv_keep_h, thr, seed);
+        HOPK_LAUNCH_CHECK("xattn_fwd_tc3");
+        return 0;
+    }
     xattn_fwd_tc_kernel<<<dim3(cdiv(M, AT), H), 256, smem, st>>>(q, k, v, o, lse, M, L, H, S, 1.f / sqrtf((float)E),
-                                                                 1.f / (1.f - p_drop), thr, seed);
+                                                                 inv_keep_h, thr, seed);
     HOPK_LAUNCH_CHECK("xattn_fwd_tc");
     return 0;
 }
@@ -538,8 +792,8 @@ extern "C" int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v,
     HOPK_REQUIRE(delta != nullptr, "delta scratch (B*H*L floats) required");
     cudaStream_t st = (cudaStream_t)stream;
     const int M = B * L;
-    uint32_t thr = (uint32_t)lrintf(p_drop * 16777216.f);
-    const float inv_keep = 1.f / (1.f - p_drop), scale = 1.f / sqrtf((float)E);
+    uint32_t thr = (uint32_t)lrintf(p_drop * 65536.f);
+    const float inv_keep = 65536.f / (65536.f - (float)thr), scale = 1.f / sqrtf((float)E);
     const size_t smem1 = 10 * AT_SLAB + 1024, smem2 = 12 * AT_SLAB + 1024;
     static bool configured = false;
     if (!configured) {

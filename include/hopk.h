@@ -133,7 +133,10 @@ int hopk_xattn_bwd(const float* q, const float* k, const float* v, const float* 
 
 /* dtype-1 variants of the two calls above: bf16 operands on tcgen05 (UMMA 128x128, TMEM accumulators), fp32
  * accumulation and fp32 I/O; head dim must be 128.  Same arguments and semantics. */
-int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v, float* o, float* lse,
+/* kv_pack: scratch of hopk_xattn_pack_bytes(S, H) bytes (K/V re-packed as bf16 UMMA slab images and streamed with
+ * cp.async.bulk); NULL selects the variant that stages K/V from fp32 with its own threads. */
+size_t hopk_xattn_pack_bytes(int S, int H);
+int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v, float* o, float* lse, void* kv_pack,
                       int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
 int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v, const float* o, const float* lse,
                       const float* dout, float* dq, float* dk, float* dv, float* delta,

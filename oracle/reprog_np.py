@@ -31,19 +31,31 @@ def _lowbias32(x):
     return x
 
 
+def dropout_threshold(p):
+    """16-bit integer threshold of the mask; the realised drop probability is thr / 65536 (0.100006 for p = 0.1)."""
+    return int(round(float(p) * 65536.0))
+
+
+def dropout_scale(p):
+    """1 / (1 - realised drop probability): what kept probabilities are multiplied by (keeps the layer unbiased)."""
+    return 65536.0 / (65536.0 - dropout_threshold(p))
+
+
 def dropout_keep(seed, idx, p):
     """Keep-mask for flat element indices ``idx`` (uint64) under 64-bit ``seed``.
 
-    u = top 24 bits of h(idx_lo + h(idx_hi ^ seed_hi) ^ seed_lo); keep iff u >= p * 2^24 (integer compare).
-    The CUDA kernel (csrc/xattn.cu: keep_mask()) evaluates exactly this.
+    One 32-bit hash serves two neighbouring elements: q = idx >> 1, h = f(q_lo + f(q_hi ^ seed_hi) ^ seed_lo) with
+    f = lowbias32; element idx uses the low (even idx) or high (odd idx) 16 bits of h and is kept iff that field is
+    >= round(p * 65536).  The CUDA kernels (csrc/xattn.cu: keep_mask(), csrc/xattn_tc.cu) evaluate exactly this.
     """
     idx = np.asarray(idx, dtype=np.uint64)
     seed = np.uint64(seed)
     s_lo, s_hi = seed & _M32, seed >> np.uint64(32)
-    i_lo, i_hi = idx & _M32, idx >> np.uint64(32)
-    h = _lowbias32(((i_lo + _lowbias32(i_hi ^ s_hi)) & _M32) ^ s_lo)
-    thr = np.uint64(int(round(float(p) * (1 << 24))))
-    return (h >> np.uint64(8)) >= thr
+    q = idx >> np.uint64(1)
+    q_lo, q_hi = q & _M32, q >> np.uint64(32)
+    h = _lowbias32(((q_lo + _lowbias32(q_hi ^ s_hi)) & _M32) ^ s_lo)
+    field = np.where((idx & np.uint64(1)) == 1, h >> np.uint64(16), h & np.uint64(0xFFFF))
+    return field >= np.uint64(dropout_threshold(p))
 
 
 def _id(a):
@@ -73,7 +85,7 @@ def forward(P, target, source, value, n_heads, p_drop=0.0, seed=0, keep=False, q
     pr /= pr.sum(axis=-1, keepdims=True)
     if p_drop > 0:
         idx = np.arange(B * H * L * S, dtype=np.uint64).reshape(B, H, L, S)
-        mask = dropout_keep(seed, idx, p_drop) / (1.0 - p_drop)
+        mask = dropout_keep(seed, idx, p_drop) * dropout_scale(p_drop)
     else:
         mask = np.ones_like(pr)
     pd = pr * mask

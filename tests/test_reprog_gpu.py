@@ -92,7 +92,7 @@ def test_reprog_dropout_matches_oracle_mask(name, cuda):
     sc = np.einsum('blhe,she->bhls', q, k) / np.sqrt(E)
     pr = np.exp(sc - sc.max(-1, keepdims=True)); pr /= pr.sum(-1, keepdims=True)
     idx = np.arange(B * H * L * S, dtype=np.uint64).reshape(B, H, L, S)
-    mask = reprog_np.dropout_keep(drop_seed, idx, p) / (1 - p)
+    mask = reprog_np.dropout_keep(drop_seed, idx, p) * reprog_np.dropout_scale(p)
     o_ref = np.einsum('bhls,she->blhe', pr * mask, v)
     dpd = np.einsum('blhe,she->bhls', do, v)
     dv_ref = np.einsum('bhls,blhe->she', pr * mask, do)
@@ -184,7 +184,7 @@ def test_xattn_tcgen05_backward(B, L, H, S, p, cuda):
     pr = torch.softmax(sc, -1)
     if p > 0:
         idx = np.arange(B * H * L * S, dtype=np.uint64).reshape(B, H, L, S)
-        pr = pr * torch.from_numpy(reprog_np.dropout_keep(99, idx, p) / (1 - p))
+        pr = pr * torch.from_numpy(reprog_np.dropout_keep(99, idx, p) * reprog_np.dropout_scale(p))
     torch.einsum('bhls,she->blhe', pr, v).backward(do)
     qg, kg, vg = [t.detach().float().to(cuda).requires_grad_(True) for t in (q, k, v)]
     _XattnFn.apply(qg, kg, vg, p, 99, True).backward(do.float().to(cuda))
