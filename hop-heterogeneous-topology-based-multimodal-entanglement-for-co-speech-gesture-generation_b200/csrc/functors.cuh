@@ -111,6 +111,34 @@ struct EpiStore {
     // tensor-core skeleton (gemm_tc.cuh): 32 consecutive columns of one row
     __device__ __forceinline__ void row32(int m, bool valid, int n0, float (&v)[32], float*) {
         if (!valid) return;
+        const long base = (long)m * ld + n0;
+        const bool fast = n0 + 32 <= N && (ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias) |
+                                                              reinterpret_cast<uintptr_t>(aux)) & 15) == 0;
+        if (fast) {                                          // 128-bit loads / stores, loads batched ahead of the stores
+            float4 bb[8], aa[8];
+            if (bias) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) bb[q] = __ldg(reinterpret_cast<const float4*>(bias + n0) + q);
+            }
+            if (flags & 4) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) aa[q] = __ldg(reinterpret_cast<const float4*>(aux + base) + q);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 x = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                if (bias) { x.x += bb[q].x; x.y += bb[q].y; x.z += bb[q].z; x.w += bb[q].w; }
+                if (flags & 1) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                if (flags & 4) {
+                    x.x = aa[q].x > 0.f ? x.x : 0.f; x.y = aa[q].y > 0.f ? x.y : 0.f;
+                    x.z = aa[q].z > 0.f ? x.z : 0.f; x.w = aa[q].w > 0.f ? x.w : 0.f;
+                }
+                float* o = out + base + 4 * q;
+                if (flags & 2) { atomicAdd(o, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w); }
+                else *reinterpret_cast<float4*>(o) = x;
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             int n = n0 + j;

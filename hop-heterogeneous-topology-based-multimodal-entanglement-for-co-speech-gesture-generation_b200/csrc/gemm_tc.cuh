@@ -33,56 +33,77 @@ template <class T, class = void> struct has_ld8mn : std::false_type {};
 template <class T>
 struct has_ld8mn<T, std::void_t<decltype(std::declval<const T&>().ld8mn(0, 0, 0, std::declval<float (&)[8]>()))>> : std::true_type {};
 
+// Staging is split into a LOAD phase (global -> registers) and a STORE phase (registers -> bf16 -> swizzled smem) so
+// that all global loads of a slab are in flight together (one memory latency per slab instead of one per 16-byte
+// chunk), and so that the loads of slab k+1 can be issued before the barrier / UMMAs of slab k.
+template <int ROWS>
+struct SlabRegs { float f[(ROWS * 8) / TC_THREADS][8]; };
+
 // B operand whose N index is contiguous in memory: staged as [64 K-rows][BN columns] slabs and read MN-major
 template <int BN, class L>
-__device__ __forceinline__ void tc_stage_slab_mn(uint8_t* slabs, const L& ld, int n0, int N, int k0, int kmax)
+__device__ __forceinline__ void tc_load_slab_mn(SlabRegs<BN>& r, const L& ld, int n0, int N, int k0, int kmax)
 {
 #pragma unroll
     for (int it = 0; it < (TC_BK * (BN / 8)) / TC_THREADS; ++it) {
         int idx = threadIdx.x + it * TC_THREADS;
         int ch = idx % (BN / 8), krow = idx / (BN / 8);
-        float f[8];
-        if (k0 + krow < kmax) ld.ld8mn(k0 + krow, n0 + ch * 8, N, f);
+        if (k0 + krow < kmax) ld.ld8mn(k0 + krow, n0 + ch * 8, N, r.f[it]);
         else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+            for (int j = 0; j < 8; ++j) r.f[it][j] = 0.f;
         }
-        tc::slab_store8(slabs + (ch >> 3) * tc::slab_bytes(TC_BK), krow, ch & 7, f);
+    }
+}
+template <int BN>
+__device__ __forceinline__ void tc_store_slab_mn(uint8_t* slabs, const SlabRegs<BN>& r)
+{
+#pragma unroll
+    for (int it = 0; it < (TC_BK * (BN / 8)) / TC_THREADS; ++it) {
+        int idx = threadIdx.x + it * TC_THREADS;
+        int ch = idx % (BN / 8), krow = idx / (BN / 8);
+        tc::slab_store8(slabs + (ch >> 3) * tc::slab_bytes(TC_BK), krow, ch & 7, r.f[it]);
     }
 }
 
+// item -> (row, chunk): lane order follows the loader's contiguous index so global reads coalesce
 template <int ROWS, class L>
-__device__ __forceinline__ void tc_stage_slab(uint8_t* slab, const L& ld, int row0, int nrows_valid, int k0, int kmax)
+__device__ __forceinline__ void tc_item(int it, int& row, int& ch)
 {
-    if constexpr (has_ld8<L>::value) {
-#pragma unroll
-        for (int it = 0; it < (ROWS * 8) / TC_THREADS; ++it) {
-            int idx = threadIdx.x + it * TC_THREADS;
-            int ch = idx & 7, row = idx >> 3;
-            float f[8];
-            if (row0 + row < nrows_valid) ld.ld8(row0 + row, k0 + ch * 8, kmax, f);
-            else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = 0.f;
-            }
-            tc::slab_store8(slab, row, ch, f);
-        }
-        return;
-    }
-    // ROWS rows x 8 chunks; lane order follows the loader's contiguous index so global reads coalesce
+    int idx = threadIdx.x + it * TC_THREADS;
+    if (has_ld8<L>::value || L::kFast) { ch = idx & 7; row = idx >> 3; } else { row = idx % ROWS; ch = idx / ROWS; }
+}
+
+template <int ROWS, class L>
+__device__ __forceinline__ void tc_load_slab(SlabRegs<ROWS>& r, const L& ld, int row0, int nrows_valid, int k0, int kmax)
+{
 #pragma unroll
     for (int it = 0; it < (ROWS * 8) / TC_THREADS; ++it) {
-        int idx = threadIdx.x + it * TC_THREADS;
         int row, ch;
-        if (L::kFast) { ch = idx & 7; row = idx >> 3; } else { row = idx % ROWS; ch = idx / ROWS; }
-        float f[8];
-        int i = row0 + row;
+        tc_item<ROWS, L>(it, row, ch);
+        const int i = row0 + row;
+        if constexpr (has_ld8<L>::value) {
+            if (i < nrows_valid) ld.ld8(i, k0 + ch * 8, kmax, r.f[it]);
+            else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            int k = k0 + ch * 8 + j;
-            f[j] = (i < nrows_valid && k < kmax) ? ld(i, k) : 0.f;
+                for (int j = 0; j < 8; ++j) r.f[it][j] = 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int k = k0 + ch * 8 + j;
+                r.f[it][j] = (i < nrows_valid && k < kmax) ? ld(i, k) : 0.f;
+            }
         }
-        tc::slab_store8(slab, row, ch, f);
+    }
+}
+template <int ROWS, class L>
+__device__ __forceinline__ void tc_store_slab(uint8_t* slab, const SlabRegs<ROWS>& r)
+{
+#pragma unroll
+    for (int it = 0; it < (ROWS * 8) / TC_THREADS; ++it) {
+        int row, ch;
+        tc_item<ROWS, L>(it, row, ch);
+        tc::slab_store8(slab, row, ch, r.f[it]);
     }
 }
 
@@ -134,14 +155,23 @@ gemm_tc_kernel(int M, int N, int K, int k_per_split, ALoad aload, BLoad bload, E
     constexpr uint32_t idesc = tc::idesc_bf16(TC_BM, BN, 0, B_MN ? 1 : 0);
 
     const int nslabs = k_end > k_begin ? (k_end - k_begin + TC_BK - 1) / TC_BK : 0;
+    SlabRegs<TC_BM> ra;
+    SlabRegs<BN> rb;
+    auto load_regs = [&](int ks) {
+        tc_load_slab<TC_BM>(ra, aload, m0, M, k_begin + ks * TC_BK, k_end);
+        if constexpr (B_MN) tc_load_slab_mn<BN>(rb, bload, n0, N, k_begin + ks * TC_BK, k_end);
+        else tc_load_slab<BN>(rb, bload, n0, N, k_begin + ks * TC_BK, k_end);
+    };
+    if (nslabs > 0) load_regs(0);
     for (int ks = 0; ks < nslabs; ++ks) {
         const int buf = ks & 1;
         if (ks >= 2) tc::mbar_wait(&bars[buf], ((ks >> 1) - 1) & 1);      // UMMAs that read this stage are done
         uint8_t* sa = smem + buf * STAGE;
         uint8_t* sb = sa + A_BYTES;
-        tc_stage_slab<TC_BM>(sa, aload, m0, M, k_begin + ks * TC_BK, k_end);
-        if constexpr (B_MN) tc_stage_slab_mn<BN>(sb, bload, n0, N, k_begin + ks * TC_BK, k_end);
-        else tc_stage_slab<BN>(sb, bload, n0, N, k_begin + ks * TC_BK, k_end);
+        tc_store_slab<TC_BM, ALoad>(sa, ra);
+        if constexpr (B_MN) tc_store_slab_mn<BN>(sb, rb);
+        else tc_store_slab<BN, BLoad>(sb, rb);
+        if (ks + 1 < nslabs) load_regs(ks + 1);                          // in flight across the barrier and the UMMAs
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {

@@ -47,40 +47,55 @@ gemm_tc_wgrad_kernel(int R, int Mo, int No, int r_per_split, ALoad aload, BLoad 
     for (int q = 0; q < 8; ++q) bsum[q] = 0.f;
 
     const int nslabs = r_end > r_begin ? (r_end - r_begin + WG_ROWS - 1) / WG_ROWS : 0;
+    constexpr int A_ITEMS = (WG_ROWS * 16) / TC_THREADS, B_ITEMS = (WG_ROWS * (BN / 8)) / TC_THREADS;
+    float fa[A_ITEMS][8], fb[B_ITEMS][8];
+    // load phase: every global load of a slab in flight together (and across the barrier / UMMAs of the previous slab)
+    auto load_regs = [&](int ks) {
+        const int r0 = r_begin + ks * WG_ROWS;
+#pragma unroll
+        for (int it = 0; it < A_ITEMS; ++it) {                                // A: 64 rows x 16 chunks of 8 columns
+            int idx = tid + it * TC_THREADS;
+            int ch = idx & 15, row = idx >> 4;
+            if (r0 + row < r_end) aload.ld8(r0 + row, i0 + ch * 8, fa[it]);
+            else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) fa[it][q] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < B_ITEMS; ++it) {                                // B: 64 rows x BN/8 chunks
+            int idx = tid + it * TC_THREADS;
+            int ch = idx % (BN / 8), row = idx / (BN / 8);
+            if (r0 + row < r_end) bload.ld8(r0 + row, j0 + ch * 8, fb[it]);
+            else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) fb[it][q] = 0.f;
+            }
+        }
+    };
+    if (nslabs > 0) load_regs(0);
     for (int ks = 0; ks < nslabs; ++ks) {
         const int buf = ks & 1;
         if (ks >= 2) tc::mbar_wait(&bars[buf], ((ks >> 1) - 1) & 1);
         uint8_t* sa = smem + buf * STAGE;
         uint8_t* sb = sa + A_BYTES;
-        const int r0 = r_begin + ks * WG_ROWS;
 #pragma unroll
-        for (int it = 0; it < (WG_ROWS * 16) / TC_THREADS; ++it) {            // A: 64 rows x 16 chunks of 8 columns
+        for (int it = 0; it < A_ITEMS; ++it) {
             int idx = tid + it * TC_THREADS;
             int ch = idx & 15, row = idx >> 4;
-            float f[8];
-            if (r0 + row < r_end) aload.ld8(r0 + row, i0 + ch * 8, f);
-            else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) f[q] = 0.f;
-            }
             if (do_bias) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) bsum[q] += f[q];
+                for (int q = 0; q < 8; ++q) bsum[q] += fa[it][q];
             }
-            tc::slab_store8(sa + (ch >> 3) * WG_SLAB, row, ch & 7, f);
+            tc::slab_store8(sa + (ch >> 3) * WG_SLAB, row, ch & 7, fa[it]);
         }
 #pragma unroll
-        for (int it = 0; it < (WG_ROWS * (BN / 8)) / TC_THREADS; ++it) {      // B: 64 rows x BN/8 chunks
+        for (int it = 0; it < B_ITEMS; ++it) {
             int idx = tid + it * TC_THREADS;
             int ch = idx % (BN / 8), row = idx / (BN / 8);
-            float f[8];
-            if (r0 + row < r_end) bload.ld8(r0 + row, j0 + ch * 8, f);
-            else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) f[q] = 0.f;
-            }
-            tc::slab_store8(sb + (ch >> 3) * WG_SLAB, row, ch & 7, f);
+            tc::slab_store8(sb + (ch >> 3) * WG_SLAB, row, ch & 7, fb[it]);
         }
+        if (ks + 1 < nslabs) load_regs(ks + 1);
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {

@@ -596,6 +596,20 @@ struct SkipEpi {             // relu(sum + sum_l bias_l)
     __device__ __forceinline__ void flush(int) {}
     __device__ __forceinline__ void row32(int m, bool valid, int n0, float (&v)[32], float*) {
         if (!valid) return;
+        if (n0 + 32 <= N && (N & 3) == 0) {
+            for (int l = 0; l < L; ++l) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 bb = __ldg(reinterpret_cast<const float4*>(b[l] + n0) + q);
+                    v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+                }
+            }
+            float4* o = reinterpret_cast<float4*>(out + (size_t)m * N + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                o[q] = make_float4(fmaxf(v[4 * q], 0.f), fmaxf(v[4 * q + 1], 0.f), fmaxf(v[4 * q + 2], 0.f), fmaxf(v[4 * q + 3], 0.f));
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             int n = n0 + j;
@@ -680,6 +694,28 @@ struct DyEpi {               // dy (+ skip-path gradient) -> df, dg   (Appendix 
         int vv = m % g.V; int bt = m / g.V; int t = bt % g.To; int b = bt / g.To;
         int tt = t - (g.To - Tl);
         const float* dyc = tt >= 0 ? dycat + ((size_t)(b * Tl + tt) * g.V + vv) * ((size_t)L * g.C) + (size_t)layer * g.C : nullptr;
+        if (n0 + 32 <= g.C && (g.C & 3) == 0) {              // 128-bit path, loads batched ahead of the stores
+            const size_t o = (size_t)m * g.C + n0;
+            float4 tf[8], sg[8], dc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                tf[q] = __ldg(reinterpret_cast<const float4*>(TF + o) + q);
+                sg[q] = __ldg(reinterpret_cast<const float4*>(SG + o) + q);
+                dc[q] = dyc ? __ldg(reinterpret_cast<const float4*>(dyc + n0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 dy = make_float4(v[4 * q] + dc[q].x, v[4 * q + 1] + dc[q].y, v[4 * q + 2] + dc[q].z, v[4 * q + 3] + dc[q].w);
+                float4 df, dg;
+                df.x = dy.x * sg[q].x * (1.f - tf[q].x * tf[q].x); dg.x = dy.x * tf[q].x * sg[q].x * (1.f - sg[q].x);
+                df.y = dy.y * sg[q].y * (1.f - tf[q].y * tf[q].y); dg.y = dy.y * tf[q].y * sg[q].y * (1.f - sg[q].y);
+                df.z = dy.z * sg[q].z * (1.f - tf[q].z * tf[q].z); dg.z = dy.z * tf[q].z * sg[q].z * (1.f - sg[q].z);
+                df.w = dy.w * sg[q].w * (1.f - tf[q].w * tf[q].w); dg.w = dy.w * tf[q].w * sg[q].w * (1.f - sg[q].w);
+                reinterpret_cast<float4*>(DF + o)[q] = df;
+                reinterpret_cast<float4*>(DG + o)[q] = dg;
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             int n = n0 + j;
@@ -819,6 +855,18 @@ struct DxB {                 // B(n = c, k) = W_fg[o][c][tap]
         int q = k / C; int o = k - q * C; int tap = q >> 1, fg = q & 1;
         return __ldg((fg ? wg : wf) + (size_t)o * 2 * C + 2 * n + tap);
     }
+    __device__ __forceinline__ void ld8mn(int k, int n, int nmax, float (&f)[8]) const {    // C % 8 == 0
+        if (n >= nmax) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            return;
+        }
+        int q4 = k / C; int o = k - q4 * C; int tap = q4 >> 1, fg = q4 & 1;
+        const float4* p = reinterpret_cast<const float4*>((fg ? wg : wf) + (size_t)o * 2 * C + 2 * n);
+        float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+        if (tap) { f[0] = a.y; f[1] = a.w; f[2] = b.y; f[3] = b.w; f[4] = c.y; f[5] = c.w; f[6] = d.y; f[7] = d.w; }
+        else     { f[0] = a.x; f[1] = a.z; f[2] = b.x; f[3] = b.z; f[4] = c.x; f[5] = c.z; f[6] = d.x; f[7] = d.z; }
+    }
 };
 template <int NG>
 struct DxEpi {               // + residual gradient du[t-d]; BatchNorm-backward sums for the previous layer
@@ -829,16 +877,41 @@ struct DxEpi {               // + residual gradient du[t-d]; BatchNorm-backward 
         int vv = 0, t = 0, b = 0;
         if (valid) { vv = m % g.V; int bt = m / g.V; t = bt % g.Ti; b = bt / g.Ti; }
         const float* du = (valid && DU && t >= g.d) ? DU + ((size_t)(b * g.To + t - g.d) * g.V + vv) * g.C : nullptr;
+        if (n0 + 32 <= g.C && (g.C & 3) == 0) {              // 128-bit path
+            float4 dd[8], uu[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            int n = n0 + j;
-            float dx = 0.f, xh = 0.f;
-            if (valid && n < g.C) {
-                dx = v[j] + (du ? __ldg(du + n) : 0.f);
-                DX[(size_t)m * g.C + n] = dx;
-                if (sums_prev) xh = (__ldg(uprev + (size_t)m * g.C + n) - __ldg(mr_prev + n)) * __ldg(mr_prev + g.C + n);
+            for (int q = 0; q < 8; ++q) {
+                dd[q] = du ? __ldg(reinterpret_cast<const float4*>(du + n0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                uu[q] = (valid && sums_prev) ? __ldg(reinterpret_cast<const float4*>(uprev + (size_t)m * g.C + n0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            v[j] = dx; w[j] = dx * xh;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu;
+                if (sums_prev) {
+                    mu = __ldg(reinterpret_cast<const float4*>(mr_prev + n0) + q);
+                    rs = __ldg(reinterpret_cast<const float4*>(mr_prev + g.C + n0) + q);
+                }
+                float4 dx = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) {
+                    dx = make_float4(v[4 * q] + dd[q].x, v[4 * q + 1] + dd[q].y, v[4 * q + 2] + dd[q].z, v[4 * q + 3] + dd[q].w);
+                    reinterpret_cast<float4*>(DX + (size_t)m * g.C + n0)[q] = dx;
+                }
+                v[4 * q] = dx.x; v[4 * q + 1] = dx.y; v[4 * q + 2] = dx.z; v[4 * q + 3] = dx.w;
+                w[4 * q] = dx.x * (uu[q].x - mu.x) * rs.x; w[4 * q + 1] = dx.y * (uu[q].y - mu.y) * rs.y;
+                w[4 * q + 2] = dx.z * (uu[q].z - mu.z) * rs.z; w[4 * q + 3] = dx.w * (uu[q].w - mu.w) * rs.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                int n = n0 + j;
+                float dx = 0.f, xh = 0.f;
+                if (valid && n < g.C) {
+                    dx = v[j] + (du ? __ldg(du + n) : 0.f);
+                    DX[(size_t)m * g.C + n] = dx;
+                    if (sums_prev) xh = (__ldg(uprev + (size_t)m * g.C + n) - __ldg(mr_prev + n)) * __ldg(mr_prev + g.C + n);
+                }
+                v[j] = dx; w[j] = dx * xh;
+            }
         }
         if (sums_prev) {
             float a = warp_transpose_sum(v), c = warp_transpose_sum(w);

@@ -101,17 +101,22 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
     // ---- 1. stage the gate operands
     {
         W8GateX ld{a.up, a.ss, a.g, 2 * C};
+        float f[(128 * 16) / 256][8];
+#pragma unroll
+        for (int it = 0; it < (128 * 16) / 256; ++it) {      // load phase: all global loads in flight together
+            int idx = tid + it * 256;
+            int ch = idx & 15, row = idx >> 4;
+            if (row < nrows) ld.ld8(r0 + row, ch * 8, f[it]);
+            else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[it][q] = 0.f;
+            }
+        }
 #pragma unroll
         for (int it = 0; it < (128 * 16) / 256; ++it) {
             int idx = tid + it * 256;
             int ch = idx & 15, row = idx >> 4;
-            float f[8];
-            if (row < nrows) ld.ld8(r0 + row, ch * 8, f);
-            else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) f[q] = 0.f;
-            }
-            tc::slab_store8(A1 + (ch >> 3) * SL128, row, ch & 7, f);
+            tc::slab_store8(A1 + (ch >> 3) * SL128, row, ch & 7, f[it]);
         }
         const uint4* src = reinterpret_cast<const uint4*>(a.pack);
         uint4* dst = reinterpret_cast<uint4*>(Wg);
@@ -236,15 +241,22 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
         float v[32], sq[32];
         tc::tmem_ld32(tmem_h + lane_off + half * 32, v);
         const long rr = rvalid ? a.g.in_row(m) + (long)a.g.d * V : 0;
+        float4 xr[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            int n = half * 32 + j;
-            float u = 0.f;
+        for (int q = 0; q < 8; ++q)
+            xr[q] = rvalid ? __ldg(reinterpret_cast<const float4*>(a.up + rr * C + half * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int n = half * 32 + 4 * q;
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(a.ss + n)), sh = __ldg(reinterpret_cast<const float4*>(a.ss + C + n));
+            const float4 bm = __ldg(reinterpret_cast<const float4*>(a.bm + n));
+            float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
             if (rvalid) {
-                float x = fmaf(__ldg(a.up + rr * C + n), __ldg(a.ss + n), __ldg(a.ss + C + n));
-                u = v[j] + __ldg(a.bm + n) + x;
+                u0 = v[4 * q] + bm.x + fmaf(xr[q].x, sc.x, sh.x); u1 = v[4 * q + 1] + bm.y + fmaf(xr[q].y, sc.y, sh.y);
+                u2 = v[4 * q + 2] + bm.z + fmaf(xr[q].z, sc.z, sh.z); u3 = v[4 * q + 3] + bm.w + fmaf(xr[q].w, sc.w, sh.w);
             }
-            v[j] = u; sq[j] = u * u;
+            v[4 * q] = u0; v[4 * q + 1] = u1; v[4 * q + 2] = u2; v[4 * q + 3] = u3;
+            sq[4 * q] = u0 * u0; sq[4 * q + 1] = u1 * u1; sq[4 * q + 2] = u2 * u2; sq[4 * q + 3] = u3 * u3;
         }
         if (rvalid) {
 #pragma unroll
