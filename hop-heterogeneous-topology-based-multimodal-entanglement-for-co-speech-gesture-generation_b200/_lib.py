@@ -36,7 +36,8 @@ class GwnetGrads(C.Structure):
                 ('filter_w', _LAYER_ARR), ('filter_b', _LAYER_ARR), ('gate_w', _LAYER_ARR), ('gate_b', _LAYER_ARR),
                 ('skip_w', _LAYER_ARR), ('skip_b', _LAYER_ARR), ('mlp_w', _LAYER_ARR), ('mlp_b', _LAYER_ARR),
                 ('bn_w', _LAYER_ARR), ('bn_b', _LAYER_ARR),
-                ('end1_w', _vp), ('end1_b', _vp), ('end2_w', _vp), ('end2_b', _vp)]
+                ('end1_w', _vp), ('end1_b', _vp), ('end2_w', _vp), ('end2_b', _vp),
+                ('flat', _vp), ('flat_bytes', C.c_size_t)]
 
 
 # every symbol include/hopk.h declares, with its ctypes signature (restype int unless noted)

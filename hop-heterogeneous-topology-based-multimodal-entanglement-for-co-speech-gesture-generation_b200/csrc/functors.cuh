@@ -196,6 +196,13 @@ struct EpiWgrad {
     __device__ __forceinline__ void flush(int) {}
     __device__ __forceinline__ void row32(int n, bool valid, int k0, float (&v)[32], float*) {
         if (!valid) return;
+        float* row = dw + (long)n * ld + k0;
+        if (k0 + 32 <= K && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {          // 128-bit reductions (sm_90+)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                atomicAdd(reinterpret_cast<float4*>(row) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             int k = k0 + j;

@@ -33,8 +33,10 @@ struct GwLayout {
         x1[HOPK_MAX_LAYERS], x2[HOPK_MAX_LAYERS];
     size_t ycat, r0, r1, orow, ss, mr, A, A2, At, A2t, Z, stats, pack, total;
     // scratch (backward)
-    size_t s_du, s_p1, s_p2, s_g, s_df, s_dg, s_dxa, s_dxb, s_dorow, s_de1, s_dskip, s_dycat, s_bnsum, s_m12, s_dA,
-        s_total;
+    // du / G / df / dg are kept per layer so that the weight-gradient and dA kernels can run on side streams while the
+    // main stream walks down the layers
+    size_t s_du[HOPK_MAX_LAYERS], s_g[HOPK_MAX_LAYERS], s_df[HOPK_MAX_LAYERS], s_dg[HOPK_MAX_LAYERS];
+    size_t s_p1, s_p2, s_dxa, s_dxb, s_dorow, s_de1, s_dskip, s_dycat, s_bnsum, s_m12, s_dA, s_total;
 };
 
 static int receptive_field(const HopkGwnetShape* s)
@@ -84,9 +86,11 @@ static GwLayout make_layout(const HopkGwnetShape* s)
 
     cur = 0;
     size_t nmax = BV * g.Tlen[0] * s->C * f;
-    g.s_du = bump(cur, nmax); g.s_p1 = bump(cur, nmax); g.s_p2 = bump(cur, nmax);
-    g.s_g = bump(cur, 2 * nmax);
-    g.s_df = bump(cur, nmax); g.s_dg = bump(cur, nmax);
+    g.s_p1 = bump(cur, nmax); g.s_p2 = bump(cur, nmax);
+    for (int i = 0; i < s->L; ++i) {
+        size_t n = BV * g.Tlen[i + 1] * s->C * f;
+        g.s_du[i] = bump(cur, n); g.s_g[i] = bump(cur, 2 * n); g.s_df[i] = bump(cur, n); g.s_dg[i] = bump(cur, n);
+    }
     g.s_dxa = bump(cur, nmax); g.s_dxb = bump(cur, nmax);
     g.s_dorow = bump(cur, BV * g.Tl * s->out_dim * f);
     g.s_de1 = bump(cur, BV * g.Tl * s->E * f);
@@ -237,43 +241,69 @@ __global__ void node_mix_kernel(const float* __restrict__ in, const float* __res
 }
 
 // dA Gram accumulation: M1[v][w] += sum_{g,c} Y[(g,v)][c] G[(g,w)][c], M2 with G[..][C + c]   (G has ld 2C)
-__global__ void gram_kernel(const float* __restrict__ Y, const float* __restrict__ G, float* __restrict__ M12,
-                            int groups, int V, int C, int gpb)
+// Persistent CTAs stride over chunks of GRAM_GPI node groups; thread = (pair slot, channel slice); partial sums stay in
+// registers across the whole loop, are combined in shared memory and leave the CTA as one atomic per matrix entry.
+constexpr int GRAM_GPI = 4;                  // node groups staged per iteration
+constexpr int GRAM_MAXP = 8;                 // pairs per thread: V*V <= 8*256  (V <= 45)
+__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ Y, const float* __restrict__ G, float* __restrict__ M12,
+                                                   int groups, int V, int C)
 {
     extern __shared__ float sm[];
-    float* sy = sm;                 // V * (C+1)
-    float* sg = sy + V * (C + 1);   // V * (2C+1)
-    constexpr int MAXP = 8;         // pairs per thread: V*V <= 8*256  (V <= 45)
-    float a1[MAXP], a2[MAXP];
+    const int VV = V * V;
+    const int ldy = C + 1, ldg = 2 * C + 1;
+    float* sy = sm;                                   // GRAM_GPI * V * ldy
+    float* sg = sy + GRAM_GPI * V * ldy;              // GRAM_GPI * V * ldg
+    float* acc = sg + GRAM_GPI * V * ldg;             // 2 * VV
+    const int NS = VV >= 256 ? 1 : 256 / VV;          // channel slices per pair
+    const int slice = VV >= 256 ? 0 : (int)threadIdx.x / VV;
+    const int p0 = VV >= 256 ? (int)threadIdx.x : (int)threadIdx.x % VV;
+    const bool active = slice < NS;
+    float a1[GRAM_MAXP], a2[GRAM_MAXP];
 #pragma unroll
-    for (int p = 0; p < MAXP; ++p) { a1[p] = 0.f; a2[p] = 0.f; }
-    int g0 = blockIdx.x * gpb;
-    int ng = min(gpb, groups - g0);
-    for (int g = 0; g < ng; ++g) {
-        const float* yp = Y + (size_t)(g0 + g) * V * C;
-        const float* gp = G + (size_t)(g0 + g) * V * 2 * C;
+    for (int p = 0; p < GRAM_MAXP; ++p) { a1[p] = 0.f; a2[p] = 0.f; }
+    for (int i = threadIdx.x; i < 2 * VV; i += blockDim.x) acc[i] = 0.f;
+    for (int g0 = blockIdx.x * GRAM_GPI; g0 < groups; g0 += gridDim.x * GRAM_GPI) {
+        const int ng = min(GRAM_GPI, groups - g0);
         __syncthreads();
-        for (int i = threadIdx.x; i < V * C; i += blockDim.x) sy[(i / C) * (C + 1) + i % C] = yp[i];
-        for (int i = threadIdx.x; i < V * 2 * C; i += blockDim.x) sg[(i / (2 * C)) * (2 * C + 1) + i % (2 * C)] = gp[i];
+        const float4* yp = reinterpret_cast<const float4*>(Y + (size_t)g0 * V * C);
+        const float4* gp = reinterpret_cast<const float4*>(G + (size_t)g0 * V * 2 * C);
+        for (int i = threadIdx.x; i < ng * V * C / 4; i += blockDim.x) {
+            float4 x = __ldg(yp + i);
+            int e = i * 4; int r = e / C, c = e - r * C;
+            float* d = sy + r * ldy + c; d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+        }
+        for (int i = threadIdx.x; i < ng * V * 2 * C / 4; i += blockDim.x) {
+            float4 x = __ldg(gp + i);
+            int e = i * 4; int r = e / (2 * C), c = e - r * 2 * C;
+            float* d = sg + r * ldg + c; d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+        }
         __syncthreads();
+        if (active) {
 #pragma unroll
-        for (int p = 0; p < MAXP; ++p) {
-            int pair = threadIdx.x + p * blockDim.x;
-            if (pair < V * V) {
-                int v = pair / V, w = pair % V;
-                const float* yr = sy + v * (C + 1);
-                const float* gr = sg + w * (2 * C + 1);
-                float s1 = 0.f, s2 = 0.f;
-                for (int c = 0; c < C; ++c) { s1 = fmaf(yr[c], gr[c], s1); s2 = fmaf(yr[c], gr[C + c], s2); }
-                a1[p] += s1; a2[p] += s2;
+            for (int p = 0; p < GRAM_MAXP; ++p) {
+                int pair = p0 + p * 256;
+                if (pair < VV && (p == 0 || VV >= 256)) {
+                    int v = pair / V, w = pair - v * V;
+                    float s1 = 0.f, s2 = 0.f;
+                    for (int g = 0; g < ng; ++g) {
+                        const float* yr = sy + (g * V + v) * ldy;
+                        const float* gr = sg + (g * V + w) * ldg;
+                        for (int c = slice; c < C; c += NS) { s1 = fmaf(yr[c], gr[c], s1); s2 = fmaf(yr[c], gr[C + c], s2); }
+                    }
+                    a1[p] += s1; a2[p] += s2;
+                }
             }
         }
     }
+    if (active) {
 #pragma unroll
-    for (int p = 0; p < MAXP; ++p) {
-        int pair = threadIdx.x + p * blockDim.x;
-        if (pair < V * V) { atomicAdd(M12 + pair, a1[p]); atomicAdd(M12 + V * V + pair, a2[p]); }
+        for (int p = 0; p < GRAM_MAXP; ++p) {
+            int pair = p0 + p * 256;
+            if (pair < VV && (p == 0 || VV >= 256)) { atomicAdd(acc + pair, a1[p]); atomicAdd(acc + VV + pair, a2[p]); }
+        }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * VV; i += blockDim.x) atomicAdd(M12 + i, acc[i]);
 }
 
 // BatchNorm backward, elementwise part: du = gamma*rstd*(dxn - mean(dxn) - xhat*mean(dxn*xhat))
@@ -811,17 +841,38 @@ struct W8GateX {             // columns j = tap*C + c : BN_{i-1}-folded layer in
         f[4] = fmaf(b.x, s1.x, h1.x); f[5] = fmaf(b.y, s1.y, h1.y); f[6] = fmaf(b.z, s1.z, h1.z); f[7] = fmaf(b.w, s1.w, h1.w);
     }
 };
-struct GateWgEpi2 {          // out[i = fg*C + o][j = tap*C + c] -> d(filter|gate)_w[o][c][tap]; bias = column sums of [DF|DG]
+struct W8GateXI {            // columns j = 2c + tap (the weight's own [c][tap] order): BN-folded layer input at (b, t + tap*d, v)
+    const float* up; const float* ss; LayerGeom g; int ncols;
+    __device__ __forceinline__ void ld8(int r, int c0, float (&f)[8]) const {
+        if (c0 >= ncols) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            return;
+        }
+        const int c = c0 >> 1;                                    // 4 channels x 2 taps
+        const float* p0 = up + (size_t)g.in_row(r) * g.C + c;
+        const float* p1 = p0 + (size_t)g.d * g.V * g.C;
+        float4 a = __ldg(reinterpret_cast<const float4*>(p0)), b = __ldg(reinterpret_cast<const float4*>(p1));
+        float4 sc = __ldg(reinterpret_cast<const float4*>(ss + c)), sh = __ldg(reinterpret_cast<const float4*>(ss + g.C + c));
+        f[0] = fmaf(a.x, sc.x, sh.x); f[1] = fmaf(b.x, sc.x, sh.x); f[2] = fmaf(a.y, sc.y, sh.y); f[3] = fmaf(b.y, sc.y, sh.y);
+        f[4] = fmaf(a.z, sc.z, sh.z); f[5] = fmaf(b.z, sc.z, sh.z); f[6] = fmaf(a.w, sc.w, sh.w); f[7] = fmaf(b.w, sc.w, sh.w);
+    }
+};
+struct GateWgEpi2 {          // out[i = fg*C + o][j = 2c + tap] -> d(filter|gate)_w[o][c][tap]; bias = column sums of [DF|DG]
     float* dwf; float* dwg; float* dbf; float* dbg; int C;
     __device__ __forceinline__ void row32(int i, bool valid, int j0, float (&v)[32], float*) {
         if (!valid) return;
         int fg = i >= C; int o = i - fg * C;
-        float* dw = (fg ? dwg : dwf) + (size_t)o * 2 * C;
+        float* dw = (fg ? dwg : dwf) + (size_t)o * 2 * C + j0;
+        if (j0 + 32 <= 2 * C && (reinterpret_cast<uintptr_t>(dw) & 15) == 0) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-            int j = j0 + jj;
-            if (j < 2 * C) { int tap = j >= C; int c = j - tap * C; atomicAdd(dw + 2 * c + tap, v[jj]); }
+            for (int q = 0; q < 8; ++q)
+                atomicAdd(reinterpret_cast<float4*>(dw) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            return;
         }
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+            if (j0 + jj < 2 * C) atomicAdd(dw + jj, v[jj]);
     }
     __device__ __forceinline__ void finish(float*) {}
     __device__ __forceinline__ void bias(int i, float v) { int fg = i >= C; atomicAdd((fg ? dbg : dbf) + (i - fg * C), v); }
@@ -1006,6 +1057,51 @@ static int launch_node_mix(const float* in, const float* M1, const float* M2, fl
 using namespace hopk;
 
 // ============================================================================ C ABI
+// ============================================================================ backward plumbing
+struct SideStreams {
+    cudaStream_t s[3];
+    cudaEvent_t ev_du[HOPK_MAX_LAYERS], ev_dfg[HOPK_MAX_LAYERS], ev_join[3];
+};
+// created once per process (one process drives one GPU); non-blocking so they never serialise against stream 0
+static SideStreams* side_streams()
+{
+    static SideStreams sd;
+    static int state = 0;                       // 0 = not created, 1 = ok, -1 = failed
+    if (state == 0) {
+        state = 1;
+        for (int k = 0; k < 3; ++k) {
+            if (cudaStreamCreateWithFlags(&sd.s[k], cudaStreamNonBlocking) != cudaSuccess) state = -1;
+            if (cudaEventCreateWithFlags(&sd.ev_join[k], cudaEventDisableTiming) != cudaSuccess) state = -1;
+        }
+        for (int l = 0; l < HOPK_MAX_LAYERS; ++l) {
+            if (cudaEventCreateWithFlags(&sd.ev_du[l], cudaEventDisableTiming) != cudaSuccess) state = -1;
+            if (cudaEventCreateWithFlags(&sd.ev_dfg[l], cudaEventDisableTiming) != cudaSuccess) state = -1;
+        }
+    }
+    return state == 1 ? &sd : nullptr;
+}
+
+static int zero_param_grads(const HopkGwnetShape* s, const HopkGwnetGrads* gr, cudaStream_t st)
+{
+    if (gr->flat && gr->flat_bytes) {
+        HOPK_CUDA(cudaMemsetAsync(gr->flat, 0, gr->flat_bytes, st));
+        return 0;
+    }
+    const size_t f = sizeof(float);
+    const size_t C = s->C, Sk = s->S, E = s->E, O = s->out_dim;
+    auto z = [&](float* p, size_t n) -> cudaError_t { return p ? cudaMemsetAsync(p, 0, n * f, st) : cudaSuccess; };
+    HOPK_CUDA(z(gr->start_w, C * s->in_dim)); HOPK_CUDA(z(gr->start_b, C));
+    HOPK_CUDA(z(gr->end1_w, E * Sk)); HOPK_CUDA(z(gr->end1_b, E));
+    HOPK_CUDA(z(gr->end2_w, O * E)); HOPK_CUDA(z(gr->end2_b, O));
+    for (int l = 0; l < s->L; ++l) {
+        HOPK_CUDA(z(gr->filter_w[l], C * 2 * C)); HOPK_CUDA(z(gr->filter_b[l], C));
+        HOPK_CUDA(z(gr->gate_w[l], C * 2 * C)); HOPK_CUDA(z(gr->gate_b[l], C));
+        HOPK_CUDA(z(gr->skip_w[l], Sk * C)); HOPK_CUDA(z(gr->skip_b[l], Sk));
+        HOPK_CUDA(z(gr->mlp_w[l], C * 3 * C)); HOPK_CUDA(z(gr->mlp_b[l], C));
+    }
+    return 0;
+}
+
 extern "C" size_t hopk_gwnet_workspace_bytes(const HopkGwnetShape* s) { return make_layout(s).total; }
 extern "C" size_t hopk_gwnet_scratch_bytes(const HopkGwnetShape* s) { return make_layout(s).s_total; }
 extern "C" int hopk_gwnet_out_steps(const HopkGwnetShape* s) { return make_layout(s).Tl; }
@@ -1161,6 +1257,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
     double* bnsum = reinterpret_cast<double*>(sc + g.s_bnsum);
     HOPK_CUDA(cudaMemsetAsync(bnsum, 0, (size_t)L * 2 * C * sizeof(double), st));
     HOPK_CUDA(cudaMemsetAsync(S(g.s_m12), 0, 2 * (size_t)V * V * sizeof(float), st));
+    if (int rc = zero_param_grads(s, gr, st)) return rc;      // split-K / atomic epilogues accumulate into zeroed buffers
 
     // ---- head backward
     const int M4 = B * g.Tl * V;
@@ -1168,8 +1265,6 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
         nchw_to_rows_kernel<<<cdiv((long)M4 * O, 256), 256, 0, st>>>(dout, S(g.s_dorow), B, O, V, g.Tl);
         HOPK_LAUNCH_CHECK("dout_rows");
         // end_conv_2
-        HOPK_CUDA(cudaMemsetAsync(gr->end2_w, 0, (size_t)O * E * sizeof(float), st));
-        HOPK_CUDA(cudaMemsetAsync(gr->end2_b, 0, (size_t)O * sizeof(float), st));
         {
             Ld2D<false, 0> a{S(g.s_dorow), nullptr, O};
             Ld2DOnes<false> b{F(g.r1), E, E};
@@ -1183,8 +1278,6 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             HOPK_LAUNCH_CHECK("end2_dgrad");
         }
         // end_conv_1
-        HOPK_CUDA(cudaMemsetAsync(gr->end1_w, 0, (size_t)E * Sk * sizeof(float), st));
-        HOPK_CUDA(cudaMemsetAsync(gr->end1_b, 0, (size_t)E * sizeof(float), st));
         {
             Ld2D<false, 0> a{S(g.s_de1), nullptr, E};
             Ld2DOnes<false> b{F(g.r0), Sk, Sk};
@@ -1198,10 +1291,6 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             HOPK_LAUNCH_CHECK("end1_dgrad");
         }
         // skip convs: one concat GEMM each way
-        for (int l = 0; l < L; ++l) {
-            HOPK_CUDA(cudaMemsetAsync(gr->skip_w[l], 0, (size_t)Sk * C * sizeof(float), st));
-            HOPK_CUDA(cudaMemsetAsync(gr->skip_b[l], 0, (size_t)Sk * sizeof(float), st));
-        }
         {
             Ld2D<false, 0> a{S(g.s_dskip), nullptr, Sk};
             Ld2DOnes<false> b{F(g.ycat), (long)L * C, L * C};
@@ -1217,7 +1306,11 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
         }
     }
 
-    // ---- layers, last to first
+    // ---- layers, last to first.  The caller's stream carries the dependent chain (BN backward -> node mix -> dy -> dx);
+    // the weight-gradient GEMMs and the dA Gram products only feed parameter gradients, so they run on three side
+    // streams forked from / joined back to the caller's stream with events (du, G, df, dg are kept per layer).
+    SideStreams* sd = side_streams();
+    if (!sd) return fail(3, "side streams", "cudaStreamCreate failed");
     float* dxn = nullptr;                 // gradient w.r.t. BN_i output (= layer i+1 input)
     float* dx_buf[2] = {S(g.s_dxa), S(g.s_dxb)};
     int flip = 0;
@@ -1228,7 +1321,9 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
         const float* uprev = i == 0 ? F(g.x0) : F(g.u[i - 1]);
         const float* ss = F(g.ss) + (size_t)i * 2 * C;
         const bool has_du = dxn != nullptr;
-        float* DU = S(g.s_du);
+        float* DU = S(g.s_du[i]);
+        float* DF = S(g.s_df[i]);
+        float* DG = S(g.s_dg[i]);
         if (has_du) {
             size_t smem = 5 * C * sizeof(float);
             long n4 = (long)M * C / 4;
@@ -1237,39 +1332,44 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
                                                      bnsum + (size_t)i * 2 * C, (double)M, DU, gr->bn_w[i], gr->bn_b[i],
                                                      (size_t)M, C, s->training);
             HOPK_LAUNCH_CHECK("bn_bwd");
-            // P1 = A du, P2 = A^2 du  (node mix with the transposed supports)
+            HOPK_CUDA(cudaEventRecord(sd->ev_du[i], st));
             int groups = B * lg.To;
-            if (int rc = launch_node_mix(DU, F(g.At), F(g.A2t), S(g.s_p1), S(g.s_p2), groups, V, C, st)) return rc;
-            // mlp weight + bias gradient
-            HOPK_CUDA(cudaMemsetAsync(gr->mlp_w[i], 0, (size_t)C * 3 * C * sizeof(float), st));
-            HOPK_CUDA(cudaMemsetAsync(gr->mlp_b[i], 0, (size_t)C * sizeof(float), st));
-            if (tc && C % 8 == 0) {          // MN-major tensor-core weight gradient: dWm[o][k] = sum_r du[r][o] [y|x1|x2][r][k]
-                W8Plain a{DU, nullptr, C, C, 0};
-                W8Seg3 b{F(g.y[i]), F(g.x1[i]), F(g.x2[i]), C, 3 * C};
-                EpiWgrad<2> e{gr->mlp_w[i], (long)3 * C, gr->mlp_b[i], 3 * C, C};
-                HOPK_CUDA(launch_gemm_tc_wgrad<128>(M, C, 3 * C, a, b, e, true, st));
-                HOPK_LAUNCH_CHECK("mlp_wgrad_tc");
-            } else {
-                Ld2D<false, 0> a{DU, nullptr, C};
-                Seg3AT b{F(g.y[i]), F(g.x1[i]), F(g.x2[i]), C};
-                EpiWgrad<2> e{gr->mlp_w[i], (long)3 * C, gr->mlp_b[i], 3 * C, C};
-                if (C <= 64) launch_gemm<1, 2>(tc, C, 3 * C + 1, M, pick_splits(tc, C, 3 * C + 1, M, 1, 2), a, b, e, st);
-                else launch_gemm<2, 2>(tc, C, 3 * C + 1, M, pick_splits(tc, C, 3 * C + 1, M, 2, 2), a, b, e, st);
-                HOPK_LAUNCH_CHECK("mlp_wgrad");
-            }
-            // G = du [Wm1 | Wm2]  and the Gram products for dA
+            // side stream 0: mlp weight + bias gradient
             {
+                cudaStream_t s0 = sd->s[0];
+                HOPK_CUDA(cudaStreamWaitEvent(s0, sd->ev_du[i], 0));
+                if (tc && C % 8 == 0) {      // MN-major tensor-core weight gradient: dWm[o][k] = sum_r du[r][o] [y|x1|x2][r][k]
+                    W8Plain a{DU, nullptr, C, C, 0};
+                    W8Seg3 b{F(g.y[i]), F(g.x1[i]), F(g.x2[i]), C, 3 * C};
+                    EpiWgrad<2> e{gr->mlp_w[i], (long)3 * C, gr->mlp_b[i], 3 * C, C};
+                    HOPK_CUDA(launch_gemm_tc_wgrad<128>(M, C, 3 * C, a, b, e, true, s0));
+                    HOPK_LAUNCH_CHECK("mlp_wgrad_tc");
+                } else {
+                    Ld2D<false, 0> a{DU, nullptr, C};
+                    Seg3AT b{F(g.y[i]), F(g.x1[i]), F(g.x2[i]), C};
+                    EpiWgrad<2> e{gr->mlp_w[i], (long)3 * C, gr->mlp_b[i], 3 * C, C};
+                    if (C <= 64) launch_gemm<1, 2>(tc, C, 3 * C + 1, M, pick_splits(tc, C, 3 * C + 1, M, 1, 2), a, b, e, s0);
+                    else launch_gemm<2, 2>(tc, C, 3 * C + 1, M, pick_splits(tc, C, 3 * C + 1, M, 2, 2), a, b, e, s0);
+                    HOPK_LAUNCH_CHECK("mlp_wgrad");
+                }
+            }
+            // side stream 1: G = du [Wm1 | Wm2]  and the Gram products for dA
+            {
+                cudaStream_t s1 = sd->s[1];
+                HOPK_CUDA(cudaStreamWaitEvent(s1, sd->ev_du[i], 0));
                 Ld2D<true, 0> a{DU, nullptr, C};
                 Ld2D<false, 0> b{p->mlp_w[i] + C, nullptr, (long)3 * C};
-                EpiStore<2> e{S(g.s_g), (long)2 * C, nullptr, nullptr, 2 * C, 0};
-                launch_gemm<2, 2>(tc, M, 2 * C, C, 1, a, b, e, st);
+                EpiStore<2> e{S(g.s_g[i]), (long)2 * C, nullptr, nullptr, 2 * C, 0};
+                launch_gemm<2, 2>(tc, M, 2 * C, C, 1, a, b, e, s1);
                 HOPK_LAUNCH_CHECK("g_gemm");
-                int gpb2 = 8;
-                size_t smem3 = ((size_t)V * (C + 1) + (size_t)V * (2 * C + 1)) * sizeof(float);
+                size_t smem3 = ((size_t)GRAM_GPI * V * (3 * C + 2) + 2 * (size_t)V * V) * sizeof(float);
                 if (smem3 > 48 * 1024) HOPK_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-                gram_kernel<<<cdiv(groups, gpb2), 256, smem3, st>>>(F(g.y[i]), S(g.s_g), S(g.s_m12), groups, V, C, gpb2);
+                int gblocks = cdiv(groups, GRAM_GPI); if (gblocks > 148) gblocks = 148;
+                gram_kernel<<<gblocks, 256, smem3, s1>>>(F(g.y[i]), S(g.s_g[i]), S(g.s_m12), groups, V, C);
                 HOPK_LAUNCH_CHECK("gram");
             }
+            // P1 = A du, P2 = A^2 du  (node mix with the transposed supports)
+            if (int rc = launch_node_mix(DU, F(g.At), F(g.A2t), S(g.s_p1), S(g.s_p2), groups, V, C, st)) return rc;
         }
         // dy (+ skip path) -> df, dg
         {
@@ -1277,35 +1377,36 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             DyB b{p->mlp_w[i], C};
             int K = has_du ? 3 * C : 0;
             if (C <= 64) {
-                DyEpi<1> e{F(g.tf[i]), F(g.sg[i]), S(g.s_dycat), S(g.s_df), S(g.s_dg), lg, i, L, g.Tl};
+                DyEpi<1> e{F(g.tf[i]), F(g.sg[i]), S(g.s_dycat), DF, DG, lg, i, L, g.Tl};
                 launch_gemm<2, 1>(tc, M, C, K, 1, a, b, e, st);
             } else {
-                DyEpi<2> e{F(g.tf[i]), F(g.sg[i]), S(g.s_dycat), S(g.s_df), S(g.s_dg), lg, i, L, g.Tl};
+                DyEpi<2> e{F(g.tf[i]), F(g.sg[i]), S(g.s_dycat), DF, DG, lg, i, L, g.Tl};
                 launch_gemm<2, 2>(tc, M, C, K, 1, a, b, e, st);
             }
             HOPK_LAUNCH_CHECK("dy_gemm");
+            HOPK_CUDA(cudaEventRecord(sd->ev_dfg[i], st));
         }
-        // gate conv weight + bias gradients
-        HOPK_CUDA(cudaMemsetAsync(gr->filter_w[i], 0, (size_t)C * 2 * C * sizeof(float), st));
-        HOPK_CUDA(cudaMemsetAsync(gr->gate_w[i], 0, (size_t)C * 2 * C * sizeof(float), st));
-        HOPK_CUDA(cudaMemsetAsync(gr->filter_b[i], 0, (size_t)C * sizeof(float), st));
-        HOPK_CUDA(cudaMemsetAsync(gr->gate_b[i], 0, (size_t)C * sizeof(float), st));
-        if (tc && C % 8 == 0) {
-            W8Seg3 a{S(g.s_df), S(g.s_dg), S(g.s_dg), C, 2 * C};
-            W8GateX b{uprev, ss, lg, 2 * C};
-            GateWgEpi2 e{gr->filter_w[i], gr->gate_w[i], gr->filter_b[i], gr->gate_b[i], C};
-            HOPK_CUDA(launch_gemm_tc_wgrad<128>(M, 2 * C, 2 * C, a, b, e, true, st));
-            HOPK_LAUNCH_CHECK("gate_wgrad_tc");
-        } else {
-            GateWgA a{S(g.s_df), S(g.s_dg), C};
-            GateWgB b{uprev, ss, lg};
-            GateWgEpi<2> e{gr->filter_w[i], gr->gate_w[i], gr->filter_b[i], gr->gate_b[i], C};
-            launch_gemm<2, 2>(tc, 2 * C, 2 * C + 1, M, pick_splits(tc, 2 * C, 2 * C + 1, M, 2, 2), a, b, e, st);
-            HOPK_LAUNCH_CHECK("gate_wgrad");
+        // side stream 2: gate conv weight + bias gradients
+        {
+            cudaStream_t s2 = sd->s[2];
+            HOPK_CUDA(cudaStreamWaitEvent(s2, sd->ev_dfg[i], 0));
+            if (tc && C % 8 == 0) {
+                W8Seg3 a{DF, DG, DG, C, 2 * C};
+                W8GateXI b{uprev, ss, lg, 2 * C};
+                GateWgEpi2 e{gr->filter_w[i], gr->gate_w[i], gr->filter_b[i], gr->gate_b[i], C};
+                HOPK_CUDA(launch_gemm_tc_wgrad<128>(M, 2 * C, 2 * C, a, b, e, true, s2));
+                HOPK_LAUNCH_CHECK("gate_wgrad_tc");
+            } else {
+                GateWgA a{DF, DG, C};
+                GateWgB b{uprev, ss, lg};
+                GateWgEpi<2> e{gr->filter_w[i], gr->gate_w[i], gr->filter_b[i], gr->gate_b[i], C};
+                launch_gemm<2, 2>(tc, 2 * C, 2 * C + 1, M, pick_splits(tc, 2 * C, 2 * C + 1, M, 2, 2), a, b, e, s2);
+                HOPK_LAUNCH_CHECK("gate_wgrad");
+            }
         }
         // dx of the layer input (+ residual gradient) and BN-backward sums of layer i-1
         {
-            DxA a{S(g.s_df), S(g.s_dg), lg};
+            DxA a{DF, DG, lg};
             DxB b{p->filter_w[i], p->gate_w[i], C};
             float* DX = dx_buf[flip];
             if (C <= 64) {
@@ -1325,6 +1426,11 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             dxn = DX; flip ^= 1;
         }
     }
+    // join the side streams: everything below (and everything the caller enqueues next) sees the finished gradients
+    for (int k = 0; k < 3; ++k) {
+        HOPK_CUDA(cudaEventRecord(sd->ev_join[k], sd->s[k]));
+        HOPK_CUDA(cudaStreamWaitEvent(st, sd->ev_join[k], 0));
+    }
 
     // ---- adaptive adjacency and start conv
     adp_bwd_kernel<<<1, 256, V * V * sizeof(float), st>>>(p->nodevec1, p->nodevec2, F(g.A), F(g.Z), S(g.s_m12),
@@ -1332,8 +1438,6 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
     HOPK_LAUNCH_CHECK("adp_bwd");
     {
         int M = B * g.Tp * V;
-        HOPK_CUDA(cudaMemsetAsync(gr->start_w, 0, (size_t)C * s->in_dim * sizeof(float), st));
-        HOPK_CUDA(cudaMemsetAsync(gr->start_b, 0, (size_t)C * sizeof(float), st));
         Ld2D<false, 0> a{dxn, nullptr, C};
         StartAT b{x, g.Tp, V, g.pad, s->in_dim, (long)xs[0], (long)xs[1], (long)xs[2], (long)xs[3]};
         EpiWgrad<2> e{gr->start_w, s->in_dim, gr->start_b, s->in_dim, C};

@@ -155,6 +155,7 @@ class _GwnetFn(torch.autograd.Function):
             grads[i] = flat[off:off + n].view(params[i].shape)
             off += n
         g = GwnetGrads()
+        g.flat, g.flat_bytes = ptr(flat), flat.numel() * 4
         for i, (name, layer) in enumerate(mod._param_names()):
             if layer is None:
                 setattr(g, name, ptr(grads[i]))

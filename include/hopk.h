@@ -76,6 +76,9 @@ typedef struct HopkGwnetGrads {
     float *mlp_w[HOPK_MAX_LAYERS], *mlp_b[HOPK_MAX_LAYERS];
     float *bn_w[HOPK_MAX_LAYERS], *bn_b[HOPK_MAX_LAYERS];
     float *end1_w, *end1_b, *end2_w, *end2_b;
+    /* optional: when every buffer above is a view into one allocation, its base and size; it is then cleared with a
+     * single memset (the weight-gradient kernels accumulate split-K partials).  NULL: each buffer is cleared separately. */
+    void* flat; size_t flat_bytes;
 } HopkGwnetGrads;
 
 /* bytes of the forward workspace (holds everything backward re-reads) and of backward's scratch */

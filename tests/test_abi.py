@@ -34,7 +34,7 @@ def test_struct_sizes_match_header():
     from hop_b200 import _lib
     assert ctypes.sizeof(_lib.GwnetShape) == 4 * (9 + 16 + 3)
     assert ctypes.sizeof(_lib.GwnetParams) == 8 * (4 + 13 * 16 + 4)
-    assert ctypes.sizeof(_lib.GwnetGrads) == 8 * (4 + 10 * 16 + 4)
+    assert ctypes.sizeof(_lib.GwnetGrads) == 8 * (4 + 10 * 16 + 4 + 2)
 
 
 def test_workspace_queries_run_on_host():
