@@ -31,7 +31,7 @@ struct GwLayout {
     int Tp, pad, Tl;
     size_t x0, u[HOPK_MAX_LAYERS], tf[HOPK_MAX_LAYERS], sg[HOPK_MAX_LAYERS], y[HOPK_MAX_LAYERS],
         x1[HOPK_MAX_LAYERS], x2[HOPK_MAX_LAYERS];
-    size_t ycat, r0, r1, orow, ss, mr, A, A2, At, A2t, Z, stats, pack, total;
+    size_t ycat, r0, r1, orow, ss, mr, A, A2, At, A2t, Z, stats, pack, ticket, total;
     // scratch (backward)
     // du / G / df / dg are kept per layer so that the weight-gradient and dA kernels can run on side streams while the
     // main stream walks down the layers
@@ -81,7 +81,8 @@ static GwLayout make_layout(const HopkGwnetShape* s)
     size_t vv = (size_t)s->V * s->V * f;
     g.A = bump(cur, vv); g.A2 = bump(cur, vv); g.At = bump(cur, vv); g.A2t = bump(cur, vv); g.Z = bump(cur, vv);
     g.stats = bump(cur, (size_t)s->L * 2 * s->C * sizeof(double));
-    g.pack = bump(cur, (size_t)s->L * 57344 + 1024);          // packed bf16 weight slabs of the fused layer kernel
+    g.pack = bump(cur, (size_t)s->L * 57344 + 32768 + 1024);  // packed bf16 weight slabs + diffusion operator of the fused layer kernel
+    g.ticket = bump(cur, (size_t)HOPK_MAX_LAYERS * sizeof(unsigned int));
     g.total = cur;
 
     cur = 0;
@@ -1153,14 +1154,19 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
     const float* uprev = F(g.x0);
     const bool fused = tc && C == FZ_C && V <= 64;                   // one kernel per layer (gwnet_fused.cuh)
     uint8_t* pack = reinterpret_cast<uint8_t*>(((uintptr_t)(ws + g.pack) + 1023) & ~uintptr_t(1023));
+    uint8_t* bd = pack + (size_t)L * FZ_PACK_BYTES;
+    unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + g.ticket);
     if (fused) {
         static bool configured = false;
         if (!configured) {
-            HOPK_CUDA(cudaFuncSetAttribute(fz_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_smem_bytes(64)));
+            HOPK_CUDA(cudaFuncSetAttribute(fz_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_smem_bytes()));
             configured = true;
         }
+        HOPK_CUDA(cudaMemsetAsync(tickets, 0, HOPK_MAX_LAYERS * sizeof(unsigned int), st));
         fz_pack_weights_kernel<<<L, 256, 0, st>>>(*p, L, pack);
         HOPK_LAUNCH_CHECK("fz_pack");
+        fz_pack_bd_kernel<<<16, 256, 0, st>>>(F(g.A), V, bd);
+        HOPK_LAUNCH_CHECK("fz_pack_bd");
     }
     for (int i = 0; i < L; ++i) {
         LayerGeom lg{V, C, g.Tlen[i], g.Tlen[i + 1], s->dil[i]};
@@ -1168,18 +1174,16 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
         const float* ss = F(g.ss) + (size_t)i * 2 * C;
         if (fused) {
             FzArgs fa;
-            fa.up = uprev; fa.ss = ss; fa.pack = pack + (size_t)i * FZ_PACK_BYTES;
-            fa.bf = p->filter_b[i]; fa.bg = p->gate_b[i]; fa.bm = p->mlp_b[i]; fa.A = F(g.A);
+            fa.up = uprev; fa.ss = ss; fa.pack = pack + (size_t)i * FZ_PACK_BYTES; fa.bd = bd;
+            fa.bf = p->filter_b[i]; fa.bg = p->gate_b[i]; fa.bm = p->mlp_b[i];
             fa.TF = F(g.tf[i]); fa.SG = F(g.sg[i]); fa.Y = F(g.y[i]); fa.X1 = F(g.x1[i]); fa.X2 = F(g.x2[i]); fa.U = F(g.u[i]);
             fa.ycat = F(g.ycat); fa.stats = stats + (size_t)i * 2 * C;
             fa.g = lg; fa.layer = i; fa.L = L; fa.Tl = g.Tl; fa.groups = B * lg.To; fa.gpt = 128 / V;
-            fz_layer_fwd_kernel<<<cdiv(fa.groups, fa.gpt), 256, fz_smem_bytes(V), st>>>(fa);
+            fa.ticket = tickets + i; fa.count = (double)M; fa.gamma = p->bn_w[i]; fa.beta = p->bn_b[i];
+            fa.rmean = p->bn_mean[i]; fa.rvar = p->bn_var[i]; fa.nbt = (long long*)p->bn_nbt[i];
+            fa.mr = F(g.mr) + (size_t)i * 2 * C; fa.ss_next = F(g.ss) + (size_t)(i + 1) * 2 * C; fa.training = s->training;
+            fz_layer_fwd_kernel<<<cdiv(fa.groups, fa.gpt), 256, fz_smem_bytes(), st>>>(fa);
             HOPK_LAUNCH_CHECK("fz_layer_fwd");
-            bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats + (size_t)i * 2 * C, (double)M, p->bn_w[i], p->bn_b[i],
-                                                              p->bn_mean[i], p->bn_var[i], (long long*)p->bn_nbt[i],
-                                                              F(g.mr) + (size_t)i * 2 * C, F(g.ss) + (size_t)(i + 1) * 2 * C, C,
-                                                              s->training);
-            HOPK_LAUNCH_CHECK("bn_finalize");
             uprev = F(g.u[i]);
             continue;
         }

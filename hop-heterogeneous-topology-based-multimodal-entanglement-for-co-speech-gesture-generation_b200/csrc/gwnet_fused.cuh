@@ -48,16 +48,37 @@ __global__ void fz_pack_weights_kernel(const HopkGwnetParams p, int L, uint8_t* 
     }
 }
 
+// bf16 slab image of the block-diagonal diffusion operator of one 128-row tile: BD[(g, w)][(g, v)] = A[v][w]
+// (x1 = BD . y applies A^T inside every complete (b, t) node group of the tile; gwnet.py:12-14 on the rows layout)
+constexpr uint32_t FZ_BD_BYTES = 2 * tc::slab_bytes(128);            // [128 rows][128 k]: 32 KB
+__global__ void fz_pack_bd_kernel(const float* __restrict__ A, int V, uint8_t* __restrict__ img)
+{
+    const int G = 128 / V;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 128 * 128; idx += gridDim.x * blockDim.x) {
+        int r = idx >> 7, k = idx & 127;
+        int gr = r / V, w = r - gr * V, gk = k / V, v = k - gk * V;
+        float val = (gr == gk && gr < G) ? A[v * V + w] : 0.f;
+        int slab = k >> 6, col = k & 63;
+        uint32_t off = slab * tc::slab_bytes(128) + tc::slab_chunk_off(r, col >> 3) + (col & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(val);
+    }
+}
+
 struct FzArgs {
     const float* up; const float* ss;                 // layer input (pre-BN of the previous layer or start conv) + folded scale/shift
     const uint8_t* pack;                              // this layer's packed weights
+    const uint8_t* bd;                                // block-diagonal diffusion operator (fz_pack_bd_kernel)
     const float* bf; const float* bg; const float* bm;
-    const float* A;                                   // adaptive adjacency (V x V)
     float* TF; float* SG; float* Y; float* X1; float* X2; float* U; float* ycat; double* stats;
     LayerGeom g; int layer, L, Tl, groups, gpt;       // groups = B*To, gpt = groups per tile
+    // BatchNorm finalize by the last CTA to finish (gwnet.py:120,237)
+    unsigned int* ticket; double count; const float* gamma; const float* beta; float* rmean; float* rvar; long long* nbt;
+    float* mr; float* ss_next; int training;
 };
 
-constexpr size_t fz_smem_bytes(int V) { return 73728 + (size_t)((V * V + 3) & ~3) * 4 + 1024; }   // 3 CTAs / SM
+constexpr uint32_t FZ_R1 = 3 * tc::slab_bytes(128);                  // gate weights, then the diffusion operator
+constexpr uint32_t FZ_R2 = FZ_R1 + FZ_WG_BYTES;                      // mlp weights
+constexpr size_t fz_smem_bytes() { return FZ_R2 + FZ_WM_BYTES + 1024; }   // 105 KB: two CTAs / SM
 
 __device__ __forceinline__ float tanh_fast(float x)
 {
@@ -65,39 +86,49 @@ __device__ __forceinline__ float tanh_fast(float x)
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// 8 bf16 channels of one slab row -> fp32
-__device__ __forceinline__ void slab_load8(const uint8_t* slab, int row, int ch, float (&f)[8])
+
+// one diffusion hop on the tensor core: D[128 x 64] = BD[128 x 128] . X[128 x 64], X = slab `src` read MN-major
+__device__ __forceinline__ void fz_issue_hop(uint32_t tmem_d, uint32_t bd_addr, uint32_t src_addr, uint64_t* bar)
 {
-    uint4 v = *reinterpret_cast<const uint4*>(slab + tc::slab_chunk_off(row, ch));
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    constexpr uint32_t idesc = tc::idesc_bf16(128, 64, 0, 1);
+    constexpr uint32_t SL128 = tc::slab_bytes(128);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { float2 t = __bfloat1622float2(h[q]); f[2 * q] = t.x; f[2 * q + 1] = t.y; }
+    for (int t = 0; t < 8; ++t)
+        tc::mma_bf16(tmem_d, tc::desc_kmajor(bd_addr + (t >> 2) * SL128, t & 3), tc::desc_mnmajor(src_addr, SL128, t), idesc, t != 0);
+    tc::mma_commit(bar);
 }
 
 __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t bars[4];                      // 0: gate weights, 1: mlp weights, 2: diffusion operator, 3: UMMA completion
     __shared__ uint32_t tmem_base_smem;
     __shared__ float red[256];
+    __shared__ unsigned int is_last;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int C = FZ_C;
     constexpr uint32_t SL128 = tc::slab_bytes(128), SL64 = tc::slab_bytes(64);
     uint8_t* A1 = smem;                       // phase 1: [x_t | x_{t+d}] 2 slabs        phase 2: [y | x1 | x2] 3 slabs
-    uint8_t* Wg = smem + 2 * SL128;           // phase 1: gate weights 2 slabs (32 KB)
-    uint8_t* A2 = smem;                       // 48 KB
-    uint8_t* Wm = smem + 3 * SL128;           // phase 2: mlp weights 3 x 8 KB (ends at 72 KB)
-    float* As = reinterpret_cast<float*>(smem + 73728);
+    uint8_t* A2 = smem;
+    uint8_t* Wg = smem + FZ_R1;               // phase 1: gate weights; phase 2: diffusion operator BD
+    uint8_t* Wm = smem + FZ_R2;               // mlp weights 3 x 8 KB
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = a.g.V;
     const int g0 = blockIdx.x * a.gpt;
     const int ng = min(a.gpt, a.groups - g0);
     const int r0 = g0 * V, nrows = ng * V;               // rows of this tile in the layer's output rows layout
 
-    if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_barrier_init(); }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&bars[0], FZ_WG_BYTES);
+        tc::bulk_g2s(Wg, a.pack, FZ_WG_BYTES, &bars[0]);
+        tc::mbar_expect_tx(&bars[1], FZ_WM_BYTES);
+        tc::bulk_g2s(Wm, a.pack + FZ_WG_BYTES, FZ_WM_BYTES, &bars[1]);
+    }
     red[tid] = 0.f;
     if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 256);
-    for (int i = tid; i < V * V; i += 256) As[i] = __ldg(a.A + i);
     // ---- 1. stage the gate operands
     {
         W8GateX ld{a.up, a.ss, a.g, 2 * C};
@@ -118,17 +149,16 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
             int ch = idx & 15, row = idx >> 4;
             tc::slab_store8(A1 + (ch >> 3) * SL128, row, ch & 7, f[it]);
         }
-        const uint4* src = reinterpret_cast<const uint4*>(a.pack);
-        uint4* dst = reinterpret_cast<uint4*>(Wg);
-        for (int i = tid; i < (int)(FZ_WG_BYTES / 16); i += 256) dst[i] = __ldg(src + i);
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem_g = tmem_base_smem, tmem_h = tmem_base_smem + 128;
+    const uint32_t tmem_g = tmem_base_smem, tmem_h = tmem_base_smem + 128, tmem_x = tmem_base_smem + 192;
+    uint32_t mma_phase = 0;
     // ---- 2. gate UMMA
     if (tid == 0) {
+        tc::mbar_wait(&bars[0], 0);                                   // gate weights landed
         constexpr uint32_t idesc = tc::idesc_bf16(128, 128, 0, 0);
         const uint32_t aa = tc::smem_u32(A1), wa = tc::smem_u32(Wg);
 #pragma unroll
@@ -136,10 +166,15 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
 #pragma unroll
             for (int t = 0; t < 4; ++t)
                 tc::mma_bf16(tmem_g, tc::desc_kmajor(aa + c * SL128, t), tc::desc_kmajor(wa + c * SL128, t), idesc, (c | t) != 0);
-        tc::mma_commit(&bars[0]);
+        tc::mma_commit(&bars[3]);
     }
-    tc::mbar_wait(&bars[0], 0);
+    tc::mbar_wait(&bars[3], mma_phase); mma_phase ^= 1;
     tc::fence_after_sync();
+    // the gate weights are dead: the diffusion operator takes their place while the gating epilogue runs
+    if (tid == 0) {
+        tc::mbar_expect_tx(&bars[2], FZ_BD_BYTES);
+        tc::bulk_g2s(Wg, a.bd, FZ_BD_BYTES, &bars[2]);
+    }
     // ---- 3. gating epilogue: two threads per row, each 32 channels (two [16 f | 16 g] column blocks)
     const int row = (warp & 3) * 32 + lane;
     const int half = warp >> 2;
@@ -152,12 +187,6 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
         tt = t - (a.g.To - a.Tl);
         if (tt >= 0) ycat_off = ((size_t)(b * a.Tl + tt) * V + vv) * ((size_t)a.L * C) + (size_t)a.layer * C;
     }
-    // mlp weights arrive while the gate epilogue runs (their smem region was the gate's B operand: UMMA 1 is complete)
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(a.pack + FZ_WG_BYTES);
-        uint4* dst = reinterpret_cast<uint4*>(Wm);
-        for (int i = tid; i < (int)(FZ_WM_BYTES / 16); i += 256) dst[i] = __ldg(src + i);
-    }
 #pragma unroll 1
     for (int blk = 0; blk < 2; ++blk) {
         const int c0 = (half * 2 + blk) * 16;                 // first channel of this 32-column block
@@ -165,11 +194,17 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
         tc::tmem_ld32(tmem_g + lane_off + (half * 2 + blk) * 32, v);
         float y[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float tf = tanh_fast(v[j] + __ldg(a.bf + c0 + j));                       // MUFU.TANH (2^-11 rel. error << bf16)
-            float sg = fmaf(0.5f, tanh_fast(0.5f * (v[16 + j] + __ldg(a.bg + c0 + j))), 0.5f);   // sigmoid(x) = (1 + tanh(x/2)) / 2
-            y[j] = rvalid ? tf * sg : 0.f;
-            v[j] = tf; v[16 + j] = sg;
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bf + c0 + j4)), b2 = __ldg(reinterpret_cast<const float4*>(a.bg + c0 + j4));
+            const float bfv[4] = {b1.x, b1.y, b1.z, b1.w}, bgv[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j4 + q;
+                float tf = tanh_fast(v[j] + bfv[q]);                                    // MUFU.TANH (2^-11 rel. error << bf16)
+                float sg = fmaf(0.5f, tanh_fast(0.5f * (v[16 + j] + bgv[q])), 0.5f);    // sigmoid(x) = (1 + tanh(x/2)) / 2
+                y[j] = rvalid ? tf * sg : 0.f;
+                v[j] = tf; v[16 + j] = sg;
+            }
         }
         if (rvalid) {
             size_t o = (size_t)m * C + c0;
@@ -189,35 +224,33 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
             tc::slab_store8(A2, row, (c0 >> 3) + q8, f);
         }
     }
-    __syncthreads();
-    // ---- 4. diffusion in shared memory on the bf16 slabs (fp32 accumulate): items = (row, 8 channels)
+    // ---- 4. diffusion on the tensor core: x1 = BD . y, x2 = BD . x1 (bf16 operands, fp32 accumulate, like the mlp)
 #pragma unroll 1
     for (int hop = 0; hop < 2; ++hop) {
-        const uint8_t* src = A2 + hop * SL128;                // hop 0 reads y (slab 0), hop 1 reads x1 (slab 1)
-        float* gout = hop == 0 ? a.X1 : a.X2;
-#pragma unroll 1
-        for (int it = 0; it < (128 * 8) / 256; ++it) {
-            int idx = tid + it * 256;
-            int c8 = idx & 7, rr = idx >> 3;                  // rr = (group, w)
-            float acc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-            if (rr < nrows) {
-                int gidx = rr / V, w = rr - gidx * V;
-                for (int v = 0; v < V; ++v) {
-                    float av = As[v * V + w];
-                    float x[8];
-                    slab_load8(src, gidx * V + v, c8, x);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(av, x[j], acc[j]);
-                }
-                float* go = gout + (size_t)(r0 + rr) * C + c8 * 8;
-                *reinterpret_cast<float4*>(go) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                *reinterpret_cast<float4*>(go + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            }
-            tc::slab_store8(A2 + (1 + hop) * SL128, rr, c8, acc);
-        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
         __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            if (hop == 0) tc::mbar_wait(&bars[2], 0);                 // diffusion operator landed
+            fz_issue_hop(tmem_x, tc::smem_u32(Wg), tc::smem_u32(A2 + hop * SL128), &bars[3]);
+        }
+        tc::mbar_wait(&bars[3], mma_phase); mma_phase ^= 1;
+        tc::fence_after_sync();
+        float v[32];
+        tc::tmem_ld32(tmem_x + lane_off + half * 32, v);
+        if (rvalid) {
+            float* go = (hop == 0 ? a.X1 : a.X2) + (size_t)m * C + half * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(go + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = v[q8 * 8 + j];
+            tc::slab_store8(A2 + (1 + hop) * SL128, row, half * 4 + q8, f);
+        }
     }
     // ---- 5. mlp UMMA: [y | x1 | x2] (K = 192) x Wm^T (N = 64)
     tc::fence_async_smem();
@@ -225,6 +258,7 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
     __syncthreads();
     if (tid == 0) {
         tc::fence_after_sync();
+        tc::mbar_wait(&bars[1], 0);                                   // mlp weights landed (long ago)
         constexpr uint32_t idesc = tc::idesc_bf16(128, 64, 0, 0);
         const uint32_t aa = tc::smem_u32(A2), wa = tc::smem_u32(Wm);
 #pragma unroll
@@ -232,19 +266,20 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
 #pragma unroll
             for (int t = 0; t < 4; ++t)
                 tc::mma_bf16(tmem_h, tc::desc_kmajor(aa + s * SL128, t), tc::desc_kmajor(wa + s * SL64, t), idesc, (s | t) != 0);
-        tc::mma_commit(&bars[1]);
+        tc::mma_commit(&bars[3]);
     }
-    tc::mbar_wait(&bars[1], 0);
+    // residual operands travel while the UMMA runs
+    const long rr = rvalid ? a.g.in_row(m) + (long)a.g.d * V : 0;
+    float4 xr[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        xr[q] = rvalid ? __ldg(reinterpret_cast<const float4*>(a.up + rr * C + half * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    tc::mbar_wait(&bars[3], mma_phase); mma_phase ^= 1;
     tc::fence_after_sync();
     // ---- 6. bias + residual + statistics: thread = (row, 32 output channels)
     {
         float v[32], sq[32];
         tc::tmem_ld32(tmem_h + lane_off + half * 32, v);
-        const long rr = rvalid ? a.g.in_row(m) + (long)a.g.d * V : 0;
-        float4 xr[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            xr[q] = rvalid ? __ldg(reinterpret_cast<const float4*>(a.up + rr * C + half * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int n = half * 32 + 4 * q;
@@ -268,11 +303,39 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (tid < C && a.stats) {
+    if (tid < C) {
         atomicAdd(a.stats + tid, (double)red[tid]);
         atomicAdd(a.stats + C + tid, (double)red[128 + tid]);
     }
     if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);
+    // ---- 7. the last CTA to arrive turns the statistics into mean / rstd / folded scale+shift / running stats
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (is_last && tid < C) {
+        __threadfence();
+        const int c = tid;
+        float mean, rstd;
+        if (a.training) {
+            const double s1 = __ldcg(a.stats + c), s2 = __ldcg(a.stats + C + c);
+            double mu = s1 / a.count;
+            double var = s2 / a.count - mu * mu;
+            if (var < 0) var = 0;
+            mean = (float)mu;
+            rstd = (float)(1.0 / sqrt(var + 1e-5));
+            double unb = a.count > 1 ? var * a.count / (a.count - 1) : var;
+            a.rmean[c] = 0.9f * a.rmean[c] + 0.1f * mean;
+            a.rvar[c] = 0.9f * a.rvar[c] + 0.1f * (float)unb;
+            if (c == 0 && a.nbt) *a.nbt += 1;
+        } else {
+            mean = a.rmean[c];
+            rstd = 1.f / sqrtf(a.rvar[c] + 1e-5f);
+        }
+        a.mr[c] = mean; a.mr[C + c] = rstd;
+        float sc = a.gamma[c] * rstd;
+        a.ss_next[c] = sc; a.ss_next[C + c] = a.beta[c] - mean * sc;
+    }
 }
 
 }  // namespace hopk
