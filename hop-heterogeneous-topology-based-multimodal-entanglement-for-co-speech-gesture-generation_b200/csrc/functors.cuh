@@ -133,9 +133,17 @@ struct EpiStore {
                     x.x = aa[q].x > 0.f ? x.x : 0.f; x.y = aa[q].y > 0.f ? x.y : 0.f;
                     x.z = aa[q].z > 0.f ? x.z : 0.f; x.w = aa[q].w > 0.f ? x.w : 0.f;
                 }
-                float* o = out + base + 4 * q;
-                if (flags & 2) { atomicAdd(o, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w); }
-                else *reinterpret_cast<float4*>(o) = x;
+                if (flags & 2) { float* o = out + base + 4 * q; atomicAdd(o, x.x); atomicAdd(o + 1, x.y); atomicAdd(o + 2, x.z); atomicAdd(o + 3, x.w); }
+                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+            }
+            if (!(flags & 2)) {
+                if ((reinterpret_cast<uintptr_t>(out + base) & 31) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) tc::stg256(out + base + j, v + j);      // full 32-byte sectors
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + base + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
             }
             return;
         }

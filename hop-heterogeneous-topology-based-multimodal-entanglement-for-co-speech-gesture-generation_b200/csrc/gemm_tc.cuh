@@ -171,7 +171,6 @@ gemm_tc_kernel(int M, int N, int K, int k_per_split, ALoad aload, BLoad bload, E
         tc_store_slab<TC_BM, ALoad>(sa, ra);
         if constexpr (B_MN) tc_store_slab_mn<BN>(sb, rb);
         else tc_store_slab<BN, BLoad>(sb, rb);
-        if (ks + 1 < nslabs) load_regs(ks + 1);                          // in flight across the barrier and the UMMAs
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
@@ -183,6 +182,8 @@ gemm_tc_kernel(int M, int N, int K, int k_per_split, ALoad aload, BLoad bload, E
                              B_MN ? tc::desc_mnmajor(b_addr, tc::slab_bytes(TC_BK), j) : tc::desc_kmajor(b_addr, j), idesc, (ks | j) != 0);
             tc::mma_commit(&bars[buf]);
         }
+        // next slab's global loads fly under the UMMAs (issued after the proxy fence: MEMBAR would wait for them)
+        if (ks + 1 < nslabs) load_regs(ks + 1);
     }
     if (nslabs > 0) {
         const int last = nslabs - 1;

@@ -95,7 +95,6 @@ gemm_tc_wgrad_kernel(int R, int Mo, int No, int r_per_split, ALoad aload, BLoad 
             int ch = idx % (BN / 8), row = idx / (BN / 8);
             tc::slab_store8(sb + (ch >> 3) * WG_SLAB, row, ch & 7, fb[it]);
         }
-        if (ks + 1 < nslabs) load_regs(ks + 1);
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
@@ -106,6 +105,8 @@ gemm_tc_wgrad_kernel(int R, int Mo, int No, int r_per_split, ALoad aload, BLoad 
                 tc::mma_bf16(tmem, tc::desc_mnmajor(a_addr, WG_SLAB, t), tc::desc_mnmajor(b_addr, WG_SLAB, t), idesc, (ks | t) != 0);
             tc::mma_commit(&bars[buf]);
         }
+        // next slab's global loads fly under the UMMAs (issued after the proxy fence: MEMBAR would wait for them)
+        if (ks + 1 < nslabs) load_regs(ks + 1);
     }
     if (nslabs > 0) {
         const int last = nslabs - 1;

@@ -16,6 +16,7 @@
 //             gate derivative, gate weight-grad GEMM (+bias columns), dx GEMM (4C contraction over taps x {f,g})
 //             fused with the residual gradient and the BatchNorm-backward sums of the previous layer.
 //   dA = M1 + A^T M2 + M2 A^T is finished once, then pushed through softmax(relu(E1 E2)).
+#include <stdlib.h>
 #include "functors.cuh"
 #include "common.cuh"
 #include "../../include/hopk.h"
@@ -36,7 +37,7 @@ struct GwLayout {
     // du / G / df / dg are kept per layer so that the weight-gradient and dA kernels can run on side streams while the
     // main stream walks down the layers
     size_t s_du[HOPK_MAX_LAYERS], s_g[HOPK_MAX_LAYERS], s_df[HOPK_MAX_LAYERS], s_dg[HOPK_MAX_LAYERS];
-    size_t s_p1, s_p2, s_dxa, s_dxb, s_dorow, s_de1, s_dskip, s_dycat, s_bnsum, s_m12, s_dA, s_total;
+    size_t s_p1[HOPK_MAX_LAYERS], s_p2[HOPK_MAX_LAYERS], s_dxa, s_dxb, s_dorow, s_de1, s_dskip, s_dycat, s_bnsum, s_m12, s_dA, s_total;
 };
 
 static int receptive_field(const HopkGwnetShape* s)
@@ -87,9 +88,9 @@ static GwLayout make_layout(const HopkGwnetShape* s)
 
     cur = 0;
     size_t nmax = BV * g.Tlen[0] * s->C * f;
-    g.s_p1 = bump(cur, nmax); g.s_p2 = bump(cur, nmax);
     for (int i = 0; i < s->L; ++i) {
         size_t n = BV * g.Tlen[i + 1] * s->C * f;
+        g.s_p1[i] = bump(cur, n); g.s_p2[i] = bump(cur, n);
         g.s_du[i] = bump(cur, n); g.s_g[i] = bump(cur, 2 * n); g.s_df[i] = bump(cur, n); g.s_dg[i] = bump(cur, n);
     }
     g.s_dxa = bump(cur, nmax); g.s_dxb = bump(cur, nmax);
@@ -246,8 +247,8 @@ __global__ void node_mix_kernel(const float* __restrict__ in, const float* __res
 // registers across the whole loop, are combined in shared memory and leave the CTA as one atomic per matrix entry.
 constexpr int GRAM_GPI = 4;                  // node groups staged per iteration
 constexpr int GRAM_MAXP = 8;                 // pairs per thread: V*V <= 8*256  (V <= 45)
-__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ Y, const float* __restrict__ G, float* __restrict__ M12,
-                                                   int groups, int V, int C)
+__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ TF, const float* __restrict__ SG, const float* __restrict__ G,
+                                                   float* __restrict__ M12, int groups, int V, int C)
 {
     extern __shared__ float sm[];
     const int VV = V * V;
@@ -266,10 +267,12 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ Y, 
     for (int g0 = blockIdx.x * GRAM_GPI; g0 < groups; g0 += gridDim.x * GRAM_GPI) {
         const int ng = min(GRAM_GPI, groups - g0);
         __syncthreads();
-        const float4* yp = reinterpret_cast<const float4*>(Y + (size_t)g0 * V * C);
+        const float4* yp = reinterpret_cast<const float4*>(TF + (size_t)g0 * V * C);      // y = tanh(f) * sigmoid(g), recomputed
+        const float4* zp = reinterpret_cast<const float4*>(SG + (size_t)g0 * V * C);
         const float4* gp = reinterpret_cast<const float4*>(G + (size_t)g0 * V * 2 * C);
         for (int i = threadIdx.x; i < ng * V * C / 4; i += blockDim.x) {
-            float4 x = __ldg(yp + i);
+            float4 x = __ldg(yp + i); const float4 z = __ldg(zp + i);
+            x.x *= z.x; x.y *= z.y; x.z *= z.z; x.w *= z.w;
             int e = i * 4; int r = e / C, c = e - r * C;
             float* d = sy + r * ldy + c; d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
         }
@@ -635,10 +638,16 @@ struct SkipEpi {             // relu(sum + sum_l bias_l)
                     v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
                 }
             }
-            float4* o = reinterpret_cast<float4*>(out + (size_t)m * N + n0);
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                o[q] = make_float4(fmaxf(v[4 * q], 0.f), fmaxf(v[4 * q + 1], 0.f), fmaxf(v[4 * q + 2], 0.f), fmaxf(v[4 * q + 3], 0.f));
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            float* o = out + (size_t)m * N + n0;
+            if ((N & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) tc::stg256(o + j, v + j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
             return;
         }
 #pragma unroll
@@ -725,7 +734,7 @@ struct DyEpi {               // dy (+ skip-path gradient) -> df, dg   (Appendix 
         int vv = m % g.V; int bt = m / g.V; int t = bt % g.To; int b = bt / g.To;
         int tt = t - (g.To - Tl);
         const float* dyc = tt >= 0 ? dycat + ((size_t)(b * Tl + tt) * g.V + vv) * ((size_t)L * g.C) + (size_t)layer * g.C : nullptr;
-        if (n0 + 32 <= g.C && (g.C & 3) == 0) {              // 128-bit path, loads batched ahead of the stores
+        if (n0 + 32 <= g.C && (g.C & 7) == 0) {              // 128-bit path, loads batched ahead of the stores
             const size_t o = (size_t)m * g.C + n0;
             float4 tf[8], sg[8], dc[8];
 #pragma unroll
@@ -742,8 +751,14 @@ struct DyEpi {               // dy (+ skip-path gradient) -> df, dg   (Appendix 
                 df.y = dy.y * sg[q].y * (1.f - tf[q].y * tf[q].y); dg.y = dy.y * tf[q].y * sg[q].y * (1.f - sg[q].y);
                 df.z = dy.z * sg[q].z * (1.f - tf[q].z * tf[q].z); dg.z = dy.z * tf[q].z * sg[q].z * (1.f - sg[q].z);
                 df.w = dy.w * sg[q].w * (1.f - tf[q].w * tf[q].w); dg.w = dy.w * tf[q].w * sg[q].w * (1.f - sg[q].w);
-                reinterpret_cast<float4*>(DF + o)[q] = df;
-                reinterpret_cast<float4*>(DG + o)[q] = dg;
+                v[4 * q] = df.x; v[4 * q + 1] = df.y; v[4 * q + 2] = df.z; v[4 * q + 3] = df.w;
+                reinterpret_cast<float*>(&tf[q])[0] = dg.x; reinterpret_cast<float*>(&tf[q])[1] = dg.y;
+                reinterpret_cast<float*>(&tf[q])[2] = dg.z; reinterpret_cast<float*>(&tf[q])[3] = dg.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {                    // full 32-byte sectors
+                tc::stg256(DF + o + j, v + j);
+                tc::stg256(DG + o + j, tf[j / 4].x, tf[j / 4].y, tf[j / 4].z, tf[j / 4].w, tf[j / 4 + 1].x, tf[j / 4 + 1].y, tf[j / 4 + 1].z, tf[j / 4 + 1].w);
             }
             return;
         }
@@ -842,6 +857,40 @@ struct W8GateX {             // columns j = tap*C + c : BN_{i-1}-folded layer in
         f[4] = fmaf(b.x, s1.x, h1.x); f[5] = fmaf(b.y, s1.y, h1.y); f[6] = fmaf(b.z, s1.z, h1.z); f[7] = fmaf(b.w, s1.w, h1.w);
     }
 };
+struct W8Prod {              // y = tanh(f) * sigmoid(g) recomputed from the two saved factors (C % 8 == 0)
+    const float* p; const float* q; int C; int ncols;
+    __device__ __forceinline__ void ld8(int r, int c0, float (&f)[8]) const {
+        if (c0 >= ncols) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = 0.f;
+            return;
+        }
+        float g[8];
+        tc::ldg256(p + (size_t)r * C + c0, f);
+        tc::ldg256(q + (size_t)r * C + c0, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] *= g[k];
+    }
+};
+struct MlpWgEpi2 {           // out[i = seg*C + o][j = c] = sum_r [du|p1|p2][r][i] y[r][c]  ->  dWm[o][seg*C + c]; bias = column sums of du
+    float* dw; float* db; int C;
+    __device__ __forceinline__ void row32(int i, bool valid, int j0, float (&v)[32], float*) {
+        if (!valid) return;
+        const int seg = i / C, o = i - seg * C;
+        float* row = dw + (size_t)o * 3 * C + seg * C + j0;
+        if (j0 + 32 <= C && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                atomicAdd(reinterpret_cast<float4*>(row) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            return;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+            if (j0 + jj < C) atomicAdd(row + jj, v[jj]);
+    }
+    __device__ __forceinline__ void finish(float*) {}
+    __device__ __forceinline__ void bias(int i, float v) { if (i < C && db) atomicAdd(db + i, v); }
+};
 struct W8GateXI {            // columns j = 2c + tap (the weight's own [c][tap] order): BN-folded layer input at (b, t + tap*d, v)
     const float* up; const float* ss; LayerGeom g; int ncols;
     __device__ __forceinline__ void ld8(int r, int c0, float (&f)[8]) const {
@@ -929,7 +978,7 @@ struct DxEpi {               // + residual gradient du[t-d]; BatchNorm-backward 
         int vv = 0, t = 0, b = 0;
         if (valid) { vv = m % g.V; int bt = m / g.V; t = bt % g.Ti; b = bt / g.Ti; }
         const float* du = (valid && DU && t >= g.d) ? DU + ((size_t)(b * g.To + t - g.d) * g.V + vv) * g.C : nullptr;
-        if (n0 + 32 <= g.C && (g.C & 3) == 0) {              // 128-bit path
+        if (n0 + 32 <= g.C && (g.C & 7) == 0) {              // 128-bit path
             float4 dd[8], uu[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -946,11 +995,14 @@ struct DxEpi {               // + residual gradient du[t-d]; BatchNorm-backward 
                 float4 dx = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {
                     dx = make_float4(v[4 * q] + dd[q].x, v[4 * q + 1] + dd[q].y, v[4 * q + 2] + dd[q].z, v[4 * q + 3] + dd[q].w);
-                    reinterpret_cast<float4*>(DX + (size_t)m * g.C + n0)[q] = dx;
                 }
                 v[4 * q] = dx.x; v[4 * q + 1] = dx.y; v[4 * q + 2] = dx.z; v[4 * q + 3] = dx.w;
                 w[4 * q] = dx.x * (uu[q].x - mu.x) * rs.x; w[4 * q + 1] = dx.y * (uu[q].y - mu.y) * rs.y;
                 w[4 * q + 2] = dx.z * (uu[q].z - mu.z) * rs.z; w[4 * q + 3] = dx.w * (uu[q].w - mu.w) * rs.w;
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) tc::stg256(DX + (size_t)m * g.C + n0 + j, v + j);      // full 32-byte sectors
             }
         } else {
 #pragma unroll
@@ -1176,12 +1228,14 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
             FzArgs fa;
             fa.up = uprev; fa.ss = ss; fa.pack = pack + (size_t)i * FZ_PACK_BYTES; fa.bd = bd;
             fa.bf = p->filter_b[i]; fa.bg = p->gate_b[i]; fa.bm = p->mlp_b[i];
-            fa.TF = F(g.tf[i]); fa.SG = F(g.sg[i]); fa.Y = F(g.y[i]); fa.X1 = F(g.x1[i]); fa.X2 = F(g.x2[i]); fa.U = F(g.u[i]);
+            fa.TF = F(g.tf[i]); fa.SG = F(g.sg[i]); fa.U = F(g.u[i]);
+            fa.Y = nullptr; fa.X1 = nullptr; fa.X2 = nullptr;        // backward recomputes y = tf * sg and never needs x1, x2
             fa.ycat = F(g.ycat); fa.stats = stats + (size_t)i * 2 * C;
             fa.g = lg; fa.layer = i; fa.L = L; fa.Tl = g.Tl; fa.groups = B * lg.To; fa.gpt = 128 / V;
             fa.ticket = tickets + i; fa.count = (double)M; fa.gamma = p->bn_w[i]; fa.beta = p->bn_b[i];
             fa.rmean = p->bn_mean[i]; fa.rvar = p->bn_var[i]; fa.nbt = (long long*)p->bn_nbt[i];
             fa.mr = F(g.mr) + (size_t)i * 2 * C; fa.ss_next = F(g.ss) + (size_t)(i + 1) * 2 * C; fa.training = s->training;
+            { static const char* e = getenv("HOPK_FZ_STOP"); fa.stop = e ? atoi(e) : 0; }
             fz_layer_fwd_kernel<<<cdiv(fa.groups, fa.gpt), 256, fz_smem_bytes(), st>>>(fa);
             HOPK_LAUNCH_CHECK("fz_layer_fwd");
             uprev = F(g.u[i]);
@@ -1336,17 +1390,21 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
                                                      bnsum + (size_t)i * 2 * C, (double)M, DU, gr->bn_w[i], gr->bn_b[i],
                                                      (size_t)M, C, s->training);
             HOPK_LAUNCH_CHECK("bn_bwd");
-            HOPK_CUDA(cudaEventRecord(sd->ev_du[i], st));
             int groups = B * lg.To;
+            // P1 = A du, P2 = A^2 du  (node mix with the transposed supports)
+            if (int rc = launch_node_mix(DU, F(g.At), F(g.A2t), S(g.s_p1[i]), S(g.s_p2[i]), groups, V, C, st)) return rc;
+            HOPK_CUDA(cudaEventRecord(sd->ev_du[i], st));
             // side stream 0: mlp weight + bias gradient
             {
                 cudaStream_t s0 = sd->s[0];
                 HOPK_CUDA(cudaStreamWaitEvent(s0, sd->ev_du[i], 0));
-                if (tc && C % 8 == 0) {      // MN-major tensor-core weight gradient: dWm[o][k] = sum_r du[r][o] [y|x1|x2][r][k]
-                    W8Plain a{DU, nullptr, C, C, 0};
-                    W8Seg3 b{F(g.y[i]), F(g.x1[i]), F(g.x2[i]), C, 3 * C};
-                    EpiWgrad<2> e{gr->mlp_w[i], (long)3 * C, gr->mlp_b[i], 3 * C, C};
-                    HOPK_CUDA(launch_gemm_tc_wgrad<128>(M, C, 3 * C, a, b, e, true, s0));
+                if (tc && C % 8 == 0) {
+                    // dWm[o][seg*C + c] = sum_r du[r][o] x_seg[r][c] with x1 = A^T y, x2 = (A^2)^T y inside every node group
+                    //                   = sum_r [du | A du | A^2 du][r][seg*C + o] y[r][c]:  the forward never stores y, x1, x2
+                    W8Seg3 a{DU, S(g.s_p1[i]), S(g.s_p2[i]), C, 3 * C};
+                    W8Prod b{F(g.tf[i]), F(g.sg[i]), C, C};
+                    MlpWgEpi2 e{gr->mlp_w[i], gr->mlp_b[i], C};
+                    HOPK_CUDA(launch_gemm_tc_wgrad<64>(M, 3 * C, C, a, b, e, true, s0));
                     HOPK_LAUNCH_CHECK("mlp_wgrad_tc");
                 } else {
                     Ld2D<false, 0> a{DU, nullptr, C};
@@ -1369,15 +1427,13 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
                 size_t smem3 = ((size_t)GRAM_GPI * V * (3 * C + 2) + 2 * (size_t)V * V) * sizeof(float);
                 if (smem3 > 48 * 1024) HOPK_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
                 int gblocks = cdiv(groups, GRAM_GPI); if (gblocks > 148) gblocks = 148;
-                gram_kernel<<<gblocks, 256, smem3, s1>>>(F(g.y[i]), S(g.s_g[i]), S(g.s_m12), groups, V, C);
+                gram_kernel<<<gblocks, 256, smem3, s1>>>(F(g.tf[i]), F(g.sg[i]), S(g.s_g[i]), S(g.s_m12), groups, V, C);
                 HOPK_LAUNCH_CHECK("gram");
             }
-            // P1 = A du, P2 = A^2 du  (node mix with the transposed supports)
-            if (int rc = launch_node_mix(DU, F(g.At), F(g.A2t), S(g.s_p1), S(g.s_p2), groups, V, C, st)) return rc;
         }
         // dy (+ skip path) -> df, dg
         {
-            Seg3A a{DU, S(g.s_p1), S(g.s_p2), C};
+            Seg3A a{DU, S(g.s_p1[i]), S(g.s_p2[i]), C};
             DyB b{p->mlp_w[i], C};
             int K = has_du ? 3 * C : 0;
             if (C <= 64) {

@@ -74,6 +74,7 @@ struct FzArgs {
     // BatchNorm finalize by the last CTA to finish (gwnet.py:120,237)
     unsigned int* ticket; double count; const float* gamma; const float* beta; float* rmean; float* rvar; long long* nbt;
     float* mr; float* ss_next; int training;
+    int stop;                                         // timing experiments only (HOPK_FZ_STOP): leave the kernel after stage `stop`
 };
 
 constexpr uint32_t FZ_R1 = 3 * tc::slab_bytes(128);                  // gate weights, then the diffusion operator
@@ -98,12 +99,23 @@ __device__ __forceinline__ void fz_issue_hop(uint32_t tmem_d, uint32_t bd_addr, 
     tc::mma_commit(bar);
 }
 
+#define FZ_STOP_AT(k)                                                                               \
+    if (a.stop == (k)) {                                                                            \
+        if (tid == 0) { tc::mbar_wait(&bars[0], 0); tc::mbar_wait(&bars[1], 0); if ((k) >= 3) tc::mbar_wait(&bars[2], 0); } \
+        tc::fence_before_sync();                                                                    \
+        __syncthreads();                                                                            \
+        if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);                                       \
+        return;                                                                                     \
+    }
+
 __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
 {
+    if (a.stop == -1) return;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[4];                      // 0: gate weights, 1: mlp weights, 2: diffusion operator, 3: UMMA completion
     __shared__ uint32_t tmem_base_smem;
     __shared__ float red[256];
+    __shared__ __align__(16) float cst[5 * FZ_C];     // filter bias | gate bias | mlp bias | BN scale | BN shift
     __shared__ unsigned int is_last;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int C = FZ_C;
@@ -128,6 +140,10 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
         tc::bulk_g2s(Wm, a.pack + FZ_WG_BYTES, FZ_WM_BYTES, &bars[1]);
     }
     red[tid] = 0.f;
+    if (tid < FZ_C) {
+        cst[tid] = __ldg(a.bf + tid); cst[FZ_C + tid] = __ldg(a.bg + tid); cst[2 * FZ_C + tid] = __ldg(a.bm + tid);
+        cst[3 * FZ_C + tid] = __ldg(a.ss + tid); cst[4 * FZ_C + tid] = __ldg(a.ss + FZ_C + tid);
+    }
     if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 256);
     // ---- 1. stage the gate operands
     {
@@ -156,6 +172,7 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
     tc::fence_after_sync();
     const uint32_t tmem_g = tmem_base_smem, tmem_h = tmem_base_smem + 128, tmem_x = tmem_base_smem + 192;
     uint32_t mma_phase = 0;
+    FZ_STOP_AT(1)
     // ---- 2. gate UMMA
     if (tid == 0) {
         tc::mbar_wait(&bars[0], 0);                                   // gate weights landed
@@ -175,9 +192,13 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
         tc::mbar_expect_tx(&bars[2], FZ_BD_BYTES);
         tc::bulk_g2s(Wg, a.bd, FZ_BD_BYTES, &bars[2]);
     }
-    // ---- 3. gating epilogue: two threads per row, each 32 channels (two [16 f | 16 g] column blocks)
+    FZ_STOP_AT(3)
+    // ---- 3..6: warp roles.  Warps 0-3 ("feeders") turn TMEM results into the next bf16 operand slabs and execute the
+    // proxy fences; warps 4-7 ("writers") read the same TMEM lanes and own every global store plus the statistics.
+    // The split matters because fence.proxy.async is MEMBAR.ALL.CTA in SASS: a thread that fences with global stores
+    // in flight waits for all of them, which serialised every stage on a store round trip.
     const int row = (warp & 3) * 32 + lane;
-    const int half = warp >> 2;
+    const bool writer = warp >= 4;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const bool rvalid = row < nrows;
     const int m = r0 + row;                                   // global output row
@@ -187,15 +208,24 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
         tt = t - (a.g.To - a.Tl);
         if (tt >= 0) ycat_off = ((size_t)(b * a.Tl + tt) * V + vv) * ((size_t)a.L * C) + (size_t)a.layer * C;
     }
+    // residual operand of the last stage: requested now, consumed at the very end (writers only)
+    float4 xr[16];
+    if (writer) {
+        const long rr = rvalid ? a.g.in_row(m) + (long)a.g.d * V : 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            xr[q] = rvalid ? __ldg(reinterpret_cast<const float4*>(a.up + rr * C) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // ---- gating: 4 column blocks of [16 filter | 16 gate] pre-activations per row
 #pragma unroll 1
-    for (int blk = 0; blk < 2; ++blk) {
-        const int c0 = (half * 2 + blk) * 16;                 // first channel of this 32-column block
+    for (int blk = 0; blk < 4; ++blk) {
+        const int c0 = blk * 16;
         float v[32];
-        tc::tmem_ld32(tmem_g + lane_off + (half * 2 + blk) * 32, v);
+        tc::tmem_ld32(tmem_g + lane_off + blk * 32, v);
         float y[16];
 #pragma unroll
         for (int j4 = 0; j4 < 16; j4 += 4) {
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bf + c0 + j4)), b2 = __ldg(reinterpret_cast<const float4*>(a.bg + c0 + j4));
+            const float4 b1 = *reinterpret_cast<const float4*>(cst + c0 + j4), b2 = *reinterpret_cast<const float4*>(cst + FZ_C + c0 + j4);
             const float bfv[4] = {b1.x, b1.y, b1.z, b1.w}, bgv[4] = {b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -206,28 +236,31 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
                 v[j] = tf; v[16 + j] = sg;
             }
         }
-        if (rvalid) {
-            size_t o = (size_t)m * C + c0;
+        if (a.stop == 31) continue;                           // timing experiment: TMEM reads + math only
+        if (!writer) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                *reinterpret_cast<float4*>(a.TF + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                *reinterpret_cast<float4*>(a.SG + o + j) = make_float4(v[16 + j], v[17 + j], v[18 + j], v[19 + j]);
-                *reinterpret_cast<float4*>(a.Y + o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-                if (tt >= 0) *reinterpret_cast<float4*>(a.ycat + ycat_off + c0 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            for (int q8 = 0; q8 < 2; ++q8) {                  // y as bf16 into slab 0 of the mlp A operand
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = y[q8 * 8 + j];
+                tc::slab_store8(A2, row, (c0 >> 3) + q8, f);
+            }
+        } else if (rvalid && a.stop != 32) {
+            const size_t o = (size_t)m * C + c0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {                 // full 32-byte sectors per store
+                tc::stg256(a.TF + o + j, v + j);
+                tc::stg256(a.SG + o + j, v + 16 + j);
+                if (a.Y) tc::stg256(a.Y + o + j, y + j);
+                if (tt >= 0) tc::stg256(a.ycat + ycat_off + c0 + j, y + j);
             }
         }
-#pragma unroll
-        for (int q8 = 0; q8 < 2; ++q8) {                      // y as bf16 into slab 0 of the mlp A operand
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = y[q8 * 8 + j];
-            tc::slab_store8(A2, row, (c0 >> 3) + q8, f);
-        }
     }
+    FZ_STOP_AT(4) FZ_STOP_AT(31) FZ_STOP_AT(32)
     // ---- 4. diffusion on the tensor core: x1 = BD . y, x2 = BD . x1 (bf16 operands, fp32 accumulate, like the mlp)
 #pragma unroll 1
     for (int hop = 0; hop < 2; ++hop) {
-        tc::fence_async_smem();
+        if (!writer) tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
         if (tid == 0) {
@@ -237,23 +270,28 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
         }
         tc::mbar_wait(&bars[3], mma_phase); mma_phase ^= 1;
         tc::fence_after_sync();
-        float v[32];
-        tc::tmem_ld32(tmem_x + lane_off + half * 32, v);
-        if (rvalid) {
-            float* go = (hop == 0 ? a.X1 : a.X2) + (size_t)m * C + half * 32;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tc::tmem_ld32(tmem_x + lane_off + c * 32, v);
+            if (!writer) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(go + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
+                for (int q8 = 0; q8 < 4; ++q8) {
+                    float f[8];
 #pragma unroll
-        for (int q8 = 0; q8 < 4; ++q8) {
-            float f[8];
+                    for (int j = 0; j < 8; ++j) f[j] = v[q8 * 8 + j];
+                    tc::slab_store8(A2 + (1 + hop) * SL128, row, c * 4 + q8, f);
+                }
+            } else if (rvalid && a.X1) {
+                float* go = (hop == 0 ? a.X1 : a.X2) + (size_t)m * C + c * 32;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = v[q8 * 8 + j];
-            tc::slab_store8(A2 + (1 + hop) * SL128, row, half * 4 + q8, f);
+                for (int j = 0; j < 32; j += 8) tc::stg256(go + j, v + j);
+            }
         }
     }
+    FZ_STOP_AT(5)
     // ---- 5. mlp UMMA: [y | x1 | x2] (K = 192) x Wm^T (N = 64)
-    tc::fence_async_smem();
+    if (!writer) tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     if (tid == 0) {
@@ -268,51 +306,52 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
                 tc::mma_bf16(tmem_h, tc::desc_kmajor(aa + s * SL128, t), tc::desc_kmajor(wa + s * SL64, t), idesc, (s | t) != 0);
         tc::mma_commit(&bars[3]);
     }
-    // residual operands travel while the UMMA runs
-    const long rr = rvalid ? a.g.in_row(m) + (long)a.g.d * V : 0;
-    float4 xr[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-        xr[q] = rvalid ? __ldg(reinterpret_cast<const float4*>(a.up + rr * C + half * 32) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     tc::mbar_wait(&bars[3], mma_phase); mma_phase ^= 1;
     tc::fence_after_sync();
-    // ---- 6. bias + residual + statistics: thread = (row, 32 output channels)
-    {
-        float v[32], sq[32];
-        tc::tmem_ld32(tmem_h + lane_off + half * 32, v);
+    FZ_STOP_AT(6)
+    // ---- 6. bias + residual + statistics (writers): thread = one row, two blocks of 32 output channels
+    if (writer) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            float uv[32], w[32];
+            tc::tmem_ld32(tmem_h + lane_off + c * 32, uv);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int n = half * 32 + 4 * q;
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(a.ss + n)), sh = __ldg(reinterpret_cast<const float4*>(a.ss + C + n));
-            const float4 bm = __ldg(reinterpret_cast<const float4*>(a.bm + n));
-            float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
-            if (rvalid) {
-                u0 = v[4 * q] + bm.x + fmaf(xr[q].x, sc.x, sh.x); u1 = v[4 * q + 1] + bm.y + fmaf(xr[q].y, sc.y, sh.y);
-                u2 = v[4 * q + 2] + bm.z + fmaf(xr[q].z, sc.z, sh.z); u3 = v[4 * q + 3] + bm.w + fmaf(xr[q].w, sc.w, sh.w);
+            for (int q = 0; q < 8; ++q) {
+                const int n = c * 32 + 4 * q;
+                const float4 sc = *reinterpret_cast<const float4*>(cst + 3 * FZ_C + n), sh = *reinterpret_cast<const float4*>(cst + 4 * FZ_C + n);
+                const float4 bm = *reinterpret_cast<const float4*>(cst + 2 * FZ_C + n);
+                const float4 x = c == 0 ? xr[q] : xr[8 + q];
+                float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+                if (rvalid) {
+                    u0 = uv[4 * q] + bm.x + fmaf(x.x, sc.x, sh.x); u1 = uv[4 * q + 1] + bm.y + fmaf(x.y, sc.y, sh.y);
+                    u2 = uv[4 * q + 2] + bm.z + fmaf(x.z, sc.z, sh.z); u3 = uv[4 * q + 3] + bm.w + fmaf(x.w, sc.w, sh.w);
+                }
+                uv[4 * q] = u0; uv[4 * q + 1] = u1; uv[4 * q + 2] = u2; uv[4 * q + 3] = u3;
+                w[4 * q] = u0 * u0; w[4 * q + 1] = u1 * u1; w[4 * q + 2] = u2 * u2; w[4 * q + 3] = u3 * u3;
             }
-            v[4 * q] = u0; v[4 * q + 1] = u1; v[4 * q + 2] = u2; v[4 * q + 3] = u3;
-            sq[4 * q] = u0 * u0; sq[4 * q + 1] = u1 * u1; sq[4 * q + 2] = u2 * u2; sq[4 * q + 3] = u3 * u3;
-        }
-        if (rvalid) {
+            if (rvalid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(a.U + (size_t)m * C + half * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 8) tc::stg256(a.U + (size_t)m * C + c * 32 + j, uv + j);
+            }
+            const float s2 = warp_transpose_sum(w);
+            const float s1 = warp_transpose_sum(uv);
+            atomicAdd(red + c * 32 + lane, s1);
+            atomicAdd(red + 128 + c * 32 + lane, s2);
         }
-        float s1 = warp_transpose_sum(v), s2 = warp_transpose_sum(sq);
-        atomicAdd(red + half * 32 + lane, s1);
-        atomicAdd(red + 128 + half * 32 + lane, s2);
     }
+    FZ_STOP_AT(7)
     tc::fence_before_sync();
     __syncthreads();
-    if (tid < C) {
+    if (tid < C) {                                                    // feeder threads: no global stores of their own in flight
         atomicAdd(a.stats + tid, (double)red[tid]);
         atomicAdd(a.stats + C + tid, (double)red[128 + tid]);
+        __threadfence();                                              // statistics visible before the ticket
     }
     if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);
-    // ---- 7. the last CTA to arrive turns the statistics into mean / rstd / folded scale+shift / running stats
-    __threadfence();
     __syncthreads();
     if (tid == 0) is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
+    // ---- 7. the last CTA to arrive turns the statistics into mean / rstd / folded scale+shift / running stats
     if (is_last && tid < C) {
         __threadfence();
         const int c = tid;

@@ -45,6 +45,21 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 // make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---------------------------------------------------------------- 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256)
+// One thread = one full 32-byte sector per instruction: row-per-thread epilogues (TMEM lane = row) write whole sectors
+// instead of two partial 16-byte halves, which the L2 would have to merge.
+__device__ __forceinline__ void stg256(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6), "f"(a7) : "memory");
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) { stg256(p, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]); }
+__device__ __forceinline__ void ldg256(const float* p, float (&f)[8])
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
+}
+
 // ---------------------------------------------------------------- bulk copies (TMA engine, no tensor map)
 // contiguous global -> shared copy issued by ONE thread; completion is signalled on `bar` as `bytes` transaction bytes
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
