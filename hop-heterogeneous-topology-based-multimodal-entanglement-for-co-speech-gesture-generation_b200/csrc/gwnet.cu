@@ -1369,6 +1369,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
     // streams forked from / joined back to the caller's stream with events (du, G, df, dg are kept per layer).
     SideStreams* sd = side_streams();
     if (!sd) return fail(3, "side streams", "cudaStreamCreate failed");
+    static const bool skip_side = getenv("HOPK_BWD_SKIP_SIDE") != nullptr;     // timing experiments only: wrong gradients
     float* dxn = nullptr;                 // gradient w.r.t. BN_i output (= layer i+1 input)
     float* dx_buf[2] = {S(g.s_dxa), S(g.s_dxb)};
     int flip = 0;
@@ -1395,7 +1396,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             if (int rc = launch_node_mix(DU, F(g.At), F(g.A2t), S(g.s_p1[i]), S(g.s_p2[i]), groups, V, C, st)) return rc;
             HOPK_CUDA(cudaEventRecord(sd->ev_du[i], st));
             // side stream 0: mlp weight + bias gradient
-            {
+            if (!skip_side) {
                 cudaStream_t s0 = sd->s[0];
                 HOPK_CUDA(cudaStreamWaitEvent(s0, sd->ev_du[i], 0));
                 if (tc && C % 8 == 0) {
@@ -1416,7 +1417,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
                 }
             }
             // side stream 1: G = du [Wm1 | Wm2]  and the Gram products for dA
-            {
+            if (!skip_side) {
                 cudaStream_t s1 = sd->s[1];
                 HOPK_CUDA(cudaStreamWaitEvent(s1, sd->ev_du[i], 0));
                 Ld2D<true, 0> a{DU, nullptr, C};
@@ -1447,7 +1448,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             HOPK_CUDA(cudaEventRecord(sd->ev_dfg[i], st));
         }
         // side stream 2: gate conv weight + bias gradients
-        {
+        if (!skip_side) {
             cudaStream_t s2 = sd->s[2];
             HOPK_CUDA(cudaStreamWaitEvent(s2, sd->ev_dfg[i], 0));
             if (tc && C % 8 == 0) {

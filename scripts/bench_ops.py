@@ -29,7 +29,8 @@ def timeit(fn, iters, flush):
     for _ in range(iters):
         flush.zero_()                                   # > L2 (126 MB): evict the working set
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record()
+        torch.cuda._sleep(3_000_000)                    # ~1.5 ms of GPU spin: the host runs ahead, so host-side launch
+        e0.record(); fn(); e1.record()                  # preparation is not inside the timed region
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     ms.sort()

@@ -14,6 +14,6 @@ with torch.no_grad():
     ts = []
     for _ in range(30):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); m(x); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+        torch.cuda._sleep(3_000_000); e0.record(); m(x); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 ts.sort()
 print(json.dumps({'stop': os.environ.get('HOPK_FZ_STOP', '0'), 'B': B, 'fwd_ms_median': ts[len(ts) // 2], 'min': ts[0]}))
