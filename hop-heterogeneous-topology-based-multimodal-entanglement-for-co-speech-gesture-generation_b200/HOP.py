@@ -74,6 +74,7 @@ class _XattnFn(torch.autograd.Function):
                                            stream_ptr()))
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.p_drop, ctx.seed, ctx.tc = float(p_drop), int(seed), bool(tc and E == 128)
+        ctx.pack = pack if ctx.tc else None              # bf16 K/V records: the backward streams the same ones
         return o
 
     @staticmethod
@@ -84,10 +85,13 @@ class _XattnFn(torch.autograd.Function):
         do = f32c(do)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         delta = torch.empty_like(lse)
-        bwd = lib().hopk_xattn_bwd_tc if ctx.tc else lib().hopk_xattn_bwd
         with profiler.span('xattn_bwd'):
-            check(bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
-                                       ptr(delta), B, L, H, E, S, ctx.p_drop, ctx.seed, stream_ptr()))
+            if ctx.tc:
+                check(lib().hopk_xattn_bwd_tc(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
+                                              ptr(delta), ptr(ctx.pack), B, L, H, E, S, ctx.p_drop, ctx.seed, stream_ptr()))
+            else:
+                check(lib().hopk_xattn_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
+                                           ptr(delta), B, L, H, E, S, ctx.p_drop, ctx.seed, stream_ptr()))
         return dq, dk, dv, None, None, None
 
 

@@ -596,6 +596,183 @@ xattn_bwd_dq_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K,
     if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------ backward: dQ, v3
+// Same organisation as the v3 forward: K / V arrive as packed bf16 records (the forward's pack is reused) through a
+// 3-stage cp.async.bulk ring, S and dP are double-buffered in TMEM (2 x 64 columns each), dS is double-buffered in
+// shared memory, and a control warp issues every UMMA so that  S_{j+1} = Q K_{j+1}^T,  dP_{j+1} = dO V_{j+1}^T  run while
+// the 16 softmax warps (four threads per query row, 16 prototypes each) turn tile j into dS_j.
+// TMEM columns: S [0,128)  dP [128,256)  dQ [256,384).
+__global__ void __launch_bounds__(FWD3_THREADS, 1)
+xattn_bwd_dq_tc3_kernel(const float* __restrict__ Q, const uint8_t* __restrict__ kvpack, const float* __restrict__ O,
+                        const float* __restrict__ LSE, const float* __restrict__ dO, float* __restrict__ dQ,
+                        float* __restrict__ delta, int M, int L, int H, int S, float scale, float inv_keep, uint32_t thr,
+                        uint64_t seed)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[KV_STAGES], bar_s[2], bar_p[2], bar_q[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float xch[4][AT];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* Qs = smem; uint8_t* dOs = Qs + 2 * AT_SLAB; uint8_t* dSs = dOs + 2 * AT_SLAB;   // dS: 2 buffers of [128][64]
+    uint8_t* ring = dSs + 2 * AT_SLAB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.y, m0 = blockIdx.x * AT;
+    const int ntiles = (S + FS - 1) / FS;
+    const uint8_t* recs = kvpack + (size_t)h * ntiles * KV_REC;
+
+    if (tid == 512) {
+#pragma unroll
+        for (int i = 0; i < KV_STAGES; ++i) tc::mbar_init(&bar_full[i], 1);
+        tc::mbar_init(&bar_s[0], 1); tc::mbar_init(&bar_s[1], 1);
+        tc::mbar_init(&bar_p[0], 512); tc::mbar_init(&bar_p[1], 512); tc::mbar_init(&bar_q[0], 1); tc::mbar_init(&bar_q[1], 1);
+        tc::fence_barrier_init();
+        for (int t = 0; t < KV_STAGES && t < ntiles; ++t) {            // fill the ring
+            mbar_expect_tx(&bar_full[t], KV_REC);
+            bulk_g2s(ring + t * KV_REC, recs + (size_t)t * KV_REC, KV_REC, &bar_full[t]);
+        }
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 512);
+    if (tid < 256) stage_rows_f32(Qs, Q, m0, M, H, h);
+    else if (tid < 512) {                                              // warps 8-15 stage dO with the same item map
+#pragma unroll
+        for (int it = 0; it < (AT * 16) / 256; ++it) {
+            int idx = (tid - 256) + it * 256;
+            int ch16 = idx & 15, row = idx >> 4;
+            float f[8];
+            if (m0 + row < M) tc::ldg256(dO + ((size_t)(m0 + row) * H + h) * AT + ch16 * 8, f);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.f;
+            }
+            tc::slab_store8(dOs + (ch16 >> 3) * AT_SLAB, row, ch16 & 7, f);
+        }
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_s0 = tmem_base_smem, tmem_dp0 = tmem_base_smem + 128, tmem_dq = tmem_base_smem + 256;
+
+    if (warp == 16) {
+        // ------------------------------------------------------------------ control warp
+        if (lane == 0) {
+            constexpr uint32_t idesc_sk = tc::idesc_bf16(AT, FS, 0, 0);
+            constexpr uint32_t idesc_dq = tc::idesc_bf16(AT, AT, 0, 1);
+            const uint32_t qa = tc::smem_u32(Qs), da = tc::smem_u32(dOs), sa = tc::smem_u32(dSs);
+            auto issue_sdp = [&](int t) {                               // S_t, dP_t into TMEM buffer t & 1
+                tc::mbar_wait(&bar_full[t % KV_STAGES], (t / KV_STAGES) & 1);
+                tc::fence_after_sync();
+                const uint32_t ka = tc::smem_u32(ring + (t % KV_STAGES) * KV_REC), va = ka + 2 * FS_SLAB;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::mma_bf16(tmem_s0 + (t & 1) * 64, tc::desc_kmajor(qa + c * AT_SLAB, k), tc::desc_kmajor(ka + c * FS_SLAB, k),
+                                     idesc_sk, (c | k) != 0);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::mma_bf16(tmem_dp0 + (t & 1) * 64, tc::desc_kmajor(da + c * AT_SLAB, k), tc::desc_kmajor(va + c * FS_SLAB, k),
+                                     idesc_sk, (c | k) != 0);
+                tc::mma_commit(&bar_s[t & 1]);
+            };
+            issue_sdp(0);
+            for (int j = 0; j < ntiles; ++j) {
+                if (j + 1 < ntiles) issue_sdp(j + 1);                    // runs while the softmax warps work on tile j
+                if (j > 0 && j + 2 < ntiles) {                           // dQ UMMA of tile j-1 done -> its ring stage is free
+                    tc::mbar_wait(&bar_q[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                    const int t = j + 2;
+                    mbar_expect_tx(&bar_full[t % KV_STAGES], KV_REC);
+                    bulk_g2s(ring + (t % KV_STAGES) * KV_REC, recs + (size_t)t * KV_REC, KV_REC, &bar_full[t % KV_STAGES]);
+                }
+                tc::mbar_wait(&bar_p[j & 1], (j >> 1) & 1);              // dS_j written by all softmax threads
+                tc::fence_after_sync();
+                const uint32_t ka = tc::smem_u32(ring + (j % KV_STAGES) * KV_REC);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)       // dQ[row][e] += sum_s dS[row][s] K[s][e]  (K read MN-major)
+                    tc::mma_bf16(tmem_dq, tc::desc_kmajor(sa + (j & 1) * AT_SLAB, t), tc::desc_mnmajor(ka, FS_SLAB, t), idesc_dq,
+                                 (j | t) != 0);
+                tc::mma_commit(&bar_q[j & 1]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps
+        const int row = (warp & 3) * 32 + lane;
+        const int quad = warp >> 2;                              // which 16 of the 64 prototypes / which 32 of the 128 outputs
+        const int m = m0 + row;
+        const bool rvalid = m < M;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const size_t li = rvalid ? ((size_t)(m / L) * H + h) * L + (m % L) : 0;
+        const uint64_t drop_base = (uint64_t)li * (uint64_t)S;
+        const float sc2 = scale * 1.4426950408889634f;
+        // delta = rowsum(dO * O) in fp32 from global: each of the row's four threads sums 32 columns
+        float part = 0.f;
+        if (rvalid) {
+            const float* o = O + ((size_t)m * H + h) * AT + quad * 32;
+            const float* d = dO + ((size_t)m * H + h) * AT + quad * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float a[8], b[8];
+                tc::ldg256(o + 8 * i, a); tc::ldg256(d + 8 * i, b);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) part = fmaf(a[k], b[k], part);
+            }
+        }
+        xch[quad][row] = part;
+        named_bar_sync(1 + (warp & 3), 128);
+        const float dl = xch[0][row] + xch[1][row] + xch[2][row] + xch[3][row];
+        const float lse2 = rvalid ? __ldg(LSE + li) * 1.4426950408889634f : 0.f;
+        if (rvalid && quad == 0) delta[li] = dl;
+        for (int j = 0; j < ntiles; ++j) {
+            const int s0 = j * FS;
+            tc::mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
+            tc::fence_after_sync();
+            float sv[16], dv[16];
+            tc::tmem_ld16(tmem_s0 + (j & 1) * 64 + lane_off + quad * 16, sv);
+            tc::tmem_ld16(tmem_dp0 + (j & 1) * 64 + lane_off + quad * 16, dv);
+            const int sb = s0 + quad * 16;
+            if (thr) {
+                const uint64_t idx0 = drop_base + (uint64_t)sb;
+                if ((idx0 & 1) == 0) dropout_run_even<16>(dv, idx0, seed, thr, inv_keep);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) dv[i] = keep_mask_tc(seed, idx0 + (uint64_t)i, thr) ? dv[i] * inv_keep : 0.f;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float p = ex2f(fmaf(sv[i], sc2, -lse2));
+                sv[i] = (rvalid && sb + i < S) ? p * (dv[i] - dl) * scale : 0.f;
+            }
+            if (j >= 2) tc::mbar_wait(&bar_q[j & 1], ((j >> 1) - 1) & 1);    // dQ UMMA of tile j-2 done: dS buffer j & 1 is free
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = sv[q8 * 8 + i];
+                tc::slab_store8(dSs + (j & 1) * AT_SLAB, row, quad * 2 + q8, f);
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            tc::mbar_arrive(&bar_p[j & 1]);
+        }
+        if (ntiles >= 2) tc::mbar_wait(&bar_q[(ntiles - 2) & 1], ((ntiles - 2) >> 1) & 1);
+        tc::mbar_wait(&bar_q[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+        tc::fence_after_sync();
+        float v[32];
+        tc::tmem_ld32(tmem_dq + lane_off + quad * 32, v);
+        if (rvalid) {
+            float* qrow = dQ + ((size_t)m * H + h) * AT + quad * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) tc::stg256(qrow + i, v + i);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
 // One CTA per (128 prototypes, head); loops over the query-row tiles.  TMEM: S [0,128) dP [128,256) dK [256,384) dV [384,512).
 // P~ and dS are written row-major [row][s]; the dV / dK UMMAs read them (and dO / Q) through MN-major views.
@@ -783,8 +960,8 @@ extern "C" int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v,
 }
 
 extern "C" int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v, const float* o, const float* lse,
-                                 const float* dout, float* dq, float* dk, float* dv, float* delta, int B, int L, int H, int E,
-                                 int S, float p_drop, uint64_t seed, void* stream)
+                                 const float* dout, float* dq, float* dk, float* dv, float* delta, void* kv_pack, int B, int L,
+                                 int H, int E, int S, float p_drop, uint64_t seed, void* stream)
 {
     HOPK_REQUIRE(B > 0 && L > 0 && H > 0 && S > 0, "xattn sizes");
     HOPK_REQUIRE(E == 128, "tensor-core attention is specialised for head dim 128");
@@ -801,9 +978,22 @@ extern "C" int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v,
         HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         configured = true;
     }
-    xattn_bwd_dq_tc_kernel<<<dim3(cdiv(M, AT), H), 256, smem1, st>>>(q, k, v, o, lse, dout, dq, delta, M, L, H, S, scale,
-                                                                     inv_keep, thr, seed);
-    HOPK_LAUNCH_CHECK("xattn_bwd_dq_tc");
+    if (kv_pack) {                              // v3: K / V records packed by the forward (same K, V), bulk-copy ring
+        const size_t smem3 = 6 * AT_SLAB + KV_STAGES * KV_REC + 1024;
+        static bool configured3 = false;
+        if (!configured3) {
+            HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dq_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            configured3 = true;
+        }
+        const uint8_t* pack = reinterpret_cast<const uint8_t*>(((uintptr_t)kv_pack + 1023) & ~uintptr_t(1023));
+        xattn_bwd_dq_tc3_kernel<<<dim3(cdiv(M, AT), H), FWD3_THREADS, smem3, st>>>(q, pack, o, lse, dout, dq, delta, M, L, H, S,
+                                                                                scale, inv_keep, thr, seed);
+        HOPK_LAUNCH_CHECK("xattn_bwd_dq_tc3");
+    } else {
+        xattn_bwd_dq_tc_kernel<<<dim3(cdiv(M, AT), H), 256, smem1, st>>>(q, k, v, o, lse, dout, dq, delta, M, L, H, S, scale,
+                                                                         inv_keep, thr, seed);
+        HOPK_LAUNCH_CHECK("xattn_bwd_dq_tc");
+    }
     xattn_bwd_dkv_tc_kernel<<<dim3(cdiv(S, AT), H), 256, smem2, st>>>(q, k, v, lse, delta, dout, dk, dv, M, L, H, S, scale,
                                                                       inv_keep, thr, seed);
     HOPK_LAUNCH_CHECK("xattn_bwd_dkv_tc");

@@ -142,7 +142,7 @@ size_t hopk_xattn_pack_bytes(int S, int H);
 int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v, float* o, float* lse, void* kv_pack,
                       int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
 int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v, const float* o, const float* lse,
-                      const float* dout, float* dq, float* dk, float* dv, float* delta,
+                      const float* dout, float* dq, float* dk, float* dv, float* delta, void* kv_pack,
                       int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
 
 #ifdef __cplusplus
