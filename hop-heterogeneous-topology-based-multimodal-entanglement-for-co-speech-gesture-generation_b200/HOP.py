@@ -87,8 +87,10 @@ class _XattnFn(torch.autograd.Function):
         delta = torch.empty_like(lse)
         with profiler.span('xattn_bwd'):
             if ctx.tc:
+                scratch = torch.empty(lib().hopk_xattn_bwd_scratch_bytes(B, L, H), device=q.device, dtype=torch.uint8)
                 check(lib().hopk_xattn_bwd_tc(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
-                                              ptr(delta), ptr(ctx.pack), B, L, H, E, S, ctx.p_drop, ctx.seed, stream_ptr()))
+                                              ptr(delta), ptr(ctx.pack), ptr(scratch), B, L, H, E, S, ctx.p_drop, ctx.seed,
+                                              stream_ptr()))
             else:
                 check(lib().hopk_xattn_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
                                            ptr(delta), B, L, H, E, S, ctx.p_drop, ctx.seed, stream_ptr()))

@@ -605,8 +605,8 @@ xattn_bwd_dq_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K,
 __global__ void __launch_bounds__(FWD3_THREADS, 1)
 xattn_bwd_dq_tc3_kernel(const float* __restrict__ Q, const uint8_t* __restrict__ kvpack, const float* __restrict__ O,
                         const float* __restrict__ LSE, const float* __restrict__ dO, float* __restrict__ dQ,
-                        float* __restrict__ delta, int M, int L, int H, int S, float scale, float inv_keep, uint32_t thr,
-                        uint64_t seed)
+                        float* __restrict__ delta, uint4* __restrict__ rowstat, int M, int L, int H, int S, float scale,
+                        float inv_keep, uint32_t thr, uint64_t seed)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[KV_STAGES], bar_s[2], bar_p[2], bar_q[2];
@@ -723,7 +723,11 @@ xattn_bwd_dq_tc3_kernel(const float* __restrict__ Q, const uint8_t* __restrict__
         named_bar_sync(1 + (warp & 3), 128);
         const float dl = xch[0][row] + xch[1][row] + xch[2][row] + xch[3][row];
         const float lse2 = rvalid ? __ldg(LSE + li) * 1.4426950408889634f : 0.f;
-        if (rvalid && quad == 0) delta[li] = dl;
+        if (rvalid && quad == 0) {
+            delta[li] = dl;
+            // per-(head, row) record for the dK/dV pass: {lse * log2(e), delta, dropout base index}
+            if (rowstat) rowstat[(size_t)h * M + m] = make_uint4(__float_as_uint(lse2), __float_as_uint(dl), (uint32_t)drop_base, (uint32_t)(drop_base >> 32));
+        }
         for (int j = 0; j < ntiles; ++j) {
             const int s0 = j * FS;
             tc::mbar_wait(&bar_s[j & 1], (j >> 1) & 1);
@@ -910,6 +914,184 @@ xattn_bwd_dkv_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K
     if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------ backward: dK, dV, v3
+// One CTA per (128 prototypes, head, chunk of query-row tiles).  Everything is computed TRANSPOSED so that the CTA's own
+// prototypes are the TMEM lanes:   S^T = K Q_i^T,  dP^T = V dO_i^T   (M = 128 prototypes, N = 64 query rows per tile),
+// which makes P~^T and dS^T plain K-major A operands written one row per thread, and dV += P~^T dO_i, dK += dS^T Q_i
+// read Q_i / dO_i MN-major from the very records that fed the first two products.  Q / dO are packed once per call into
+// bf16 records (same format and kernel as the K / V records) and streamed through a 3-stage cp.async.bulk ring; S^T and
+// dP^T are double-buffered in TMEM, so the UMMAs of tile i+1 run under the softmax arithmetic of tile i.
+// TMEM columns: S^T [0,128)  dP^T [128,256)  dK [256,384)  dV [384,512).  Row chunks combine with 128-bit atomics.
+__global__ void __launch_bounds__(FWD3_THREADS, 1)
+xattn_bwd_dkv_tc3_kernel(const float* __restrict__ K, const float* __restrict__ V, const uint8_t* __restrict__ qdopack,
+                         const uint4* __restrict__ rowstat, float* __restrict__ dK, float* __restrict__ dV, int M, int H, int S,
+                         int tiles_per_chunk, float scale, float inv_keep, uint32_t thr, uint64_t seed, int use_atomics)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[KV_STAGES], bar_s[2], bar_p, bar_kv;
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* Ks = smem; uint8_t* Vs = Ks + 2 * AT_SLAB; uint8_t* Ps = Vs + 2 * AT_SLAB; uint8_t* dSs = Ps + AT_SLAB;
+    uint8_t* ring = dSs + AT_SLAB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int h = blockIdx.y, s0 = blockIdx.x * AT;
+    const int ntiles_all = (M + FS - 1) / FS;
+    const int t_begin = blockIdx.z * tiles_per_chunk;
+    const int ntiles = min(tiles_per_chunk, ntiles_all - t_begin);           // >= 1 by construction of the grid
+    const uint8_t* recs = qdopack + ((size_t)h * ntiles_all + t_begin) * KV_REC;
+
+    if (tid == 512) {
+#pragma unroll
+        for (int i = 0; i < KV_STAGES; ++i) tc::mbar_init(&bar_full[i], 1);
+        tc::mbar_init(&bar_s[0], 1); tc::mbar_init(&bar_s[1], 1);
+        tc::mbar_init(&bar_p, 512); tc::mbar_init(&bar_kv, 1);
+        tc::fence_barrier_init();
+        for (int t = 0; t < KV_STAGES && t < ntiles; ++t) {
+            mbar_expect_tx(&bar_full[t], KV_REC);
+            bulk_g2s(ring + t * KV_REC, recs + (size_t)t * KV_REC, KV_REC, &bar_full[t]);
+        }
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 512);
+    if (tid < 256) stage_rows_f32(Ks, K, s0, S, H, h);
+    else if (tid < 512) {                                              // warps 8-15 stage V with the same item map
+#pragma unroll
+        for (int it = 0; it < (AT * 16) / 256; ++it) {
+            int idx = (tid - 256) + it * 256;
+            int ch16 = idx & 15, row = idx >> 4;
+            float f[8];
+            if (s0 + row < S) tc::ldg256(V + ((size_t)(s0 + row) * H + h) * AT + ch16 * 8, f);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.f;
+            }
+            tc::slab_store8(Vs + (ch16 >> 3) * AT_SLAB, row, ch16 & 7, f);
+        }
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_s0 = tmem_base_smem, tmem_dp0 = tmem_base_smem + 128, tmem_dk = tmem_base_smem + 256,
+                   tmem_dv = tmem_base_smem + 384;
+
+    if (warp == 16) {
+        // ------------------------------------------------------------------ control warp
+        if (lane == 0) {
+            constexpr uint32_t idesc_st = tc::idesc_bf16(AT, FS, 0, 0);      // [128 protos] x [64 rows], both K-major (K = e)
+            constexpr uint32_t idesc_kv = tc::idesc_bf16(AT, AT, 0, 1);      // A = P~^T / dS^T K-major (K = rows), B = dO / Q MN-major
+            const uint32_t ka = tc::smem_u32(Ks), va = tc::smem_u32(Vs), pa = tc::smem_u32(Ps), sa = tc::smem_u32(dSs);
+            auto issue_sdp = [&](int t) {
+                tc::mbar_wait(&bar_full[t % KV_STAGES], (t / KV_STAGES) & 1);
+                tc::fence_after_sync();
+                const uint32_t qa = tc::smem_u32(ring + (t % KV_STAGES) * KV_REC), da = qa + 2 * FS_SLAB;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::mma_bf16(tmem_s0 + (t & 1) * 64, tc::desc_kmajor(ka + c * AT_SLAB, k), tc::desc_kmajor(qa + c * FS_SLAB, k),
+                                     idesc_st, (c | k) != 0);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::mma_bf16(tmem_dp0 + (t & 1) * 64, tc::desc_kmajor(va + c * AT_SLAB, k), tc::desc_kmajor(da + c * FS_SLAB, k),
+                                     idesc_st, (c | k) != 0);
+                tc::mma_commit(&bar_s[t & 1]);
+            };
+            issue_sdp(0);
+            for (int i = 0; i < ntiles; ++i) {
+                if (i + 1 < ntiles) issue_sdp(i + 1);                    // runs under the softmax arithmetic of tile i
+                if (i > 0 && i + 2 < ntiles) {                           // dK/dV UMMAs of tile i-1 done -> its ring stage is free
+                    tc::mbar_wait(&bar_kv, (i - 1) & 1);
+                    const int t = i + 2;
+                    mbar_expect_tx(&bar_full[t % KV_STAGES], KV_REC);
+                    bulk_g2s(ring + (t % KV_STAGES) * KV_REC, recs + (size_t)t * KV_REC, KV_REC, &bar_full[t % KV_STAGES]);
+                }
+                tc::mbar_wait(&bar_p, i & 1);                            // P~^T_i, dS^T_i written by all softmax threads
+                tc::fence_after_sync();
+                const uint32_t qa = tc::smem_u32(ring + (i % KV_STAGES) * KV_REC), da = qa + 2 * FS_SLAB;
+#pragma unroll
+                for (int t = 0; t < 4; ++t)       // dV[s][e] += sum_row P~^T[s][row] dO[row][e]
+                    tc::mma_bf16(tmem_dv, tc::desc_kmajor(pa, t), tc::desc_mnmajor(da, FS_SLAB, t), idesc_kv, (i | t) != 0);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)       // dK[s][e] += sum_row dS^T[s][row] Q[row][e]
+                    tc::mma_bf16(tmem_dk, tc::desc_kmajor(sa, t), tc::desc_mnmajor(qa, FS_SLAB, t), idesc_kv, (i | t) != 0);
+                tc::mma_commit(&bar_kv);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps: thread = (prototype, 16 query rows)
+        const int srow = (warp & 3) * 32 + lane;                 // prototype inside the tile = TMEM lane
+        const int quad = warp >> 2;
+        const int s = s0 + srow;
+        const bool svalid = s < S;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const float sc2 = scale * 1.4426950408889634f;
+        const uint4* rs_h = rowstat + (size_t)h * M;
+        for (int i = 0; i < ntiles; ++i) {
+            const int mb = (t_begin + i) * FS + quad * 16;      // first of this thread's 16 query rows
+            tc::mbar_wait(&bar_s[i & 1], (i >> 1) & 1);
+            tc::fence_after_sync();
+            float sv[16], dv[16];
+            tc::tmem_ld16(tmem_s0 + (i & 1) * 64 + lane_off + quad * 16, sv);
+            tc::tmem_ld16(tmem_dp0 + (i & 1) * 64 + lane_off + quad * 16, dv);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int m = mb + k;
+                float pt = 0.f, ds = 0.f;
+                if (svalid && m < M) {
+                    const uint4 r = __ldg(rs_h + m);             // same address across the warp: one broadcast transaction
+                    const float p = ex2f(fmaf(sv[k], sc2, -__uint_as_float(r.x)));
+                    float d = dv[k];
+                    pt = p;
+                    if (thr) {
+                        const uint64_t idx = (((uint64_t)r.w << 32) | (uint64_t)r.z) + (uint64_t)s;
+                        const bool kp = keep_mask_tc(seed, idx, thr);
+                        pt = kp ? p * inv_keep : 0.f;
+                        d = kp ? d * inv_keep : 0.f;
+                    }
+                    ds = p * (d - __uint_as_float(r.y)) * scale;
+                }
+                sv[k] = pt; dv[k] = ds;
+            }
+            if (i > 0) tc::mbar_wait(&bar_kv, (i - 1) & 1);      // dK/dV UMMAs of tile i-1 done: P / dS buffers are free
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8) {
+                float f[8], g[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { f[k] = sv[q8 * 8 + k]; g[k] = dv[q8 * 8 + k]; }
+                tc::slab_store8(Ps, srow, quad * 2 + q8, f);
+                tc::slab_store8(dSs, srow, quad * 2 + q8, g);
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            tc::mbar_arrive(&bar_p);
+        }
+        tc::mbar_wait(&bar_kv, (ntiles - 1) & 1);
+        tc::fence_after_sync();
+        float a[32], b[32];
+        tc::tmem_ld32(tmem_dk + lane_off + quad * 32, a);
+        tc::tmem_ld32(tmem_dv + lane_off + quad * 32, b);
+        if (svalid) {
+            float* kr = dK + ((size_t)s * H + h) * AT + quad * 32;
+            float* vr = dV + ((size_t)s * H + h) * AT + quad * 32;
+            if (use_atomics) {
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    atomicAdd(reinterpret_cast<float4*>(kr + k), make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]));
+                    atomicAdd(reinterpret_cast<float4*>(vr + k), make_float4(b[k], b[k + 1], b[k + 2], b[k + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; k += 8) { tc::stg256(kr + k, a + k); tc::stg256(vr + k, b + k); }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 512);
+}
+
 }  // namespace hopk
 using namespace hopk;
 
@@ -920,6 +1102,9 @@ extern "C" int hopk_debug_set(void* mapped_host_ints)
 }
 
 extern "C" size_t hopk_xattn_pack_bytes(int S, int H) { return (size_t)H * ((S + FS - 1) / FS) * KV_REC + 1024; }
+// backward scratch: Q / dO records (same format, rows = B*L) followed by the per-(head, row) statistics of the dK/dV pass
+static size_t qdo_pack_bytes(int M, int H) { return (size_t)H * ((M + FS - 1) / FS) * KV_REC; }
+extern "C" size_t hopk_xattn_bwd_scratch_bytes(int B, int L, int H) { return qdo_pack_bytes(B * L, H) + (size_t)H * B * L * sizeof(uint4) + 1024; }
 
 extern "C" int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v, float* o, float* lse, void* kv_pack, int B,
                                  int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream)
@@ -960,8 +1145,8 @@ extern "C" int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v,
 }
 
 extern "C" int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v, const float* o, const float* lse,
-                                 const float* dout, float* dq, float* dk, float* dv, float* delta, void* kv_pack, int B, int L,
-                                 int H, int E, int S, float p_drop, uint64_t seed, void* stream)
+                                 const float* dout, float* dq, float* dk, float* dv, float* delta, void* kv_pack, void* scratch,
+                                 int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream)
 {
     HOPK_REQUIRE(B > 0 && L > 0 && H > 0 && S > 0, "xattn sizes");
     HOPK_REQUIRE(E == 128, "tensor-core attention is specialised for head dim 128");
@@ -978,22 +1163,41 @@ extern "C" int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v,
         HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         configured = true;
     }
-    if (kv_pack) {                              // v3: K / V records packed by the forward (same K, V), bulk-copy ring
+    if (kv_pack && scratch) {                   // v3: K / V records packed by the forward (same K, V), bulk-copy rings
         const size_t smem3 = 6 * AT_SLAB + KV_STAGES * KV_REC + 1024;
         static bool configured3 = false;
         if (!configured3) {
             HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dq_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dkv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
             configured3 = true;
         }
         const uint8_t* pack = reinterpret_cast<const uint8_t*>(((uintptr_t)kv_pack + 1023) & ~uintptr_t(1023));
-        xattn_bwd_dq_tc3_kernel<<<dim3(cdiv(M, AT), H), FWD3_THREADS, smem3, st>>>(q, pack, o, lse, dout, dq, delta, M, L, H, S,
-                                                                                scale, inv_keep, thr, seed);
+        uint8_t* qdo = reinterpret_cast<uint8_t*>(((uintptr_t)scratch + 1023) & ~uintptr_t(1023));
+        uint4* rowstat = reinterpret_cast<uint4*>(qdo + qdo_pack_bytes(M, H));
+        const int mt = cdiv(M, FS);
+        xattn_pack_kv_kernel<<<dim3(mt, H), 256, 0, st>>>(q, dout, qdo, M, H, mt);       // Q / dO records
+        HOPK_LAUNCH_CHECK("xattn_pack_qdo");
+        xattn_bwd_dq_tc3_kernel<<<dim3(cdiv(M, AT), H), FWD3_THREADS, smem3, st>>>(q, pack, o, lse, dout, dq, delta, rowstat, M, L, H,
+                                                                                S, scale, inv_keep, thr, seed);
         HOPK_LAUNCH_CHECK("xattn_bwd_dq_tc3");
-    } else {
-        xattn_bwd_dq_tc_kernel<<<dim3(cdiv(M, AT), H), 256, smem1, st>>>(q, k, v, o, lse, dout, dq, delta, M, L, H, S, scale,
-                                                                         inv_keep, thr, seed);
-        HOPK_LAUNCH_CHECK("xattn_bwd_dq_tc");
+        const int kvt = cdiv(S, AT);
+        int chunks = (2 * 148 + kvt * H / 2) / (kvt * H);                   // about two waves of CTAs
+        if (chunks < 1) chunks = 1;
+        if (chunks > mt) chunks = mt;
+        const int per = cdiv(mt, chunks);
+        chunks = cdiv(mt, per);
+        if (chunks > 1) {
+            HOPK_CUDA(cudaMemsetAsync(dk, 0, (size_t)S * H * E * sizeof(float), st));
+            HOPK_CUDA(cudaMemsetAsync(dv, 0, (size_t)S * H * E * sizeof(float), st));
+        }
+        xattn_bwd_dkv_tc3_kernel<<<dim3(kvt, H, chunks), FWD3_THREADS, smem3, st>>>(k, v, qdo, rowstat, dk, dv, M, H, S, per, scale,
+                                                                                  inv_keep, thr, seed, chunks > 1 ? 1 : 0);
+        HOPK_LAUNCH_CHECK("xattn_bwd_dkv_tc3");
+        return 0;
     }
+    xattn_bwd_dq_tc_kernel<<<dim3(cdiv(M, AT), H), 256, smem1, st>>>(q, k, v, o, lse, dout, dq, delta, M, L, H, S, scale,
+                                                                     inv_keep, thr, seed);
+    HOPK_LAUNCH_CHECK("xattn_bwd_dq_tc");
     xattn_bwd_dkv_tc_kernel<<<dim3(cdiv(S, AT), H), 256, smem2, st>>>(q, k, v, lse, delta, dout, dk, dv, M, L, H, S, scale,
                                                                       inv_keep, thr, seed);
     HOPK_LAUNCH_CHECK("xattn_bwd_dkv_tc");

@@ -141,8 +141,11 @@ int hopk_xattn_bwd(const float* q, const float* k, const float* v, const float* 
 size_t hopk_xattn_pack_bytes(int S, int H);
 int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v, float* o, float* lse, void* kv_pack,
                       int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
+/* backward v3: kv_pack = the forward's packed K/V records (K, V unchanged), scratch = hopk_xattn_bwd_scratch_bytes(B, L, H)
+ * bytes (Q / dO records + per-row statistics).  Either NULL selects the kernels that stage fp32 operands themselves. */
+size_t hopk_xattn_bwd_scratch_bytes(int B, int L, int H);
 int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v, const float* o, const float* lse,
-                      const float* dout, float* dq, float* dk, float* dv, float* delta, void* kv_pack,
+                      const float* dout, float* dq, float* dk, float* dv, float* delta, void* kv_pack, void* scratch,
                       int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
 
 #ifdef __cplusplus
