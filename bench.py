@@ -270,35 +270,53 @@ def peaks():
         return 6650.0, 1400.0, 'fallback'
 
 
-def roofline(spans, a, world):
-    """Dominant hand-written kernel group of the step: the cross-attention backward (dQ + dK/dV kernels).
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per call of each kernel group, from the committed ncu capture
+    (profiles/r1_traffic.json, written by scripts/traffic_from_ncu.py; TED, B = 128).  None when absent."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
 
-    Algorithmic FLOPs per launch group: forward 4*B*L*S*H*E; backward recomputes QK^T and dO V^T in both
-    passes: (2+2+1+2)*2*B*L*S*H*E = 14*B*L*S*H*E.  bf16 precision: tcgen05 UMMA kernels (csrc/xattn_tc.cu); fp32
-    precision: FFMA kernels, still reported against the measured dense-bf16 tensor peak (honest about the gap)."""
+
+def roofline(spans, a, world):
+    """Roofline position of every hand-written kernel group timed inside the step (CUDA events around the C-ABI calls);
+    the top-level entry is the group that takes the most time per step.
+
+    Algorithmic work per call:
+      gwnet forward  : fused-floor bytes of SURVEY 8(d) (fp32 activations), backward = 2x        -> HBM roofline
+      attention      : forward 4*B*L*S*H*E FLOPs; backward 14*B*L*S*H*E (both passes recompute)  -> tensor roofline
+    bf16 precision: tcgen05 UMMA kernels; fp32 precision: FFMA kernels, still reported against the same peaks."""
     B, L, S, H, E = a.batch, 34, 1500, 8, 128
     hbm, tf, which = peaks()
-    out = {}
-    groups = {'xattn_bwd': 14.0 * B * L * S * H * E, 'xattn_fwd': 4.0 * B * L * S * H * E}
-    name = max((k for k in groups if k in spans), key=lambda k: spans[k][1], default=None)
-    if name is None:
-        return None
-    calls, total_ms = spans[name]
-    flops = groups[name]
-    achieved = flops / (total_ms / calls * 1e-3) / 1e12
-    out = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': tf, 'unit': 'TFLOP/s', 'frac': achieved / tf,
-           'traffic': None, 'peak_source': which + ' (bf16_tflops_sustained)', 'launches_timed': calls,
-           'avg_ms': total_ms / calls,
-           'arithmetic': 'bf16 tcgen05 UMMA, fp32 accumulate in TMEM' if a.precision == 'bf16' else 'fp32 FFMA'}
-    # the memory-bound side: whole gwnet block vs its fused-floor traffic (SURVEY 8(d)); informational
     V, s = (9, 4) if a.datasets == 'TED' else (42, 4)
     floor_fwd = s * B * V * (173 * 16 + 64 * 16 + 64 * (88 + 76) + 2 * 8 * 64 * 4 + 173 * 4)
-    for k, mult in (('gwnet_fwd', 1.0), ('gwnet_bwd', 2.0)):
-        if k in spans:
-            c, t = spans[k]
-            gbs = floor_fwd * mult / (t / c * 1e-3) / 1e9
-            out[k] = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm,
-                      'algorithmic_bytes': floor_fwd * mult, 'avg_ms': t / c}
+    work = {'xattn_bwd': ('tensor', 14.0 * B * L * S * H * E), 'xattn_fwd': ('tensor', 4.0 * B * L * S * H * E),
+            'gwnet_fwd': ('hbm', float(floor_fwd)), 'gwnet_bwd': ('hbm', 2.0 * floor_fwd)}
+    traffic = measured_traffic() if (a.datasets == 'TED' and a.batch == 128) else {}
+    groups = {}
+    for k, (bound, amount) in work.items():
+        if k not in spans:
+            continue
+        calls, total_ms = spans[k]
+        sec = total_ms / calls * 1e-3
+        if bound == 'tensor':
+            ach, peak, unit = amount / sec / 1e12, tf, 'TFLOP/s'
+            extra = {'algorithmic_flops': amount,
+                     'arithmetic': 'bf16 tcgen05 UMMA, fp32 accumulate in TMEM' if a.precision == 'bf16' else 'fp32 FFMA'}
+        else:
+            ach, peak, unit = amount / sec / 1e9, hbm, 'GB/s'
+            extra = {'algorithmic_bytes': amount}
+        groups[k] = {'bound': bound, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
+                     'traffic': traffic.get(k), 'avg_ms': total_ms / calls, 'launches_timed': calls,
+                     'ms_per_step': total_ms / a.steps} | extra
+    if not groups:
+        return None
+    top = max(groups, key=lambda k: groups[k]['ms_per_step'])
+    out = {'kernel': top} | groups[top]
+    out['peak_source'] = which + (' (hbm_gbs)' if groups[top]['bound'] == 'hbm' else ' (bf16_tflops_sustained)')
+    out['groups'] = groups
     return out
 
 
