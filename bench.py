@@ -181,8 +181,9 @@ def run_ours(a):
     pose = 27 if a.datasets == 'TED' else 126
     disc = ConvDiscriminator(pose).to(dev)
     lr = 4e-4 if a.datasets == 'TED' else 2e-4                # OneCycleLR start value, never stepped
-    gen_opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr, betas=(0.5, 0.999))
-    dis_opt = torch.optim.Adam(disc.parameters(), lr=lr, betas=(0.5, 0.999))
+    # same Adam as the reference (run_ted.py: lr, betas (0.5, 0.999)); fused=True only changes how many kernels apply it
+    gen_opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr, betas=(0.5, 0.999), fused=True)
+    dis_opt = torch.optim.Adam(disc.parameters(), lr=lr, betas=(0.5, 0.999), fused=True)
     engine = DataParallel([model, disc])
     sargs = step_args(a.datasets)
     gen = torch.Generator().manual_seed(SEED + rank)

@@ -12,6 +12,7 @@
 Modules are created in the reference's order with the same initialisers, so a given
 ``torch.manual_seed`` reproduces the reference's initial weights.
 """
+import copy
 from math import sqrt
 
 import torch
@@ -260,6 +261,7 @@ class Model(nn.Module):
         hand-written path (mapping GEMM, align, frozen BERT, beat MLP, GRU, out MLP) run under bf16 autocast."""
         self.amp_dtype = {'fp32': None, 'bf16': torch.bfloat16}[name]
         self._we_cast = None
+        self.__dict__['_llm_shadow'] = None
         self.gwnet.set_precision(name)
         self.reprogramming_layer.set_precision(name)
         return self
@@ -273,6 +275,27 @@ class Model(nn.Module):
         if key not in self._win_idx:
             self._win_idx[key] = (torch.arange(16 * J, device=device) % 16).view(16, J)
         return self._win_idx[key]
+
+    def _llm(self):
+        """The frozen encoder the forward runs through.  In bf16 mode this is a bf16 *shadow* of ``llm_model`` made once
+        (the weights are frozen, reference HOP.py:90-91), so autocast does not re-cast 67 M weights in every forward; the
+        fp32 module stays the one that ``state_dict()`` / ``load_state_dict()`` see."""
+        if self.amp_dtype is None:
+            return self.llm_model
+        sh = self.__dict__.get('_llm_shadow')
+        dev = self.word_embeddings.device
+        if sh is None or next(sh.parameters()).device != dev:
+            sh = copy.deepcopy(self.llm_model).to(device=dev, dtype=self.amp_dtype).eval()
+            for p in sh.parameters():
+                p.requires_grad_(False)
+            self.__dict__['_llm_shadow'] = sh                # deliberately not a registered sub-module
+        return sh
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.__dict__['_llm_shadow'] = None                 # frozen-weight caches follow the loaded weights
+        self._we_cast = None
+        return out
 
     def source_embeddings(self):
         """Text prototypes (1500, d_llm) = mapping_layer(word_embeddings^T)^T  (HOP.py:200); batch independent."""
@@ -306,7 +329,7 @@ class Model(nn.Module):
             source = self.source_embeddings()
         enc_out = self.reprogramming_layer(x_enc, source, source)
         llama_enc_out = self.align_layer(torch.cat([enc_out, text_embeddings], dim=2))
-        dec_out = self.llm_model(inputs_embeds=llama_enc_out).last_hidden_state
+        dec_out = self._llm()(inputs_embeds=llama_enc_out).last_hidden_state
 
         # beat features: the reference runs the MLP on J identical copies of the 16 windows and then
         # *reinterprets* (B,J,16,170) as (B,16,J,170) (HOP.py:210-212); equal to MLP-once + gather.
