@@ -182,8 +182,9 @@ def run_ours(a):
     disc = ConvDiscriminator(pose).to(dev)
     lr = 4e-4 if a.datasets == 'TED' else 2e-4                # OneCycleLR start value, never stepped
     # same Adam as the reference (run_ted.py: lr, betas (0.5, 0.999)); fused=True only changes how many kernels apply it
-    gen_opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr, betas=(0.5, 0.999), fused=True)
-    dis_opt = torch.optim.Adam(disc.parameters(), lr=lr, betas=(0.5, 0.999), fused=True)
+    gen_opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr, betas=(0.5, 0.999), fused=True,
+                               capturable=bool(a.graph))
+    dis_opt = torch.optim.Adam(disc.parameters(), lr=lr, betas=(0.5, 0.999), fused=True, capturable=bool(a.graph))
     engine = DataParallel([model, disc])
     sargs = step_args(a.datasets)
     gen = torch.Generator().manual_seed(SEED + rank)
@@ -203,29 +204,53 @@ def run_ours(a):
     losses = []
     for _ in range(a.warmup):
         losses.append(step(resident)['loss'])
+    # ---- per-kernel-group timing: eager steps with CUDA events around every C-ABI call (feeds `roofline`)
+    prof_steps = max(1, min(a.steps, 5))
+    profiler.enable(True)
+    for _ in range(prof_steps):
+        losses.append(step(resident)['loss'])
+    torch.cuda.synchronize()
+    spans = profiler.summary()
+    profiler.enable(False)
+    # ---- the step as one CUDA graph (hop_b200/graphed.py); falls back to eager launches if capture is refused
+    graphed, graph_error = None, None
+    run = step
+    if a.graph:
+        try:
+            from hop_b200.graphed import GraphedTrainStep
+            graphed = GraphedTrainStep(sargs, epoch, model, disc, gen_opt, dis_opt, engine, resident)
+            run = graphed
+        except Exception as exc:                                # noqa: BLE001 -- report and measure the eager path instead
+            graph_error = f'{type(exc).__name__}: {exc}'[:300]
+            sys.stderr.write('CUDA graph capture failed, running eagerly: ' + graph_error + '\n')
+            torch.cuda.synchronize()
+    ok = torch.tensor([0 if graphed is None else 1], device=dev)
+    if world > 1:                                               # all ranks replay or none does
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok) == 0:
+        graphed, run = None, step
+    for _ in range(2):
+        losses.append(run(resident)['loss'])
     # ---- timed region 1: device-resident inputs
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    profiler.enable(True)
     launches0 = lib.hopk_launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        losses.append(step(resident)['loss'])
+        losses.append(run(resident)['loss'])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = lib.hopk_launch_count() - launches0
-    spans = profiler.summary()
-    profiler.enable(False)
+    launches = graphed.launches_per_step * a.steps if graphed is not None else lib.hopk_launch_count() - launches0
     # ---- timed region 2: end to end from pinned host buffers (H2D of the batch, D2H of the loss scalars)
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         batch = [t.to(dev, non_blocking=True) for t in host]
-        out = step(batch)                                       # returns host floats: one D2H read per step
+        out = run(batch)                                        # returns host floats: one D2H read per step
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -241,6 +266,8 @@ def run_ours(a):
                 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32' if a.precision == 'fp32' else 'bf16+fp32', 'data': 'synthetic',
                 'config': workload_config(a, world) | {'tf32_library_gemms': bool(a.tf32), 'gan_phase': bool(a.gan),
+                                                       'cuda_graph': graphed is not None, 'graph_error': graph_error,
+                                                       'kernel_group_timing': f'{prof_steps} eagerly launched steps before the timed region',
                                                        'precision': a.precision + (' (gwnet + reprogramming on tcgen05 bf16 UMMA kernels, fp32 accumulate; '
                                                                                    'stock BERT/GRU/MLP parts under bf16 autocast)'
                                                                                    if a.precision == 'bf16' else ' (FFMA kernels, reference numerics)')},
@@ -249,8 +276,8 @@ def run_ours(a):
                         'd2h_bytes_per_step': 4 * len(out)},
                 'gpu_launches': int(launches),
                 'loss_first_last': [losses[0], losses[-1]],
-                'roofline': roofline(spans, a, world),
-                'kernel_ms_per_step': {k: round(v[1] / a.steps, 4) for k, v in sorted(spans.items())},
+                'roofline': roofline(spans, a, world, prof_steps),
+                'kernel_ms_per_step': {k: round(v[1] / prof_steps, 4) for k, v in sorted(spans.items())},
                 'dp': engine.stats if world > 1 else None}
         if world == 1 and not a.no_cpu_baseline:
             rate, sec, threads = cpu_oracle_rate(a.datasets, a.cpu_batch, 1, 1)
@@ -281,7 +308,7 @@ def measured_traffic():
         return {}
 
 
-def roofline(spans, a, world):
+def roofline(spans, a, world, nsteps):
     """Roofline position of every hand-written kernel group timed inside the step (CUDA events around the C-ABI calls);
     the top-level entry is the group that takes the most time per step.
 
@@ -311,7 +338,7 @@ def roofline(spans, a, world):
             extra = {'algorithmic_bytes': amount}
         groups[k] = {'bound': bound, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
                      'traffic': traffic.get(k), 'avg_ms': total_ms / calls, 'launches_timed': calls,
-                     'ms_per_step': total_ms / a.steps} | extra
+                     'ms_per_step': total_ms / nsteps} | extra
     if not groups:
         return None
     top = max(groups, key=lambda k: groups[k]['ms_per_step'])
@@ -351,6 +378,7 @@ def main():
     ap.add_argument('--gan', action='store_true', help='epoch > 10 variant (adds the discriminator step)')
     ap.add_argument('--tf32', type=int, default=0, help='allow TF32 in the stock cuBLAS/cuDNN parts (off = fp32 like the reference)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--graph', type=int, default=1, help='replay the whole training step as one CUDA graph (0 = launch eagerly)')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help='bf16 (BASELINE configs[1]): stock cuBLAS/cuDNN parts under bf16 autocast; fp32: reference numerics')
     a = ap.parse_args()

@@ -61,6 +61,7 @@ SIGNATURES = {
     'hopk_conv1x1_nchw_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'hopk_conv1x1_nchw_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'hopk_xattn_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp]),
+    'hopk_dropout_epoch_advance': (_i, [_i, _vp]),
     'hopk_xattn_pack_bytes': (_sz, [_i, _i]),
     'hopk_xattn_fwd_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp]),
     'hopk_xattn_bwd_scratch_bytes': (_sz, [_i, _i, _i]),

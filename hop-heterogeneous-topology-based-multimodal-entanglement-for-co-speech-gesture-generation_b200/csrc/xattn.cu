@@ -18,6 +18,12 @@ namespace hopk {
 constexpr int XT = 64;            // tile edge (rows and S)
 constexpr int XLDP = XT + 4;      // leading dim of the 64 x 64 probability tiles
 
+// added to every call's seed; advanced by a (graph-capturable) kernel so that replays of a captured training step do not
+// repeat the dropout mask that was baked into the launch arguments at capture time.  0 until advanced.
+__device__ unsigned long long g_drop_epoch_a = 0ull;
+__global__ void drop_epoch_bump_a() { g_drop_epoch_a += 0x9E3779B97F4A7C15ull; }
+__global__ void drop_epoch_reset_a() { g_drop_epoch_a = 0ull; }
+
 __device__ __forceinline__ uint32_t lowbias32(uint32_t x)
 {
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
@@ -135,6 +141,7 @@ xattn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const
                  float* __restrict__ LSE, int M, int L, int H, int E, int S, float scale, float inv_keep, uint32_t thr,
                  uint64_t seed)
 {
+    seed += g_drop_epoch_a;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ __align__(16) float sm[];
     const int ld = E + 4;
     float* Qs = sm; float* Ks = Qs + XT * ld; float* Vs = Ks + XT * ld; float* Ps = Vs + XT * ld;
@@ -213,6 +220,7 @@ xattn_bwd_dq_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
                     float* __restrict__ dQ, float* __restrict__ delta, int M, int L, int H, int E, int S, float scale,
                     float inv_keep, uint32_t thr, uint64_t seed)
 {
+    seed += g_drop_epoch_a;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ __align__(16) float sm[];
     const int ld = E + 4;
     float* Qs = sm; float* dOs = Qs + XT * ld; float* Ks = dOs + XT * ld; float* Vs = Ks + XT * ld; float* Ss = Vs + XT * ld;
@@ -294,6 +302,7 @@ xattn_bwd_dkv_kernel(const float* __restrict__ Q, const float* __restrict__ K, c
                      float* __restrict__ dK, float* __restrict__ dV, int M, int L, int H, int E, int S, float scale,
                      float inv_keep, uint32_t thr, uint64_t seed)
 {
+    seed += g_drop_epoch_a;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ __align__(16) float sm[];
     const int ld = E + 4;
     float* Ks = sm; float* Vs = Ks + XT * ld; float* Qs = Vs + XT * ld; float* dOs = Qs + XT * ld;
@@ -376,6 +385,13 @@ static int xattn_check(int B, int L, int H, int E, int S, float p)
     HOPK_REQUIRE(p >= 0.f && p < 1.f, "dropout p in [0,1)");
     return 0;
 }
+
+namespace hopk {
+void drop_epoch_launch_a(int reset, cudaStream_t st)
+{
+    if (reset) drop_epoch_reset_a<<<1, 1, 0, st>>>(); else drop_epoch_bump_a<<<1, 1, 0, st>>>();
+}
+}  // namespace hopk
 
 extern "C" int hopk_xattn_fwd(const float* q, const float* k, const float* v, float* o, float* lse, int B, int L, int H, int E,
                               int S, float p_drop, uint64_t seed, void* stream)

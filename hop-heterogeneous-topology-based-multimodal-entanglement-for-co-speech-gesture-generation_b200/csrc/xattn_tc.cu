@@ -21,6 +21,10 @@ __device__ volatile int* g_dbg = nullptr;      // optional progress markers in m
 constexpr int AT = 128;                       // tile edge: query rows, prototypes per tile, head dim
 constexpr uint32_t AT_SLAB = tc::slab_bytes(AT);        // 16 KB: [128 rows][64 bf16]
 
+__device__ unsigned long long g_drop_epoch_b = 0ull;       // see csrc/xattn.cu: g_drop_epoch_a (one copy per translation unit)
+__global__ void drop_epoch_bump_b() { g_drop_epoch_b += 0x9E3779B97F4A7C15ull; }
+__global__ void drop_epoch_reset_b() { g_drop_epoch_b = 0ull; }
+
 __device__ __forceinline__ uint32_t lowbias32_tc(uint32_t x)
 {
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
@@ -112,6 +116,7 @@ xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, co
                     float* __restrict__ O, float* __restrict__ LSE, int M, int L, int H, int S, float scale,
                     float inv_keep, uint32_t thr, uint64_t seed)
 {
+    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_s, bar_o;
     __shared__ uint32_t tmem_base_smem;
@@ -304,6 +309,7 @@ xattn_fwd_tc3_kernel(const float* __restrict__ Q, const uint8_t* __restrict__ kv
                      float* __restrict__ LSE, int M, int L, int H, int S, float scale, float inv_keep, uint32_t thr,
                      uint64_t seed)
 {
+    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[KV_STAGES], bar_s[2], bar_p[2], bar_o[2];
     __shared__ uint32_t tmem_base_smem;
@@ -471,6 +477,7 @@ xattn_bwd_dq_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                        float* __restrict__ dQ, float* __restrict__ delta, int M, int L, int H, int S, float scale,
                        float inv_keep, uint32_t thr, uint64_t seed)
 {
+    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_s, bar_q;
     __shared__ uint32_t tmem_base_smem;
@@ -608,6 +615,7 @@ xattn_bwd_dq_tc3_kernel(const float* __restrict__ Q, const uint8_t* __restrict__
                         float* __restrict__ delta, uint4* __restrict__ rowstat, int M, int L, int H, int S, float scale,
                         float inv_keep, uint32_t thr, uint64_t seed)
 {
+    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[KV_STAGES], bar_s[2], bar_p[2], bar_q[2];
     __shared__ uint32_t tmem_base_smem;
@@ -786,6 +794,7 @@ xattn_bwd_dkv_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K
                         float* __restrict__ dK, float* __restrict__ dV, int M, int L, int H, int S, float scale,
                         float inv_keep, uint32_t thr, uint64_t seed)
 {
+    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_s, bar_kv;
     __shared__ uint32_t tmem_base_smem;
@@ -927,6 +936,7 @@ xattn_bwd_dkv_tc3_kernel(const float* __restrict__ K, const float* __restrict__ 
                          const uint4* __restrict__ rowstat, float* __restrict__ dK, float* __restrict__ dV, int M, int H, int S,
                          int tiles_per_chunk, float scale, float inv_keep, uint32_t thr, uint64_t seed, int use_atomics)
 {
+    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[KV_STAGES], bar_s[2], bar_p, bar_kv;
     __shared__ uint32_t tmem_base_smem;
@@ -1099,6 +1109,16 @@ extern "C" int hopk_debug_set(void* mapped_host_ints)
 {
     int* p = (int*)mapped_host_ints;
     return cudaMemcpyToSymbol(hopk::g_dbg, &p, sizeof(p)) == cudaSuccess ? 0 : 1;
+}
+
+namespace hopk { void drop_epoch_launch_a(int reset, cudaStream_t st); }
+extern "C" int hopk_dropout_epoch_advance(int reset, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    hopk::drop_epoch_launch_a(reset, st);
+    if (reset) hopk::drop_epoch_reset_b<<<1, 1, 0, st>>>(); else hopk::drop_epoch_bump_b<<<1, 1, 0, st>>>();
+    HOPK_LAUNCH_CHECK("dropout_epoch");
+    return 0;
 }
 
 extern "C" size_t hopk_xattn_pack_bytes(int S, int H) { return (size_t)H * ((S + FS - 1) / FS) * KV_REC + 1024; }

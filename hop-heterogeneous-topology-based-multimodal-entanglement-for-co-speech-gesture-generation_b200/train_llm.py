@@ -26,6 +26,23 @@ def _forward(model, in_audio, log_melspec, text, pre_seq, vids, source):
 
 def train_llm(args, epoch, in_audio, log_melspec, text_token_padded, target_dir_vec, vid_indices,
               model, discriminator, model_optim, dis_optimizer, accelerator):
+    names, dev = train_llm_device(args, epoch, in_audio, log_melspec, text_token_padded, target_dir_vec, vid_indices,
+                                  model, discriminator, model_optim, dis_optimizer, accelerator)
+    return finish_losses(names, dev.tolist())                   # one device->host read for all reported scalars
+
+
+def finish_losses(names, host):
+    ret = dict(zip(names, host))
+    for k in ('KLD', 'DIV_REG'):                                # the reference drops falsy entries (`if kld:`)
+        if k in ret and not ret[k]:
+            del ret[k]
+    return ret
+
+
+def train_llm_device(args, epoch, in_audio, log_melspec, text_token_padded, target_dir_vec, vid_indices,
+                     model, discriminator, model_optim, dis_optimizer, accelerator):
+    """The whole step without its single host read: returns (names, stacked device tensor of the reported scalars).
+    Free of host synchronisation, so it can be captured in a CUDA graph (hop_b200.graphed.GraphedTrainStep)."""
     pre_seq = target_dir_vec[:, 0:16]
     dis_error = None
     core = getattr(model, 'module', model)
@@ -79,7 +96,6 @@ def train_llm(args, epoch, in_audio, log_melspec, text_token_padded, target_dir_
     accelerator.backward(loss)
     model_optim.step()
 
-    # one device->host read for all reported scalars
     names, vals = ['loss'], [args.loss_regression_weight * huber_loss.detach()]
     if kld is not None:
         names.append('KLD'); vals.append(args.loss_kld_weight * kld.detach())
@@ -87,9 +103,4 @@ def train_llm(args, epoch, in_audio, log_melspec, text_token_padded, target_dir_
         names.append('DIV_REG'); vals.append(args.loss_reg_weight * div_reg.detach())
     if gan:
         names += ['gen', 'dis']; vals += [args.loss_gan_weight * gen_error.detach(), dis_error.detach()]
-    host = torch.stack([v.float().reshape(()) for v in vals]).tolist()
-    ret = dict(zip(names, host))
-    for k in ('KLD', 'DIV_REG'):                                # the reference drops falsy entries (`if kld:`)
-        if k in ret and not ret[k]:
-            del ret[k]
-    return ret
+    return names, torch.stack([v.float().reshape(()) for v in vals])

@@ -134,6 +134,11 @@ int hopk_xattn_bwd(const float* q, const float* k, const float* v, const float* 
                    const float* dout, float* dq, float* dk, float* dv, float* delta,
                    int B, int L, int H, int E, int S, float p_drop, uint64_t seed, void* stream);
 
+/* Dropout epoch: a device-side value added to the `seed` argument of every attention call.  A training step captured in
+ * a CUDA graph bakes `seed` into its launch arguments; capturing one call of this function (reset = 0) at the top of the
+ * step makes every replay draw a fresh mask.  reset = 1 puts the epoch back to 0 (the state tests and oracles assume). */
+int hopk_dropout_epoch_advance(int reset, void* stream);
+
 /* dtype-1 variants of the two calls above: bf16 operands on tcgen05 (UMMA 128x128, TMEM accumulators), fp32
  * accumulation and fp32 I/O; head dim must be 128.  Same arguments and semantics. */
 /* kv_pack: scratch of hopk_xattn_pack_bytes(S, H) bytes (K/V re-packed as bf16 UMMA slab images and streamed with

@@ -1,0 +1,84 @@
+"""GPU: the whole training step replayed as one CUDA graph (hop_b200/graphed.py).
+
+(1) the dropout epoch: a captured attention call draws a fresh mask on every replay and reproduces the eager result
+    once the epoch is reset;  (2) a graphed TED step follows the eagerly launched one: with every noise source switched
+    off (dropout p = 0, reparameterisation noise = 0, identity speaker permutation) the replayed losses match the eager
+    losses of the same steps."""
+import copy
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _reset_epoch():
+    from hop_b200._lib import check, lib, stream_ptr
+    check(lib().hopk_dropout_epoch_advance(1, stream_ptr()))
+    torch.cuda.synchronize()
+
+
+def test_dropout_epoch_gives_fresh_masks_per_replay(cuda):
+    from hop_b200.HOP import _XattnFn
+    from hop_b200._lib import check, lib, stream_ptr
+    _reset_epoch()
+    torch.manual_seed(0)
+    q = torch.randn(2, 34, 8, 128, device=cuda)
+    k = torch.randn(300, 8, 128, device=cuda)
+    v = torch.randn(300, 8, 128, device=cuda)
+    eager = _XattnFn.apply(q, k, v, 0.5, 1234, True).clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        _XattnFn.apply(q, k, v, 0.5, 1234, True)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        check(lib().hopk_dropout_epoch_advance(0, stream_ptr()))
+        out = _XattnFn.apply(q, k, v, 0.5, 1234, True)
+    g.replay(); a = out.clone()
+    g.replay(); b = out.clone()
+    torch.cuda.synchronize()
+    assert torch.isfinite(a).all() and torch.isfinite(b).all()
+    assert float((a - b).abs().max()) > 0, 'two replays must not share a dropout mask'
+    assert float((a - eager).abs().max()) > 0, 'an advanced epoch must not reproduce the epoch-0 mask'
+    _reset_epoch()
+    again = _XattnFn.apply(q, k, v, 0.5, 1234, True)
+    assert torch.equal(again, eager), 'after a reset the eager result is reproduced bit for bit'
+
+
+def test_graphed_step_follows_eager_step(cuda, monkeypatch):
+    import bench
+    from hop_b200 import HOP, train_llm as TL
+    from hop_b200.HOP import Model
+    from hop_b200.discriminator import ConvDiscriminator
+    from hop_b200.graphed import GraphedTrainStep
+    _reset_epoch()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    monkeypatch.setattr(HOP, 'reparameterize', lambda mu, logvar: mu)
+    monkeypatch.setattr(torch, 'randperm', lambda n, device=None, **kw: torch.arange(n - 1, -1, -1, device=device))
+    torch.manual_seed(3)
+    model = Model(bench.model_cfg('TED'), bench.build_bert(), bench._Tok(), bench._Spk()).float().to(cuda).set_precision('bf16')
+    model.reprogramming_layer.dropout.p = 0.0
+    disc = ConvDiscriminator(27).to(cuda)
+    gen = torch.Generator().manual_seed(11)
+    batch = [t.to(cuda) for t in bench.synthetic_batch(8, 'TED', gen)]
+    sargs = bench.step_args('TED')
+    acc = types.SimpleNamespace(backward=lambda loss: loss.backward())
+
+    def make(m, d):
+        go = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=4e-4, betas=(0.5, 0.999), fused=True, capturable=True)
+        do = torch.optim.Adam(d.parameters(), lr=4e-4, betas=(0.5, 0.999), fused=True, capturable=True)
+        return go, do
+
+    m2, d2 = copy.deepcopy(model), copy.deepcopy(disc)
+    go, do = make(model, disc)
+    eager = [TL.train_llm(sargs, 1, *batch, model, disc, go, do, acc)['loss'] for _ in range(6)]
+    go2, do2 = make(m2, d2)
+    graphed = GraphedTrainStep(sargs, 1, m2, d2, go2, do2, acc, batch, warmup=3)      # 3 eager steps inside
+    replayed = [graphed(batch)['loss'] for _ in range(3)]
+    assert graphed.launches_per_step > 50
+    for e, r in zip(eager[3:], replayed):
+        assert abs(e - r) <= 1e-2 * abs(e), (eager, replayed)
