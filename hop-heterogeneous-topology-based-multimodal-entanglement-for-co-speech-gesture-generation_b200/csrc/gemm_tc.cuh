@@ -126,7 +126,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32])
 }
 
 template <int BN, class ALoad, class BLoad, class Epi>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(int M, int N, int K, int k_per_split, ALoad aload, BLoad bload, Epi epi)
 {
     extern __shared__ uint8_t smem_raw[];
