@@ -10,7 +10,8 @@
 // Epilogue contract (thread-private copy, like the FFMA skeleton):
 //   void row32(int m, bool valid, int n0, float (&v)[32], float* red);  // 32 consecutive columns of row m; called by
 //                                                                       // every lane of warps 0-3 (valid = m < M)
-//   void finish(float* red);        // by all 256 threads after a __syncthreads; red = 256 zero-initialised smem floats
+//   void finish(float* red);        // by all 256 threads after a __syncthreads; red = 1024 zero-initialised smem floats
+//                                   // (convention: warp w of the four epilogue warps owns red[256 w .. 256 w + 255])
 #pragma once
 #include <type_traits>
 #include <utility>
@@ -132,7 +133,7 @@ gemm_tc_kernel(int M, int N, int K, int k_per_split, ALoad aload, BLoad bload, E
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float red[256];
+    __shared__ float red[1024];                      // 4 lane-quarter warps x 256: per-warp slots, combined in a fixed order (deterministic)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr uint32_t A_BYTES = tc::slab_bytes(TC_BM), B_BYTES = tc::slab_bytes(BN), STAGE = A_BYTES + B_BYTES;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -145,7 +146,7 @@ gemm_tc_kernel(int M, int N, int K, int k_per_split, ALoad aload, BLoad bload, E
         tc::mbar_init(&bars[1], 1);
         tc::fence_barrier_init();
     }
-    red[tid] = 0.f;
+    for (int i = tid; i < 1024; i += TC_THREADS) red[i] = 0.f;
     if (warp == 0) tc::tmem_alloc(&tmem_base_smem, BN);
     tc::fence_before_sync();
     __syncthreads();

@@ -534,14 +534,15 @@ struct MlpEpi {              // u = h + bias + residual (gwnet.py:43-45, 233) an
             v[j] = u; sq[j] = u * u;
         }
         float a = warp_transpose_sum(v), b = warp_transpose_sum(sq);
-        int slot = (n0 + (threadIdx.x & 31)) & 127;
-        atomicAdd(red + slot, a); atomicAdd(red + 128 + slot, b);
+        int slot = (int)(threadIdx.x >> 5) * 256 + ((n0 + (threadIdx.x & 31)) & 127);      // this warp's own slots: no atomics
+        red[slot] = a; red[128 + slot] = b;
     }
     __device__ __forceinline__ void finish(float* red) {
         int n = blockIdx.x * tc_bn + threadIdx.x;
         if ((int)threadIdx.x < tc_bn && n < g.C && stats) {
-            atomicAdd(stats + n, (double)red[n & 127]);
-            atomicAdd(stats + g.C + n, (double)red[128 + (n & 127)]);
+            const int q = n & 127;
+            atomicAdd(stats + n, (double)((red[q] + red[256 + q]) + (red[512 + q] + red[768 + q])));
+            atomicAdd(stats + g.C + n, (double)((red[128 + q] + red[384 + q]) + (red[640 + q] + red[896 + q])));
         }
     }
     __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[4 * NG]) {
@@ -1019,15 +1020,16 @@ struct DxEpi {               // + residual gradient du[t-d]; BatchNorm-backward 
         }
         if (sums_prev) {
             float a = warp_transpose_sum(v), c = warp_transpose_sum(w);
-            int slot = (n0 + (threadIdx.x & 31)) & 127;
-            atomicAdd(red + slot, a); atomicAdd(red + 128 + slot, c);
+            int slot = (int)(threadIdx.x >> 5) * 256 + ((n0 + (threadIdx.x & 31)) & 127);  // this warp's own slots: no atomics
+            red[slot] = a; red[128 + slot] = c;
         }
     }
     __device__ __forceinline__ void finish(float* red) {
         int n = blockIdx.x * tc_bn + threadIdx.x;
         if (sums_prev && (int)threadIdx.x < tc_bn && n < g.C) {
-            atomicAdd(sums_prev + n, (double)red[n & 127]);
-            atomicAdd(sums_prev + g.C + n, (double)red[128 + (n & 127)]);
+            const int q = n & 127;
+            atomicAdd(sums_prev + n, (double)((red[q] + red[256 + q]) + (red[512 + q] + red[768 + q])));
+            atomicAdd(sums_prev + g.C + n, (double)((red[128 + q] + red[384 + q]) + (red[640 + q] + red[896 + q])));
         }
     }
     __device__ __forceinline__ void operator()(int m, int nb, const float (&v)[4 * NG]) {

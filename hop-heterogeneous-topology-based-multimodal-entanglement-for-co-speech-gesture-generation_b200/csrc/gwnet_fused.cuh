@@ -335,16 +335,19 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
             }
             const float s2 = warp_transpose_sum(w);
             const float s1 = warp_transpose_sum(uv);
-            atomicAdd(red + c * 32 + lane, s1);
-            atomicAdd(red + 128 + c * 32 + lane, s2);
+            // per-warp slots in the (now dead) operand region, combined below in a fixed order: bit-reproducible statistics
+            float* part = reinterpret_cast<float*>(A2) + (warp & 3) * 128;
+            part[c * 32 + lane] = s1;
+            part[64 + c * 32 + lane] = s2;
         }
     }
     FZ_STOP_AT(7)
     tc::fence_before_sync();
     __syncthreads();
     if (tid < C) {                                                    // feeder threads: no global stores of their own in flight
-        atomicAdd(a.stats + tid, (double)red[tid]);
-        atomicAdd(a.stats + C + tid, (double)red[128 + tid]);
+        const float* part = reinterpret_cast<const float*>(A2);
+        atomicAdd(a.stats + tid, (double)((part[tid] + part[128 + tid]) + (part[256 + tid] + part[384 + tid])));
+        atomicAdd(a.stats + C + tid, (double)((part[64 + tid] + part[192 + tid]) + (part[320 + tid] + part[448 + tid])));
         __threadfence();                                              // statistics visible before the ticket
     }
     if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);
