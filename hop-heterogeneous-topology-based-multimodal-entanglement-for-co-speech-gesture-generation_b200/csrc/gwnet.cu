@@ -1115,7 +1115,7 @@ using namespace hopk;
 // ============================================================================ backward plumbing
 struct SideStreams {
     cudaStream_t s[3];
-    cudaEvent_t ev_du[HOPK_MAX_LAYERS], ev_dfg[HOPK_MAX_LAYERS], ev_join[3];
+    cudaEvent_t ev_du[HOPK_MAX_LAYERS], ev_dfg[HOPK_MAX_LAYERS], ev_join[3], ev_head[3], ev_tail;
 };
 // created once per process (one process drives one GPU); non-blocking so they never serialise against stream 0
 static SideStreams* side_streams()
@@ -1127,7 +1127,9 @@ static SideStreams* side_streams()
         for (int k = 0; k < 3; ++k) {
             if (cudaStreamCreateWithFlags(&sd.s[k], cudaStreamNonBlocking) != cudaSuccess) state = -1;
             if (cudaEventCreateWithFlags(&sd.ev_join[k], cudaEventDisableTiming) != cudaSuccess) state = -1;
+            if (cudaEventCreateWithFlags(&sd.ev_head[k], cudaEventDisableTiming) != cudaSuccess) state = -1;
         }
+        if (cudaEventCreateWithFlags(&sd.ev_tail, cudaEventDisableTiming) != cudaSuccess) state = -1;
         for (int l = 0; l < HOPK_MAX_LAYERS; ++l) {
             if (cudaEventCreateWithFlags(&sd.ev_du[l], cudaEventDisableTiming) != cudaSuccess) state = -1;
             if (cudaEventCreateWithFlags(&sd.ev_dfg[l], cudaEventDisableTiming) != cudaSuccess) state = -1;
@@ -1319,17 +1321,23 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
     HOPK_CUDA(cudaMemsetAsync(S(g.s_m12), 0, 2 * (size_t)V * V * sizeof(float), st));
     if (int rc = zero_param_grads(s, gr, st)) return rc;      // split-K / atomic epilogues accumulate into zeroed buffers
 
-    // ---- head backward
+    SideStreams* sd = side_streams();
+    if (!sd) return fail(3, "side streams", "cudaStreamCreate failed");
+    static const bool skip_side = getenv("HOPK_BWD_SKIP_SIDE") != nullptr;     // timing experiments only: wrong gradients
+
+    // ---- head backward: the dgrad GEMMs form the dependent chain, the three weight-gradient GEMMs go to the side streams
     const int M4 = B * g.Tl * V;
     {
         nchw_to_rows_kernel<<<cdiv((long)M4 * O, 256), 256, 0, st>>>(dout, S(g.s_dorow), B, O, V, g.Tl);
         HOPK_LAUNCH_CHECK("dout_rows");
         // end_conv_2
         {
+            HOPK_CUDA(cudaEventRecord(sd->ev_head[0], st));
+            HOPK_CUDA(cudaStreamWaitEvent(sd->s[0], sd->ev_head[0], 0));
             Ld2D<false, 0> a{S(g.s_dorow), nullptr, O};
             Ld2DOnes<false> b{F(g.r1), E, E};
             EpiWgrad<2> e{gr->end2_w, E, gr->end2_b, E, O};
-            launch_gemm<1, 2>(tc, O, E + 1, M4, pick_splits(tc, O, E + 1, M4, 1, 2), a, b, e, st);
+            launch_gemm<1, 2>(tc, O, E + 1, M4, pick_splits(tc, O, E + 1, M4, 1, 2), a, b, e, sd->s[0]);
             HOPK_LAUNCH_CHECK("end2_wgrad");
             Ld2D<true, 0> a2{S(g.s_dorow), nullptr, O};
             Ld2D<false, 0> b2{p->end2_w, nullptr, E};
@@ -1339,10 +1347,12 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
         }
         // end_conv_1
         {
+            HOPK_CUDA(cudaEventRecord(sd->ev_head[1], st));
+            HOPK_CUDA(cudaStreamWaitEvent(sd->s[1], sd->ev_head[1], 0));
             Ld2D<false, 0> a{S(g.s_de1), nullptr, E};
             Ld2DOnes<false> b{F(g.r0), Sk, Sk};
             EpiWgrad<2> e{gr->end1_w, Sk, gr->end1_b, Sk, E};
-            launch_gemm<1, 2>(tc, E, Sk + 1, M4, pick_splits(tc, E, Sk + 1, M4, 1, 2), a, b, e, st);
+            launch_gemm<1, 2>(tc, E, Sk + 1, M4, pick_splits(tc, E, Sk + 1, M4, 1, 2), a, b, e, sd->s[1]);
             HOPK_LAUNCH_CHECK("end1_wgrad");
             Ld2D<true, 0> a2{S(g.s_de1), nullptr, E};
             Ld2D<false, 0> b2{p->end1_w, nullptr, Sk};
@@ -1352,11 +1362,13 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
         }
         // skip convs: one concat GEMM each way
         {
+            HOPK_CUDA(cudaEventRecord(sd->ev_head[2], st));
+            HOPK_CUDA(cudaStreamWaitEvent(sd->s[2], sd->ev_head[2], 0));
             Ld2D<false, 0> a{S(g.s_dskip), nullptr, Sk};
             Ld2DOnes<false> b{F(g.ycat), (long)L * C, L * C};
             SkipWgradEpi<2> e; e.C = C; e.L = L;
             for (int l = 0; l < L; ++l) { e.dw[l] = gr->skip_w[l]; e.db[l] = gr->skip_b[l]; }
-            launch_gemm<1, 2>(tc, Sk, L * C + 1, M4, pick_splits(tc, Sk, L * C + 1, M4, 1, 2), a, b, e, st);
+            launch_gemm<1, 2>(tc, Sk, L * C + 1, M4, pick_splits(tc, Sk, L * C + 1, M4, 1, 2), a, b, e, sd->s[2]);
             HOPK_LAUNCH_CHECK("skip_wgrad");
             Ld2D<true, 0> a2{S(g.s_dskip), nullptr, Sk};
             SkipWT b2; b2.C = C; for (int l = 0; l < L; ++l) b2.w[l] = p->skip_w[l];
@@ -1369,9 +1381,6 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
     // ---- layers, last to first.  The caller's stream carries the dependent chain (BN backward -> node mix -> dy -> dx);
     // the weight-gradient GEMMs and the dA Gram products only feed parameter gradients, so they run on three side
     // streams forked from / joined back to the caller's stream with events (du, G, df, dg are kept per layer).
-    SideStreams* sd = side_streams();
-    if (!sd) return fail(3, "side streams", "cudaStreamCreate failed");
-    static const bool skip_side = getenv("HOPK_BWD_SKIP_SIDE") != nullptr;     // timing experiments only: wrong gradients
     float* dxn = nullptr;                 // gradient w.r.t. BN_i output (= layer i+1 input)
     float* dx_buf[2] = {S(g.s_dxa), S(g.s_dxb)};
     int flip = 0;
@@ -1489,23 +1498,19 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             dxn = DX; flip ^= 1;
         }
     }
-    // join the side streams: everything below (and everything the caller enqueues next) sees the finished gradients
-    for (int k = 0; k < 3; ++k) {
-        HOPK_CUDA(cudaEventRecord(sd->ev_join[k], sd->s[k]));
-        HOPK_CUDA(cudaStreamWaitEvent(st, sd->ev_join[k], 0));
-    }
-
-    // ---- adaptive adjacency and start conv
-    adp_bwd_kernel<<<1, 256, V * V * sizeof(float), st>>>(p->nodevec1, p->nodevec2, F(g.A), F(g.Z), S(g.s_m12),
-                                                           S(g.s_m12) + V * V, V, s->rank, gr->nodevec1, gr->nodevec2);
+    // ---- adaptive adjacency (side stream 1, behind the Gram kernels it consumes) and start conv
+    HOPK_CUDA(cudaEventRecord(sd->ev_tail, st));                 // the gradient w.r.t. the start conv output is complete
+    adp_bwd_kernel<<<1, 256, V * V * sizeof(float), sd->s[1]>>>(p->nodevec1, p->nodevec2, F(g.A), F(g.Z), S(g.s_m12),
+                                                                 S(g.s_m12) + V * V, V, s->rank, gr->nodevec1, gr->nodevec2);
     HOPK_LAUNCH_CHECK("adp_bwd");
     {
         int M = B * g.Tp * V;
+        HOPK_CUDA(cudaStreamWaitEvent(sd->s[0], sd->ev_tail, 0));
         Ld2D<false, 0> a{dxn, nullptr, C};
         StartAT b{x, g.Tp, V, g.pad, s->in_dim, (long)xs[0], (long)xs[1], (long)xs[2], (long)xs[3]};
         EpiWgrad<2> e{gr->start_w, s->in_dim, gr->start_b, s->in_dim, C};
-        if (C <= 64) launch_gemm<1, 2>(tc, C, s->in_dim + 1, M, pick_splits(tc, C, s->in_dim + 1, M, 1, 2), a, b, e, st);
-        else launch_gemm<2, 2>(tc, C, s->in_dim + 1, M, pick_splits(tc, C, s->in_dim + 1, M, 2, 2), a, b, e, st);
+        if (C <= 64) launch_gemm<1, 2>(tc, C, s->in_dim + 1, M, pick_splits(tc, C, s->in_dim + 1, M, 1, 2), a, b, e, sd->s[0]);
+        else launch_gemm<2, 2>(tc, C, s->in_dim + 1, M, pick_splits(tc, C, s->in_dim + 1, M, 2, 2), a, b, e, sd->s[0]);
         HOPK_LAUNCH_CHECK("start_wgrad");
         if (dx) {
             Ld2D<true, 0> a2{dxn, nullptr, C};
@@ -1514,6 +1519,11 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             launch_gemm<2, 2>(tc, M, s->in_dim, C, 1, a2, b2, e2, st);
             HOPK_LAUNCH_CHECK("start_dgrad");
         }
+    }
+    // join the side streams: everything the caller enqueues next sees the finished gradients
+    for (int k = 0; k < 3; ++k) {
+        HOPK_CUDA(cudaEventRecord(sd->ev_join[k], sd->s[k]));
+        HOPK_CUDA(cudaStreamWaitEvent(st, sd->ev_join[k], 0));
     }
     return 0;
 }
