@@ -325,6 +325,25 @@ class Model(nn.Module):
         self._we_cast = None
         return out
 
+    def _gwnet_bn_buffers(self):
+        return [t for bn in self.gwnet.bn for t in (bn.running_mean, bn.running_var)]
+
+    @torch.no_grad()
+    def _repeat_bn_update(self, shared):
+        """One more train-mode BatchNorm buffer update with the batch statistics of the forward that produced
+        ``shared['feature']``: with momentum m, r1 = (1-m) r0 + m s and r2 = (1-m) r1 + m s = (2-m) r1 - (1-m) r0."""
+        prev = shared.get('bn_prev')
+        if prev is None or not self.training:
+            return
+        cur = self._gwnet_bn_buffers()
+        keep = [c.clone() for c in cur]
+        m = float(self.gwnet.bn[0].momentum)
+        torch._foreach_mul_(cur, 2.0 - m)
+        torch._foreach_add_(cur, prev, alpha=-(1.0 - m))
+        shared['bn_prev'] = keep
+        for bn in self.gwnet.bn:
+            bn.num_batches_tracked.add_(1)
+
     def source_embeddings(self):
         """Text prototypes (1500, d_llm) = mapping_layer(word_embeddings^T)^T  (HOP.py:200); batch independent."""
         dt = self.amp_dtype or torch.float32
@@ -335,12 +354,12 @@ class Model(nn.Module):
             we = self._we_cast
         return _SourceFn.apply(self.mapping_layer.weight, self.mapping_layer.bias, we, self._source_reducer, dt)
 
-    def forecast(self, in_audio, x_enc, text, pre_seq, vid_indices, source=None):
+    def forecast(self, in_audio, x_enc, text, pre_seq, vid_indices, source=None, shared=None):
         with torch.autocast('cuda', dtype=self.amp_dtype or torch.bfloat16, enabled=self.amp_dtype is not None):
-            out = self._forecast(in_audio, x_enc, text, pre_seq, vid_indices, source)
+            out = self._forecast(in_audio, x_enc, text, pre_seq, vid_indices, source, shared)
         return tuple(t.float() if t is not None else None for t in out)     # callers (losses, discriminator) see fp32
 
-    def _forecast(self, in_audio, x_enc, text, pre_seq, vid_indices, source=None):
+    def _forecast(self, in_audio, x_enc, text, pre_seq, vid_indices, source=None, shared=None):
         B = pre_seq.shape[0]
         J = int(pre_seq.shape[2] / 3)
         if self.z_obj:
@@ -361,11 +380,22 @@ class Model(nn.Module):
 
         # beat features: the reference runs the MLP on J identical copies of the 16 windows and then
         # *reinterprets* (B,J,16,170) as (B,16,J,170) (HOP.py:210-212); equal to MLP-once + gather.
-        windows = in_audio.unfold(1, 3400, 2191)                         # (B, 16, 3400)
-        feat = self.beat(windows)                                        # (B, 16, 170)
-        feat = feat[:, self._window_index(J, feat.device)]               # (B, 16, J, 170)
-        seq_audio = torch.cat([pre_seq.view(B, 16, -1, 3), feat.float()], dim=3)  # (B, 16, J, 173) == rows layout
-        feature = self.gwnet(seq_audio.permute(0, 3, 2, 1))               # strided view, read in place
+        if shared is not None and 'feature' in shared and (shared['feature_has_graph'] or not torch.is_grad_enabled()):
+            # Second / third forward of the same training step (train_llm.py:17,42,58): same audio, same seed poses, same
+            # weights, no dropout on this branch -- the reference recomputes bit-identical beat features and Graph-WaveNet
+            # output.  Reuse them and give the BatchNorm running statistics the update the recomputation would have made.
+            feature = shared['feature']
+            self._repeat_bn_update(shared)
+        else:
+            if shared is not None and self.training:
+                shared['bn_prev'] = [b.clone() for b in self._gwnet_bn_buffers()]
+            windows = in_audio.unfold(1, 3400, 2191)                         # (B, 16, 3400)
+            feat = self.beat(windows)                                        # (B, 16, 170)
+            feat = feat[:, self._window_index(J, feat.device)]               # (B, 16, J, 170)
+            seq_audio = torch.cat([pre_seq.view(B, 16, -1, 3), feat.float()], dim=3)  # (B, 16, J, 173) == rows layout
+            feature = self.gwnet(seq_audio.permute(0, 3, 2, 1))               # strided view, read in place
+            if shared is not None:
+                shared['feature'], shared['feature_has_graph'] = feature, torch.is_grad_enabled()
 
         g_seq = feature[:, :3, :, :]
         beat = feature[:, 3:, :, :].reshape(B, 34, -1)

@@ -7,6 +7,9 @@ change the arithmetic:
     once per step and shared by the 2-3 generator forwards (the reference recomputes them);
   * the random-speaker pass, whose outputs the reference only uses ``.detach()``-ed, runs under
     ``torch.no_grad()`` (its BatchNorm running-stat updates and dropout draws still happen);
+  * the beat features and the Graph-WaveNet output -- a function of the audio, the seed poses and the weights only, with
+    no dropout on that branch -- are computed by the first forward of the step and reused by the others (the reference
+    recomputes identical values); the BatchNorm running statistics still receive one update per forward;
   * the 2-5 ``.item()`` host syncs are folded into one device->host read at the end.
 ``accelerator`` only needs ``.backward(loss)`` (hop_b200.dp.DataParallel provides it; so does HF Accelerate).
 """
@@ -14,13 +17,16 @@ import torch
 import torch.nn.functional as F
 
 
+SHARE_STEP_FEATURES = True
+
+
 def add_noise(data):
     return data + torch.randn_like(data) * 0.1
 
 
-def _forward(model, in_audio, log_melspec, text, pre_seq, vids, source):
+def _forward(model, in_audio, log_melspec, text, pre_seq, vids, source, shared=None):
     if source is not None:
-        return model.forecast(in_audio, log_melspec, text, pre_seq, vids, source=source)
+        return model.forecast(in_audio, log_melspec, text, pre_seq, vids, source=source, shared=shared)
     return model(in_audio, log_melspec, text, pre_seq, vids)
 
 
@@ -47,13 +53,15 @@ def train_llm_device(args, epoch, in_audio, log_melspec, text_token_padded, targ
     dis_error = None
     core = getattr(model, 'module', model)
     source = core.source_embeddings() if hasattr(core, 'source_embeddings') else None
+    # beat features + Graph-WaveNet output are identical in every forward of a step (SHARE_STEP_FEATURES = False recomputes)
+    shared = {} if (source is not None and SHARE_STEP_FEATURES) else None
     gan = epoch > 10 and args.loss_gan_weight > 0.0
 
     if gan:                                                     # discriminator step (train_llm.py:15-36)
         dis_optimizer.zero_grad()
         with torch.no_grad():
             outputs, *_ = _forward(core, in_audio, log_melspec, text_token_padded, pre_seq, vid_indices,
-                                   None if source is None else source.detach())
+                                   None if source is None else source.detach(), shared)
         dis_real = discriminator(add_noise(target_dir_vec), text_token_padded)
         dis_fake = discriminator(add_noise(outputs.detach()), text_token_padded)
         dis_error = torch.sum(-torch.mean(torch.log(dis_real + 1e-8) + torch.log(1 - dis_fake + 1e-8)))
@@ -62,7 +70,7 @@ def train_llm_device(args, epoch, in_audio, log_melspec, text_token_padded, targ
 
     model_optim.zero_grad()                                     # generator step (train_llm.py:38-86)
     outputs, z_context, z_mu, z_logvar = _forward(core, in_audio, log_melspec, text_token_padded, pre_seq,
-                                                   vid_indices, source)
+                                                   vid_indices, source, shared)
     dis_output = discriminator(outputs, text_token_padded)      # computed every step, like train_llm.py:43-44
     gen_error = -torch.mean(torch.log(dis_output + 1e-8))
     huber_loss = F.smooth_l1_loss(outputs / 0.1, target_dir_vec / 0.1) * 0.1
@@ -75,7 +83,7 @@ def train_llm_device(args, epoch, in_audio, log_melspec, text_token_padded, targ
             rand_vids = None
         with torch.no_grad():
             out_dir_vec_rand_vid, z_rand_vid, _, _ = _forward(core, in_audio, log_melspec, text_token_padded, pre_seq,
-                                                              rand_vids, None if source is None else source.detach())
+                                                              rand_vids, None if source is None else source.detach(), shared)
         beta = 0.05
         pose_l1 = F.smooth_l1_loss(outputs / beta, out_dir_vec_rand_vid.detach() / beta, reduction='none') * beta
         pose_l1 = pose_l1.sum(dim=1).sum(dim=1)

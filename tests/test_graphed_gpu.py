@@ -82,3 +82,44 @@ def test_graphed_step_follows_eager_step(cuda, monkeypatch):
     assert graphed.launches_per_step > 50
     for e, r in zip(eager[3:], replayed):
         assert abs(e - r) <= 1e-2 * abs(e), (eager, replayed)
+
+
+def test_shared_step_features_keep_losses_and_bn_buffers(cuda, monkeypatch):
+    """Reusing the beat features + Graph-WaveNet output across the forwards of a step must not change the step: same
+    losses, same parameters, same BatchNorm running statistics as recomputing them (the reference's behaviour)."""
+    import bench
+    from hop_b200 import HOP, train_llm as TL
+    from hop_b200.HOP import Model
+    from hop_b200.discriminator import ConvDiscriminator
+    _reset_epoch()
+    monkeypatch.setattr(HOP, 'reparameterize', lambda mu, logvar: mu)
+    monkeypatch.setattr(torch, 'randperm', lambda n, device=None, **kw: torch.arange(n - 1, -1, -1, device=device))
+    torch.manual_seed(5)
+    model = Model(bench.model_cfg('TED'), bench.build_bert(), bench._Tok(), bench._Spk()).float().to(cuda).set_precision('fp32')   # exact mode: no bf16 rounding flips to amplify
+    model.reprogramming_layer.dropout.p = 0.0
+    disc = ConvDiscriminator(27).to(cuda)
+    gen = torch.Generator().manual_seed(12)
+    batch = [t.to(cuda) for t in bench.synthetic_batch(8, 'TED', gen)]
+    sargs = bench.step_args('TED')
+    acc = types.SimpleNamespace(backward=lambda loss: loss.backward())
+    results = []
+    for share in (True, False):
+        monkeypatch.setattr(TL, 'SHARE_STEP_FEATURES', share)
+        m, d = copy.deepcopy(model), copy.deepcopy(disc)
+        m.gru.flatten_parameters()
+        go = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=4e-4, betas=(0.5, 0.999))
+        do = torch.optim.Adam(d.parameters(), lr=4e-4, betas=(0.5, 0.999))
+        first = TL.train_llm(sargs, 1, *batch, m, d, go, do, acc)['loss']
+        after_one = [b.clone() for b in m._gwnet_bn_buffers()]
+        losses = [first] + [TL.train_llm(sargs, ep, *batch, m, d, go, do, acc)['loss'] for ep in (1, 11)]   # 11: GAN phase, 3 forwards
+        results.append((losses, after_one, [b.clone() for b in m._gwnet_bn_buffers()], int(m.gwnet.bn[0].num_batches_tracked),
+                        m.gwnet.filter_convs[0].weight.detach().clone()))
+    (l1, a1, b1, n1, w1), (l2, a2, b2, n2, w2) = results
+    assert n1 == n2 == 2 + 2 + 3
+    rel = lambda x, y: float((x - y).abs().max() / (y.abs().max() + 1e-12))
+    assert abs(l1[0] - l2[0]) <= 1e-6 * abs(l2[0]), (l1, l2)             # before any update: identical computation
+    assert max(rel(x, y) for x, y in zip(a1, a2)) < 1e-5                  # two BatchNorm updates from one set of statistics
+    for x, y in zip(l1, l2):                                              # later steps: Adam amplifies atomics-order noise
+        assert abs(x - y) <= 2e-3 * abs(y), (l1, l2)
+    assert max(rel(x, y) for x, y in zip(b1, b2)) < 2e-3
+    assert rel(w1, w2) < 2e-2
