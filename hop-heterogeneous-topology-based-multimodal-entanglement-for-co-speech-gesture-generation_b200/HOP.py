@@ -55,6 +55,9 @@ class _LinearFn(torch.autograd.Function):
         return (dx.view(ctx.shp) if dx is not None else None), dw, db, None
 
 
+XATTN_PACKED = True
+
+
 class _XattnFn(torch.autograd.Function):
     """softmax(Q K^T / sqrt(E)) -> dropout -> . V without materialising the (B,H,L,S) scores."""
 
@@ -67,7 +70,9 @@ class _XattnFn(torch.autograd.Function):
         lse = torch.empty((B, H, L), device=q.device, dtype=torch.float32)
         with profiler.span('xattn_fwd'):
             if tc and E == 128:
-                pack = torch.empty(lib().hopk_xattn_pack_bytes(S, H), device=q.device, dtype=torch.uint8)
+                # packed bf16 K/V records + bulk-copy rings (v3 kernels); XATTN_PACKED = False selects the kernels that
+                # stage fp32 operands with their own threads (kept behind the same ABI, exercised by the tests)
+                pack = torch.empty(lib().hopk_xattn_pack_bytes(S, H), device=q.device, dtype=torch.uint8) if XATTN_PACKED else None
                 check(lib().hopk_xattn_fwd_tc(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(pack), B, L, H, E, S,
                                               float(p_drop), int(seed), stream_ptr()))
             else:
@@ -88,7 +93,8 @@ class _XattnFn(torch.autograd.Function):
         delta = torch.empty_like(lse)
         with profiler.span('xattn_bwd'):
             if ctx.tc:
-                scratch = torch.empty(lib().hopk_xattn_bwd_scratch_bytes(B, L, H), device=q.device, dtype=torch.uint8)
+                scratch = (torch.empty(lib().hopk_xattn_bwd_scratch_bytes(B, L, H), device=q.device, dtype=torch.uint8)
+                           if ctx.pack is not None else None)
                 check(lib().hopk_xattn_bwd_tc(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
                                               ptr(delta), ptr(ctx.pack), ptr(scratch), B, L, H, E, S, ctx.p_drop, ctx.seed,
                                               stream_ptr()))

@@ -170,11 +170,15 @@ def test_xattn_tcgen05_forward_exact(cuda):
     assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 2e-3
 
 
-@pytest.mark.parametrize('B,L,H,S,p', [(2, 34, 8, 1500, 0.0), (3, 7, 1, 300, 0.0), (5, 34, 2, 128, 0.1)])
-def test_xattn_tcgen05_backward(B, L, H, S, p, cuda):
+@pytest.mark.parametrize('B,L,H,S,p,packed', [(2, 34, 8, 1500, 0.0, True), (3, 7, 1, 300, 0.0, True), (5, 34, 2, 128, 0.1, True),
+                                              (3, 34, 2, 300, 0.1, False)])
+def test_xattn_tcgen05_backward(B, L, H, S, p, packed, cuda, monkeypatch):
     """Tensor-core attention backward (dQ and dK/dV passes) against float64 on bf16-representable inputs.
-    Remaining error: bf16 rounding of P~ and dS (2^-9 relative per element) -> 5e-3 in relative 2-norm."""
+    Remaining error: bf16 rounding of P~ and dS (2^-9 relative per element) -> 5e-3 in relative 2-norm.
+    packed = True: v3 kernels (bf16 operand records through bulk-copy rings); False: the kernels that stage fp32 operands."""
+    from hop_b200 import HOP
     from hop_b200.HOP import _XattnFn
+    monkeypatch.setattr(HOP, 'XATTN_PACKED', packed)
     torch.manual_seed(B + S)
     q = torch.randn(B, L, H, 128).bfloat16().double().requires_grad_(True)
     k = torch.randn(S, H, 128).bfloat16().double().requires_grad_(True)
