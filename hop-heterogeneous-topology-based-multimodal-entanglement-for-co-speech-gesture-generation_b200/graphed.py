@@ -47,8 +47,16 @@ class GraphedTrainStep:
         return train_llm_device(self.args, self.epoch, *self.static, self.model, self.discriminator, self.model_optim,
                                 self.dis_optimizer, self.accelerator)
 
-    def __call__(self, batch):
+    def launch(self, batch):
+        """Enqueue one step (copy the batch into the static inputs, replay) without waiting for it."""
         for s, t in zip(self.static, batch):
             s.copy_(t, non_blocking=True)
         self.graph.replay()
+
+    def result(self):
+        """The reported scalars of the last launched step (the step's only host synchronisation)."""
         return finish_losses(self.names, self.out.tolist())
+
+    def __call__(self, batch):
+        self.launch(batch)
+        return self.result()
