@@ -929,6 +929,51 @@ struct GateWgEpi2 {          // out[i = fg*C + o][j = 2c + tap] -> d(filter|gate
     __device__ __forceinline__ void bias(int i, float v) { int fg = i >= C; atomicAdd((fg ? dbg : dbf) + (i - fg * C), v); }
 };
 
+// ---- dA Gram products as ONE tensor-core weight-gradient GEMM (used for large graphs, V*V >= 256):
+//   M1[v][w] = sum_{g,c} y[(g,v)][c] G[(g,w)][c],  M2[v][w] = sum_{g,c} y[(g,v)][c] G[(g,w)][C + c]
+// is out[i][j] = sum_r A(r, i) B(r, j) with contraction rows r = (group g, channel c), i = v and j = w | V + w.
+struct W8GramY {             // A(r = g*C + c, i = v) = tanh f * sigmoid g at row (g, v), channel c
+    const float* tf; const float* sg; int V, C;
+    __device__ __forceinline__ void ld8(int r, int c0, float (&f)[8]) const {
+        const int g = r / C, c = r - g * C;
+        const size_t base = (size_t)g * V * C + c;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int v = c0 + q;
+            f[q] = v < V ? __ldg(tf + base + (size_t)v * C) * __ldg(sg + base + (size_t)v * C) : 0.f;
+        }
+    }
+};
+struct W8GramG {             // B(r = g*C + c, j) = G[(g, j)][c] for j < V, G[(g, j - V)][C + c] for V <= j < 2V   (G has ld 2C)
+    const float* G; int V, C;
+    __device__ __forceinline__ void ld8(int r, int c0, float (&f)[8]) const {
+        const int g = r / C, c = r - g * C;
+        const size_t base = (size_t)g * V * 2 * C + c;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = c0 + q;
+            float x = 0.f;
+            if (j < V) x = __ldg(G + base + (size_t)j * 2 * C);
+            else if (j < 2 * V) x = __ldg(G + base + (size_t)(j - V) * 2 * C + C);
+            f[q] = x;
+        }
+    }
+};
+struct GramEpi {             // out[v][j] -> M12[v*V + w] (j = w < V) or M12[V*V + v*V + w] (j = V + w)
+    float* M12; int V;
+    __device__ __forceinline__ void row32(int i, bool valid, int j0, float (&v)[32], float*) {
+        if (!valid || i >= V) return;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+            const int j = j0 + jj;
+            if (j < V) atomicAdd(M12 + i * V + j, v[jj]);
+            else if (j < 2 * V) atomicAdd(M12 + V * V + i * V + (j - V), v[jj]);
+        }
+    }
+    __device__ __forceinline__ void finish(float*) {}
+    __device__ __forceinline__ void bias(int, float) {}
+};
+
 struct DxA {                 // A(m_in, k = (tap*2 + fg)*C + o) = (fg?DG:DF)[(b, t - tap*d, v)][o], 0 outside [0, To)
     static constexpr bool kFast = true;
     const float* DF; const float* DG; LayerGeom g;
@@ -1436,11 +1481,19 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
                 EpiStore<2> e{S(g.s_g[i]), (long)2 * C, nullptr, nullptr, 2 * C, 0};
                 launch_gemm<2, 2>(tc, M, 2 * C, C, 1, a, b, e, s1);
                 HOPK_LAUNCH_CHECK("g_gemm");
+                if (tc && C % 8 == 0 && V * V >= 256 && 2 * V <= 128) {      // large graph: the Gram products as one UMMA GEMM
+                    W8GramY ga{F(g.tf[i]), F(g.sg[i]), V, C};
+                    W8GramG gb{S(g.s_g[i]), V, C};
+                    GramEpi ge{S(g.s_m12), V};
+                    HOPK_CUDA(launch_gemm_tc_wgrad<128>(groups * C, V, 2 * V, ga, gb, ge, false, s1));
+                    HOPK_LAUNCH_CHECK("gram_tc");
+                } else {
                 size_t smem3 = ((size_t)GRAM_GPI * V * (3 * C + 2) + 2 * (size_t)V * V) * sizeof(float);
                 if (smem3 > 48 * 1024) HOPK_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
                 int gblocks = cdiv(groups, GRAM_GPI); if (gblocks > 148) gblocks = 148;
                 gram_kernel<<<gblocks, 256, smem3, s1>>>(F(g.tf[i]), F(g.sg[i]), S(g.s_g[i]), S(g.s_m12), groups, V, C);
                 HOPK_LAUNCH_CHECK("gram");
+                }
             }
         }
         // dy (+ skip path) -> df, dg
