@@ -20,7 +20,8 @@ _LAYER_ARR = _vp * MAX_LAYERS
 class GwnetShape(C.Structure):
     _fields_ = [('B', C.c_int), ('V', C.c_int), ('T', C.c_int), ('in_dim', C.c_int), ('out_dim', C.c_int),
                 ('C', C.c_int), ('S', C.c_int), ('E', C.c_int), ('L', C.c_int), ('dil', C.c_int * MAX_LAYERS),
-                ('rank', C.c_int), ('training', C.c_int), ('dtype', C.c_int)]
+                ('rank', C.c_int), ('training', C.c_int), ('dtype', C.c_int),
+                ('bn_momentum', C.c_float), ('bn_eps', C.c_float)]
 
 
 class GwnetParams(C.Structure):
@@ -48,10 +49,10 @@ SIGNATURES = {
     'hopk_last_error': (C.c_char_p, []),
     'hopk_version': (_i, []),
     'hopk_launch_count': (C.c_longlong, []),
-    'hopk_debug_set': (_i, [_vp]),
     'hopk_gwnet_workspace_bytes': (_sz, [_SHP]),
     'hopk_gwnet_scratch_bytes': (_sz, [_SHP]),
     'hopk_gwnet_out_steps': (_i, [_SHP]),
+    'hopk_gwnet_ws_field': (_i, [_SHP, C.c_char_p, _i, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
     'hopk_gwnet_forward': (_i, [_SHP, _PRM, _vp, _I64x4, _vp, _vp, _vp]),
     'hopk_gwnet_backward': (_i, [_SHP, _PRM, _vp, _I64x4, _vp, _vp, _vp, _GRD, _vp, _vp]),
     'hopk_nconv_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -27,6 +27,11 @@ long long& launch_counter();        // kernels launched by this library since lo
     do { hopk::launch_counter() += 1; cudaError_t _e = cudaGetLastError(); \
          if (_e != cudaSuccess) return hopk::fail(4, "launch failed: " name, cudaGetErrorString(_e)); } while (0)
 
+// device address of the dropout epoch on the current device (api.cu); nullptr on failure
+const unsigned long long* drop_epoch_ptr();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) (api.cu)
+cudaError_t configure_smem_once(const void* func, size_t bytes);
+
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace hopk

@@ -13,6 +13,7 @@
 //   void finish(float* red);        // by all 256 threads after a __syncthreads; red = 1024 zero-initialised smem floats
 //                                   // (convention: warp w of the four epilogue warps owns red[256 w .. 256 w + 255])
 #pragma once
+#include "common.cuh"
 #include <type_traits>
 #include <utility>
 #include "tc_core.cuh"
@@ -217,11 +218,9 @@ template <int BN, class AL, class BL, class EP>
 static cudaError_t launch_gemm_tc(int M, int N, int K, int splits, AL a, BL b, EP e, cudaStream_t st)
 {
     auto kern = gemm_tc_kernel<BN, AL, BL, EP>;
-    static bool configured = false;             // per instantiation
-    if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<BN>());
+    {
+        cudaError_t err = configure_smem_once((const void*)kern, tc_smem_bytes<BN>());      // once per (device, instantiation)
         if (err != cudaSuccess) return err;
-        configured = true;
     }
     int kper = K;
     if (splits > 1) { kper = (((K + splits - 1) / splits + TC_BK - 1) / TC_BK) * TC_BK; splits = (K + kper - 1) / kper; }

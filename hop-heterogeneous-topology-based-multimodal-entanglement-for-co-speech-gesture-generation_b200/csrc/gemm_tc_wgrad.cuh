@@ -9,6 +9,7 @@
 // Loader contract:  int ncols;  void ld8(int r, int c0, float (&f)[8]) const;   // 8 consecutive columns, 0 outside
 // Epilogue contract: row32 / finish as in gemm_tc.cuh, plus  void bias(int i, float v);  // column sum of A (atomic)
 #pragma once
+#include "common.cuh"
 #include "gemm_tc.cuh"
 
 namespace hopk {
@@ -146,11 +147,9 @@ template <int BN, class AL, class BL, class EP>
 static cudaError_t launch_gemm_tc_wgrad(int R, int Mo, int No, AL a, BL b, EP e, bool want_bias, cudaStream_t st)
 {
     auto kern = gemm_tc_wgrad_kernel<BN, AL, BL, EP>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem_bytes<BN>());
+    {
+        cudaError_t err = configure_smem_once((const void*)kern, wg_smem_bytes<BN>());      // once per (device, instantiation)
         if (err != cudaSuccess) return err;
-        configured = true;
     }
     const int tiles = ((Mo + TC_BM - 1) / TC_BM) * ((No + BN - 1) / BN);
     int splits = (2 * 148 + tiles - 1) / tiles;                       // about two CTAs per SM

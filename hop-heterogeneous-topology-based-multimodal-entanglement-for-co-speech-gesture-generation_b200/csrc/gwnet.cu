@@ -17,14 +17,12 @@
 //             fused with the residual gradient and the BatchNorm-backward sums of the previous layer.
 //   dA = M1 + A^T M2 + M2 A^T is finished once, then pushed through softmax(relu(E1 E2)).
 #include <stdlib.h>
+#include <mutex>
 #include "functors.cuh"
 #include "common.cuh"
 #include "../../include/hopk.h"
 
 namespace hopk {
-
-constexpr float BN_EPS = 1e-5f;
-constexpr float BN_MOM = 0.1f;
 
 // ============================================================================ layouts
 struct GwLayout {
@@ -187,7 +185,7 @@ __global__ void fill_identity_kernel(float* ss, int C)
 // BatchNorm2d finalize (gwnet.py:120,237): statistics -> mean/rstd, folded scale/shift, running stats
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* rmean, float* rvar, long long* nbt,
-                                   float* mr, float* ss, int C, int training)
+                                   float* mr, float* ss, int C, int training, float BN_MOM, float BN_EPS)
 {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -1146,7 +1144,7 @@ static int launch_node_mix(const float* in, const float* M1, const float* M2, fl
 {
     int gpb = 48 / V > 0 ? 48 / V : 1;
     size_t smem = node_mix_smem(V, C, gpb);
-    if (smem > 48 * 1024) HOPK_CUDA(cudaFuncSetAttribute(node_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) HOPK_CUDA(configure_smem_once((const void*)node_mix_kernel, 200 * 1024));
     node_mix_kernel<<<cdiv(groups, gpb), 256, smem, st>>>(in, M1, M2, o1, o2, groups, V, C, gpb);
     HOPK_LAUNCH_CHECK("node_mix");
     return 0;
@@ -1162,11 +1160,20 @@ struct SideStreams {
     cudaStream_t s[3];
     cudaEvent_t ev_du[HOPK_MAX_LAYERS], ev_dfg[HOPK_MAX_LAYERS], ev_join[3], ev_head[3], ev_tail;
 };
-// created once per process (one process drives one GPU); non-blocking so they never serialise against stream 0
+// created once per device (keyed by the current device, so a process that drives several GPUs gets streams and events
+// on the right one); non-blocking so they never serialise against stream 0.  Calls on one device are expected from one
+// host thread at a time (the autograd thread of that device's rank): events are reused from call to call.
 static SideStreams* side_streams()
 {
-    static SideStreams sd;
-    static int state = 0;                       // 0 = not created, 1 = ok, -1 = failed
+    constexpr int MAXDEV = 64;
+    static SideStreams table[MAXDEV];
+    static int states[MAXDEV] = {0};            // 0 = not created, 1 = ok, -1 = failed
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    SideStreams& sd = table[dev];
+    int& state = states[dev];
     if (state == 0) {
         state = 1;
         for (int k = 0; k < 3; ++k) {
@@ -1208,8 +1215,31 @@ extern "C" size_t hopk_gwnet_workspace_bytes(const HopkGwnetShape* s) { return m
 extern "C" size_t hopk_gwnet_scratch_bytes(const HopkGwnetShape* s) { return make_layout(s).s_total; }
 extern "C" int hopk_gwnet_out_steps(const HopkGwnetShape* s) { return make_layout(s).Tl; }
 
+extern "C" int hopk_gwnet_ws_field(const HopkGwnetShape* s, const char* name, int layer, size_t* offset, size_t* bytes,
+                                   int* elem_bytes)
+{
+    HOPK_REQUIRE(s && name && offset && bytes && elem_bytes, "null argument");
+    HOPK_REQUIRE(s->L >= 1 && s->L <= HOPK_MAX_LAYERS && layer >= 0 && layer < s->L, "layer index");
+    GwLayout g = make_layout(s);
+    const size_t f = sizeof(float), BV = (size_t)s->B * s->V;
+    const size_t nl = BV * g.Tlen[layer + 1] * s->C * f;
+    *elem_bytes = 4;
+    if (!strcmp(name, "x0")) { *offset = g.x0; *bytes = BV * g.Tp * s->C * f; }
+    else if (!strcmp(name, "u")) { *offset = g.u[layer]; *bytes = nl; }
+    else if (!strcmp(name, "tf")) { *offset = g.tf[layer]; *bytes = nl; }
+    else if (!strcmp(name, "sg")) { *offset = g.sg[layer]; *bytes = nl; }
+    else if (!strcmp(name, "ycat")) { *offset = g.ycat; *bytes = BV * g.Tl * s->L * s->C * f; }
+    else if (!strcmp(name, "r0")) { *offset = g.r0; *bytes = BV * g.Tl * s->S * f; }
+    else if (!strcmp(name, "r1")) { *offset = g.r1; *bytes = BV * g.Tl * s->E * f; }
+    else if (!strcmp(name, "mr")) { *offset = g.mr + (size_t)layer * 2 * s->C * f; *bytes = 2 * s->C * f; }
+    else if (!strcmp(name, "A")) { *offset = g.A; *bytes = (size_t)s->V * s->V * f; }
+    else return fail(2, "bad argument: unknown workspace field", name);
+    return 0;
+}
+
 static int check_shape(const HopkGwnetShape* s)
 {
+    HOPK_REQUIRE(s->bn_momentum >= 0.f && s->bn_momentum <= 1.f && s->bn_eps > 0.f, "BatchNorm momentum in [0,1] and eps > 0");
     HOPK_REQUIRE(s->dtype == 0 || s->dtype == 1, "gwnet: dtype must be 0 (fp32 FFMA) or 1 (bf16 tensor-core math)");
     HOPK_REQUIRE(s->L >= 1 && s->L <= HOPK_MAX_LAYERS, "layer count");
     HOPK_REQUIRE(s->C % 4 == 0 && s->C >= 4 && s->C <= 256, "C must be a multiple of 4, <= 256");
@@ -1258,11 +1288,7 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
     uint8_t* bd = pack + (size_t)L * FZ_PACK_BYTES;
     unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + g.ticket);
     if (fused) {
-        static bool configured = false;
-        if (!configured) {
-            HOPK_CUDA(cudaFuncSetAttribute(fz_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_smem_bytes()));
-            configured = true;
-        }
+        HOPK_CUDA(configure_smem_once((const void*)fz_layer_fwd_kernel, fz_smem_bytes()));
         HOPK_CUDA(cudaMemsetAsync(tickets, 0, HOPK_MAX_LAYERS * sizeof(unsigned int), st));
         fz_pack_weights_kernel<<<L, 256, 0, st>>>(*p, L, pack);
         HOPK_LAUNCH_CHECK("fz_pack");
@@ -1284,7 +1310,10 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
             fa.ticket = tickets + i; fa.count = (double)M; fa.gamma = p->bn_w[i]; fa.beta = p->bn_b[i];
             fa.rmean = p->bn_mean[i]; fa.rvar = p->bn_var[i]; fa.nbt = (long long*)p->bn_nbt[i];
             fa.mr = F(g.mr) + (size_t)i * 2 * C; fa.ss_next = F(g.ss) + (size_t)(i + 1) * 2 * C; fa.training = s->training;
+            fa.bn_momentum = s->bn_momentum; fa.bn_eps = s->bn_eps;
+#ifdef HOPK_DEBUG
             { static const char* e = getenv("HOPK_FZ_STOP"); fa.stop = e ? atoi(e) : 0; }
+#endif
             fz_layer_fwd_kernel<<<cdiv(fa.groups, fa.gpt), 256, fz_smem_bytes(), st>>>(fa);
             HOPK_LAUNCH_CHECK("fz_layer_fwd");
             uprev = F(g.u[i]);
@@ -1320,7 +1349,7 @@ extern "C" int hopk_gwnet_forward(const HopkGwnetShape* s, const HopkGwnetParams
         bn_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(stats + (size_t)i * 2 * C, (double)M, p->bn_w[i], p->bn_b[i],
                                                           p->bn_mean[i], p->bn_var[i], (long long*)p->bn_nbt[i],
                                                           F(g.mr) + (size_t)i * 2 * C, F(g.ss) + (size_t)(i + 1) * 2 * C, C,
-                                                          s->training);
+                                                          s->training, s->bn_momentum, s->bn_eps);
         HOPK_LAUNCH_CHECK("bn_finalize");
         uprev = F(g.u[i]);
     }
@@ -1368,7 +1397,11 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
 
     SideStreams* sd = side_streams();
     if (!sd) return fail(3, "side streams", "cudaStreamCreate failed");
+#ifdef HOPK_DEBUG
     static const bool skip_side = getenv("HOPK_BWD_SKIP_SIDE") != nullptr;     // timing experiments only: wrong gradients
+#else
+    constexpr bool skip_side = false;
+#endif
 
     // ---- head backward: the dgrad GEMMs form the dependent chain, the three weight-gradient GEMMs go to the side streams
     const int M4 = B * g.Tl * V;
@@ -1489,7 +1522,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
                     HOPK_LAUNCH_CHECK("gram_tc");
                 } else {
                 size_t smem3 = ((size_t)GRAM_GPI * V * (3 * C + 2) + 2 * (size_t)V * V) * sizeof(float);
-                if (smem3 > 48 * 1024) HOPK_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                if (smem3 > 48 * 1024) HOPK_CUDA(configure_smem_once((const void*)gram_kernel, 200 * 1024));
                 int gblocks = cdiv(groups, GRAM_GPI); if (gblocks > 148) gblocks = 148;
                 gram_kernel<<<gblocks, 256, smem3, s1>>>(F(g.tf[i]), F(g.sg[i]), S(g.s_g[i]), S(g.s_m12), groups, V, C);
                 HOPK_LAUNCH_CHECK("gram");

@@ -74,7 +74,10 @@ struct FzArgs {
     // BatchNorm finalize by the last CTA to finish (gwnet.py:120,237)
     unsigned int* ticket; double count; const float* gamma; const float* beta; float* rmean; float* rvar; long long* nbt;
     float* mr; float* ss_next; int training;
+    float bn_momentum, bn_eps;                        // of the module's BatchNorm2d (gwnet.py:120)
+#ifdef HOPK_DEBUG
     int stop;                                         // timing experiments only (HOPK_FZ_STOP): leave the kernel after stage `stop`
+#endif
 };
 
 constexpr uint32_t FZ_R1 = 3 * tc::slab_bytes(128);                  // gate weights, then the diffusion operator
@@ -99,6 +102,7 @@ __device__ __forceinline__ void fz_issue_hop(uint32_t tmem_d, uint32_t bd_addr, 
     tc::mma_commit(bar);
 }
 
+#ifdef HOPK_DEBUG
 #define FZ_STOP_AT(k)                                                                               \
     if (a.stop == (k)) {                                                                            \
         if (tid == 0) { tc::mbar_wait(&bars[0], 0); tc::mbar_wait(&bars[1], 0); if ((k) >= 3) tc::mbar_wait(&bars[2], 0); } \
@@ -107,10 +111,17 @@ __device__ __forceinline__ void fz_issue_hop(uint32_t tmem_d, uint32_t bd_addr, 
         if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);                                       \
         return;                                                                                     \
     }
+#define FZ_STOP_IS(k) (a.stop == (k))
+#else
+#define FZ_STOP_AT(k)
+#define FZ_STOP_IS(k) false
+#endif
 
 __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
 {
+#ifdef HOPK_DEBUG
     if (a.stop == -1) return;
+#endif
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[4];                      // 0: gate weights, 1: mlp weights, 2: diffusion operator, 3: UMMA completion
     __shared__ uint32_t tmem_base_smem;
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
                 v[j] = tf; v[16 + j] = sg;
             }
         }
-        if (a.stop == 31) continue;                           // timing experiment: TMEM reads + math only
+        if (FZ_STOP_IS(31)) continue;                           // timing experiment: TMEM reads + math only
         if (!writer) {
 #pragma unroll
             for (int q8 = 0; q8 < 2; ++q8) {                  // y as bf16 into slab 0 of the mlp A operand
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
                 for (int j = 0; j < 8; ++j) f[j] = y[q8 * 8 + j];
                 tc::slab_store8(A2, row, (c0 >> 3) + q8, f);
             }
-        } else if (rvalid && a.stop != 32) {
+        } else if (rvalid && !FZ_STOP_IS(32)) {
             const size_t o = (size_t)m * C + c0;
 #pragma unroll
             for (int j = 0; j < 16; j += 8) {                 // full 32-byte sectors per store
@@ -365,14 +376,14 @@ __global__ void __launch_bounds__(256, 2) fz_layer_fwd_kernel(const FzArgs a)
             double var = s2 / a.count - mu * mu;
             if (var < 0) var = 0;
             mean = (float)mu;
-            rstd = (float)(1.0 / sqrt(var + 1e-5));
+            rstd = (float)(1.0 / sqrt(var + (double)a.bn_eps));
             double unb = a.count > 1 ? var * a.count / (a.count - 1) : var;
-            a.rmean[c] = 0.9f * a.rmean[c] + 0.1f * mean;
-            a.rvar[c] = 0.9f * a.rvar[c] + 0.1f * (float)unb;
+            a.rmean[c] = (1.f - a.bn_momentum) * a.rmean[c] + a.bn_momentum * mean;
+            a.rvar[c] = (1.f - a.bn_momentum) * a.rvar[c] + a.bn_momentum * (float)unb;
             if (c == 0 && a.nbt) *a.nbt += 1;
         } else {
             mean = a.rmean[c];
-            rstd = 1.f / sqrtf(a.rvar[c] + 1e-5f);
+            rstd = 1.f / sqrtf(a.rvar[c] + a.bn_eps);
         }
         a.mr[c] = mean; a.mr[C + c] = rstd;
         float sc = a.gamma[c] * rstd;

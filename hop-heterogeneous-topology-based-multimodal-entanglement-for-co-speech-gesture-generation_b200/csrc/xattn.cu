@@ -18,11 +18,6 @@ namespace hopk {
 constexpr int XT = 64;            // tile edge (rows and S)
 constexpr int XLDP = XT + 4;      // leading dim of the 64 x 64 probability tiles
 
-// added to every call's seed; advanced by a (graph-capturable) kernel so that replays of a captured training step do not
-// repeat the dropout mask that was baked into the launch arguments at capture time.  0 until advanced.
-__device__ unsigned long long g_drop_epoch_a = 0ull;
-__global__ void drop_epoch_bump_a() { g_drop_epoch_a += 0x9E3779B97F4A7C15ull; }
-__global__ void drop_epoch_reset_a() { g_drop_epoch_a = 0ull; }
 
 __device__ __forceinline__ uint32_t lowbias32(uint32_t x)
 {
@@ -139,9 +134,9 @@ __device__ __forceinline__ float group16_sum(float v)
 __global__ void __launch_bounds__(256)
 xattn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, float* __restrict__ O,
                  float* __restrict__ LSE, int M, int L, int H, int E, int S, float scale, float inv_keep, uint32_t thr,
-                 uint64_t seed)
+                 uint64_t seed, const unsigned long long* __restrict__ epoch)
 {
-    seed += g_drop_epoch_a;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
+    seed += *epoch;                                     // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ __align__(16) float sm[];
     const int ld = E + 4;
     float* Qs = sm; float* Ks = Qs + XT * ld; float* Vs = Ks + XT * ld; float* Ps = Vs + XT * ld;
@@ -218,9 +213,9 @@ __global__ void __launch_bounds__(256)
 xattn_bwd_dq_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                     const float* __restrict__ O, const float* __restrict__ LSE, const float* __restrict__ dO,
                     float* __restrict__ dQ, float* __restrict__ delta, int M, int L, int H, int E, int S, float scale,
-                    float inv_keep, uint32_t thr, uint64_t seed)
+                    float inv_keep, uint32_t thr, uint64_t seed, const unsigned long long* __restrict__ epoch)
 {
-    seed += g_drop_epoch_a;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
+    seed += *epoch;                                     // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ __align__(16) float sm[];
     const int ld = E + 4;
     float* Qs = sm; float* dOs = Qs + XT * ld; float* Ks = dOs + XT * ld; float* Vs = Ks + XT * ld; float* Ss = Vs + XT * ld;
@@ -300,9 +295,9 @@ __global__ void __launch_bounds__(256)
 xattn_bwd_dkv_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                      const float* __restrict__ LSE, const float* __restrict__ delta, const float* __restrict__ dO,
                      float* __restrict__ dK, float* __restrict__ dV, int M, int L, int H, int E, int S, float scale,
-                     float inv_keep, uint32_t thr, uint64_t seed)
+                     float inv_keep, uint32_t thr, uint64_t seed, const unsigned long long* __restrict__ epoch)
 {
-    seed += g_drop_epoch_a;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
+    seed += *epoch;                                     // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ __align__(16) float sm[];
     const int ld = E + 4;
     float* Ks = sm; float* Vs = Ks + XT * ld; float* Qs = Vs + XT * ld; float* dOs = Qs + XT * ld;
@@ -386,13 +381,6 @@ static int xattn_check(int B, int L, int H, int E, int S, float p)
     return 0;
 }
 
-namespace hopk {
-void drop_epoch_launch_a(int reset, cudaStream_t st)
-{
-    if (reset) drop_epoch_reset_a<<<1, 1, 0, st>>>(); else drop_epoch_bump_a<<<1, 1, 0, st>>>();
-}
-}  // namespace hopk
-
 extern "C" int hopk_xattn_fwd(const float* q, const float* k, const float* v, float* o, float* lse, int B, int L, int H, int E,
                               int S, float p_drop, uint64_t seed, void* stream)
 {
@@ -404,7 +392,9 @@ extern "C" int hopk_xattn_fwd(const float* q, const float* k, const float* v, fl
     uint32_t thr = (uint32_t)lrintf(p_drop * 65536.f);
     float inv_keep = 65536.f / (65536.f - (float)thr);
     dim3 grid(cdiv(M, XT), H);
-    xattn_fwd_kernel<<<grid, 256, smem, st>>>(q, k, v, o, lse, M, L, H, E, S, 1.f / sqrtf((float)E), inv_keep, thr, seed);
+    const unsigned long long* epoch = drop_epoch_ptr();
+    HOPK_REQUIRE(epoch != nullptr, "dropout epoch symbol");
+    xattn_fwd_kernel<<<grid, 256, smem, st>>>(q, k, v, o, lse, M, L, H, E, S, 1.f / sqrtf((float)E), inv_keep, thr, seed, epoch);
     HOPK_LAUNCH_CHECK("xattn_fwd");
     return 0;
 }
@@ -422,13 +412,15 @@ extern "C" int hopk_xattn_bwd(const float* q, const float* k, const float* v, co
     float scale = 1.f / sqrtf((float)E);
     size_t smem1 = ((size_t)4 * XT * (E + 4) + XT * XLDP) * sizeof(float);
     HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    const unsigned long long* epoch = drop_epoch_ptr();
+    HOPK_REQUIRE(epoch != nullptr, "dropout epoch symbol");
     xattn_bwd_dq_kernel<<<dim3(cdiv(M, XT), H), 256, smem1, st>>>(q, k, v, o, lse, dout, dq, delta, M, L, H, E, S, scale,
-                                                                  inv_keep, thr, seed);
+                                                                  inv_keep, thr, seed, epoch);
     HOPK_LAUNCH_CHECK("xattn_bwd_dq");
     size_t smem2 = ((size_t)4 * XT * (E + 4) + 2 * XT * XLDP) * sizeof(float);
     HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     xattn_bwd_dkv_kernel<<<dim3(cdiv(S, XT), H), 256, smem2, st>>>(q, k, v, lse, delta, dout, dk, dv, M, L, H, E, S, scale,
-                                                                   inv_keep, thr, seed);
+                                                                   inv_keep, thr, seed, epoch);
     HOPK_LAUNCH_CHECK("xattn_bwd_dkv");
     return 0;
 }

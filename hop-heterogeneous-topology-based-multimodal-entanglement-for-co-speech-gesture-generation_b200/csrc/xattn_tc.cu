@@ -15,15 +15,16 @@
 
 namespace hopk {
 
-__device__ volatile int* g_dbg = nullptr;      // optional progress markers in mapped host memory (debug builds of tests)
+#ifdef HOPK_DEBUG                               // progress markers in mapped host memory (nvcc -DHOPK_DEBUG; never in the release library)
+__device__ volatile int* g_dbg = nullptr;
 #define DBG(slot, val) do { if (g_dbg && blockIdx.x == 0 && blockIdx.y == 0) { g_dbg[slot] = (val); __threadfence_system(); } } while (0)
+#else
+#define DBG(slot, val) do { } while (0)
+#endif
 
 constexpr int AT = 128;                       // tile edge: query rows, prototypes per tile, head dim
 constexpr uint32_t AT_SLAB = tc::slab_bytes(AT);        // 16 KB: [128 rows][64 bf16]
 
-__device__ unsigned long long g_drop_epoch_b = 0ull;       // see csrc/xattn.cu: g_drop_epoch_a (one copy per translation unit)
-__global__ void drop_epoch_bump_b() { g_drop_epoch_b += 0x9E3779B97F4A7C15ull; }
-__global__ void drop_epoch_reset_b() { g_drop_epoch_b = 0ull; }
 
 __device__ __forceinline__ uint32_t lowbias32_tc(uint32_t x)
 {
@@ -111,145 +112,6 @@ __device__ __forceinline__ void stage_rows64_f32(uint8_t* slabs, const float* __
     }
 }
 
-__global__ void __launch_bounds__(256, 2)
-xattn_fwd_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
-                    float* __restrict__ O, float* __restrict__ LSE, int M, int L, int H, int S, float scale,
-                    float inv_keep, uint32_t thr, uint64_t seed)
-{
-    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_s, bar_o;
-    __shared__ uint32_t tmem_base_smem;
-    __shared__ float xch[2][AT];                             // partial row maxima / sums of the two column halves
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* Qs = smem; uint8_t* Ks = Qs + 2 * AT_SLAB; uint8_t* Vs = Ks + 2 * FS_SLAB; uint8_t* Ps = Vs + 2 * FS_SLAB;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int h = blockIdx.y, m0 = blockIdx.x * AT;
-
-    if (tid == 0) { tc::mbar_init(&bar_s, 1); tc::mbar_init(&bar_o, 1); tc::fence_barrier_init(); }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 256);
-    stage_rows_f32(Qs, Q, m0, M, H, h);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem_s = tmem_base_smem, tmem_o = tmem_base_smem + 64;
-    constexpr uint32_t idesc_qk = tc::idesc_bf16(AT, FS, 0, 0);
-    constexpr uint32_t idesc_pv = tc::idesc_bf16(AT, AT, 0, 1);
-
-    const int row = (warp & 3) * 32 + lane;                 // query row inside the tile; two threads per row
-    const int half = warp >> 2;                             // which 32 of the 64 score columns / which 64 of the 128 outputs
-    const int m = m0 + row;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint64_t drop_base = m < M ? (((uint64_t)(m / L) * H + h) * (uint64_t)L + (uint64_t)(m % L)) * (uint64_t)S : 0;
-    const uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
-    const float sc2 = scale * 1.4426950408889634f;           // scores are tracked in the log2 domain
-    float mrow = -INFINITY, lrow = 0.f;                      // lrow: partial sum over this thread's columns
-    const int ntiles = (S + FS - 1) / FS;
-
-    for (int j = 0; j < ntiles; ++j) {
-        const int s0 = j * FS;
-        if (j > 0) tc::mbar_wait(&bar_o, (j - 1) & 1);      // P V of the previous tile done: K/V/P smem and O are free
-        stage_rows64_f32(Ks, K, s0, S, H, h);
-        stage_rows64_f32(Vs, V, s0, S, H, h);
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const uint32_t qa = tc::smem_u32(Qs), ka = tc::smem_u32(Ks);
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    tc::mma_bf16(tmem_s, tc::desc_kmajor(qa + c * AT_SLAB, t), tc::desc_kmajor(ka + c * FS_SLAB, t), idesc_qk,
-                                 (c | t) != 0);
-            tc::mma_commit(&bar_s);
-        }
-        tc::mbar_wait(&bar_s, j & 1);
-        tc::fence_after_sync();
-        float v[32];
-        tc::tmem_ld32(tmem_s + lane_off + half * 32, v);
-        const int sb = s0 + half * 32;                       // first prototype of this thread's columns
-        float mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            v[i] = sb + i < S ? v[i] * sc2 : -INFINITY;
-            mx = fmaxf(mx, v[i]);
-        }
-        xch[half][row] = mx;
-        __syncthreads();
-        const float mnew = fmaxf(mrow, fmaxf(mx, xch[half ^ 1][row]));
-        const float corr = ex2f(mrow - mnew);
-        if (j > 0 && __any_sync(0xffffffffu, mnew > mrow)) {   // rescale this thread's 64 output columns in TMEM
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                float o[32];
-                tc::tmem_ld32(tmem_o + lane_off + half * 64 + c * 32, o);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] *= corr;
-                tc::tmem_st32(tmem_o + lane_off + half * 64 + c * 32, o);
-            }
-        }
-        float rs = 0.f;
-        const uint64_t idx0 = drop_base + (uint64_t)sb;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            v[i] = ex2f(v[i] - mnew);
-            rs += v[i];
-        }
-        if (thr) {
-            if ((idx0 & 1) == 0) dropout_run_even<32>(v, idx0, seed, thr, inv_keep);
-            else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = keep_mask_tc(seed, idx0 + (uint64_t)i, thr) ? v[i] * inv_keep : 0.f;
-            }
-        }
-#pragma unroll
-        for (int q8 = 0; q8 < 4; ++q8) {
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = v[q8 * 8 + i];
-            tc::slab_store8(Ps, row, half * 4 + q8, f);
-        }
-        lrow = lrow * corr + rs;
-        mrow = mnew;
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const uint32_t pa = tc::smem_u32(Ps), va = tc::smem_u32(Vs);
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                tc::mma_bf16(tmem_o, tc::desc_kmajor(pa, t), tc::desc_mnmajor(va, FS_SLAB, t), idesc_pv, (j | t) != 0);
-            tc::mma_commit(&bar_o);
-        }
-    }
-    tc::mbar_wait(&bar_o, (ntiles - 1) & 1);
-    tc::fence_after_sync();
-    xch[half][row] = lrow;
-    __syncthreads();
-    const float ltot = lrow + xch[half ^ 1][row];
-    {                                                        // tcgen05.ld is warp-collective: no per-lane guard around it
-        const float inv = 1.f / ltot;
-        float* orow = O + ((size_t)(m < M ? m : 0) * H + h) * AT + half * 64;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            float o[32];
-            tc::tmem_ld32(tmem_o + lane_off + half * 64 + c * 32, o);
-            if (m < M) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(orow + c * 32 + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
-            }
-        }
-        if (m < M && half == 0) LSE[((size_t)(m / L) * H + h) * L + (m % L)] = (mrow + log2f(ltot)) * 0.6931471805599453f;
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);
-}
-
 // ------------------------------------------------------------------------------------------------ forward v3
 // K / V are packed ONCE per call into bf16 slab images, one contiguous 32 KB record per (head, 64-prototype tile):
 // [K e<64 | K e>=64 | V e<64 | V e>=64], byte-for-byte what the UMMA descriptors expect in shared memory.  The main
@@ -307,9 +169,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 __global__ void __launch_bounds__(FWD3_THREADS, 1)
 xattn_fwd_tc3_kernel(const float* __restrict__ Q, const uint8_t* __restrict__ kvpack, float* __restrict__ O,
                      float* __restrict__ LSE, int M, int L, int H, int S, float scale, float inv_keep, uint32_t thr,
-                     uint64_t seed)
+                     uint64_t seed, const unsigned long long* __restrict__ epoch)
 {
-    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
+    seed += *epoch;                                     // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[KV_STAGES], bar_s[2], bar_p[2], bar_o[2];
     __shared__ uint32_t tmem_base_smem;
@@ -469,140 +331,6 @@ xattn_fwd_tc3_kernel(const float* __restrict__ Q, const uint8_t* __restrict__ kv
     if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 256);
 }
 
-// ------------------------------------------------------------------------------------------------ backward: dQ (+ delta)
-// TMEM: S [0,128)  dP [128,256)  dQ [256,384).  smem slabs: Q, dO, K_j, V_j, dS (2 each).
-__global__ void __launch_bounds__(256, 1)
-xattn_bwd_dq_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
-                       const float* __restrict__ O, const float* __restrict__ LSE, const float* __restrict__ dO,
-                       float* __restrict__ dQ, float* __restrict__ delta, int M, int L, int H, int S, float scale,
-                       float inv_keep, uint32_t thr, uint64_t seed)
-{
-    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_s, bar_q;
-    __shared__ uint32_t tmem_base_smem;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* Qs = smem; uint8_t* dOs = Qs + 2 * AT_SLAB; uint8_t* Ks = dOs + 2 * AT_SLAB; uint8_t* Vs = Ks + 2 * AT_SLAB;
-    uint8_t* dSs = Vs + 2 * AT_SLAB;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int h = blockIdx.y, m0 = blockIdx.x * AT;
-
-    if (tid == 0) { tc::mbar_init(&bar_s, 1); tc::mbar_init(&bar_q, 1); tc::fence_barrier_init(); }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 512);
-    stage_rows_f32(Qs, Q, m0, M, H, h);
-    stage_rows_f32(dOs, dO, m0, M, H, h);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem_s = tmem_base_smem, tmem_dp = tmem_base_smem + 128, tmem_dq = tmem_base_smem + 256;
-    constexpr uint32_t idesc_kk = tc::idesc_bf16(AT, AT, 0, 0);
-    constexpr uint32_t idesc_kmn = tc::idesc_bf16(AT, AT, 0, 1);
-
-    const int row = warp * 32 + lane;
-    const int m = m0 + row;
-    const bool rvalid = warp < 4 && m < M;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const size_t li = rvalid ? ((size_t)(m / L) * H + h) * L + (m % L) : 0;
-    const uint64_t drop_base = (uint64_t)li * (uint64_t)S;
-    float lse = 0.f, dl = 0.f;
-    if (rvalid) {                                            // delta = rowsum(dO * O) in fp32 from global
-        lse = __ldg(LSE + li);
-        const float4* o4 = reinterpret_cast<const float4*>(O + ((size_t)m * H + h) * AT);
-        const float4* d4 = reinterpret_cast<const float4*>(dO + ((size_t)m * H + h) * AT);
-#pragma unroll 4
-        for (int i = 0; i < AT / 4; ++i) {
-            float4 a = __ldg(o4 + i), b = __ldg(d4 + i);
-            dl += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-        }
-        delta[li] = dl;
-    }
-    const int ntiles = (S + AT - 1) / AT;
-    for (int j = 0; j < ntiles; ++j) {
-        const int s0 = j * AT;
-        if (j > 0) tc::mbar_wait(&bar_q, (j - 1) & 1);      // dQ UMMAs of the previous tile done: K_j / dS smem free
-        stage_rows_f32(Ks, K, s0, S, H, h);
-        stage_rows_f32(Vs, V, s0, S, H, h);
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const uint32_t qa = tc::smem_u32(Qs), ka = tc::smem_u32(Ks), da = tc::smem_u32(dOs), va = tc::smem_u32(Vs);
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    tc::mma_bf16(tmem_s, tc::desc_kmajor(qa + c * AT_SLAB, t), tc::desc_kmajor(ka + c * AT_SLAB, t), idesc_kk, (c | t) != 0);
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    tc::mma_bf16(tmem_dp, tc::desc_kmajor(da + c * AT_SLAB, t), tc::desc_kmajor(va + c * AT_SLAB, t), idesc_kk, (c | t) != 0);
-            tc::mma_commit(&bar_s);
-        }
-        if (warp < 4) {
-            tc::mbar_wait(&bar_s, j & 1);
-            tc::fence_after_sync();
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float sv[32], dv[32];
-                tc::tmem_ld32(tmem_s + lane_off + c * 32, sv);
-                tc::tmem_ld32(tmem_dp + lane_off + c * 32, dv);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    int s = s0 + c * 32 + i;
-                    float ds = 0.f;
-                    if (rvalid && s < S) {
-                        float p = __expf(sv[i] * scale - lse);
-                        float d = dv[i];
-                        if (thr) d = keep_mask_tc(seed, drop_base + (uint64_t)s, thr) ? d * inv_keep : 0.f;
-                        ds = p * (d - dl) * scale;
-                    }
-                    sv[i] = ds;
-                }
-#pragma unroll
-                for (int q8 = 0; q8 < 4; ++q8) {
-                    float f[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = sv[q8 * 8 + i];
-                    int col = c * 32 + q8 * 8;
-                    tc::slab_store8(dSs + (col >> 6) * AT_SLAB, row, (col & 63) >> 3, f);
-                }
-            }
-        }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const uint32_t sa = tc::smem_u32(dSs), ka = tc::smem_u32(Ks);
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-                tc::mma_bf16(tmem_dq, tc::desc_kmajor(sa + (t >> 2) * AT_SLAB, t & 3), tc::desc_mnmajor(ka, AT_SLAB, t), idesc_kmn,
-                             (j | t) != 0);
-            tc::mma_commit(&bar_q);
-        }
-    }
-    tc::mbar_wait(&bar_q, (ntiles - 1) & 1);
-    tc::fence_after_sync();
-    if (warp < 4) {
-        float* qrow = dQ + ((size_t)(m < M ? m : 0) * H + h) * AT;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            float v[32];
-            tc::tmem_ld32(tmem_dq + lane_off + c * 32, v);
-            if (m < M) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(qrow + c * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
-        }
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 512);
-}
-
 // ------------------------------------------------------------------------------------------------ backward: dQ, v3
 // Same organisation as the v3 forward: K / V arrive as packed bf16 records (the forward's pack is reused) through a
 // 3-stage cp.async.bulk ring, S and dP are double-buffered in TMEM (2 x 64 columns each), dS is double-buffered in
@@ -613,9 +341,9 @@ __global__ void __launch_bounds__(FWD3_THREADS, 1)
 xattn_bwd_dq_tc3_kernel(const float* __restrict__ Q, const uint8_t* __restrict__ kvpack, const float* __restrict__ O,
                         const float* __restrict__ LSE, const float* __restrict__ dO, float* __restrict__ dQ,
                         float* __restrict__ delta, uint4* __restrict__ rowstat, int M, int L, int H, int S, float scale,
-                        float inv_keep, uint32_t thr, uint64_t seed)
+                        float inv_keep, uint32_t thr, uint64_t seed, const unsigned long long* __restrict__ epoch)
 {
-    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
+    seed += *epoch;                                     // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[KV_STAGES], bar_s[2], bar_p[2], bar_q[2];
     __shared__ uint32_t tmem_base_smem;
@@ -785,144 +513,6 @@ xattn_bwd_dq_tc3_kernel(const float* __restrict__ Q, const uint8_t* __restrict__
     if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 512);
 }
 
-// ------------------------------------------------------------------------------------------------ backward: dK, dV
-// One CTA per (128 prototypes, head); loops over the query-row tiles.  TMEM: S [0,128) dP [128,256) dK [256,384) dV [384,512).
-// P~ and dS are written row-major [row][s]; the dV / dK UMMAs read them (and dO / Q) through MN-major views.
-__global__ void __launch_bounds__(256, 1)
-xattn_bwd_dkv_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
-                        const float* __restrict__ LSE, const float* __restrict__ delta, const float* __restrict__ dO,
-                        float* __restrict__ dK, float* __restrict__ dV, int M, int L, int H, int S, float scale,
-                        float inv_keep, uint32_t thr, uint64_t seed)
-{
-    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_s, bar_kv;
-    __shared__ uint32_t tmem_base_smem;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* Ks = smem; uint8_t* Vs = Ks + 2 * AT_SLAB; uint8_t* Qs = Vs + 2 * AT_SLAB; uint8_t* dOs = Qs + 2 * AT_SLAB;
-    uint8_t* Ps = dOs + 2 * AT_SLAB; uint8_t* dSs = Ps + 2 * AT_SLAB;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int h = blockIdx.y, s0 = blockIdx.x * AT;
-
-    if (tid == 0) { tc::mbar_init(&bar_s, 1); tc::mbar_init(&bar_kv, 1); tc::fence_barrier_init(); }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 512);
-    stage_rows_f32(Ks, K, s0, S, H, h);
-    stage_rows_f32(Vs, V, s0, S, H, h);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem_s = tmem_base_smem, tmem_dp = tmem_base_smem + 128, tmem_dk = tmem_base_smem + 256,
-                   tmem_dv = tmem_base_smem + 384;
-    constexpr uint32_t idesc_kk = tc::idesc_bf16(AT, AT, 0, 0);
-    constexpr uint32_t idesc_mm = tc::idesc_bf16(AT, AT, 1, 1);
-    const int row = warp * 32 + lane;                       // a query row inside the current row tile (softmax threads)
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const int ntiles = (M + AT - 1) / AT;
-    for (int i = 0; i < ntiles; ++i) {
-        const int m0 = i * AT;
-        if (i > 0) tc::mbar_wait(&bar_kv, (i - 1) & 1);     // dK/dV UMMAs of the previous row tile done
-        stage_rows_f32(Qs, Q, m0, M, H, h);
-        stage_rows_f32(dOs, dO, m0, M, H, h);
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const uint32_t qa = tc::smem_u32(Qs), ka = tc::smem_u32(Ks), da = tc::smem_u32(dOs), va = tc::smem_u32(Vs);
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    tc::mma_bf16(tmem_s, tc::desc_kmajor(qa + c * AT_SLAB, t), tc::desc_kmajor(ka + c * AT_SLAB, t), idesc_kk, (c | t) != 0);
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    tc::mma_bf16(tmem_dp, tc::desc_kmajor(da + c * AT_SLAB, t), tc::desc_kmajor(va + c * AT_SLAB, t), idesc_kk, (c | t) != 0);
-            tc::mma_commit(&bar_s);
-        }
-        if (warp < 4) {
-            const int m = m0 + row;
-            const bool rvalid = m < M;
-            const size_t li = rvalid ? ((size_t)(m / L) * H + h) * L + (m % L) : 0;
-            const float lse = rvalid ? __ldg(LSE + li) : 0.f;
-            const float dl = rvalid ? __ldg(delta + li) : 0.f;
-            const uint64_t drop_base = (uint64_t)li * (uint64_t)S;
-            tc::mbar_wait(&bar_s, i & 1);
-            tc::fence_after_sync();
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float sv[32], dv[32];
-                tc::tmem_ld32(tmem_s + lane_off + c * 32, sv);
-                tc::tmem_ld32(tmem_dp + lane_off + c * 32, dv);
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    int s = s0 + c * 32 + k;
-                    float pt = 0.f, ds = 0.f;
-                    if (rvalid && s < S) {
-                        float p = __expf(sv[k] * scale - lse);
-                        float d = dv[k];
-                        pt = p;
-                        if (thr) {
-                            bool kp = keep_mask_tc(seed, drop_base + (uint64_t)s, thr);
-                            pt = kp ? p * inv_keep : 0.f;
-                            d = kp ? d * inv_keep : 0.f;
-                        }
-                        ds = p * (d - dl) * scale;
-                    }
-                    sv[k] = pt; dv[k] = ds;
-                }
-#pragma unroll
-                for (int q8 = 0; q8 < 4; ++q8) {
-                    float f[8], g[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { f[k] = sv[q8 * 8 + k]; g[k] = dv[q8 * 8 + k]; }
-                    int col = c * 32 + q8 * 8;
-                    tc::slab_store8(Ps + (col >> 6) * AT_SLAB, row, (col & 63) >> 3, f);
-                    tc::slab_store8(dSs + (col >> 6) * AT_SLAB, row, (col & 63) >> 3, g);
-                }
-            }
-        }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const uint32_t pa = tc::smem_u32(Ps), sa = tc::smem_u32(dSs), da = tc::smem_u32(dOs), qa = tc::smem_u32(Qs);
-#pragma unroll
-            for (int t = 0; t < 8; ++t)       // dV[s][e] += sum_row P~[row][s] dO[row][e]
-                tc::mma_bf16(tmem_dv, tc::desc_mnmajor(pa, AT_SLAB, t), tc::desc_mnmajor(da, AT_SLAB, t), idesc_mm, (i | t) != 0);
-#pragma unroll
-            for (int t = 0; t < 8; ++t)       // dK[s][e] += sum_row dS[row][s] Q[row][e]
-                tc::mma_bf16(tmem_dk, tc::desc_mnmajor(sa, AT_SLAB, t), tc::desc_mnmajor(qa, AT_SLAB, t), idesc_mm, (i | t) != 0);
-            tc::mma_commit(&bar_kv);
-        }
-    }
-    tc::mbar_wait(&bar_kv, (ntiles - 1) & 1);
-    tc::fence_after_sync();
-    if (warp < 4) {
-        const int s = s0 + row;
-        float* kr = dK + ((size_t)(s < S ? s : 0) * H + h) * AT;
-        float* vr = dV + ((size_t)(s < S ? s : 0) * H + h) * AT;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            float a[32], b[32];
-            tc::tmem_ld32(tmem_dk + lane_off + c * 32, a);
-            tc::tmem_ld32(tmem_dv + lane_off + c * 32, b);
-            if (s < S) {
-#pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    *reinterpret_cast<float4*>(kr + c * 32 + k) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
-                    *reinterpret_cast<float4*>(vr + c * 32 + k) = make_float4(b[k], b[k + 1], b[k + 2], b[k + 3]);
-                }
-            }
-        }
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base_smem, 512);
-}
-
 // ------------------------------------------------------------------------------------------------ backward: dK, dV, v3
 // One CTA per (128 prototypes, head, chunk of query-row tiles).  Everything is computed TRANSPOSED so that the CTA's own
 // prototypes are the TMEM lanes:   S^T = K Q_i^T,  dP^T = V dO_i^T   (M = 128 prototypes, N = 64 query rows per tile),
@@ -934,9 +524,9 @@ xattn_bwd_dkv_tc_kernel(const float* __restrict__ Q, const float* __restrict__ K
 __global__ void __launch_bounds__(FWD3_THREADS, 1)
 xattn_bwd_dkv_tc3_kernel(const float* __restrict__ K, const float* __restrict__ V, const uint8_t* __restrict__ qdopack,
                          const uint4* __restrict__ rowstat, float* __restrict__ dK, float* __restrict__ dV, int M, int H, int S,
-                         int tiles_per_chunk, float scale, float inv_keep, uint32_t thr, uint64_t seed, int use_atomics)
+                         int tiles_per_chunk, float scale, float inv_keep, uint32_t thr, uint64_t seed, int use_atomics, const unsigned long long* __restrict__ epoch)
 {
-    seed += g_drop_epoch_b;                              // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
+    seed += *epoch;                                     // dropout epoch (hopk_dropout_epoch_advance): lets a captured CUDA graph draw a fresh mask per replay
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[KV_STAGES], bar_s[2], bar_p, bar_kv;
     __shared__ uint32_t tmem_base_smem;
@@ -1105,21 +695,13 @@ xattn_bwd_dkv_tc3_kernel(const float* __restrict__ K, const float* __restrict__ 
 }  // namespace hopk
 using namespace hopk;
 
+#ifdef HOPK_DEBUG
 extern "C" int hopk_debug_set(void* mapped_host_ints)
 {
     int* p = (int*)mapped_host_ints;
     return cudaMemcpyToSymbol(hopk::g_dbg, &p, sizeof(p)) == cudaSuccess ? 0 : 1;
 }
-
-namespace hopk { void drop_epoch_launch_a(int reset, cudaStream_t st); }
-extern "C" int hopk_dropout_epoch_advance(int reset, void* stream)
-{
-    cudaStream_t st = (cudaStream_t)stream;
-    hopk::drop_epoch_launch_a(reset, st);
-    if (reset) hopk::drop_epoch_reset_b<<<1, 1, 0, st>>>(); else hopk::drop_epoch_bump_b<<<1, 1, 0, st>>>();
-    HOPK_LAUNCH_CHECK("dropout_epoch");
-    return 0;
-}
+#endif
 
 extern "C" size_t hopk_xattn_pack_bytes(int S, int H) { return (size_t)H * ((S + FS - 1) / FS) * KV_REC + 1024; }
 // backward scratch: Q / dO records (same format, rows = B*L) followed by the per-(head, row) statistics of the dK/dV pass
@@ -1132,35 +714,23 @@ extern "C" int hopk_xattn_fwd_tc(const float* q, const float* k, const float* v,
     HOPK_REQUIRE(B > 0 && L > 0 && H > 0 && S > 0, "xattn sizes");
     HOPK_REQUIRE(E == 128, "tensor-core attention is specialised for head dim 128");
     HOPK_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "dropout p in [0,1)");
+    HOPK_REQUIRE(kv_pack != nullptr, "kv_pack scratch (hopk_xattn_pack_bytes) required");
     cudaStream_t st = (cudaStream_t)stream;
     const int M = B * L;
-    const size_t smem = 2 * AT_SLAB + 4 * FS_SLAB + AT_SLAB + 1024;       // Q + K + V + P = 80 KB (+ alignment): 2 CTAs / SM
-    static bool configured = false;
-    if (!configured) {
-        HOPK_CUDA(cudaFuncSetAttribute(xattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     uint32_t thr = (uint32_t)lrintf(p_drop * 65536.f);
     const float inv_keep_h = 65536.f / (65536.f - (float)thr);
-    if (kv_pack) {                              // v3: packed bf16 K/V + bulk-copy ring + double-buffered S
-        const size_t smem3 = 4 * AT_SLAB + KV_STAGES * KV_REC + 1024;
-        static bool configured3 = false;
-        if (!configured3) {
-            HOPK_CUDA(cudaFuncSetAttribute(xattn_fwd_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-            configured3 = true;
-        }
-        uint8_t* pack = reinterpret_cast<uint8_t*>(((uintptr_t)kv_pack + 1023) & ~uintptr_t(1023));
-        const int ntiles = cdiv(S, FS);
-        xattn_pack_kv_kernel<<<dim3(ntiles, H), 256, 0, st>>>(k, v, pack, S, H, ntiles);
-        HOPK_LAUNCH_CHECK("xattn_pack_kv");
-        xattn_fwd_tc3_kernel<<<dim3(cdiv(M, AT), H), FWD3_THREADS, smem3, st>>>(q, pack, o, lse, M, L, H, S, 1.f / sqrtf((float)E),
-                                                                       inv_keep_h, thr, seed);
-        HOPK_LAUNCH_CHECK("xattn_fwd_tc3");
-        return 0;
-    }
-    xattn_fwd_tc_kernel<<<dim3(cdiv(M, AT), H), 256, smem, st>>>(q, k, v, o, lse, M, L, H, S, 1.f / sqrtf((float)E),
-                                                                 inv_keep_h, thr, seed);
-    HOPK_LAUNCH_CHECK("xattn_fwd_tc");
+    const unsigned long long* epoch = drop_epoch_ptr();
+    HOPK_REQUIRE(epoch != nullptr, "dropout epoch symbol");
+    // packed bf16 K/V records + bulk-copy ring + double-buffered S
+    const size_t smem3 = 4 * AT_SLAB + KV_STAGES * KV_REC + 1024;
+    HOPK_CUDA(configure_smem_once((const void*)xattn_fwd_tc3_kernel, smem3));
+    uint8_t* pack = reinterpret_cast<uint8_t*>(((uintptr_t)kv_pack + 1023) & ~uintptr_t(1023));
+    const int ntiles = cdiv(S, FS);
+    xattn_pack_kv_kernel<<<dim3(ntiles, H), 256, 0, st>>>(k, v, pack, S, H, ntiles);
+    HOPK_LAUNCH_CHECK("xattn_pack_kv");
+    xattn_fwd_tc3_kernel<<<dim3(cdiv(M, AT), H), FWD3_THREADS, smem3, st>>>(q, pack, o, lse, M, L, H, S, 1.f / sqrtf((float)E),
+                                                                   inv_keep_h, thr, seed, epoch);
+    HOPK_LAUNCH_CHECK("xattn_fwd_tc3");
     return 0;
 }
 
@@ -1172,54 +742,38 @@ extern "C" int hopk_xattn_bwd_tc(const float* q, const float* k, const float* v,
     HOPK_REQUIRE(E == 128, "tensor-core attention is specialised for head dim 128");
     HOPK_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "dropout p in [0,1)");
     HOPK_REQUIRE(delta != nullptr, "delta scratch (B*H*L floats) required");
+    HOPK_REQUIRE(kv_pack != nullptr && scratch != nullptr, "the forward's kv_pack and hopk_xattn_bwd_scratch_bytes() of scratch required");
     cudaStream_t st = (cudaStream_t)stream;
     const int M = B * L;
     uint32_t thr = (uint32_t)lrintf(p_drop * 65536.f);
     const float inv_keep = 65536.f / (65536.f - (float)thr), scale = 1.f / sqrtf((float)E);
-    const size_t smem1 = 10 * AT_SLAB + 1024, smem2 = 12 * AT_SLAB + 1024;
-    static bool configured = false;
-    if (!configured) {
-        HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        configured = true;
+    const unsigned long long* epoch = drop_epoch_ptr();
+    HOPK_REQUIRE(epoch != nullptr, "dropout epoch symbol");
+    // K / V records packed by the forward (same K, V), bulk-copy rings
+    const size_t smem3 = 6 * AT_SLAB + KV_STAGES * KV_REC + 1024;
+    HOPK_CUDA(configure_smem_once((const void*)xattn_bwd_dq_tc3_kernel, smem3));
+    HOPK_CUDA(configure_smem_once((const void*)xattn_bwd_dkv_tc3_kernel, smem3));
+    const uint8_t* pack = reinterpret_cast<const uint8_t*>(((uintptr_t)kv_pack + 1023) & ~uintptr_t(1023));
+    uint8_t* qdo = reinterpret_cast<uint8_t*>(((uintptr_t)scratch + 1023) & ~uintptr_t(1023));
+    uint4* rowstat = reinterpret_cast<uint4*>(qdo + qdo_pack_bytes(M, H));
+    const int mt = cdiv(M, FS);
+    xattn_pack_kv_kernel<<<dim3(mt, H), 256, 0, st>>>(q, dout, qdo, M, H, mt);       // Q / dO records
+    HOPK_LAUNCH_CHECK("xattn_pack_qdo");
+    xattn_bwd_dq_tc3_kernel<<<dim3(cdiv(M, AT), H), FWD3_THREADS, smem3, st>>>(q, pack, o, lse, dout, dq, delta, rowstat, M, L, H,
+                                                                            S, scale, inv_keep, thr, seed, epoch);
+    HOPK_LAUNCH_CHECK("xattn_bwd_dq_tc3");
+    const int kvt = cdiv(S, AT);
+    int chunks = (2 * 148 + kvt * H / 2) / (kvt * H);                   // about two waves of CTAs
+    if (chunks < 1) chunks = 1;
+    if (chunks > mt) chunks = mt;
+    const int per = cdiv(mt, chunks);
+    chunks = cdiv(mt, per);
+    if (chunks > 1) {
+        HOPK_CUDA(cudaMemsetAsync(dk, 0, (size_t)S * H * E * sizeof(float), st));
+        HOPK_CUDA(cudaMemsetAsync(dv, 0, (size_t)S * H * E * sizeof(float), st));
     }
-    if (kv_pack && scratch) {                   // v3: K / V records packed by the forward (same K, V), bulk-copy rings
-        const size_t smem3 = 6 * AT_SLAB + KV_STAGES * KV_REC + 1024;
-        static bool configured3 = false;
-        if (!configured3) {
-            HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dq_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-            HOPK_CUDA(cudaFuncSetAttribute(xattn_bwd_dkv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-            configured3 = true;
-        }
-        const uint8_t* pack = reinterpret_cast<const uint8_t*>(((uintptr_t)kv_pack + 1023) & ~uintptr_t(1023));
-        uint8_t* qdo = reinterpret_cast<uint8_t*>(((uintptr_t)scratch + 1023) & ~uintptr_t(1023));
-        uint4* rowstat = reinterpret_cast<uint4*>(qdo + qdo_pack_bytes(M, H));
-        const int mt = cdiv(M, FS);
-        xattn_pack_kv_kernel<<<dim3(mt, H), 256, 0, st>>>(q, dout, qdo, M, H, mt);       // Q / dO records
-        HOPK_LAUNCH_CHECK("xattn_pack_qdo");
-        xattn_bwd_dq_tc3_kernel<<<dim3(cdiv(M, AT), H), FWD3_THREADS, smem3, st>>>(q, pack, o, lse, dout, dq, delta, rowstat, M, L, H,
-                                                                                S, scale, inv_keep, thr, seed);
-        HOPK_LAUNCH_CHECK("xattn_bwd_dq_tc3");
-        const int kvt = cdiv(S, AT);
-        int chunks = (2 * 148 + kvt * H / 2) / (kvt * H);                   // about two waves of CTAs
-        if (chunks < 1) chunks = 1;
-        if (chunks > mt) chunks = mt;
-        const int per = cdiv(mt, chunks);
-        chunks = cdiv(mt, per);
-        if (chunks > 1) {
-            HOPK_CUDA(cudaMemsetAsync(dk, 0, (size_t)S * H * E * sizeof(float), st));
-            HOPK_CUDA(cudaMemsetAsync(dv, 0, (size_t)S * H * E * sizeof(float), st));
-        }
-        xattn_bwd_dkv_tc3_kernel<<<dim3(kvt, H, chunks), FWD3_THREADS, smem3, st>>>(k, v, qdo, rowstat, dk, dv, M, H, S, per, scale,
-                                                                                  inv_keep, thr, seed, chunks > 1 ? 1 : 0);
-        HOPK_LAUNCH_CHECK("xattn_bwd_dkv_tc3");
-        return 0;
-    }
-    xattn_bwd_dq_tc_kernel<<<dim3(cdiv(M, AT), H), 256, smem1, st>>>(q, k, v, o, lse, dout, dq, delta, M, L, H, S, scale,
-                                                                     inv_keep, thr, seed);
-    HOPK_LAUNCH_CHECK("xattn_bwd_dq_tc");
-    xattn_bwd_dkv_tc_kernel<<<dim3(cdiv(S, AT), H), 256, smem2, st>>>(q, k, v, lse, delta, dout, dk, dv, M, L, H, S, scale,
-                                                                      inv_keep, thr, seed);
-    HOPK_LAUNCH_CHECK("xattn_bwd_dkv_tc");
+    xattn_bwd_dkv_tc3_kernel<<<dim3(kvt, H, chunks), FWD3_THREADS, smem3, st>>>(k, v, qdo, rowstat, dk, dv, M, H, S, per, scale,
+                                                                              inv_keep, thr, seed, chunks > 1 ? 1 : 0, epoch);
+    HOPK_LAUNCH_CHECK("xattn_bwd_dkv_tc3");
     return 0;
 }

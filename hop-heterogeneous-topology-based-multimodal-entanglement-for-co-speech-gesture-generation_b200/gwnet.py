@@ -134,12 +134,18 @@ class _GwnetFn(torch.autograd.Function):
         xs = _lib._I64x4(*x.stride())
         with profiler.span('gwnet_fwd'):
             check(l.hopk_gwnet_forward(shape, pstruct, ptr(x), xs, ptr(out), ptr(ws), stream_ptr()))
-        ctx.mod, ctx.shape, ctx.ws, ctx.x, ctx.params, ctx.keep = mod, shape, ws, x, params, keep
+        # saved tensors (not plain attributes): autograd's version counters catch in-place edits of x / the parameters
+        # between forward and backward, and a second backward without retain_graph raises autograd's own clear error
+        ctx.save_for_backward(x, ws, *params)
+        ctx.mod, ctx.shape = mod, shape
+        if mod._keep_ws:                                   # tests / tools: inspect what backward will re-read
+            mod._last_ws, mod._last_shape = ws, shape
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        mod, shape, params, x = ctx.mod, ctx.shape, ctx.params, ctx.x
+        mod, shape = ctx.mod, ctx.shape
+        x, ws, *params = ctx.saved_tensors
         l = lib()
         dout = f32c(dout)
         pstruct, keep = mod._param_struct(params)
@@ -167,9 +173,8 @@ class _GwnetFn(torch.autograd.Function):
         scratch = torch.empty(l.hopk_gwnet_scratch_bytes(shape), device=x.device, dtype=torch.uint8)
         xs = _lib._I64x4(*x.stride())
         with profiler.span('gwnet_bwd'):
-            check(l.hopk_gwnet_backward(shape, pstruct, ptr(x), xs, ptr(dout), ptr(ctx.ws), ptr(scratch), g, ptr(dx),
+            check(l.hopk_gwnet_backward(shape, pstruct, ptr(x), xs, ptr(dout), ptr(ws), ptr(scratch), g, ptr(dx),
                                         stream_ptr()))
-        ctx.ws = None
         if dx is not None:
             dx = dx.permute(0, 3, 2, 1)          # (B, T, V, C) rows layout -> (B, C, V, T) view
         return (None, dx, *grads)
@@ -244,6 +249,8 @@ class gwnet(nn.Module):
         self._cfg = dict(in_dim=in_dim, out_dim=out_dim, C=residual_channels, D=dilation_channels, S=skip_channels,
                          E=end_channels)
         self._names = None
+        self._keep_ws = False         # True: keep a reference to the last forward's workspace in self._last_ws
+        self._last_ws = self._last_shape = None
         self.precision = 'fp32'       # 'fp32': FFMA, 1e-5 parity mode; 'bf16': tcgen05 bf16 operands, fp32 accumulate
 
     def set_precision(self, name):
@@ -267,6 +274,9 @@ class gwnet(nn.Module):
             why = 'gcn dropout > 0 in training mode is not implemented (HOP uses dropout=0)'
         elif self.blocks * self.layers > _lib.MAX_LAYERS:
             why = 'too many layers'
+        elif any(bn.momentum is None or bn.momentum != self.bn[0].momentum or bn.eps != self.bn[0].eps or not bn.affine
+                 or not bn.track_running_stats for bn in self.bn):
+            why = 'the BatchNorm2d layers must share one momentum (not None) and eps, be affine and track running stats'
         if why:
             raise NotImplementedError('hop_b200.gwnet: ' + why + ' -- no eager fallback by design')
 
@@ -306,7 +316,16 @@ class gwnet(nn.Module):
         s.rank = self.nodevec1.shape[1]
         s.training = 1 if self.training else 0
         s.dtype = 1 if self.precision == 'bf16' else 0
+        s.bn_momentum, s.bn_eps = float(self.bn[0].momentum), float(self.bn[0].eps)
         return s
+
+    def workspace_field(self, name, layer=0):
+        """fp32 view (rows layout) of a saved activation of the last forward (needs ``self._keep_ws = True``)."""
+        import ctypes as C
+        off, nbytes, eb = C.c_size_t(), C.c_size_t(), C.c_int()
+        check(lib().hopk_gwnet_ws_field(self._last_shape, name.encode(), layer, C.byref(off), C.byref(nbytes), C.byref(eb)))
+        raw = self._last_ws[off.value:off.value + nbytes.value]
+        return raw.view(torch.float32 if eb.value == 4 else torch.bfloat16)
 
     def _param_struct(self, params):
         p = GwnetParams()

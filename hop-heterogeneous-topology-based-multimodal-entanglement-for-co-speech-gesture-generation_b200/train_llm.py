@@ -11,7 +11,8 @@ change the arithmetic:
     no dropout on that branch -- are computed by the first forward of the step and reused by the others (the reference
     recomputes identical values); the BatchNorm running statistics still receive one update per forward;
   * the 2-5 ``.item()`` host syncs are folded into one device->host read at the end.
-``accelerator`` only needs ``.backward(loss)`` (hop_b200.dp.DataParallel provides it; so does HF Accelerate).
+``accelerator`` only needs ``.backward(loss)``: hop_b200.dp.DataParallel (single- and multi-GPU) or, on ONE GPU with the
+bare module, HF Accelerate.  A DDP / DeepSpeed-wrapped model is refused (see ``_check_wrapper``).
 """
 import torch
 import torch.nn.functional as F
@@ -45,12 +46,25 @@ def finish_losses(names, host):
     return ret
 
 
+def _check_wrapper(model, accelerator):
+    """The step calls ``model.module.forecast`` directly (shared text prototypes / features), which bypasses the forward
+    of a wrapping DistributedDataParallel / DeepSpeedEngine: their reducers would never be armed and the replicas
+    would silently diverge.  Gradient averaging is hop_b200.dp.DataParallel's job here -- refuse anything else."""
+    kind = type(model).__name__
+    if kind in ('DistributedDataParallel', 'DeepSpeedEngine', 'FullyShardedDataParallel'):
+        from .dp import DataParallel
+        if not isinstance(accelerator, DataParallel):
+            raise RuntimeError(f'hop_b200.train_llm: the model is wrapped in {kind}, whose gradient reduction this step '
+                               'would bypass; pass the bare module and use hop_b200.dp.DataParallel as `accelerator`')
+
+
 def train_llm_device(args, epoch, in_audio, log_melspec, text_token_padded, target_dir_vec, vid_indices,
                      model, discriminator, model_optim, dis_optimizer, accelerator):
     """The whole step without its single host read: returns (names, stacked device tensor of the reported scalars).
     Free of host synchronisation, so it can be captured in a CUDA graph (hop_b200.graphed.GraphedTrainStep)."""
     pre_seq = target_dir_vec[:, 0:16]
     dis_error = None
+    _check_wrapper(model, accelerator)
     core = getattr(model, 'module', model)
     source = core.source_embeddings() if hasattr(core, 'source_embeddings') else None
     # beat features + Graph-WaveNet output are identical in every forward of a step (SHARE_STEP_FEATURES = False recomputes)

@@ -34,7 +34,10 @@ extern "C" {
 const char* hopk_last_error(void);
 int hopk_version(void);
 long long hopk_launch_count(void);
-int hopk_debug_set(void* mapped_host_ints);   /* debugging aid: progress markers of the tensor-core kernels (NULL = off) */   /* kernels this library has launched in this process (host-side counter) */
+/* hopk_launch_count: kernels this library has launched in this process (host-side counter) */
+#ifdef HOPK_DEBUG
+int hopk_debug_set(void* mapped_host_ints);   /* debug builds only (nvcc -DHOPK_DEBUG): progress markers of the tensor-core kernels */
+#endif
 
 /* ------------------------------------------------------------------ Graph-WaveNet block */
 typedef struct HopkGwnetShape {
@@ -47,6 +50,7 @@ typedef struct HopkGwnetShape {
     int rank;                    /* adaptive-adjacency embedding width (10), gwnet.py:82-83 */
     int training;                /* 1: BatchNorm batch statistics + running-stat update */
     int dtype;                   /* see above */
+    float bn_momentum, bn_eps;   /* of the module's BatchNorm2d layers (nn.BatchNorm2d defaults 0.1 / 1e-5, gwnet.py:120) */
 } HopkGwnetShape;
 
 /* Parameter / buffer pointers, named after the reference's state_dict keys (gwnet.py:50-139).
@@ -85,6 +89,13 @@ typedef struct HopkGwnetGrads {
 size_t hopk_gwnet_workspace_bytes(const HopkGwnetShape* s);
 size_t hopk_gwnet_scratch_bytes(const HopkGwnetShape* s);
 int hopk_gwnet_out_steps(const HopkGwnetShape* s);       /* max(T, receptive_field) - rf + 1 */
+
+/* Where a saved activation lives inside the forward workspace (for tools and tests that inspect what backward will
+ * re-read).  name: "x0" (start conv output), "u" (pre-BatchNorm output of layer `layer`), "tf" / "sg" (tanh f, sigmoid g
+ * of layer `layer`), "ycat" (last-T_out slices of every layer's gated output, 8C wide), "r0" (relu(skip)), "r1"
+ * (relu(end_conv_1)), "mr" (BatchNorm mean | rstd of layer `layer`), "A" (adaptive adjacency).  All rows layout;
+ * elem_bytes is 4 (fp32) or 2 (bf16).  Returns non-zero for an unknown name. */
+int hopk_gwnet_ws_field(const HopkGwnetShape* s, const char* name, int layer, size_t* offset, size_t* bytes, int* elem_bytes);
 
 /* gwnet.forward (model/gwnet.py:143-249).
  *   x: input viewed as (B, in_dim, V, T) through element strides xs = {sB, sC, sV, sT}

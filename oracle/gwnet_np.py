@@ -81,7 +81,7 @@ def _sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
 
 
-def forward(params, x_in, blocks=4, layers=2, training=True, keep=False, q=_id):
+def forward(params, x_in, blocks=4, layers=2, training=True, keep=False, q=_id, relu_masks=None):
     """gwnet.forward (gwnet.py:143-249).
 
     Returns (out, new_buffers, cache).  ``new_buffers`` holds the updated
@@ -91,6 +91,9 @@ def forward(params, x_in, blocks=4, layers=2, training=True, keep=False, q=_id):
     ``q`` (default identity) is applied to both operands of every dense contraction -- start/gate/mlp/skip/end
     convs -- and nowhere else; with ``q=bf16_round`` this is the quantisation-aware reference of the bf16
     tensor-core mode (dtype 1: bf16 operands, fp32 accumulation, everything else fp32).
+
+    ``relu_masks`` = (m_skip (B,S,V,Tl), m_end1 (B,E,V,Tl)) of 0/1 pins the gate pattern of the two head ReLUs
+    (gwnet.py:240-243) to an implementation's own pattern (see oracle/hop_torch.py::gwnet_forward for why).
     """
     p = {k: np.asarray(v, dtype=np.float64) for k, v in params.items()}
     x = np.asarray(x_in, dtype=np.float64)
@@ -143,12 +146,14 @@ def forward(params, x_in, blocks=4, layers=2, training=True, keep=False, q=_id):
         if keep:
             cache['layers'].append(dict(x=x, tf=tf, sg=sg, y=y, x1=x1, x2=x2, xhat=xhat, rstd=rstd, d=d))
         x = xn
-    r0 = np.maximum(skip, 0.0)
+    g0 = (skip > 0) if relu_masks is None else (np.asarray(relu_masks[0]) > 0)
+    r0 = skip * g0
     e1 = _pw(r0, p['end_conv_1.weight'], p['end_conv_1.bias'], q)
-    r1 = np.maximum(e1, 0.0)
+    g1 = (e1 > 0) if relu_masks is None else (np.asarray(relu_masks[1]) > 0)
+    r1 = e1 * g1
     out = _pw(r1, p['end_conv_2.weight'], p['end_conv_2.bias'], q)
     if keep:
-        cache.update(skip=skip, r0=r0, e1=e1, r1=r1, training=training)
+        cache.update(skip=skip, r0=r0, e1=e1, r1=r1, g0=g0, g1=g1, training=training)
     return out, bufs, cache
 
 
@@ -175,9 +180,9 @@ def backward(params, cache, dout, blocks=4, layers=2, q=_id):
     G = {}
     dout = np.asarray(dout, dtype=np.float64)
     dr1, G['end_conv_2.weight'], G['end_conv_2.bias'] = _pw_bwd(cache['r1'], p['end_conv_2.weight'], dout, q)
-    de1 = dr1 * (cache['e1'] > 0)
+    de1 = dr1 * cache['g1']
     dr0, G['end_conv_1.weight'], G['end_conv_1.bias'] = _pw_bwd(cache['r0'], p['end_conv_1.weight'], de1, q)
-    dskip = dr0 * (cache['skip'] > 0)            # (B, S, V, T_last)
+    dskip = dr0 * cache['g0']                    # (B, S, V, T_last)
     Tl = dskip.shape[3]
     A = cache['A']
     M1 = np.zeros_like(A)

@@ -62,11 +62,13 @@ def _id(a):
     return a
 
 
-def forward(P, target, source, value, n_heads, p_drop=0.0, seed=0, keep=False, q=_id):
+def forward(P, target, source, value, n_heads, p_drop=0.0, seed=0, keep=False, q=_id, relu_mask=None):
     """ReprogrammingLayer.forward.  target (B,L,dm); source,value (S,dllm).  Returns (B,L,dllm).
 
     ``q`` quantises both operands of the four projection GEMMs (identity = exact reference;
-    oracle.gwnet_np.bf16_round = quantisation-aware reference of the bf16 tensor-core mode)."""
+    oracle.gwnet_np.bf16_round = quantisation-aware reference of the bf16 tensor-core mode).
+    ``relu_mask`` (B, L, H*E) of 0/1 pins the gate pattern of the ReLU in front of the out projection (HOP.py:284) to an
+    implementation's own pattern (see oracle/hop_torch.py::gwnet_forward for why)."""
     P = {k: np.asarray(v, dtype=np.float64) for k, v in P.items()}
     x = np.asarray(target, np.float64)
     src = np.asarray(source, np.float64)
@@ -90,9 +92,10 @@ def forward(P, target, source, value, n_heads, p_drop=0.0, seed=0, keep=False, q
         mask = np.ones_like(pr)
     pd = pr * mask
     O = np.einsum('bhls,she->blhe', pd, V).reshape(B, L, H * E)
-    R = np.maximum(O, 0.0)
+    gate = (O > 0) if relu_mask is None else (np.asarray(relu_mask) > 0)
+    R = O * gate
     Y = q(R) @ q(P['out_projection.weight']).T + P['out_projection.bias']
-    cache = dict(x=x, src=src, val=val, Q=Q, K=K, V=V, pr=pr, mask=mask, O=O, R=R, scale=scale) if keep else None
+    cache = dict(x=x, src=src, val=val, Q=Q, K=K, V=V, pr=pr, mask=mask, O=O, R=R, gate=gate, scale=scale) if keep else None
     return Y, cache
 
 
@@ -108,7 +111,7 @@ def backward(P, cache, dY, n_heads, q=_id):
     G['out_projection.weight'] = np.einsum('blo,bli->oi', dYq, q(c['R']))
     G['out_projection.bias'] = dYq.sum(axis=(0, 1))      # bias gradient = all-ones column of the weight-gradient GEMM
     dR = dYq @ q(P['out_projection.weight'])
-    dO = (dR * (c['O'] > 0)).reshape(B, L, H, -1)
+    dO = (dR * c['gate']).reshape(B, L, H, -1)
     dpd = np.einsum('blhe,she->bhls', dO, c['V'])
     dV = np.einsum('bhls,blhe->she', c['pr'] * c['mask'], dO)
     dpr = dpd * c['mask']

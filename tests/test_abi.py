@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     src = open(os.path.join(ROOT, 'include', 'hopk.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    src = re.sub(r'#ifdef HOPK_DEBUG.*?#endif', '', src, flags=re.S)     # debug-only entry points are not in the release library
     return sorted(set(re.findall(r'\b(hopk_\w+)\s*\(', src)))
 
 
@@ -27,12 +28,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(l, n), f'{n} declared in include/hopk.h but not exported by libhopk.so'
         assert n in _lib.SIGNATURES, f'{n} has no ctypes signature in hop_b200/_lib.py'
     assert set(_lib.SIGNATURES) == set(names)
-    assert _lib.lib().hopk_version() >= 100
+    assert _lib.lib().hopk_version() >= 200
+    assert not hasattr(l, 'hopk_debug_set'), 'debug hooks must be compiled out of the release library'
 
 
 def test_struct_sizes_match_header():
     from hop_b200 import _lib
-    assert ctypes.sizeof(_lib.GwnetShape) == 4 * (9 + 16 + 3)
+    assert ctypes.sizeof(_lib.GwnetShape) == 4 * (9 + 16 + 3 + 2)
     assert ctypes.sizeof(_lib.GwnetParams) == 8 * (4 + 13 * 16 + 4)
     assert ctypes.sizeof(_lib.GwnetGrads) == 8 * (4 + 10 * 16 + 4 + 2)
 

@@ -8,7 +8,7 @@ import torch
 
 from oracle import gwnet_np
 from tests.golden.make_golden import GW_CASES, gw_inputs
-from tests.util import GOLDEN, TOL_BF16, TOL_FP32, Report, golden_compare, l2err, relerr
+from tests.util import GOLDEN, TOL_BF16, TOL_FP32, Report, golden_compare, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -22,6 +22,7 @@ def build_module(P, V, cfg, dev, training=True):
           for k, v in P.items()}
     m.load_state_dict(sd, strict=True)          # state_dict key parity with the reference's names
     m.train(training)
+    m._keep_ws = True
     return m
 
 
@@ -40,24 +41,12 @@ def run_case(name, dev, channels_last, precision='fp32'):
     return m, out, xt, (P, x, dout, training, cfg)
 
 
-def torch_bf16_autocast_errors(P, x, dout, training, o_dx, o_G, dev):
-    """Error level of the STANDARD bf16 path (stock PyTorch ops under torch.autocast(bfloat16)) against the exact
-    oracle, per tensor, relative 2-norm.  It calibrates what "bf16 accuracy" means for this network."""
-    from oracle import hop_torch
-    sd = {'gwnet.' + k: torch.from_numpy(np.asarray(v)).to(dev) for k, v in P.items()}
-    for k, v in sd.items():
-        if v.is_floating_point():
-            sd[k] = v.float().requires_grad_('running_' not in k)
-    xt = torch.from_numpy(x).float().to(dev).requires_grad_(True)
-    with torch.autocast('cuda', dtype=torch.bfloat16):
-        out = hop_torch.gwnet_forward(sd, xt, training=training, update_buffers=False)
-    out.float().backward(torch.from_numpy(dout).float().to(dev))
-    errs = {'dx': l2err(xt.grad.cpu().numpy(), o_dx)}
-    for k, ref in o_G.items():
-        g = sd['gwnet.' + k].grad
-        if g is not None:
-            errs[k] = l2err(g.float().cpu().numpy().reshape(ref.shape), ref)
-    return errs
+def own_relu_masks(m, B, V):
+    """Gate pattern of the kernel's own forward at the two head ReLUs (gwnet.py:240-243), as (B, ch, V, Tl) arrays."""
+    S, E = m._cfg['S'], m._cfg['E']
+    m0 = (m.workspace_field('r0').view(B, -1, V, S) > 0).permute(0, 3, 2, 1).cpu().numpy()
+    m1 = (m.workspace_field('r1').view(B, -1, V, E) > 0).permute(0, 3, 2, 1).cpu().numpy()
+    return m0, m1
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
@@ -68,26 +57,25 @@ def test_gwnet_vs_oracle_and_golden(name, channels_last, precision, cuda):
 
     bf16 mode (dtype 1: GEMM operands rounded to bf16 on the tensor cores, fp32 accumulation, everything else fp32):
       * forward output within 2e-2 (max-norm) of the exact oracle / fixtures;
-      * gradients within max(2e-2, 1.5 x the error of stock PyTorch bf16 autocast on the same ops) in relative 2-norm.
-    A flat 2e-2 on gradients is unattainable for ANY bf16 implementation of this block: rounding the operands perturbs
-    the pre-activations of the two head ReLUs by eps ~ 2^-8, which flips ~eps of the gates, and every flipped gate
-    changes its gradient element completely -- a relative 2-norm error of ~sqrt(eps) ~ 5 % that then propagates through
-    all eight layers (DESIGN.md, "bf16 accuracy").  The op-level tests (test_modules_gpu.py::test_linear_tcgen05_*)
-    prove the kernels themselves are exact on bf16-representable operands.
+      * every gradient within the same flat 2e-2 (max-norm) of the exact oracle *pinned to the kernel's own gate pattern*
+        at the two head ReLUs (gwnet.py:240-243).  Rounding the operands flips the few gates whose pre-activation lies
+        within rounding distance of zero and a flipped gate changes its gradient element completely, for any
+        reduced-precision implementation; with the pattern pinned, everything that is left is the kernels' arithmetic.
+        The flip fraction itself is bounded by tests/test_baseline_parity_gpu.py::test_gwnet_bf16_gate_flip_fraction.
     """
     m, out, xt, (P, x, dout, training, cfg) = run_case(name, cuda, channels_last, precision)
+    bf16 = precision == 'bf16'
     o_out, o_bufs, cache = gwnet_np.forward(P, x, training=training, keep=True)
+    if bf16:
+        B, V = x.shape[0], x.shape[2]
+        _, _, cache = gwnet_np.forward(P, x, training=training, keep=True, relu_masks=own_relu_masks(m, B, V))
     o_dx, o_G = gwnet_np.backward(P, cache, dout)
     fix = np.load(os.path.join(GOLDEN, name + '.npz'))
-    bf16 = precision == 'bf16'
     tol = TOL_BF16 if bf16 else TOL_FP32
     rep = Report(f'{name}_{"cl" if channels_last else "nchw"}_{precision}', tol)
     rep.add('out', relerr(out.detach().cpu().numpy(), o_out))
     rep.add('out(golden)', relerr(out.detach().cpu().numpy(), fix['out']))
-    base = torch_bf16_autocast_errors(P, x, dout, training, o_dx, o_G, cuda) if bf16 else {}
-    gtol = lambda k: max(TOL_BF16, 1.5 * base.get(k, 0.0)) if bf16 else tol
-    err = l2err if bf16 else relerr
-    rep.add('dx', err(xt.grad.cpu().numpy(), o_dx), tol=gtol('dx'))
+    rep.add('dx', relerr(xt.grad.cpu().numpy(), o_dx))
     if not bf16:
         rep.add('dx(golden)', golden_compare(fix, 'dx', xt.grad.cpu().numpy()))
     gscale = max(float(np.abs(v).max()) for v in o_G.values())
@@ -102,7 +90,7 @@ def test_gwnet_vs_oracle_and_golden(name, channels_last, precision, cuda):
         if np.abs(ref).max() < 1e-9 * gscale:      # analytically zero (bias in front of train-mode BN)
             rep.add('grad0:' + k, float(np.abs(g).max()) / gscale, tol=tol)
         else:
-            rep.add('grad:' + k, err(g, ref), tol=gtol(k))
+            rep.add('grad:' + k, relerr(g, ref))
             if not bf16:
                 rep.add('grad(golden):' + k, golden_compare(fix, k, g, zero_scale=gscale))
     sd = m.state_dict()

@@ -19,47 +19,37 @@ def build(P, cfg, dev):
     return m
 
 
-def torch_bf16_autocast_errors(P, x, src, dY, H, o_dx, o_ds, o_G, dev):
-    """Error of stock PyTorch bf16 autocast on the same layer vs the exact oracle (relative 2-norm per tensor)."""
-    from oracle import hop_torch
-    sd = {'reprogramming_layer.' + k: torch.from_numpy(v).float().to(dev).requires_grad_(True) for k, v in P.items()}
-    xt = torch.from_numpy(x).float().to(dev).requires_grad_(True)
-    st = torch.from_numpy(src).float().to(dev).requires_grad_(True)
-    with torch.autocast('cuda', dtype=torch.bfloat16):
-        y = hop_torch.reprogramming_forward(sd, xt, st, st, H)
-    y.float().backward(torch.from_numpy(dY).float().to(dev))
-    errs = {'dx': l2err(xt.grad.cpu().numpy(), o_dx), 'dsource': l2err(st.grad.cpu().numpy(), o_ds)}
-    for k, ref in o_G.items():
-        errs[k] = l2err(sd['reprogramming_layer.' + k].grad.cpu().numpy().reshape(ref.shape), ref)
-    return errs
-
-
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 @pytest.mark.parametrize('name', list(RP_CASES))
 def test_reprog_vs_oracle_and_golden(name, precision, cuda):
-    """fp32: 1e-5 max-norm vs the exact oracle and the reference fixtures.  bf16 (projections on tcgen05 with bf16
-    operands): output within 2e-2, gradients within max(2e-2, 1.5 x stock PyTorch bf16 autocast error) in relative
-    2-norm (see test_gwnet_gpu.py for why a flat 2e-2 on gradients behind a ReLU is not a meaningful bar)."""
+    """fp32: 1e-5 max-norm vs the exact oracle and the reference fixtures.  bf16 (projections and attention on tcgen05 with
+    bf16 operands): output within 2e-2 of the exact oracle; every gradient within the same flat 2e-2 (max-norm) of the
+    exact oracle pinned to the kernel's own gate pattern at the ReLU in front of the out projection (HOP.py:284) -- see
+    test_gwnet_gpu.py for why the pattern is pinned."""
     seed, B, L, S, cfg = RP_CASES[name]
     P, x, src, dY = rp_inputs(seed, B, L, S, cfg)
     m = build(P, cfg, cuda).eval().set_precision(precision)   # p = 0: comparable with the reference itself
+    m._keep_attn = True
     xt = torch.from_numpy(x).float().to(cuda).requires_grad_(True)
     st = torch.from_numpy(src).float().to(cuda).requires_grad_(True)
     y = m(xt, st, st)
     y.backward(torch.from_numpy(dY).float().to(cuda))
+    bf16 = precision == 'bf16'
     o_y, cache = reprog_np.forward(P, x, src, src, cfg['n_heads'], keep=True)
+    if bf16:
+        gate = (m._last_attn > 0).cpu().numpy()
+        rep_flip = float((gate != cache['gate']).mean())
+        _, cache = reprog_np.forward(P, x, src, src, cfg['n_heads'], keep=True, relu_mask=gate)
     o_dx, o_ds, o_dv, o_G = reprog_np.backward(P, cache, dY, cfg['n_heads'])
     fix = np.load(os.path.join(GOLDEN, name + '.npz'))
-    bf16 = precision == 'bf16'
     tol = TOL_BF16 if bf16 else TOL_FP32
     rep = Report(name + '_' + precision, tol)
-    base = torch_bf16_autocast_errors(P, x, src, dY, cfg['n_heads'], o_dx, o_ds + o_dv, o_G, cuda) if bf16 else {}
-    gtol = lambda k: max(TOL_BF16, 1.5 * base.get(k, 0.0)) if bf16 else tol
-    err = l2err if bf16 else relerr
+    if bf16:
+        rep.add('flipped relu gates (fraction)', rep_flip, tol=1e-2)
     rep.add('out', relerr(y.detach().cpu().numpy(), o_y))
     rep.add('out(golden)', relerr(y.detach().cpu().numpy(), fix['out']))
-    rep.add('dx', err(xt.grad.cpu().numpy(), o_dx), tol=gtol('dx'))
-    rep.add('dsource', err(st.grad.cpu().numpy(), o_ds + o_dv), tol=gtol('dsource'))
+    rep.add('dx', relerr(xt.grad.cpu().numpy(), o_dx))
+    rep.add('dsource', relerr(st.grad.cpu().numpy(), o_ds + o_dv))
     if not bf16:
         rep.add('dsource(golden)', golden_compare(fix, 'dsource', st.grad.cpu().numpy()))
     gscale = max(float(np.abs(v).max()) for v in o_G.values())
@@ -68,7 +58,7 @@ def test_reprog_vs_oracle_and_golden(name, precision, cuda):
         if np.abs(o_G[k]).max() < 1e-9 * gscale:
             rep.add('grad0:' + k, float(np.abs(g).max()) / gscale, tol=tol)
         else:
-            rep.add('grad:' + k, err(g, o_G[k].reshape(g.shape)), tol=gtol(k))
+            rep.add('grad:' + k, relerr(g, o_G[k].reshape(g.shape)))
             if not bf16:
                 rep.add('grad(golden):' + k, golden_compare(fix, k, g, zero_scale=gscale))
     rep.finish()
@@ -170,15 +160,11 @@ def test_xattn_tcgen05_forward_exact(cuda):
     assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 2e-3
 
 
-@pytest.mark.parametrize('B,L,H,S,p,packed', [(2, 34, 8, 1500, 0.0, True), (3, 7, 1, 300, 0.0, True), (5, 34, 2, 128, 0.1, True),
-                                              (3, 34, 2, 300, 0.1, False)])
-def test_xattn_tcgen05_backward(B, L, H, S, p, packed, cuda, monkeypatch):
+@pytest.mark.parametrize('B,L,H,S,p', [(2, 34, 8, 1500, 0.0), (3, 7, 1, 300, 0.0), (5, 34, 2, 128, 0.1), (3, 34, 2, 300, 0.1)])
+def test_xattn_tcgen05_backward(B, L, H, S, p, cuda):
     """Tensor-core attention backward (dQ and dK/dV passes) against float64 on bf16-representable inputs.
-    Remaining error: bf16 rounding of P~ and dS (2^-9 relative per element) -> 5e-3 in relative 2-norm.
-    packed = True: v3 kernels (bf16 operand records through bulk-copy rings); False: the kernels that stage fp32 operands."""
-    from hop_b200 import HOP
+    Remaining error: bf16 rounding of P~ and dS (2^-9 relative per element) -> 5e-3 in relative 2-norm."""
     from hop_b200.HOP import _XattnFn
-    monkeypatch.setattr(HOP, 'XATTN_PACKED', packed)
     torch.manual_seed(B + S)
     q = torch.randn(B, L, H, 128).bfloat16().double().requires_grad_(True)
     k = torch.randn(S, H, 128).bfloat16().double().requires_grad_(True)
