@@ -86,8 +86,10 @@ def _gru(sd, x, hidden=350, layers=4):
 
 
 def model_forward(sd, bert, in_audio, x_enc, text, pre_seq, vid, noise, n_heads=8, p_drop=0.0, training=True,
-                  update_buffers=True):
-    """HOP.Model.forward.  ``noise`` (B,16) replaces reparameterize's randn so both sides share it."""
+                  update_buffers=True, literal_beat=False):
+    """HOP.Model.forward.  ``noise`` (B,16) replaces reparameterize's randn so both sides share it.
+    ``literal_beat``: run the beat MLP on the J-fold repeated windows exactly like HOP.py:210-212 (same values as the
+    de-duplicated gather, J times the work) -- what the reference itself executes, used by the timing baselines."""
     B = pre_seq.shape[0]
     J = pre_seq.shape[2] // 3
     e = F.linear(F.embedding(vid, sd['speaker_embedding.0.weight']), sd['speaker_embedding.1.weight'],
@@ -102,10 +104,16 @@ def model_forward(sd, bert, in_audio, x_enc, text, pre_seq, vid, noise, n_heads=
     h = F.linear(torch.cat([enc, text_emb], 2), sd['align_layer.weight'], sd['align_layer.bias'])
     dec = bert(inputs_embeds=h).last_hidden_state
     win = in_audio.unfold(1, 3400, 2191)
+    if literal_beat:
+        win = win.unsqueeze(1).repeat(1, J, 1, 1)                                  # (B, J, 16, 3400), HOP.py:210
     feat = F.linear(F.leaky_relu(F.linear(win, sd['beat.0.weight'], sd['beat.0.bias']), 0.2), sd['beat.2.weight'],
                     sd['beat.2.bias'])
-    idx = (torch.arange(16 * J, device=feat.device) % 16).view(16, J)
-    seq = torch.cat([pre_seq.reshape(B, 16, J, 3), feat[:, idx]], 3).permute(0, 3, 2, 1)
+    if literal_beat:
+        feat_g = feat.reshape(B, 16, J, 170)                                       # the reference's .view
+    else:
+        idx = (torch.arange(16 * J, device=feat.device) % 16).view(16, J)
+        feat_g = feat[:, idx]
+    seq = torch.cat([pre_seq.reshape(B, 16, J, 3), feat_g], 3).permute(0, 3, 2, 1)
     feature = gwnet_forward(sd, seq, training, update_buffers=update_buffers)
     g_seq = feature[:, :3].reshape(B, 3 * J, -1).permute(0, 2, 1)
     beat = feature[:, 3:].reshape(B, 34, -1)
@@ -133,37 +141,56 @@ def generator_loss(out, out_rand, z, z_rand, z_mu, z_logvar, target, w_reg=600.0
 
 
 class OracleTrainer:
-    """The reference's generator step (epoch <= 10 semantics: 2 forwards + backward + Adam(0.5, 0.999), lr const)
-    on the functional oracle.  Used as the CPU baseline / ``--impl reference`` arm of bench.py (kind "port")."""
+    """The reference's generator step (epoch <= 10 semantics, train_llm.py:38-98) on the functional oracle: generator
+    forward, discriminator forward (train_llm.py:43-44, computed every step), random-speaker forward, losses, backward,
+    Adam(0.5, 0.999) with constant lr.  Used as bench.py's CPU baseline / ``--impl reference`` arm (kind "port") and, on
+    the GPU, as the stock-PyTorch-CUDA speed bar.
 
-    def __init__(self, state_dict, bert, lr=4e-4, p_drop=0.1, datasets='TED'):
-        self.bert = bert
+    ``literal=True`` (the timing baselines) does the work the reference does: the J-fold repeated beat MLP
+    (HOP.py:210-212), the mapping GEMM and K/V projections recomputed in each forward, and the random-speaker forward
+    with autograd recording (the reference only detaches its outputs afterwards).  ``literal=False`` keeps the lighter
+    equivalents (same values) that the parity tests use.
+    """
+
+    def __init__(self, state_dict, bert, lr=4e-4, p_drop=0.1, datasets='TED', device='cpu', literal=False,
+                 discriminator=None, capturable=False):
+        self.bert = bert.to(device)
         self.sd = {}
         self.params = []
         frozen = ('llm_model.', 'word_embeddings')
         for k, v in state_dict.items():
-            t = v.detach().clone()
+            t = v.detach().clone().to(device)
             if t.is_floating_point() and not k.startswith(frozen) and 'running_' not in k:
                 t.requires_grad_(True)
                 self.params.append(t)
             self.sd[k] = t
-        for p in bert.parameters():
+        for p in self.bert.parameters():
             p.requires_grad_(False)
-        self.opt = torch.optim.Adam(self.params, lr=lr, betas=(0.5, 0.999))
+        self.opt = torch.optim.Adam(self.params, lr=lr, betas=(0.5, 0.999), capturable=capturable)
         self.p_drop = p_drop
         self.w = (600.0, 0.4, 0.6) if datasets == 'TED' else (2100.0, 0.5, 0.8)
+        self.device, self.literal = device, literal
+        self.disc = discriminator.to(device) if discriminator is not None else None
 
-    def step(self, in_audio, x_enc, text, target, vid):
+    def step_device(self, in_audio, x_enc, text, target, vid):
+        """One step without host synchronisation; returns the loss tensor."""
+        dev = self.device
         pre_seq = target[:, :16]
         self.opt.zero_grad(set_to_none=True)
-        noise = torch.randn(target.shape[0], 16)
+        noise = torch.randn(target.shape[0], 16, device=dev)
         out, z, z_mu, z_lv = model_forward(self.sd, self.bert, in_audio, x_enc, text, pre_seq, vid, noise,
-                                           p_drop=self.p_drop)
-        rand_vid = vid[torch.randperm(vid.shape[0])]
-        with torch.no_grad():
+                                           p_drop=self.p_drop, literal_beat=self.literal)
+        if self.disc is not None:                          # train_llm.py:43-44: computed, unused for epoch <= 10
+            gen_error = -torch.mean(torch.log(self.disc(out, text) + 1e-8))   # noqa: F841
+        rand_vid = vid[torch.randperm(vid.shape[0], device=dev)]
+        with torch.set_grad_enabled(self.literal):
             out_r, z_r, _, _ = model_forward(self.sd, self.bert, in_audio, x_enc, text, pre_seq, rand_vid,
-                                             torch.randn(target.shape[0], 16), p_drop=self.p_drop)
+                                             torch.randn(target.shape[0], 16, device=dev), p_drop=self.p_drop,
+                                             literal_beat=self.literal)
         loss, huber, div, kld = generator_loss(out, out_r, z, z_r, z_mu, z_lv, target, *self.w)
         loss.backward()
         self.opt.step()
-        return float(loss.detach())
+        return loss.detach()
+
+    def step(self, in_audio, x_enc, text, target, vid):
+        return float(self.step_device(in_audio, x_enc, text, target, vid))
