@@ -12,6 +12,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libhopk.so')
 MAX_LAYERS = 16
+GEMM_A_MN, GEMM_B_MN, GEMM_OUT_BF16, GEMM_ACCUMULATE, GEMM_RELU, GEMM_LEAKY, GEMM_GELU = 1, 2, 4, 8, 16, 32, 64
 
 _vp = C.c_void_p
 _LAYER_ARR = _vp * MAX_LAYERS
@@ -61,6 +62,9 @@ SIGNATURES = {
     'hopk_linear_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'hopk_conv1x1_nchw_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'hopk_conv1x1_nchw_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'hopk_gemm_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.c_long, C.c_long, C.c_long, _i, _f, _i, _vp]),
+    'hopk_cast_bf16': (_i, [_vp, _vp, C.c_long, _i, C.c_long, _i, C.c_long, _i, _vp]),
+    'hopk_colsum': (_i, [_vp, _vp, C.c_long, _i, C.c_long, _i, _vp]),
     'hopk_xattn_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp]),
     'hopk_dropout_epoch_advance': (_i, [_i, _vp]),
     'hopk_xattn_pack_bytes': (_sz, [_i, _i]),

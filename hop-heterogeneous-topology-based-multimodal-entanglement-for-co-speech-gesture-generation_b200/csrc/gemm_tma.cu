@@ -1,0 +1,381 @@
+// gemm_tma.cu -- dense bf16 GEMM on tcgen05 with TMA tensor copies: the workhorse behind every plain dense contraction of
+// the step (projections of the reprogramming layer HOP.py:276-285, the text-prototype mapping GEMM HOP.py:200, the beat MLP
+// HOP.py:130-134, the align layer HOP.py:202-203, the input / weight-gradient GEMMs of the GRU decoder HOP.py:166-167).
+//
+//     C[M][N] (+)= sum_k A(m, k) * B(n, k)  (+ bias[n]) -> act
+//
+// Operands are bf16 matrices in global memory, each either "K-major" (the contraction index is contiguous: A is [M][K],
+// B is [N][K], i.e. x @ W^T with PyTorch's Linear weight) or "MN-major" (the contraction index is the row: A is [K][M],
+// B is [K][N]) -- so dX = dY @ W (B MN-major) and dW = dY^T @ X (both MN-major) need no transposed copies.
+//
+// Kernel anatomy (persistent, warp specialised, one CTA per SM):
+//   warp 0   producer: cp.async.bulk.tensor.2d (TMA, 128B swizzle) fills a ring of STAGES x (A 16 KB | B 16/32 KB) slabs,
+//            completion by mbarrier complete_tx
+//   warp 1   MMA issuer: one lane issues tcgen05.mma (M 128, N = BN, K 16, 4 per 64-wide K block) into one of two TMEM
+//            accumulators; tcgen05.commit releases the ring slot / publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld of their TMEM lane quarter (row per thread), bias / activation / conversion, 256-bit
+//            (fp32) or 128-bit (bf16) global stores, or vector atomics for split-K
+// The second accumulator lets the MMAs of tile i+1 run under the epilogue of tile i.
+#include <cuda.h>
+#include <mutex>
+#include "tc_core.cuh"
+#include "common.cuh"
+#include "../../include/hopk.h"
+
+namespace hopk {
+
+constexpr int GT_BM = 128, GT_BK = 64;
+constexpr int GT_THREADS = 192;                         // producer warp, MMA warp, 4 epilogue warps
+
+template <int BN> constexpr int gt_stages() { return BN == 128 ? 6 : 4; }
+template <int BN> constexpr uint32_t gt_stage_bytes() { return tc::slab_bytes(GT_BM) + tc::slab_bytes(BN); }
+template <int BN> constexpr size_t gt_smem_bytes() { return (size_t)gt_stages<BN>() * gt_stage_bytes<BN>() + 1024 + 256; }
+
+struct GtArgs {
+    void* C; const float* bias; const void* addend;
+    int M, N, K;
+    long ldc;
+    int a_mn, b_mn;                                     // 1: operand is MN-major ([K][M] / [K][N] row-major)
+    int out_bf16, accumulate, act, splits, kper;        // act: 0 none, 1 relu, 2 leaky relu (slope), 3 gelu (erf)
+    float slope;
+    int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(tm), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ float gt_act(float x, int act, float slope)
+{
+    if (act == 1) return fmaxf(x, 0.f);
+    if (act == 2) return x > 0.f ? x : slope * x;
+    if (act == 3) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GtArgs g)
+{
+    constexpr int STAGES = gt_stages<BN>();
+    constexpr uint32_t A_BYTES = tc::slab_bytes(GT_BM), B_BYTES = tc::slab_bytes(BN), STAGE = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE);
+    uint64_t* full = bars;                       // [STAGES] TMA -> MMA
+    uint64_t* empty = bars + STAGES;             // [STAGES] MMA -> TMA
+    uint64_t* acc_full = bars + 2 * STAGES;      // [2]      MMA -> epilogue
+    uint64_t* acc_empty = bars + 2 * STAGES + 2; // [2]      epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 4); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * BN);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int ntiles = g.tiles_m * g.tiles_n * g.splits;
+    if (warp == 0) {
+        // ===================================================== producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int sp = tile / (g.tiles_m * g.tiles_n), t2 = tile - sp * g.tiles_m * g.tiles_n;
+                const int m0 = (t2 / g.tiles_n) * GT_BM, n0 = (t2 % g.tiles_n) * BN;
+                const int k_begin = sp * g.kper, k_end = min(g.K, k_begin + g.kper);
+                for (int k = k_begin; k < k_end; k += GT_BK) {
+                    tc::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * STAGE;
+                    uint8_t* sb = sa + A_BYTES;
+                    tc::mbar_expect_tx(&full[stage], STAGE);
+                    if (!g.a_mn) tma_load_2d(sa, &tmA, k, m0, &full[stage]);                    // box {64 k, 128 rows}
+                    else {
+#pragma unroll
+                        for (int s = 0; s < GT_BM / 64; ++s) tma_load_2d(sa + s * tc::slab_bytes(GT_BK), &tmA, m0 + 64 * s, k, &full[stage]);   // box {64 m, 64 k-rows}
+                    }
+                    if (!g.b_mn) tma_load_2d(sb, &tmB, k, n0, &full[stage]);
+                    else {
+#pragma unroll
+                        for (int s = 0; s < BN / 64; ++s) tma_load_2d(sb + s * tc::slab_bytes(GT_BK), &tmB, n0 + 64 * s, k, &full[stage]);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_bf16(GT_BM, BN, g.a_mn, g.b_mn);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int sp = tile / (g.tiles_m * g.tiles_n);
+                const int k_begin = sp * g.kper, k_end = min(g.K, k_begin + g.kper);
+                tc::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                tc::fence_after_sync();
+                const uint32_t d = tmem + acc * BN;
+                bool first = true;
+                for (int k = k_begin; k < k_end; k += GT_BK) {
+                    tc::mbar_wait(&full[stage], phase);
+                    tc::fence_after_sync();
+                    const uint32_t sa = tc::smem_u32(smem + (size_t)stage * STAGE), sb = sa + A_BYTES;
+#pragma unroll
+                    for (int t = 0; t < GT_BK / 16; ++t) {
+                        const uint64_t da = g.a_mn ? tc::desc_mnmajor(sa, tc::slab_bytes(GT_BK), t) : tc::desc_kmajor(sa, t);
+                        const uint64_t db = g.b_mn ? tc::desc_mnmajor(sb, tc::slab_bytes(GT_BK), t) : tc::desc_kmajor(sb, t);
+                        tc::mma_bf16(d, da, db, idesc, !first);
+                        first = false;
+                    }
+                    tc::mma_commit(&empty[stage]);                 // ring slot free once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc::mma_commit(&acc_full[acc]);                    // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int t2 = tile % (g.tiles_m * g.tiles_n);
+            const bool first_split = tile < g.tiles_m * g.tiles_n;         // bias / addend enter once, with K-split 0
+            const int m0 = (t2 / g.tiles_n) * GT_BM, n0 = (t2 % g.tiles_n) * BN;
+            const int m = m0 + row;
+            tc::mbar_wait(&acc_full[acc], acc_phase);
+            tc::fence_after_sync();
+            const uint32_t src = tmem + acc * BN + lane_off;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int nb = n0 + c * 32;
+                if (nb >= g.N) break;                              // uniform across the warp
+                float v[32];
+                tc::tmem_ld32(src + c * 32, v);
+                if (m < g.M) {
+                    const bool fullw = nb + 32 <= g.N;
+                    if (g.bias && first_split) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] += __ldg(g.bias + nb + j);
+                    }
+                    if (g.addend && first_split) {                                // fp32 residual / accumulate-from tensor with C's layout
+                        const float* ad = reinterpret_cast<const float*>(g.addend) + (size_t)m * g.ldc + nb;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] += __ldg(ad + j);
+                    }
+                    if (g.act) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gt_act(v[j], g.act, g.slope);
+                    }
+                    if (g.out_bf16) {
+                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + (size_t)m * g.ldc + nb;
+                        if (fullw && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 q;
+                                q.x = tc::pack_bf16x2(v[j], v[j + 1]); q.y = tc::pack_bf16x2(v[j + 2], v[j + 3]);
+                                q.z = tc::pack_bf16x2(v[j + 4], v[j + 5]); q.w = tc::pack_bf16x2(v[j + 6], v[j + 7]);
+                                *reinterpret_cast<uint4*>(dst + j) = q;
+                            }
+                        } else {
+                            for (int j = 0; j < 32 && nb + j < g.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+                        }
+                    } else {
+                        float* dst = reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + nb;
+                        if (g.splits > 1 || g.accumulate) {        // split-K partials / accumulation: vector reductions
+                            if (fullw && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
+                                                 "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                            } else {
+                                for (int j = 0; j < 32 && nb + j < g.N; ++j) atomicAdd(dst + j, v[j]);
+                            }
+                        } else if (fullw && ((reinterpret_cast<uintptr_t>(dst) & 31) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) tc::stg256(dst + j, v + j);
+                        } else {
+                            for (int j = 0; j < 32 && nb + j < g.N; ++j) dst[j] = v[j];
+                        }
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------------ small helper kernels
+// fp32 -> bf16 copy of a (rows x cols) matrix with independent leading dimensions (cols padded with zeros up to cols_out)
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long rows, int cols, long lds,
+                                 int cols_out, long ldd, int relu)
+{
+    const long n8 = rows * (cols_out / 8);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / (cols_out / 8); const int c = (int)(i - r * (cols_out / 8)) * 8;
+        float f[8];
+        const float* s = src + r * lds + c;
+        if (c + 8 <= cols && ((lds | c) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s) + 1);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = c + j < cols ? __ldg(s + j) : 0.f;
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        uint4 q;
+        q.x = tc::pack_bf16x2(f[0], f[1]); q.y = tc::pack_bf16x2(f[2], f[3]); q.z = tc::pack_bf16x2(f[4], f[5]); q.w = tc::pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(dst + r * ldd + c) = q;
+    }
+}
+
+// column sums of a bf16 or fp32 (rows x cols) matrix into fp32 out[cols] (bias gradients); out must be zeroed by the caller
+template <class T>
+__global__ void colsum_kernel(const T* __restrict__ src, float* __restrict__ out, long rows, int cols, long ld, long rows_per_block)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const long r0 = (long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float acc = 0.f;
+    for (long r = r0; r < r1; ++r) acc += (float)src[r * ld + c];
+    atomicAdd(out + c, acc);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+// 2-D bf16 tensor map over a row-major (rows x cols) matrix with leading dimension ld (elements); box = {64 cols, box_rows}
+static int make_map(CUtensorMap* tm, const void* base, long rows, long cols, long ld, int box_rows)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(3, "cuTensorMapEncodeTiled", "driver entry point not found");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[96];
+        snprintf(msg, sizeof(msg), "CUresult %d (rows %ld cols %ld ld %ld)", (int)r, rows, cols, ld);
+        return fail(3, "cuTensorMapEncodeTiled failed:", msg);
+    }
+    return 0;
+}
+
+int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, const void* addend, int M, int N, int K, long lda,
+                     long ldb, long ldc, int a_mn, int b_mn, int out_bf16, int accumulate, int act, float slope, int splits,
+                     cudaStream_t st)
+{
+    HOPK_REQUIRE(M > 0 && N > 0 && K > 0, "gemm sizes");
+    HOPK_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "operand leading dimensions must be multiples of 8 bf16 (16 bytes, TMA)");
+    HOPK_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "operands must be 16-byte aligned");
+    HOPK_REQUIRE(!(out_bf16 && (accumulate || splits > 1)), "accumulation needs an fp32 destination");
+    HOPK_REQUIRE(!(act && (accumulate || splits > 1)), "an activation cannot be combined with accumulation / split-K");
+    CUtensorMap tmA, tmB;
+    // K-major: matrix is (M rows x K cols), box {64 k, 128 rows}; MN-major: matrix is (K rows x M cols), box {64 m, 64 k-rows}
+    if (int rc = a_mn ? make_map(&tmA, A, K, M, lda, GT_BK) : make_map(&tmA, A, M, K, lda, GT_BM)) return rc;
+    const bool wide = N > 128 && ((long)cdiv(M, GT_BM) * cdiv(N, 128) * (splits > 1 ? splits : 1)) > 2 * 148;   // enough tiles: 128 x 256
+    const int BN = wide ? 256 : 128;
+    if (int rc = b_mn ? make_map(&tmB, B, K, N, ldb, GT_BK) : make_map(&tmB, B, N, K, ldb, BN)) return rc;
+    GtArgs g;
+    g.C = C; g.bias = bias; g.addend = addend; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
+    g.out_bf16 = out_bf16; g.accumulate = accumulate; g.act = act; g.slope = slope;
+    if (splits < 1) splits = 1;
+    int kper = ((cdiv(K, splits) + GT_BK - 1) / GT_BK) * GT_BK;
+    splits = cdiv(K, kper);
+    g.splits = splits; g.kper = kper;
+    g.tiles_m = cdiv(M, GT_BM); g.tiles_n = cdiv(N, BN);
+    const long ntiles = (long)g.tiles_m * g.tiles_n * splits;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    if (splits > 1 && !accumulate) HOPK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
+    if (BN == 256) {
+        HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<256>, gt_smem_bytes<256>()));
+        gemm_tma_kernel<256><<<grid, GT_THREADS, gt_smem_bytes<256>(), st>>>(tmA, tmB, g);
+    } else {
+        HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<128>, gt_smem_bytes<128>()));
+        gemm_tma_kernel<128><<<grid, GT_THREADS, gt_smem_bytes<128>(), st>>>(tmA, tmB, g);
+    }
+    HOPK_LAUNCH_CHECK("gemm_tma");
+    return 0;
+}
+
+}  // namespace hopk
+
+using namespace hopk;
+
+extern "C" int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, int M, int N, int K,
+                              long lda, long ldb, long ldc, int flags, float slope, int splits, void* stream)
+{
+    const int a_mn = (flags & HOPK_GEMM_A_MN) ? 1 : 0, b_mn = (flags & HOPK_GEMM_B_MN) ? 1 : 0;
+    const int act = (flags & HOPK_GEMM_RELU) ? 1 : (flags & HOPK_GEMM_LEAKY) ? 2 : (flags & HOPK_GEMM_GELU) ? 3 : 0;
+    return gemm_bf16_launch(A, B, C, bias, addend, M, N, K, lda, ldb, ldc, a_mn, b_mn, (flags & HOPK_GEMM_OUT_BF16) ? 1 : 0,
+                            (flags & HOPK_GEMM_ACCUMULATE) ? 1 : 0, act, slope, splits, (cudaStream_t)stream);
+}
+
+extern "C" int hopk_cast_bf16(const float* src, void* dst, long rows, int cols, long lds, int cols_out, long ldd, int relu, void* stream)
+{
+    HOPK_REQUIRE(rows > 0 && cols > 0 && cols_out >= cols && cols_out % 8 == 0 && ldd % 8 == 0, "cast_bf16: cols_out and ldd must be multiples of 8");
+    const long n8 = rows * (cols_out / 8);
+    int blocks = (int)((n8 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cast_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, rows, cols, lds, cols_out, ldd, relu);
+    HOPK_LAUNCH_CHECK("cast_bf16");
+    return 0;
+}
+
+extern "C" int hopk_colsum(const void* src, float* out, long rows, int cols, long ld, int src_bf16, void* stream)
+{
+    HOPK_REQUIRE(rows > 0 && cols > 0, "colsum sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    HOPK_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), st));
+    long per = 256;
+    dim3 grid(cdiv(cols, 128), cdiv(rows, per));
+    if (src_bf16) colsum_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16*)src, out, rows, cols, ld, per);
+    else colsum_kernel<float><<<grid, 128, 0, st>>>((const float*)src, out, rows, cols, ld, per);
+    HOPK_LAUNCH_CHECK("colsum");
+    return 0;
+}

@@ -133,6 +133,27 @@ int hopk_conv1x1_nchw_fwd(const float* x, const float* w, const float* b, float*
 int hopk_conv1x1_nchw_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
                           int B, int K, int N, int V, int T, void* stream);
 
+/* ------------------------------------------------------------------ dense bf16 GEMM (TMA + tcgen05)
+ * C[M][N] (+)= sum_k A(m,k) B(n,k) (+ bias[n] + addend[m][n]) -> activation.   A, B: bf16 in global memory, 16-byte aligned,
+ * leading dimensions (elements) multiples of 8.  Default operand layout is "K-major" (A is [M][K], B is [N][K] row-major:
+ * x @ W^T with nn.Linear's weight, HOP.py:130-134,200,202,262-265); HOPK_GEMM_A_MN / _B_MN say the operand is stored with
+ * the contraction index as the row ([K][M] / [K][N]), which covers dX = dY @ W and dW = dY^T @ X without transposes.
+ * C: fp32 (default) or bf16 (HOPK_GEMM_OUT_BF16), leading dimension ldc.  addend: optional fp32 [M][ldc].  splits > 1:
+ * split-K with vector atomics into an fp32 C (cleared by the call unless HOPK_GEMM_ACCUMULATE). */
+#define HOPK_GEMM_A_MN 1
+#define HOPK_GEMM_B_MN 2
+#define HOPK_GEMM_OUT_BF16 4
+#define HOPK_GEMM_ACCUMULATE 8
+#define HOPK_GEMM_RELU 16
+#define HOPK_GEMM_LEAKY 32     /* LeakyReLU(slope) */
+#define HOPK_GEMM_GELU 64      /* exact (erf) GELU */
+int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, int M, int N, int K,
+                   long lda, long ldb, long ldc, int flags, float slope, int splits, void* stream);
+/* fp32 (rows x cols, ld lds) -> bf16 (rows x cols_out, ld ldd), zero padding for cols <= c < cols_out, optional ReLU */
+int hopk_cast_bf16(const float* src, void* dst, long rows, int cols, long lds, int cols_out, long ldd, int relu, void* stream);
+/* out[c] = sum_r src[r][c] (bias gradients); src fp32 or bf16 */
+int hopk_colsum(const void* src, float* out, long rows, int cols, long ld, int src_bf16, void* stream);
+
 /* ------------------------------------------------------------------ reprogramming cross-attention
  * ReprogrammingLayer.reprogramming (model/HOP.py:289-299):
  *   O[b,l,h,:] = dropout(softmax_s(Q[b,l,h,:].K[s,h,:] / sqrt(E))) . V[s,h,:]
