@@ -96,7 +96,7 @@ static GwLayout make_layout(const HopkGwnetShape* s)
     g.s_de1 = bump(cur, BV * g.Tl * s->E * f);
     g.s_dskip = bump(cur, BV * g.Tl * s->S * f);
     g.s_dycat = bump(cur, BV * g.Tl * s->L * s->C * f);
-    g.s_bnsum = bump(cur, (size_t)s->L * 2 * s->C * sizeof(double));
+    g.s_bnsum = bump(cur, (size_t)(s->L + 1) * 2 * s->C * sizeof(double));   // + one slot: column sums of the start-conv output gradient
     g.s_m12 = bump(cur, 2 * vv);
     g.s_dA = bump(cur, vv);
     g.s_total = cur;
@@ -176,6 +176,12 @@ __global__ void adp_bwd_kernel(const float* __restrict__ e1, const float* __rest
     }
 }
 
+__global__ void sums_to_float_kernel(const double* __restrict__ sums, float* __restrict__ out, int C)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) out[c] = (float)sums[c];
+}
+
 __global__ void fill_identity_kernel(float* ss, int C)
 {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,17 +249,17 @@ __global__ void node_mix_kernel(const float* __restrict__ in, const float* __res
 // dA Gram accumulation: M1[v][w] += sum_{g,c} Y[(g,v)][c] G[(g,w)][c], M2 with G[..][C + c]   (G has ld 2C)
 // Persistent CTAs stride over chunks of GRAM_GPI node groups; thread = (pair slot, channel slice); partial sums stay in
 // registers across the whole loop, are combined in shared memory and leave the CTA as one atomic per matrix entry.
-constexpr int GRAM_GPI = 4;                  // node groups staged per iteration
+constexpr int GRAM_GPI = 4;                  // node groups staged per iteration (fewer when V * C is large: smem budget)
 constexpr int GRAM_MAXP = 8;                 // pairs per thread: V*V <= 8*256  (V <= 45)
 __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ TF, const float* __restrict__ SG, const float* __restrict__ G,
-                                                   float* __restrict__ M12, int groups, int V, int C)
+                                                   float* __restrict__ M12, int groups, int V, int C, int GPI)
 {
     extern __shared__ float sm[];
     const int VV = V * V;
     const int ldy = C + 1, ldg = 2 * C + 1;
-    float* sy = sm;                                   // GRAM_GPI * V * ldy
-    float* sg = sy + GRAM_GPI * V * ldy;              // GRAM_GPI * V * ldg
-    float* acc = sg + GRAM_GPI * V * ldg;             // 2 * VV
+    float* sy = sm;                                   // GPI * V * ldy
+    float* sg = sy + GPI * V * ldy;              // GPI * V * ldg
+    float* acc = sg + GPI * V * ldg;             // 2 * VV
     const int NS = VV >= 256 ? 1 : 256 / VV;          // channel slices per pair
     const int slice = VV >= 256 ? 0 : (int)threadIdx.x / VV;
     const int p0 = VV >= 256 ? (int)threadIdx.x : (int)threadIdx.x % VV;
@@ -262,8 +268,8 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ TF,
 #pragma unroll
     for (int p = 0; p < GRAM_MAXP; ++p) { a1[p] = 0.f; a2[p] = 0.f; }
     for (int i = threadIdx.x; i < 2 * VV; i += blockDim.x) acc[i] = 0.f;
-    for (int g0 = blockIdx.x * GRAM_GPI; g0 < groups; g0 += gridDim.x * GRAM_GPI) {
-        const int ng = min(GRAM_GPI, groups - g0);
+    for (int g0 = blockIdx.x * GPI; g0 < groups; g0 += gridDim.x * GPI) {
+        const int ng = min(GPI, groups - g0);
         __syncthreads();
         const float4* yp = reinterpret_cast<const float4*>(TF + (size_t)g0 * V * C);      // y = tanh(f) * sigmoid(g), recomputed
         const float4* zp = reinterpret_cast<const float4*>(SG + (size_t)g0 * V * C);
@@ -1391,7 +1397,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
     const bool tc = s->dtype == 1;
     const int tcbn = C <= 64 ? 64 : 128;
     double* bnsum = reinterpret_cast<double*>(sc + g.s_bnsum);
-    HOPK_CUDA(cudaMemsetAsync(bnsum, 0, (size_t)L * 2 * C * sizeof(double), st));
+    HOPK_CUDA(cudaMemsetAsync(bnsum, 0, (size_t)(L + 1) * 2 * C * sizeof(double), st));
     HOPK_CUDA(cudaMemsetAsync(S(g.s_m12), 0, 2 * (size_t)V * V * sizeof(float), st));
     if (int rc = zero_param_grads(s, gr, st)) return rc;      // split-K / atomic epilogues accumulate into zeroed buffers
 
@@ -1521,10 +1527,14 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
                     HOPK_CUDA(launch_gemm_tc_wgrad<128>(groups * C, V, 2 * V, ga, gb, ge, false, s1));
                     HOPK_LAUNCH_CHECK("gram_tc");
                 } else {
-                size_t smem3 = ((size_t)GRAM_GPI * V * (3 * C + 2) + 2 * (size_t)V * V) * sizeof(float);
+                int gpi = GRAM_GPI;                              // node groups staged per iteration, within the smem budget
+                auto gram_smem = [&](int n) { return ((size_t)n * V * (3 * C + 2) + 2 * (size_t)V * V) * sizeof(float); };
+                while (gpi > 1 && gram_smem(gpi) > 200 * 1024) --gpi;
+                size_t smem3 = gram_smem(gpi);
+                HOPK_REQUIRE(smem3 <= 200 * 1024, "gram kernel: V * C too large for shared memory");
                 if (smem3 > 48 * 1024) HOPK_CUDA(configure_smem_once((const void*)gram_kernel, 200 * 1024));
-                int gblocks = cdiv(groups, GRAM_GPI); if (gblocks > 148) gblocks = 148;
-                gram_kernel<<<gblocks, 256, smem3, s1>>>(F(g.tf[i]), F(g.sg[i]), S(g.s_g[i]), S(g.s_m12), groups, V, C);
+                int gblocks = cdiv(groups, gpi); if (gblocks > 148) gblocks = 148;
+                gram_kernel<<<gblocks, 256, smem3, s1>>>(F(g.tf[i]), F(g.sg[i]), S(g.s_g[i]), S(g.s_m12), groups, V, C, gpi);
                 HOPK_LAUNCH_CHECK("gram");
                 }
             }
@@ -1570,14 +1580,18 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
             if (C <= 64) {
                 DxEpi<1> e; memset(&e, 0, sizeof(e));
                 e.DU = has_du ? DU : nullptr; e.DX = DX; e.uprev = uprev; e.g = lg; e.tc_bn = tcbn;
-                e.mr_prev = i > 0 ? F(g.mr) + (size_t)(i - 1) * 2 * C : nullptr;
-                e.sums_prev = i > 0 ? bnsum + (size_t)(i - 1) * 2 * C : nullptr;
+                // layer 0: the same sums (against the identity "statistics" mean 1 / rstd 0 of ss[0]) give the start-conv
+                // bias gradient from the un-rounded fp32 gradient instead of a ones column of the bf16 weight-gradient GEMM
+                e.mr_prev = i > 0 ? F(g.mr) + (size_t)(i - 1) * 2 * C : F(g.ss);
+                e.sums_prev = i > 0 ? bnsum + (size_t)(i - 1) * 2 * C : bnsum + (size_t)L * 2 * C;
                 launch_gemm<2, 1>(tc, Min, C, 4 * C, 1, a, b, e, st);
             } else {
                 DxEpi<2> e; memset(&e, 0, sizeof(e));
                 e.DU = has_du ? DU : nullptr; e.DX = DX; e.uprev = uprev; e.g = lg; e.tc_bn = tcbn;
-                e.mr_prev = i > 0 ? F(g.mr) + (size_t)(i - 1) * 2 * C : nullptr;
-                e.sums_prev = i > 0 ? bnsum + (size_t)(i - 1) * 2 * C : nullptr;
+                // layer 0: the same sums (against the identity "statistics" mean 1 / rstd 0 of ss[0]) give the start-conv
+                // bias gradient from the un-rounded fp32 gradient instead of a ones column of the bf16 weight-gradient GEMM
+                e.mr_prev = i > 0 ? F(g.mr) + (size_t)(i - 1) * 2 * C : F(g.ss);
+                e.sums_prev = i > 0 ? bnsum + (size_t)(i - 1) * 2 * C : bnsum + (size_t)L * 2 * C;
                 launch_gemm<2, 2>(tc, Min, C, 4 * C, 1, a, b, e, st);
             }
             HOPK_LAUNCH_CHECK("dx_gemm");
@@ -1594,10 +1608,14 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
         HOPK_CUDA(cudaStreamWaitEvent(sd->s[0], sd->ev_tail, 0));
         Ld2D<false, 0> a{dxn, nullptr, C};
         StartAT b{x, g.Tp, V, g.pad, s->in_dim, (long)xs[0], (long)xs[1], (long)xs[2], (long)xs[3]};
-        EpiWgrad<2> e{gr->start_w, s->in_dim, gr->start_b, s->in_dim, C};
+        EpiWgrad<2> e{gr->start_w, s->in_dim, nullptr, s->in_dim, C};
         if (C <= 64) launch_gemm<1, 2>(tc, C, s->in_dim + 1, M, pick_splits(tc, C, s->in_dim + 1, M, 1, 2), a, b, e, sd->s[0]);
         else launch_gemm<2, 2>(tc, C, s->in_dim + 1, M, pick_splits(tc, C, s->in_dim + 1, M, 2, 2), a, b, e, sd->s[0]);
         HOPK_LAUNCH_CHECK("start_wgrad");
+        if (gr->start_b) {
+            sums_to_float_kernel<<<cdiv(C, 128), 128, 0, st>>>(bnsum + (size_t)L * 2 * C, gr->start_b, C);
+            HOPK_LAUNCH_CHECK("start_bias_grad");
+        }
         if (dx) {
             Ld2D<true, 0> a2{dxn, nullptr, C};
             Ld2D<false, 0> b2{p->start_w, nullptr, s->in_dim};

@@ -22,7 +22,8 @@ import torch.nn.functional as F
 DILATIONS = (1, 2, 1, 2, 1, 2, 1, 2)
 
 
-def gwnet_forward(sd, x, training=True, prefix='gwnet.', update_buffers=True, relu_masks=None, dilations=DILATIONS):
+def gwnet_forward(sd, x, training=True, prefix='gwnet.', update_buffers=True, relu_masks=None, dilations=DILATIONS,
+                  capture=None):
     """x (B, in, V, T) -> (B, out, V, T-12). ``sd`` maps names to tensors (leaf tensors for grads).
 
     ``relu_masks`` = (m_skip (B,S,V,Tl), m_end1 (B,E,V,Tl)), 0/1 tensors: the two head ReLUs (gwnet.py:240-243) become
@@ -53,6 +54,9 @@ def gwnet_forward(sd, x, training=True, prefix='gwnet.', update_buffers=True, re
         x = F.batch_norm(u, rm, rv, g(f'bn.{i}.weight'), g(f'bn.{i}.bias'), training, 0.1, 1e-5)
         if training and update_buffers:
             sd[prefix + f'bn.{i}.num_batches_tracked'] += 1
+    if capture is not None:                                # the exact gate pattern, for flip counting
+        capture['g0'] = (skip > 0).detach()
+        capture['g1'] = (F.conv2d(F.relu(skip), g('end_conv_1.weight'), g('end_conv_1.bias')) > 0).detach()
     if relu_masks is None:
         x = F.relu(F.conv2d(F.relu(skip), g('end_conv_1.weight'), g('end_conv_1.bias')))
     else:
@@ -81,7 +85,9 @@ def _gru(sd, x, hidden=350, layers=4):
             flat += [sd[f'gru.weight_ih_l{l}{suf}'], sd[f'gru.weight_hh_l{l}{suf}'],
                      sd[f'gru.bias_ih_l{l}{suf}'], sd[f'gru.bias_hh_l{l}{suf}']]
     h0 = x.new_zeros(2 * layers, x.shape[0], hidden)
-    out, _ = torch._VF.gru(x, h0, flat, True, layers, 0.0, False, True, True)
+    # (input, hx, params, has_biases, num_layers, dropout, train, bidirectional, batch_first); dropout is 0, `train` only
+    # tells cuDNN to keep its reserve space for backward
+    out, _ = torch._VF.gru(x, h0, flat, True, layers, 0.0, torch.is_grad_enabled(), True, True)
     return out
 
 

@@ -4,12 +4,14 @@ the C4 microbench grid (C in {32, 128, 256} x V in {10, 43}).
 The checker is oracle/hop_torch.py evaluated in float64 ON THE GPU (a 128-sample float64 pass through numpy would take
 minutes); the product path is hop_b200 through the C ABI as everywhere else.
 
-Tolerances (north_star): fp32 mode 1e-5, bf16 mode 2e-2, both max|a - ref| / max|ref| per tensor.  bf16 *gradients* are
-checked against the oracle **pinned to the kernel's own head-ReLU gate pattern** (reference gwnet.py:240-243): rounding the
-GEMM operands flips the few gates whose pre-activation lies within rounding distance of zero, and a flipped gate changes
-its gradient element completely, for ANY reduced-precision implementation.  With the gate pattern pinned every remaining
-difference is arithmetic error of the kernels and must meet the flat 2e-2; the flip fraction is reported separately and
-bounded.
+Tolerances (north_star): fp32 mode 1e-5, bf16 mode 2e-2, both max|a - ref| / max|ref| per tensor.  *Gradients* are
+checked against the oracle **pinned to the kernel's own head-ReLU gate pattern** (reference gwnet.py:240-243): rounding
+flips the few gates whose pre-activation lies within rounding distance of zero, and a flipped gate changes its gradient
+element completely, for ANY finite-precision implementation.  That holds for fp32 as well at these sizes: of the 3.5 M
+gates of a B = 128 TED batch a handful lie within 1e-6 of zero, and ONE flipped gate moves a row of dW(end_conv_1) by
+~1/sqrt(rows) = 1.5 % of its scale (measured, round 2).  With the gate pattern pinned every remaining difference is
+arithmetic error of the kernels and must meet the flat tolerance; the number of flipped gates is reported and bounded
+(fp32: at most 1e-5 of the gates, bf16: at most 1e-2).
 """
 import numpy as np
 import pytest
@@ -36,7 +38,7 @@ def _module(dev, V, C, seed, S=256, E=512, in_dim=173, out_dim=173):
     return m
 
 
-def _oracle(sd0, x, dout, masks=None):
+def _oracle(sd0, x, dout, masks=None, capture=None):
     """float64 oracle on the GPU: returns out, dx, {param grads}, {updated buffers}."""
     sd = {}
     for k, v in sd0.items():
@@ -47,7 +49,7 @@ def _oracle(sd0, x, dout, masks=None):
                 t.requires_grad_(True)
         sd['gwnet.' + k] = t
     xt = x.detach().double().requires_grad_(True)
-    out = hop_torch.gwnet_forward(sd, xt, training=True, update_buffers=True, relu_masks=masks, dilations=DIL)
+    out = hop_torch.gwnet_forward(sd, xt, training=True, update_buffers=True, relu_masks=masks, dilations=DIL, capture=capture)
     out.backward(dout.double())
     grads = {k[6:]: t.grad for k, t in sd.items() if t.is_floating_point() and t.requires_grad}
     bufs = {k[6:]: t for k, t in sd.items() if 'running_' in k or 'num_batches' in k}
@@ -82,14 +84,16 @@ def _check_gwnet(name, dev, B, V, C, precision, seed):
     bf16 = precision == 'bf16'
     tol = TOL_BF16 if bf16 else TOL_FP32
     rep = Report(name, tol)
-    o_out, o_dx, o_G, o_buf = _oracle(sd0, x, dout)
+    exact = {}
+    o_out, o_dx, o_G, o_buf = _oracle(sd0, x, dout, capture=exact)
     rep.add('out', relerr(_np(out), _np(o_out)))
-    if bf16:
-        # gate pattern of the kernel's forward vs the exact one; gradients against the oracle pinned to the kernel's pattern
-        m0, m1 = _own_masks(m, B, V)
-        e_out, e_dx, e_G, _ = _oracle(sd0, x, dout, masks=(m0, m1))
-        rep.add('out(pinned gates)', relerr(_np(out), _np(e_out)))
-        o_dx, o_G = e_dx, e_G
+    # gradients against the oracle pinned to the gate pattern of the kernel's own forward (see the module docstring)
+    m0, m1 = _own_masks(m, B, V)
+    e_out, o_dx, o_G, _ = _oracle(sd0, x, dout, masks=(m0, m1))
+    rep.add('out(pinned gates)', relerr(_np(out), _np(e_out)))
+    flip_tol = 1e-2 if bf16 else 1e-5
+    rep.add('flipped relu(skip) gates (fraction)', float(((m0 > 0) != exact['g0']).double().mean()), tol=flip_tol)
+    rep.add('flipped relu(end_conv_1) gates (fraction)', float(((m1 > 0) != exact['g1']).double().mean()), tol=flip_tol)
     rep.add('dx', relerr(_np(xt.grad), _np(o_dx)))
     rep.add('dx(l2)', l2err(_np(xt.grad), _np(o_dx)))
     gscale = max(float(v.abs().max()) for v in o_G.values() if v is not None)

@@ -55,7 +55,7 @@ def test_gemm_bf16_layouts(M, N, K, a_mn, b_mn, cuda):
     Bd = (B[:, :N].double().t() if b_mn else B[:, :K].double())
     ref = (Ad @ Bd.t()).cpu().numpy()
     C = _gemm(A, B, M, N, K, a_mn, b_mn)
-    rep = Report(f'gemm_tma_{M}_{N}_{K}_{int(a_mn)}{int(b_mn)}', 2e-5)
+    rep = Report(f'gemm_tma_{M}_{N}_{K}_{int(a_mn)}{int(b_mn)}', 2e-5 if K < 8192 else 1e-4)     # fp32 accumulation over K terms
     rep.add('C', relerr(C.double().cpu().numpy(), ref))
     rep.finish()
 
