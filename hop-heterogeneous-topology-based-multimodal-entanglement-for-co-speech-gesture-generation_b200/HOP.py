@@ -18,6 +18,7 @@ from math import sqrt
 import torch
 import torch.nn as nn
 
+from . import gru as hgru
 from . import gwnet, profiler
 from ._lib import check, f32c, lib, ptr, stream_ptr
 
@@ -98,34 +99,6 @@ class _XattnFn(torch.autograd.Function):
                 check(lib().hopk_xattn_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(do), ptr(dq), ptr(dk), ptr(dv),
                                            ptr(delta), B, L, H, E, S, ctx.p_drop, ctx.seed, stream_ptr()))
         return dq, dk, dv, None, None, None
-
-
-class _CudnnTF32(torch.autograd.Function):
-    """Identity that switches ``torch.backends.cudnn.allow_tf32`` around the ops between an ``enter`` and an ``exit``
-    instance -- in forward order for the forward pass and in reverse order for the backward pass (autograd runs the exit
-    node's backward before, and the enter node's backward after, the backward of everything in between)."""
-    _saved = []
-
-    @staticmethod
-    def _push():
-        _CudnnTF32._saved.append(torch.backends.cudnn.allow_tf32)
-        torch.backends.cudnn.allow_tf32 = True
-
-    @staticmethod
-    def _pop():
-        if _CudnnTF32._saved:
-            torch.backends.cudnn.allow_tf32 = _CudnnTF32._saved.pop()
-
-    @staticmethod
-    def forward(ctx, x, enter):
-        ctx.enter = enter
-        _CudnnTF32._push() if enter else _CudnnTF32._pop()
-        return x.view_as(x)
-
-    @staticmethod
-    def backward(ctx, g):
-        _CudnnTF32._pop() if ctx.enter else _CudnnTF32._push()
-        return g, None
 
 
 class _SourceFn(torch.autograd.Function):
@@ -282,6 +255,7 @@ class Model(nn.Module):
         self._win_idx = {}
         self._source_reducer = None
         self.amp_dtype = None          # None: everything fp32 like the reference; torch.bfloat16: see set_precision
+        self.own_gru = True            # bf16 mode: decoder GRU on the hand-written kernels (False: stock cuDNN, for A/B timing)
         self._we_cast = None
 
     def set_source_grad_reducer(self, fn):
@@ -411,16 +385,15 @@ class Model(nn.Module):
         if z_context is not None:
             dec_out = torch.cat([dec_out, z_context.unsqueeze(1).repeat(1, 34, 1)], dim=2)
 
-        # The recurrent decoder stays out of autocast: cuDNN's fp32 GRU with TF32 math allowed is its fastest variant here
-        # (hidden 350, batch 128, 34 steps, fwd+bwd: 7.8 ms with TF32, 8.6 ms under bf16 autocast, 10.0 ms in strict fp32;
-        # scripts/gru_pad_probe.py).  fp32 mode keeps whatever torch.backends.cudnn.allow_tf32 the caller chose.
+        # The recurrent decoder (HOP.py:166-167, 248).  bf16 mode: the hand-written GRU (csrc/gru.cu: input projections and
+        # weight gradients on the TMA + tcgen05 GEMM, the recurrence as a cluster-resident persistent kernel).  fp32 mode
+        # (reference numerics, 1e-5) stays on the stock fp32 module with whatever cudnn.allow_tf32 the caller chose.
         with torch.autocast('cuda', enabled=False):
             dec_in = dec_out.to(torch.float32).contiguous()
-            if self.amp_dtype is not None:                   # bf16 mode: TF32 (10-bit mantissa) is within the mode's precision
-                dec_in = _CudnnTF32.apply(dec_in, True)
-            dec_out, _ = self.gru(dec_in, None)
-            if self.amp_dtype is not None:
-                dec_out = _CudnnTF32.apply(dec_out, False)
+            if self.amp_dtype is not None and self.own_gru:
+                dec_out = hgru.run(self.gru, dec_in)
+            else:
+                dec_out, _ = self.gru(dec_in, None)
         dec_out = dec_out[:, :, :self.hidden_size] + dec_out[:, :, self.hidden_size:]
         dec_out = self.out(dec_out)
         return dec_out, z_context, z_mu, z_logvar

@@ -42,6 +42,21 @@ class GwnetGrads(C.Structure):
                 ('flat', _vp), ('flat_bytes', C.c_size_t)]
 
 
+GRU_MAX_LAYERS = 8
+_GRU_ARR = (_vp * 2) * GRU_MAX_LAYERS
+
+
+class GruShape(C.Structure):
+    _fields_ = [('B', C.c_int), ('T', C.c_int), ('I', C.c_int), ('H', C.c_int), ('L', C.c_int), ('save', C.c_int)]
+
+
+class GruParams(C.Structure):
+    _fields_ = [('w_ih', _GRU_ARR), ('w_hh', _GRU_ARR), ('b_ih', _GRU_ARR), ('b_hh', _GRU_ARR)]
+
+
+GruGrads = GruParams            # same layout: pointers indexed [layer][direction]
+
+
 # every symbol include/hopk.h declares, with its ctypes signature (restype int unless noted)
 _i, _f, _u64, _sz = C.c_int, C.c_float, C.c_uint64, C.c_size_t
 _SHP, _PRM, _GRD = C.POINTER(GwnetShape), C.POINTER(GwnetParams), C.POINTER(GwnetGrads)
@@ -62,9 +77,13 @@ SIGNATURES = {
     'hopk_linear_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'hopk_conv1x1_nchw_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'hopk_conv1x1_nchw_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    'hopk_gemm_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.c_long, C.c_long, C.c_long, _i, _f, _i, _vp]),
+    'hopk_gemm_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.c_long, C.c_long, C.c_long, _i, _f, _i, _vp]),
     'hopk_cast_bf16': (_i, [_vp, _vp, C.c_long, _i, C.c_long, _i, C.c_long, _i, _vp]),
     'hopk_colsum': (_i, [_vp, _vp, C.c_long, _i, C.c_long, _i, _vp]),
+    'hopk_gru_workspace_bytes': (_sz, [C.POINTER(GruShape)]),
+    'hopk_gru_scratch_bytes': (_sz, [C.POINTER(GruShape)]),
+    'hopk_gru_forward': (_i, [C.POINTER(GruShape), C.POINTER(GruParams), _vp, _vp, _vp, _vp]),
+    'hopk_gru_backward': (_i, [C.POINTER(GruShape), C.POINTER(GruParams), _vp, _vp, _vp, C.POINTER(GruParams), _vp, _vp]),
     'hopk_xattn_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _u64, _vp]),
     'hopk_dropout_epoch_advance': (_i, [_i, _vp]),
     'hopk_xattn_pack_bytes': (_sz, [_i, _i]),

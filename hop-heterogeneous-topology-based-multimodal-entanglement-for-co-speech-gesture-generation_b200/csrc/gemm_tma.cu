@@ -32,7 +32,9 @@ template <int BN> constexpr uint32_t gt_stage_bytes() { return tc::slab_bytes(GT
 template <int BN> constexpr size_t gt_smem_bytes() { return (size_t)gt_stages<BN>() * gt_stage_bytes<BN>() + 1024 + 256; }
 
 struct GtArgs {
-    void* C; const float* bias; const void* addend;
+    void* C; const float* bias; const void* addend; const float* mask;
+    int a_kshift, b_kshift;                             // added to the contraction (row) coordinate of an MN-major operand; rows
+                                                        // that fall outside the matrix read as zero (TMA out-of-bounds fill)
     int M, N, K;
     long ldc;
     int a_mn, b_mn;                                     // 1: operand is MN-major ([K][M] / [K][N] row-major)
@@ -105,12 +107,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (!g.a_mn) tma_load_2d(sa, &tmA, k, m0, &full[stage]);                    // box {64 k, 128 rows}
                     else {
 #pragma unroll
-                        for (int s = 0; s < GT_BM / 64; ++s) tma_load_2d(sa + s * tc::slab_bytes(GT_BK), &tmA, m0 + 64 * s, k, &full[stage]);   // box {64 m, 64 k-rows}
+                        for (int s = 0; s < GT_BM / 64; ++s) tma_load_2d(sa + s * tc::slab_bytes(GT_BK), &tmA, m0 + 64 * s, k + g.a_kshift, &full[stage]);   // box {64 m, 64 k-rows}
                     }
                     if (!g.b_mn) tma_load_2d(sb, &tmB, k, n0, &full[stage]);
                     else {
 #pragma unroll
-                        for (int s = 0; s < BN / 64; ++s) tma_load_2d(sb + s * tc::slab_bytes(GT_BK), &tmB, n0 + 64 * s, k, &full[stage]);
+                        for (int s = 0; s < BN / 64; ++s) tma_load_2d(sb + s * tc::slab_bytes(GT_BK), &tmB, n0 + 64 * s, k + g.b_kshift, &full[stage]);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -181,6 +183,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (g.act) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gt_act(v[j], g.act, g.slope);
+                    }
+                    if (g.mask) {                                  // out = mask > 0 ? out : 0 (gradient of a fused ReLU)
+                        const float* mk = g.mask + (size_t)m * g.ldc + nb;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] = __ldg(mk + j) > 0.f ? v[j] : 0.f;
                     }
                     if (g.out_bf16) {
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + (size_t)m * g.ldc + nb;
@@ -305,8 +312,10 @@ static int make_map(CUtensorMap* tm, const void* base, long rows, long cols, lon
 
 int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, const void* addend, int M, int N, int K, long lda,
                      long ldb, long ldc, int a_mn, int b_mn, int out_bf16, int accumulate, int act, float slope, int splits,
-                     cudaStream_t st)
+                     cudaStream_t st, const float* mask, int a_kshift, int b_kshift)
 {
+    HOPK_REQUIRE((a_kshift == 0 || a_mn) && (b_kshift == 0 || b_mn), "a row shift needs an MN-major operand");
+    HOPK_REQUIRE(!(mask && (accumulate || splits > 1)), "a mask cannot be combined with accumulation / split-K");
     HOPK_REQUIRE(M > 0 && N > 0 && K > 0, "gemm sizes");
     HOPK_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "operand leading dimensions must be multiples of 8 bf16 (16 bytes, TMA)");
     HOPK_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "operands must be 16-byte aligned");
@@ -319,7 +328,7 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     const int BN = wide ? 256 : 128;
     if (int rc = b_mn ? make_map(&tmB, B, K, N, ldb, GT_BK) : make_map(&tmB, B, N, K, ldb, BN)) return rc;
     GtArgs g;
-    g.C = C; g.bias = bias; g.addend = addend; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
+    g.C = C; g.bias = bias; g.addend = addend; g.mask = mask; g.a_kshift = a_kshift; g.b_kshift = b_kshift; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
     g.out_bf16 = out_bf16; g.accumulate = accumulate; g.act = act; g.slope = slope;
     if (splits < 1) splits = 1;
     int kper = ((cdiv(K, splits) + GT_BK - 1) / GT_BK) * GT_BK;
@@ -347,13 +356,13 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
 
 using namespace hopk;
 
-extern "C" int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, int M, int N, int K,
-                              long lda, long ldb, long ldc, int flags, float slope, int splits, void* stream)
+extern "C" int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, const float* mask,
+                              int M, int N, int K, long lda, long ldb, long ldc, int flags, float slope, int splits, void* stream)
 {
     const int a_mn = (flags & HOPK_GEMM_A_MN) ? 1 : 0, b_mn = (flags & HOPK_GEMM_B_MN) ? 1 : 0;
     const int act = (flags & HOPK_GEMM_RELU) ? 1 : (flags & HOPK_GEMM_LEAKY) ? 2 : (flags & HOPK_GEMM_GELU) ? 3 : 0;
     return gemm_bf16_launch(A, B, C, bias, addend, M, N, K, lda, ldb, ldc, a_mn, b_mn, (flags & HOPK_GEMM_OUT_BF16) ? 1 : 0,
-                            (flags & HOPK_GEMM_ACCUMULATE) ? 1 : 0, act, slope, splits, (cudaStream_t)stream);
+                            (flags & HOPK_GEMM_ACCUMULATE) ? 1 : 0, act, slope, splits, (cudaStream_t)stream, mask, 0, 0);
 }
 
 extern "C" int hopk_cast_bf16(const float* src, void* dst, long rows, int cols, long lds, int cols_out, long ldd, int relu, void* stream)

@@ -1,0 +1,700 @@
+// gru.cu -- the decoder tail of HOP.Model: 4-layer bidirectional GRU (hidden 350), forward and backward (dtype 1).
+//
+// Replaces cuDNN's RNN behind `self.gru(dec_out)` (reference model/HOP.py:166-167, 248) and its autograd backward.
+// PyTorch GRU cell (gate order r, z, n):
+//     r = sigmoid(W_ir x + b_ir + W_hr h + b_hr)      z = sigmoid(W_iz x + b_iz + W_hz h + b_hz)
+//     n = tanh(W_in x + b_in + r * (W_hn h + b_hn))   h' = (1 - z) * n + z * h
+//
+// Per layer:
+//   1. input projections of ALL time steps and both directions as ONE dense GEMM on the TMA + tcgen05 kernel
+//      (gemm_tma.cu):  Gi[T*B][2 x 1056] = X[T*B][I] . W_ih^T + b_ih (+ b_hr, b_hz folded in)
+//   2. the recurrence as a persistent kernel: a thread-block cluster of 8 CTAs owns one (direction, 16-sample batch slice);
+//      CTA c keeps the rows of W_hh of its 44 hidden units (r | z | n: 132 rows x 352, bf16, 102 KB) resident in shared
+//      memory for all T steps.  Each step is a tcgen05 MMA  D[gate row][sample] = W_slice . h_{t-1}^T  (M 128, N 16, K 352;
+//      accumulator in TMEM), the gate arithmetic on (sample, 4 units) threads with h carried in fp32 registers, and the
+//      new h written as bf16 straight into the B-operand buffer of all 8 CTAs through distributed shared memory
+//      (st.shared::cluster), ordered by one cluster barrier per step.  16 clusters x 8 CTAs = 128 SMs at batch 128.
+// Backward (BPTT) mirrors it: W_hh^T slices resident, per step  dh_{t-1} = dh * z + dGh . W_hh  (M 128, N 16, K 1056) with
+// the gate derivatives exchanged through DSMEM; afterwards dW_ih, dW_hh, dX are dense GEMMs over all time steps (the
+// h_{t-1} operand of dW_hh is the stored output read through a TMA row shift, out-of-range rows = the zero initial state).
+//
+// Internal layouts are time-major (row = t*B + b) and padded: hidden 350 -> 352 per direction (704 per row), gates 3 x 352.
+#include <mutex>
+#include "tc_core.cuh"
+#include "common.cuh"
+#include "../../include/hopk.h"
+
+namespace hopk {
+
+constexpr int GRU_CL = 8;                      // CTAs per cluster
+constexpr int GRU_UNITS = 44;                  // hidden units per CTA
+constexpr int GRU_HP = GRU_CL * GRU_UNITS;     // 352: padded hidden size
+constexpr int GRU_G = 3 * GRU_HP;              // 1056 gate columns per direction
+constexpr int GRU_NB = 16;                     // samples per cluster
+constexpr int GRU_THREADS = 288;               // 8 worker warps + 1 MMA-issue warp
+constexpr int GRU_GATE_THREADS = GRU_NB * (GRU_UNITS / 4);      // 176: (sample, group of 4 units)
+
+// forward A operand: rows [r 44 | z 44 | n 44] of W_hh, K = 352 -> 6 slabs of [136 rows][64 bf16]
+constexpr int GRU_FA_ROWS = 136;
+constexpr uint32_t GRU_FA_SLAB = GRU_FA_ROWS * 128;
+constexpr int GRU_FA_NSLAB = 6;
+constexpr uint32_t GRU_FA_BYTES = GRU_FA_NSLAB * GRU_FA_SLAB;               // 104448
+constexpr uint32_t GRU_B_SLAB = GRU_NB * 128;                               // [16 samples][64 bf16]
+constexpr uint32_t GRU_FB_BYTES = GRU_FA_NSLAB * GRU_B_SLAB;                // 12288 per buffer
+// backward A operand: rows = the CTA's 44 units k of W_hh^T, K = 1056 gate columns -> 17 slabs of [48 rows][64 bf16]
+constexpr int GRU_BA_ROWS = 48;
+constexpr uint32_t GRU_BA_SLAB = GRU_BA_ROWS * 128;
+constexpr int GRU_BA_NSLAB = 17;
+constexpr uint32_t GRU_BA_BYTES = GRU_BA_NSLAB * GRU_BA_SLAB;               // 104448
+constexpr uint32_t GRU_BB_BYTES = GRU_BA_NSLAB * GRU_B_SLAB;                // 34816 per buffer
+constexpr int GRU_XLD = GRU_NB + 1;                                         // fp32 pitch of the TMEM -> thread exchange tile
+
+constexpr size_t gru_fwd_smem() { return GRU_FA_BYTES + 2 * GRU_FB_BYTES + 132 * GRU_XLD * 4 + 1024; }
+constexpr size_t gru_bwd_smem() { return GRU_BA_BYTES + 2 * GRU_BB_BYTES + 64 * GRU_XLD * 4 + 1024; }
+
+// ---------------------------------------------------------------- cluster primitives
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_t b)
+{
+    asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// generic-proxy writes (own and remote shared memory) -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ float tanh_approx(float x)
+{
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+
+// byte offset of element (sample row gb, contraction index k) inside a stack of [16][64] K-major slabs; k % 4 == 0
+__device__ __forceinline__ uint32_t bop_off(int gb, int k)
+{
+    return (uint32_t)(k >> 6) * GRU_B_SLAB + (uint32_t)gb * 128u + (uint32_t)((((k & 63) >> 3) ^ (gb & 7)) << 4) + (uint32_t)(k & 7) * 2u;
+}
+
+// ---------------------------------------------------------------- forward recurrence
+struct GruFwdArgs {
+    const float* Gi;            // [T*B][2*1056]: input projections + b_ih (+ b_hr, b_hz)
+    const uint8_t* whh;         // [2 dirs][8 CTAs][GRU_FA_BYTES] packed W_hh slices
+    const float* bhn;           // [2][352]
+    __nv_bfloat16* Y;           // [T*B][704] outputs h_t (bf16): operand of the next layer's GEMM / of backward
+    float *R, *Z, *N, *HN;      // [T*B][704] saved gate values (nullable: inference / no-grad pass)
+    float* out;                 // optional (B, T, 2H) batch-first fp32 output (last layer)
+    int B, T, H;
+};
+
+__global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(const GruFwdArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t wbar, mbar;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + GRU_FA_BYTES;
+    float* xchg = reinterpret_cast<float*>(sB + 2 * GRU_FB_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cl = blockIdx.x / GRU_CL;
+    const int dir = cl & 1, b0 = (cl >> 1) * GRU_NB;
+    const int B = a.B, T = a.T;
+
+    if (tid == 0) {
+        tc::mbar_init(&wbar, 1);
+        tc::mbar_init(&mbar, 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&wbar, GRU_FA_BYTES);
+        const uint8_t* src = a.whh + (size_t)(dir * GRU_CL + rank) * GRU_FA_BYTES;
+#pragma unroll 1
+        for (int s = 0; s < GRU_FA_NSLAB; ++s) tc::bulk_g2s(sA + s * GRU_FA_SLAB, src + s * GRU_FA_SLAB, GRU_FA_SLAB, &wbar);
+    }
+    if (warp == 8) tc::tmem_alloc(&tmem_slot, 32);
+    for (int i = tid; i < (int)(2 * GRU_FB_BYTES / 16); i += GRU_THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
+    fence_proxy_async_all();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    cluster_arrive();
+    cluster_wait();                                   // every CTA's operand buffers are initialised before a peer writes into them
+
+    const bool gate_thr = tid < GRU_GATE_THREADS;
+    const int gb = tid & 15, grp = tid >> 4;
+    const int b = b0 + gb;
+    const bool act = gate_thr && b < B;
+    const int ju = (int)rank * GRU_UNITS + grp * 4;   // first of this thread's 4 hidden units (padded index)
+    float h[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 bhn = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t raddr[GRU_CL];
+    if (gate_thr) {
+        const uint32_t local = tc::smem_u32(sB) + bop_off(gb, ju);
+#pragma unroll
+        for (int r = 0; r < GRU_CL; ++r) raddr[r] = mapa(local, (uint32_t)r);
+        bhn = __ldg(reinterpret_cast<const float4*>(a.bhn + dir * GRU_HP + ju));
+    }
+    float4 gi_r = make_float4(0.f, 0.f, 0.f, 0.f), gi_z = gi_r, gi_n = gi_r;
+    if (act) {
+        const int t0 = dir ? T - 1 : 0;
+        const float* p = a.Gi + ((size_t)t0 * B + b) * (2 * GRU_G) + dir * GRU_G + ju;
+        gi_r = __ldg(reinterpret_cast<const float4*>(p));
+        gi_z = __ldg(reinterpret_cast<const float4*>(p + GRU_HP));
+        gi_n = __ldg(reinterpret_cast<const float4*>(p + 2 * GRU_HP));
+    }
+    uint32_t mphase = 0;
+#pragma unroll 1
+    for (int step = 0; step < T; ++step) {
+        const int t = dir ? T - 1 - step : step;
+        const int cur = step & 1;
+        // ---- D[gate row][sample] = W_slice . h_{t-1}^T on the tensor core
+        if (warp == 8) {
+            if (lane == 0) {
+                if (step == 0) tc::mbar_wait(&wbar, 0);
+                fence_proxy_async_all();
+                tc::fence_after_sync();
+                constexpr uint32_t idesc = tc::idesc_bf16(128, GRU_NB, 0, 0);
+                const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB) + cur * GRU_FB_BYTES;
+#pragma unroll 2
+                for (int kt = 0; kt < GRU_HP / 16; ++kt) {
+                    const uint32_t sa = a_base + (kt >> 2) * GRU_FA_SLAB, sb = b_base + (kt >> 2) * GRU_B_SLAB;
+                    const uint64_t db = tc::desc_kmajor(sb, kt & 3);
+                    tc::mma_bf16(tmem, tc::desc_kmajor(sa, kt & 3), db, idesc, kt != 0);                        // gate rows 0..127
+                    tc::mma_bf16(tmem + 16, tc::desc_kmajor(sa + 128 * 128, kt & 3), db, idesc, kt != 0);       // gate rows 128..131
+                }
+                tc::mma_commit(&mbar);
+            }
+            __syncwarp();
+        }
+        tc::mbar_wait(&mbar, mphase);
+        mphase ^= 1;
+        tc::fence_after_sync();
+        if (warp < 4) {
+            float v[16];
+            tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+            float* dst = xchg + (warp * 32 + lane) * GRU_XLD;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[j] = v[j];
+            if (warp == 0) {
+                tc::tmem_ld16(tmem + 16, v);
+                if (lane < 4) {
+                    float* d2 = xchg + (128 + lane) * GRU_XLD;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) d2[j] = v[j];
+                }
+            }
+            tc::fence_before_sync();
+        }
+        __syncthreads();
+        // ---- gates (fp32), new h
+        float rr[4], zz[4], nn[4], hn[4];
+        if (gate_thr) {
+            const float gir[4] = {gi_r.x, gi_r.y, gi_r.z, gi_r.w}, giz[4] = {gi_z.x, gi_z.y, gi_z.z, gi_z.w};
+            const float gin[4] = {gi_n.x, gi_n.y, gi_n.z, gi_n.w}, bh[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float gr = xchg[(grp * 4 + i) * GRU_XLD + gb];
+                const float gz = xchg[(GRU_UNITS + grp * 4 + i) * GRU_XLD + gb];
+                const float gn = xchg[(2 * GRU_UNITS + grp * 4 + i) * GRU_XLD + gb];
+                rr[i] = sigmoid_approx(gir[i] + gr);
+                zz[i] = sigmoid_approx(giz[i] + gz);
+                hn[i] = gn + bh[i];
+                nn[i] = tanh_approx(fmaf(rr[i], hn[i], gin[i]));
+                h[i] = act ? fmaf(zz[i], h[i] - nn[i], nn[i]) : 0.f;            // (1 - z) n + z h
+            }
+            if (step + 1 < T) {                                                 // h_t into every CTA's operand buffer of step + 1
+                const uint32_t lo = tc::pack_bf16x2(h[0], h[1]), hi = tc::pack_bf16x2(h[2], h[3]);
+                const uint32_t boff = (cur ^ 1) * GRU_FB_BYTES;
+#pragma unroll
+                for (int r = 0; r < GRU_CL; ++r) st_cluster_v2(raddr[r] + boff, lo, hi);
+            }
+        }
+        fence_proxy_async_all();
+        __syncwarp();
+        cluster_arrive();
+        // ---- results to global memory and next step's input projections while the barrier completes
+        if (act) {
+            const size_t row = (size_t)t * B + b;
+            const size_t o = row * (2 * GRU_HP) + dir * GRU_HP + ju;
+            uint2 hb;
+            hb.x = tc::pack_bf16x2(h[0], h[1]); hb.y = tc::pack_bf16x2(h[2], h[3]);
+            *reinterpret_cast<uint2*>(a.Y + o) = hb;
+            if (a.R) {
+                *reinterpret_cast<float4*>(a.R + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+                *reinterpret_cast<float4*>(a.Z + o) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+                *reinterpret_cast<float4*>(a.N + o) = make_float4(nn[0], nn[1], nn[2], nn[3]);
+                *reinterpret_cast<float4*>(a.HN + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            }
+            if (a.out) {
+                float* po = a.out + ((size_t)b * T + t) * (2 * a.H) + dir * a.H + ju;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (ju + i < a.H) po[i] = h[i];
+            }
+            if (step + 1 < T) {
+                const int tn = dir ? t - 1 : t + 1;
+                const float* p = a.Gi + ((size_t)tn * B + b) * (2 * GRU_G) + dir * GRU_G + ju;
+                gi_r = __ldg(reinterpret_cast<const float4*>(p));
+                gi_z = __ldg(reinterpret_cast<const float4*>(p + GRU_HP));
+                gi_n = __ldg(reinterpret_cast<const float4*>(p + 2 * GRU_HP));
+            }
+        }
+        __syncwarp();
+        cluster_wait();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tmem, 32);
+}
+
+// ---------------------------------------------------------------- backward recurrence (BPTT)
+struct GruBwdArgs {
+    const float* dY;             // [T*B][704] gradient w.r.t. this layer's outputs
+    const uint8_t* whhT;         // [2][8][GRU_BA_BYTES] packed W_hh^T slices
+    const __nv_bfloat16* Y;      // [T*B][704] forward outputs
+    const float *R, *Z, *N, *HN;
+    __nv_bfloat16* dGi;          // [T*B][2*1056] gradient w.r.t. the input projections
+    __nv_bfloat16* dGh;          // [T*B][2*1056] gradient w.r.t. the hidden projections (differs in the n gate: x r)
+    int B, T;
+};
+
+__global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t wbar, mbar;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + GRU_BA_BYTES;
+    float* xchg = reinterpret_cast<float*>(sB + 2 * GRU_BB_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cl = blockIdx.x / GRU_CL;
+    const int dir = cl & 1, b0 = (cl >> 1) * GRU_NB;
+    const int B = a.B, T = a.T;
+
+    if (tid == 0) {
+        tc::mbar_init(&wbar, 1);
+        tc::mbar_init(&mbar, 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&wbar, GRU_BA_BYTES);
+        const uint8_t* src = a.whhT + (size_t)(dir * GRU_CL + rank) * GRU_BA_BYTES;
+#pragma unroll 1
+        for (int s = 0; s < GRU_BA_NSLAB; ++s) tc::bulk_g2s(sA + s * GRU_BA_SLAB, src + s * GRU_BA_SLAB, GRU_BA_SLAB, &wbar);
+    }
+    if (warp == 8) tc::tmem_alloc(&tmem_slot, 32);
+    for (int i = tid; i < (int)(2 * GRU_BB_BYTES / 16); i += GRU_THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_all();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    cluster_arrive();
+    cluster_wait();
+
+    const bool gate_thr = tid < GRU_GATE_THREADS;
+    const int gb = tid & 15, grp = tid >> 4;
+    const int b = b0 + gb;
+    const bool act = gate_thr && b < B;
+    const int ju = (int)rank * GRU_UNITS + grp * 4;
+    uint32_t loff[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) loff[q] = tc::smem_u32(sB) + bop_off(gb, q * GRU_HP + ju);
+    float carry[4] = {0.f, 0.f, 0.f, 0.f};             // dh * z of the step before (direct path to h_{t-1})
+    uint32_t mphase = 0;
+#pragma unroll 1
+    for (int step = 0; step < T; ++step) {
+        const int t = dir ? step : T - 1 - step;       // reverse of the forward order
+        const int cur = step & 1;
+        // ---- (dGh of the step before) . W_hh  ->  D[unit k][sample]
+        if (warp == 8) {
+            if (lane == 0) {
+                if (step == 0) tc::mbar_wait(&wbar, 0);
+                fence_proxy_async_all();
+                tc::fence_after_sync();
+                constexpr uint32_t idesc = tc::idesc_bf16(128, GRU_NB, 0, 0);
+                const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB) + cur * GRU_BB_BYTES;
+#pragma unroll 2
+                for (int kt = 0; kt < GRU_G / 16; ++kt) {
+                    const uint32_t sa = a_base + (kt >> 2) * GRU_BA_SLAB, sb = b_base + (kt >> 2) * GRU_B_SLAB;
+                    tc::mma_bf16(tmem, tc::desc_kmajor(sa, kt & 3), tc::desc_kmajor(sb, kt & 3), idesc, kt != 0);
+                }
+                tc::mma_commit(&mbar);
+            }
+            __syncwarp();
+        }
+        // ---- this step's saved values (in flight while the MMA runs)
+        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), z4 = r4, n4 = r4, hn4 = r4, dy4 = r4;
+        uint2 hp = make_uint2(0u, 0u);
+        if (act) {
+            const size_t o = ((size_t)t * B + b) * (2 * GRU_HP) + dir * GRU_HP + ju;
+            r4 = __ldg(reinterpret_cast<const float4*>(a.R + o));
+            z4 = __ldg(reinterpret_cast<const float4*>(a.Z + o));
+            n4 = __ldg(reinterpret_cast<const float4*>(a.N + o));
+            hn4 = __ldg(reinterpret_cast<const float4*>(a.HN + o));
+            dy4 = __ldg(reinterpret_cast<const float4*>(a.dY + o));
+            const int tp = dir ? t + 1 : t - 1;        // the time step whose output was this step's h_{t-1}
+            if (tp >= 0 && tp < T) hp = __ldg(reinterpret_cast<const uint2*>(a.Y + ((size_t)tp * B + b) * (2 * GRU_HP) + dir * GRU_HP + ju));
+        }
+        tc::mbar_wait(&mbar, mphase);
+        mphase ^= 1;
+        tc::fence_after_sync();
+        if (warp < 2) {
+            float v[16];
+            tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+            float* dst = xchg + (warp * 32 + lane) * GRU_XLD;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[j] = v[j];
+            tc::fence_before_sync();
+        }
+        __syncthreads();
+        float dgr[4], dgz[4], dgni[4], dgnh[4];
+        if (gate_thr) {
+            const float r[4] = {r4.x, r4.y, r4.z, r4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w}, n[4] = {n4.x, n4.y, n4.z, n4.w};
+            const float hn[4] = {hn4.x, hn4.y, hn4.z, hn4.w}, dy[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
+            const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hp.x), h23 = *reinterpret_cast<const __nv_bfloat162*>(&hp.y);
+            const float hprev[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float dh = act ? dy[i] + carry[i] + xchg[(grp * 4 + i) * GRU_XLD + gb] : 0.f;
+                const float dn = dh * (1.f - z[i]);
+                const float dz = dh * (hprev[i] - n[i]);
+                const float dnp = dn * (1.f - n[i] * n[i]);
+                dgni[i] = dnp;
+                dgnh[i] = dnp * r[i];
+                dgr[i] = dnp * hn[i] * r[i] * (1.f - r[i]);
+                dgz[i] = dz * z[i] * (1.f - z[i]);
+                carry[i] = dh * z[i];
+            }
+            if (step + 1 < T) {
+                const uint32_t boff = (cur ^ 1) * GRU_BB_BYTES;
+                const uint32_t w0[3] = {tc::pack_bf16x2(dgr[0], dgr[1]), tc::pack_bf16x2(dgz[0], dgz[1]), tc::pack_bf16x2(dgnh[0], dgnh[1])};
+                const uint32_t w1[3] = {tc::pack_bf16x2(dgr[2], dgr[3]), tc::pack_bf16x2(dgz[2], dgz[3]), tc::pack_bf16x2(dgnh[2], dgnh[3])};
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int rk = 0; rk < GRU_CL; ++rk) st_cluster_v2(mapa(loff[q], (uint32_t)rk) + boff, w0[q], w1[q]);
+            }
+        }
+        fence_proxy_async_all();
+        __syncwarp();
+        cluster_arrive();
+        if (act) {
+            const size_t o = ((size_t)t * B + b) * (2 * GRU_G) + dir * GRU_G + ju;
+            uint2 v;
+            v.x = tc::pack_bf16x2(dgr[0], dgr[1]); v.y = tc::pack_bf16x2(dgr[2], dgr[3]);
+            *reinterpret_cast<uint2*>(a.dGi + o) = v; *reinterpret_cast<uint2*>(a.dGh + o) = v;
+            v.x = tc::pack_bf16x2(dgz[0], dgz[1]); v.y = tc::pack_bf16x2(dgz[2], dgz[3]);
+            *reinterpret_cast<uint2*>(a.dGi + o + GRU_HP) = v; *reinterpret_cast<uint2*>(a.dGh + o + GRU_HP) = v;
+            v.x = tc::pack_bf16x2(dgni[0], dgni[1]); v.y = tc::pack_bf16x2(dgni[2], dgni[3]);
+            *reinterpret_cast<uint2*>(a.dGi + o + 2 * GRU_HP) = v;
+            v.x = tc::pack_bf16x2(dgnh[0], dgnh[1]); v.y = tc::pack_bf16x2(dgnh[2], dgnh[3]);
+            *reinterpret_cast<uint2*>(a.dGh + o + 2 * GRU_HP) = v;
+        }
+        __syncwarp();
+        cluster_wait();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tmem, 32);
+}
+
+// ---------------------------------------------------------------- packing / unpacking
+// padded input width of layer l: layer 0 = I rounded up to 8; deeper layers = 704 ([fwd 350, 0, 0 | bwd 350, 0, 0])
+__host__ __device__ inline int gru_in_pad(int l, int I) { return l == 0 ? ((I + 7) & ~7) : 2 * GRU_HP; }
+// column of the padded input that holds PyTorch input column c
+__host__ __device__ inline int gru_in_col(int l, int H, int c) { return l == 0 ? c : (c < H ? c : GRU_HP + (c - H)); }
+
+// W_ih of both directions -> bf16 [2*1056][Ipad] (row = dir*1056 + gate*352 + unit); bias_comb[2*1056]; bhn[2*352]
+__global__ void gru_pack_wih_kernel(const float* __restrict__ w0, const float* __restrict__ w1, const float* __restrict__ bi0,
+                                    const float* __restrict__ bi1, const float* __restrict__ bh0, const float* __restrict__ bh1,
+                                    __nv_bfloat16* __restrict__ wp, float* __restrict__ bias, float* __restrict__ bhn, int l, int I, int Iin, int H)
+{
+    const int Ipad = gru_in_pad(l, I);
+    const int row = blockIdx.x;                       // 0 .. 2*1056-1
+    const int dir = row / GRU_G, q = (row % GRU_G) / GRU_HP, j = row % GRU_HP;
+    const float* w = dir ? w1 : w0;
+    const bool valid = j < H;
+    __nv_bfloat16* dst = wp + (size_t)row * Ipad;
+    for (int c = threadIdx.x; c < Ipad; c += blockDim.x) dst[c] = __float2bfloat16_rn(0.f);
+    __syncthreads();
+    if (valid) {
+        const float* src = w + (size_t)(q * H + j) * Iin;
+        for (int c = threadIdx.x; c < Iin; c += blockDim.x) dst[gru_in_col(l, H, c)] = __float2bfloat16_rn(src[c]);
+    }
+    if (threadIdx.x == 0) {
+        const float* bi = dir ? bi1 : bi0;
+        const float* bh = dir ? bh1 : bh0;
+        float v = 0.f;
+        if (valid) v = bi[q * H + j] + (q < 2 ? bh[q * H + j] : 0.f);
+        bias[row] = v;
+        if (q == 2) bhn[dir * GRU_HP + j] = valid ? bh[2 * H + j] : 0.f;
+    }
+}
+
+// W_hh -> per (dir, CTA) slab images: forward [r|z|n rows of the CTA's units][k], backward [unit k][gate column]
+__global__ void gru_pack_whh_kernel(const float* __restrict__ w0, const float* __restrict__ w1, uint8_t* __restrict__ fimg,
+                                    uint8_t* __restrict__ bimg, int H)
+{
+    const int dir = blockIdx.y, c = blockIdx.x;
+    const float* w = dir ? w1 : w0;
+    uint8_t* fi = fimg + (size_t)(dir * GRU_CL + c) * GRU_FA_BYTES;
+    for (int idx = threadIdx.x; idx < GRU_FA_ROWS * GRU_FA_NSLAB * 64; idx += blockDim.x) {
+        const int row = idx / (GRU_FA_NSLAB * 64), k = idx % (GRU_FA_NSLAB * 64);
+        float v = 0.f;
+        if (row < 3 * GRU_UNITS) {
+            const int q = row / GRU_UNITS, j = c * GRU_UNITS + row % GRU_UNITS;
+            if (j < H && k < H) v = w[(size_t)(q * H + j) * H + k];
+        }
+        const uint32_t off = (uint32_t)(k >> 6) * GRU_FA_SLAB + tc::slab_chunk_off(row, (k & 63) >> 3) + (uint32_t)(k & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(fi + off) = __float2bfloat16_rn(v);
+    }
+    if (!bimg) return;
+    uint8_t* bi = bimg + (size_t)(dir * GRU_CL + c) * GRU_BA_BYTES;
+    for (int idx = threadIdx.x; idx < GRU_BA_ROWS * GRU_BA_NSLAB * 64; idx += blockDim.x) {
+        const int row = idx / (GRU_BA_NSLAB * 64), g = idx % (GRU_BA_NSLAB * 64);
+        float v = 0.f;
+        if (row < GRU_UNITS && g < GRU_G) {
+            const int k = c * GRU_UNITS + row, q = g / GRU_HP, u = g % GRU_HP;
+            if (k < H && u < H) v = w[(size_t)(q * H + u) * H + k];
+        }
+        const uint32_t off = (uint32_t)(g >> 6) * GRU_BA_SLAB + tc::slab_chunk_off(row, (g & 63) >> 3) + (uint32_t)(g & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(bi + off) = __float2bfloat16_rn(v);
+    }
+}
+
+// x (B, T, I) fp32 batch-first -> bf16 [T*B][Ipad] time-major
+__global__ void gru_pack_x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int B, int T, int I, int Ipad)
+{
+    const size_t n = (size_t)B * T * Ipad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Ipad);
+        const size_t r = i / Ipad;
+        const int b = (int)(r % B), t = (int)(r / B);
+        xp[i] = __float2bfloat16_rn(c < I ? x[((size_t)b * T + t) * I + c] : 0.f);
+    }
+}
+// dout (B, T, 2H) fp32 batch-first -> fp32 [T*B][704] time-major (pad columns zero)
+__global__ void gru_pack_dy_kernel(const float* __restrict__ dy, float* __restrict__ dp, int B, int T, int H)
+{
+    const size_t n = (size_t)B * T * 2 * GRU_HP;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % (2 * GRU_HP));
+        const size_t r = i / (2 * GRU_HP);
+        const int b = (int)(r % B), t = (int)(r / B);
+        const int dir = c / GRU_HP, j = c % GRU_HP;
+        dp[i] = j < H ? dy[((size_t)b * T + t) * (2 * H) + dir * H + j] : 0.f;
+    }
+}
+// dX [T*B][Ipad] fp32 time-major -> (B, T, I) batch-first
+__global__ void gru_unpack_dx_kernel(const float* __restrict__ dxp, float* __restrict__ dx, int B, int T, int I, int Ipad)
+{
+    const size_t n = (size_t)B * T * I;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % I);
+        const size_t r = i / I;
+        const int t = (int)(r % T), b = (int)(r / T);
+        dx[i] = dxp[((size_t)t * B + b) * Ipad + c];
+    }
+}
+// packed gradients -> PyTorch parameter layouts.  dwih [2*1056][Ipad], dwhh [2*1056][352], dbi / dbh [2*1056]
+__global__ void gru_unpack_grads_kernel(const float* __restrict__ dwih, const float* __restrict__ dwhh, const float* __restrict__ dbi,
+                                        const float* __restrict__ dbh, float* gw_ih0, float* gw_ih1, float* gw_hh0, float* gw_hh1,
+                                        float* gb_ih0, float* gb_ih1, float* gb_hh0, float* gb_hh1, int l, int I, int Iin, int H)
+{
+    const int Ipad = gru_in_pad(l, I);
+    const int orow = blockIdx.x;                       // 0 .. 2*3H-1: (dir, gate*H + unit)
+    const int dir = orow / (3 * H), gj = orow % (3 * H), q = gj / H, j = gj % H;
+    const int prow = dir * GRU_G + q * GRU_HP + j;
+    float* wi = dir ? gw_ih1 : gw_ih0;
+    float* wh = dir ? gw_hh1 : gw_hh0;
+    for (int c = threadIdx.x; c < Iin; c += blockDim.x) wi[(size_t)gj * Iin + c] = dwih[(size_t)prow * Ipad + gru_in_col(l, H, c)];
+    for (int c = threadIdx.x; c < H; c += blockDim.x) wh[(size_t)gj * H + c] = dwhh[(size_t)prow * GRU_HP + c];
+    if (threadIdx.x == 0) {
+        (dir ? gb_ih1 : gb_ih0)[gj] = dbi[prow];
+        (dir ? gb_hh1 : gb_hh0)[gj] = dbh[prow];
+    }
+}
+
+// ---------------------------------------------------------------- workspace layout
+struct GruLayout {
+    int Ipad[HOPK_GRU_MAX_LAYERS];
+    size_t xb, gi, y[HOPK_GRU_MAX_LAYERS], r[HOPK_GRU_MAX_LAYERS], z[HOPK_GRU_MAX_LAYERS], n[HOPK_GRU_MAX_LAYERS], hn[HOPK_GRU_MAX_LAYERS];
+    size_t wih[HOPK_GRU_MAX_LAYERS], whh[HOPK_GRU_MAX_LAYERS], bias[HOPK_GRU_MAX_LAYERS], bhn[HOPK_GRU_MAX_LAYERS], total;
+    // backward scratch
+    size_t s_whhT, s_dya, s_dyb, s_dgi, s_dgh, s_dwih, s_dwhh, s_dbi, s_dbh, s_total;
+};
+static size_t gbump(size_t& cur, size_t bytes)
+{
+    size_t at = cur;
+    cur += (bytes + 1023) & ~size_t(1023);
+    return at;
+}
+static GruLayout gru_layout(const HopkGruShape* s)
+{
+    GruLayout g;
+    memset(&g, 0, sizeof(g));
+    const size_t TB = (size_t)s->T * s->B;
+    size_t cur = 0;
+    int ipmax = 0;
+    for (int l = 0; l < s->L; ++l) { g.Ipad[l] = gru_in_pad(l, s->I); if (g.Ipad[l] > ipmax) ipmax = g.Ipad[l]; }
+    g.xb = gbump(cur, TB * g.Ipad[0] * 2);
+    g.gi = gbump(cur, TB * 2 * GRU_G * 4);
+    for (int l = 0; l < s->L; ++l) {
+        g.y[l] = gbump(cur, TB * 2 * GRU_HP * 2);
+        if (s->save) {
+            g.r[l] = gbump(cur, TB * 2 * GRU_HP * 4); g.z[l] = gbump(cur, TB * 2 * GRU_HP * 4);
+            g.n[l] = gbump(cur, TB * 2 * GRU_HP * 4); g.hn[l] = gbump(cur, TB * 2 * GRU_HP * 4);
+        }
+        g.wih[l] = gbump(cur, (size_t)2 * GRU_G * g.Ipad[l] * 2);
+        g.whh[l] = gbump(cur, (size_t)2 * GRU_CL * GRU_FA_BYTES);
+        g.bias[l] = gbump(cur, (size_t)2 * GRU_G * 4);
+        g.bhn[l] = gbump(cur, (size_t)2 * GRU_HP * 4);
+    }
+    g.total = cur;
+    cur = 0;
+    g.s_whhT = gbump(cur, (size_t)2 * GRU_CL * GRU_BA_BYTES);
+    g.s_dya = gbump(cur, TB * ipmax * 4);
+    g.s_dyb = gbump(cur, TB * ipmax * 4);
+    g.s_dgi = gbump(cur, TB * 2 * GRU_G * 2);
+    g.s_dgh = gbump(cur, TB * 2 * GRU_G * 2);
+    g.s_dwih = gbump(cur, (size_t)2 * GRU_G * ipmax * 4);
+    g.s_dwhh = gbump(cur, (size_t)2 * GRU_G * GRU_HP * 4);
+    g.s_dbi = gbump(cur, (size_t)2 * GRU_G * 4);
+    g.s_dbh = gbump(cur, (size_t)2 * GRU_G * 4);
+    g.s_total = cur;
+    return g;
+}
+
+static int gru_check(const HopkGruShape* s)
+{
+    HOPK_REQUIRE(s->B >= 1 && s->T >= 1 && s->I >= 1, "gru sizes");
+    HOPK_REQUIRE(s->H >= 1 && s->H <= GRU_HP, "gru: hidden size must be <= 352");
+    HOPK_REQUIRE(s->L >= 1 && s->L <= HOPK_GRU_MAX_LAYERS, "gru: layer count");
+    return 0;
+}
+
+static int grid_1d(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : b); }
+
+}  // namespace hopk
+
+using namespace hopk;
+
+extern "C" size_t hopk_gru_workspace_bytes(const HopkGruShape* s) { return gru_layout(s).total; }
+extern "C" size_t hopk_gru_scratch_bytes(const HopkGruShape* s) { return gru_layout(s).s_total; }
+
+extern "C" int hopk_gru_forward(const HopkGruShape* s, const HopkGruParams* p, const float* x, float* out, void* ws_, void* stream)
+{
+    if (int rc = gru_check(s)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    GruLayout g = gru_layout(s);
+    char* ws = (char*)ws_;
+    const int B = s->B, T = s->T, H = s->H, L = s->L;
+    const int TB = T * B;
+    HOPK_CUDA(configure_smem_once((const void*)gru_fwd_kernel, gru_fwd_smem()));
+    gru_pack_x_kernel<<<grid_1d((size_t)TB * g.Ipad[0]), 256, 0, st>>>(x, (__nv_bfloat16*)(ws + g.xb), B, T, s->I, g.Ipad[0]);
+    HOPK_LAUNCH_CHECK("gru_pack_x");
+    const int slices = cdiv(B, GRU_NB);
+    for (int l = 0; l < L; ++l) {
+        const int Iin = l == 0 ? s->I : 2 * H;
+        __nv_bfloat16* wih = (__nv_bfloat16*)(ws + g.wih[l]);
+        float* bias = (float*)(ws + g.bias[l]);
+        float* bhn = (float*)(ws + g.bhn[l]);
+        gru_pack_wih_kernel<<<2 * GRU_G, 128, 0, st>>>(p->w_ih[l][0], p->w_ih[l][1], p->b_ih[l][0], p->b_ih[l][1], p->b_hh[l][0],
+                                                        p->b_hh[l][1], wih, bias, bhn, l, s->I, Iin, H);
+        HOPK_LAUNCH_CHECK("gru_pack_wih");
+        gru_pack_whh_kernel<<<dim3(GRU_CL, 2), 256, 0, st>>>(p->w_hh[l][0], p->w_hh[l][1], (uint8_t*)(ws + g.whh[l]), nullptr, H);
+        HOPK_LAUNCH_CHECK("gru_pack_whh");
+        const __nv_bfloat16* X = l == 0 ? (const __nv_bfloat16*)(ws + g.xb) : (const __nv_bfloat16*)(ws + g.y[l - 1]);
+        // Gi = X . W_ih^T + bias   (both directions: N = 2112)
+        if (int rc = gemm_bf16_launch(X, wih, ws + g.gi, bias, nullptr, TB, 2 * GRU_G, g.Ipad[l], g.Ipad[l], g.Ipad[l], 2 * GRU_G, 0, 0,
+                                      0, 0, 0, 0.f, 1, st)) return rc;
+        GruFwdArgs a;
+        a.Gi = (const float*)(ws + g.gi); a.whh = (const uint8_t*)(ws + g.whh[l]); a.bhn = bhn;
+        a.Y = (__nv_bfloat16*)(ws + g.y[l]);
+        a.R = s->save ? (float*)(ws + g.r[l]) : nullptr; a.Z = s->save ? (float*)(ws + g.z[l]) : nullptr;
+        a.N = s->save ? (float*)(ws + g.n[l]) : nullptr; a.HN = s->save ? (float*)(ws + g.hn[l]) : nullptr;
+        a.out = l == L - 1 ? out : nullptr;
+        a.B = B; a.T = T; a.H = H;
+        gru_fwd_kernel<<<2 * slices * GRU_CL, GRU_THREADS, gru_fwd_smem(), st>>>(a);
+        HOPK_LAUNCH_CHECK("gru_fwd");
+    }
+    return 0;
+}
+
+extern "C" int hopk_gru_backward(const HopkGruShape* s, const HopkGruParams* p, const float* dout, void* ws_, void* scratch_,
+                                 const HopkGruGrads* gr, float* dx, void* stream)
+{
+    if (int rc = gru_check(s)) return rc;
+    HOPK_REQUIRE(s->save, "gru backward needs a forward run with save = 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    GruLayout g = gru_layout(s);
+    char* ws = (char*)ws_;
+    char* sc = (char*)scratch_;
+    const int B = s->B, T = s->T, H = s->H, L = s->L;
+    const int TB = T * B;
+    HOPK_CUDA(configure_smem_once((const void*)gru_bwd_kernel, gru_bwd_smem()));
+    float* dy_cur = (float*)(sc + g.s_dya);
+    float* dy_next = (float*)(sc + g.s_dyb);
+    gru_pack_dy_kernel<<<grid_1d((size_t)TB * 2 * GRU_HP), 256, 0, st>>>(dout, dy_cur, B, T, H);
+    HOPK_LAUNCH_CHECK("gru_pack_dy");
+    const int slices = cdiv(B, GRU_NB);
+    __nv_bfloat16* dgi = (__nv_bfloat16*)(sc + g.s_dgi);
+    __nv_bfloat16* dgh = (__nv_bfloat16*)(sc + g.s_dgh);
+    float* dwih = (float*)(sc + g.s_dwih);
+    float* dwhh = (float*)(sc + g.s_dwhh);
+    float* dbi = (float*)(sc + g.s_dbi);
+    float* dbh = (float*)(sc + g.s_dbh);
+    for (int l = L - 1; l >= 0; --l) {
+        const int Iin = l == 0 ? s->I : 2 * H;
+        const int Ipad = g.Ipad[l];
+        gru_pack_whh_kernel<<<dim3(GRU_CL, 2), 256, 0, st>>>(p->w_hh[l][0], p->w_hh[l][1], (uint8_t*)(ws + g.whh[l]), (uint8_t*)(sc + g.s_whhT), H);
+        HOPK_LAUNCH_CHECK("gru_pack_whhT");
+        GruBwdArgs a;
+        a.dY = dy_cur; a.whhT = (const uint8_t*)(sc + g.s_whhT); a.Y = (const __nv_bfloat16*)(ws + g.y[l]);
+        a.R = (const float*)(ws + g.r[l]); a.Z = (const float*)(ws + g.z[l]); a.N = (const float*)(ws + g.n[l]); a.HN = (const float*)(ws + g.hn[l]);
+        a.dGi = dgi; a.dGh = dgh; a.B = B; a.T = T;
+        gru_bwd_kernel<<<2 * slices * GRU_CL, GRU_THREADS, gru_bwd_smem(), st>>>(a);
+        HOPK_LAUNCH_CHECK("gru_bwd");
+        const __nv_bfloat16* X = l == 0 ? (const __nv_bfloat16*)(ws + g.xb) : (const __nv_bfloat16*)(ws + g.y[l - 1]);
+        // dW_ih[2112][Ipad] = dGi^T . X   (contraction over the T*B rows: both operands MN-major)
+        if (int rc = gemm_bf16_launch(dgi, X, dwih, nullptr, nullptr, 2 * GRU_G, Ipad, TB, 2 * GRU_G, Ipad, Ipad, 1, 1, 0, 0, 0, 0.f, 2, st))
+            return rc;
+        // dW_hh[dir][1056][352] = dGh_dir^T . h_{t-1}: the stored outputs shifted by one time step (B rows), zero outside
+        for (int dir = 0; dir < 2; ++dir) {
+            if (int rc = gemm_bf16_launch(dgh + dir * GRU_G, (const __nv_bfloat16*)(ws + g.y[l]) + dir * GRU_HP, dwhh + (size_t)dir * GRU_G * GRU_HP,
+                                          nullptr, nullptr, GRU_G, GRU_HP, TB, 2 * GRU_G, 2 * GRU_HP, GRU_HP, 1, 1, 0, 0, 0, 0.f, 8, st,
+                                          nullptr, 0, dir ? B : -B))
+                return rc;
+        }
+        if (int rc = hopk_colsum(dgi, dbi, TB, 2 * GRU_G, 2 * GRU_G, 1, stream)) return rc;
+        if (int rc = hopk_colsum(dgh, dbh, TB, 2 * GRU_G, 2 * GRU_G, 1, stream)) return rc;
+        gru_unpack_grads_kernel<<<2 * 3 * H, 128, 0, st>>>(dwih, dwhh, dbi, dbh, gr->w_ih[l][0], gr->w_ih[l][1], gr->w_hh[l][0],
+                                                            gr->w_hh[l][1], gr->b_ih[l][0], gr->b_ih[l][1], gr->b_hh[l][0], gr->b_hh[l][1],
+                                                            l, s->I, Iin, H);
+        HOPK_LAUNCH_CHECK("gru_unpack_grads");
+        // dX[T*B][Ipad] = dGi . W_ih   (W_ih packed is [2112][Ipad] = [contraction][out]: B MN-major)
+        if (l > 0 || dx) {
+            if (int rc = gemm_bf16_launch(dgi, ws + g.wih[l], dy_next, nullptr, nullptr, TB, Ipad, 2 * GRU_G, 2 * GRU_G, Ipad, Ipad, 0, 1,
+                                          0, 0, 0, 0.f, 1, st)) return rc;
+            if (l == 0) {
+                gru_unpack_dx_kernel<<<grid_1d((size_t)TB * s->I), 256, 0, st>>>(dy_next, dx, B, T, s->I, Ipad);
+                HOPK_LAUNCH_CHECK("gru_unpack_dx");
+            }
+            float* tmp = dy_cur; dy_cur = dy_next; dy_next = tmp;
+        }
+    }
+    return 0;
+}

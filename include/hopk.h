@@ -138,8 +138,9 @@ int hopk_conv1x1_nchw_bwd(const float* x, const float* w, const float* dy, float
  * leading dimensions (elements) multiples of 8.  Default operand layout is "K-major" (A is [M][K], B is [N][K] row-major:
  * x @ W^T with nn.Linear's weight, HOP.py:130-134,200,202,262-265); HOPK_GEMM_A_MN / _B_MN say the operand is stored with
  * the contraction index as the row ([K][M] / [K][N]), which covers dX = dY @ W and dW = dY^T @ X without transposes.
- * C: fp32 (default) or bf16 (HOPK_GEMM_OUT_BF16), leading dimension ldc.  addend: optional fp32 [M][ldc].  splits > 1:
- * split-K with vector atomics into an fp32 C (cleared by the call unless HOPK_GEMM_ACCUMULATE). */
+ * C: fp32 (default) or bf16 (HOPK_GEMM_OUT_BF16), leading dimension ldc.  addend: optional fp32 [M][ldc] added before the
+ * activation.  mask: optional fp32 [M][ldc]; elements with mask <= 0 are written as 0 (gradient of a fused ReLU).
+ * splits > 1: split-K with vector atomics into an fp32 C (cleared by the call unless HOPK_GEMM_ACCUMULATE). */
 #define HOPK_GEMM_A_MN 1
 #define HOPK_GEMM_B_MN 2
 #define HOPK_GEMM_OUT_BF16 4
@@ -147,12 +148,38 @@ int hopk_conv1x1_nchw_bwd(const float* x, const float* w, const float* dy, float
 #define HOPK_GEMM_RELU 16
 #define HOPK_GEMM_LEAKY 32     /* LeakyReLU(slope) */
 #define HOPK_GEMM_GELU 64      /* exact (erf) GELU */
-int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, int M, int N, int K,
-                   long lda, long ldb, long ldc, int flags, float slope, int splits, void* stream);
+int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, const float* mask,
+                   int M, int N, int K, long lda, long ldb, long ldc, int flags, float slope, int splits, void* stream);
 /* fp32 (rows x cols, ld lds) -> bf16 (rows x cols_out, ld ldd), zero padding for cols <= c < cols_out, optional ReLU */
 int hopk_cast_bf16(const float* src, void* dst, long rows, int cols, long lds, int cols_out, long ldd, int relu, void* stream);
 /* out[c] = sum_r src[r][c] (bias gradients); src fp32 or bf16 */
 int hopk_colsum(const void* src, float* out, long rows, int cols, long ld, int src_bf16, void* stream);
+
+/* ------------------------------------------------------------------ GRU decoder (model/HOP.py:166-167, 248)
+ * Multi-layer bidirectional GRU, batch_first, zero initial state, PyTorch gate order (r, z, n); dtype-1 arithmetic (bf16
+ * tensor-core operands, fp32 accumulation and fp32 recurrent state).  Hidden size <= 352 (HOP: 350).
+ * Parameters are nn.GRU's own tensors: weight_ih_l{k}{_reverse} (3H, I_k), weight_hh (3H, H), bias_ih / bias_hh (3H);
+ * index [layer][direction].  I_0 = I, I_k = 2H. */
+#define HOPK_GRU_MAX_LAYERS 8
+typedef struct HopkGruShape {
+    int B, T, I, H, L;
+    int save;                    /* 1: keep what backward needs in the workspace; 0: inference / no-grad pass */
+} HopkGruShape;
+typedef struct HopkGruParams {
+    const float* w_ih[HOPK_GRU_MAX_LAYERS][2]; const float* w_hh[HOPK_GRU_MAX_LAYERS][2];
+    const float* b_ih[HOPK_GRU_MAX_LAYERS][2]; const float* b_hh[HOPK_GRU_MAX_LAYERS][2];
+} HopkGruParams;
+typedef struct HopkGruGrads {    /* same shapes as the parameters, overwritten */
+    float* w_ih[HOPK_GRU_MAX_LAYERS][2]; float* w_hh[HOPK_GRU_MAX_LAYERS][2];
+    float* b_ih[HOPK_GRU_MAX_LAYERS][2]; float* b_hh[HOPK_GRU_MAX_LAYERS][2];
+} HopkGruGrads;
+size_t hopk_gru_workspace_bytes(const HopkGruShape* s);
+size_t hopk_gru_scratch_bytes(const HopkGruShape* s);
+/* x: (B, T, I) fp32; out: (B, T, 2H) fp32 (forward | reverse halves, like nn.GRU); ws: workspace, kept until backward */
+int hopk_gru_forward(const HopkGruShape* s, const HopkGruParams* p, const float* x, float* out, void* ws, void* stream);
+/* dout: (B, T, 2H); dx: (B, T, I) or NULL */
+int hopk_gru_backward(const HopkGruShape* s, const HopkGruParams* p, const float* dout, void* ws, void* scratch,
+                      const HopkGruGrads* g, float* dx, void* stream);
 
 /* ------------------------------------------------------------------ reprogramming cross-attention
  * ReprogrammingLayer.reprogramming (model/HOP.py:289-299):

@@ -40,7 +40,7 @@ def main():
         flags = (_lib.GEMM_A_MN if a_mn else 0) | (_lib.GEMM_B_MN if b_mn else 0)
 
         def ours():
-            _lib.check(L.hopk_gemm_bf16(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), None, None, M, N, K, A.stride(0), B.stride(0),
+            _lib.check(L.hopk_gemm_bf16(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), None, None, None, M, N, K, A.stride(0), B.stride(0),
                                         C.stride(0), flags, 0.0, splits, _lib.stream_ptr()))
         Am = A[:, :M].t() if a_mn else A[:, :K]
         Bm = B[:, :N] if b_mn else B[:, :K].t()

@@ -24,7 +24,7 @@ def _gemm(A, B, M, N, K, a_mn=False, b_mn=False, bias=None, addend=None, out_bf1
         flags |= _lib.GEMM_ACCUMULATE
     else:
         C = torch.full((M, ldc), float('nan'), device=dev, dtype=torch.bfloat16 if out_bf16 else torch.float32)
-    _lib.check(L.hopk_gemm_bf16(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), _lib.ptr(bias), _lib.ptr(addend), M, N, K,
+    _lib.check(L.hopk_gemm_bf16(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), _lib.ptr(bias), _lib.ptr(addend), None, M, N, K,
                                 A.stride(0), B.stride(0), ldc, flags, float(slope), splits, _lib.stream_ptr()))
     torch.cuda.synchronize()
     return C[:, :N]
