@@ -32,7 +32,8 @@ template <int BN> constexpr uint32_t gt_stage_bytes() { return tc::slab_bytes(GT
 template <int BN> constexpr size_t gt_smem_bytes() { return (size_t)gt_stages<BN>() * gt_stage_bytes<BN>() + 1024 + 256; }
 
 struct GtArgs {
-    void* C; const float* bias; const void* addend; const float* mask;
+    void* C; const float* bias; const void* addend; const void* mask;
+    int bias_row, mask_bf16;                            // bias indexed by the output row m instead of the column n; mask stored as bf16
     int a_kshift, b_kshift;                             // added to the contraction (row) coordinate of an MN-major operand; rows
                                                         // that fall outside the matrix read as zero (TMA out-of-bounds fill)
     int M, N, K;
@@ -172,8 +173,14 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (m < g.M) {
                     const bool fullw = nb + 32 <= g.N;
                     if (g.bias && first_split) {
+                        if (g.bias_row) {
+                            const float bm = __ldg(g.bias + m);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] += __ldg(g.bias + nb + j);
+                            for (int j = 0; j < 32; ++j) v[j] += bm;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] += __ldg(g.bias + nb + j);
+                        }
                     }
                     if (g.addend && first_split) {                                // fp32 residual / accumulate-from tensor with C's layout
                         const float* ad = reinterpret_cast<const float*>(g.addend) + (size_t)m * g.ldc + nb;
@@ -184,10 +191,16 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gt_act(v[j], g.act, g.slope);
                     }
-                    if (g.mask) {                                  // out = mask > 0 ? out : 0 (gradient of a fused ReLU)
-                        const float* mk = g.mask + (size_t)m * g.ldc + nb;
+                    if (g.mask) {                                  // out *= mask > 0 ? 1 : slope  (gradient of a fused (Leaky)ReLU)
+                        if (g.mask_bf16) {
+                            const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(g.mask) + (size_t)m * g.ldc + nb;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] = __ldg(mk + j) > 0.f ? v[j] : 0.f;
+                            for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] = __bfloat162float(mk[j]) > 0.f ? v[j] : g.slope * v[j];
+                        } else {
+                            const float* mk = reinterpret_cast<const float*>(g.mask) + (size_t)m * g.ldc + nb;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] = __ldg(mk + j) > 0.f ? v[j] : g.slope * v[j];
+                        }
                     }
                     if (g.out_bf16) {
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + (size_t)m * g.ldc + nb;
@@ -216,6 +229,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         } else if (fullw && ((reinterpret_cast<uintptr_t>(dst) & 31) == 0)) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) tc::stg256(dst + j, v + j);
+                        } else if (fullw && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {      // rows that are only 8-byte aligned
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[j], v[j + 1]);
                         } else {
                             for (int j = 0; j < 32 && nb + j < g.N; ++j) dst[j] = v[j];
                         }
@@ -257,6 +273,24 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
         uint4 q;
         q.x = tc::pack_bf16x2(f[0], f[1]); q.y = tc::pack_bf16x2(f[2], f[3]); q.z = tc::pack_bf16x2(f[4], f[5]); q.w = tc::pack_bf16x2(f[6], f[7]);
         *reinterpret_cast<uint4*>(dst + r * ldd + c) = q;
+    }
+}
+
+// overlapping windows of a 1-D signal as a bf16 matrix: out[(b*nwin + k)][c] = x[b][k*hop + c]  (Tensor.unfold + cast)
+__global__ void unfold_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int nwin, int win, int hop,
+                                   long ldx, long ldo)
+{
+    const long n = (long)B * nwin * (ldo / 8);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / (ldo / 8); const int c = (int)(i - r * (ldo / 8)) * 8;
+        const int b = (int)(r / nwin), k = (int)(r % nwin);
+        const float* s = x + (long)b * ldx + (long)k * hop + c;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = c + j < win ? __ldg(s + j) : 0.f;
+        uint4 q;
+        q.x = tc::pack_bf16x2(f[0], f[1]); q.y = tc::pack_bf16x2(f[2], f[3]); q.z = tc::pack_bf16x2(f[4], f[5]); q.w = tc::pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(out + r * ldo + c) = q;
     }
 }
 
@@ -312,7 +346,7 @@ static int make_map(CUtensorMap* tm, const void* base, long rows, long cols, lon
 
 int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, const void* addend, int M, int N, int K, long lda,
                      long ldb, long ldc, int a_mn, int b_mn, int out_bf16, int accumulate, int act, float slope, int splits,
-                     cudaStream_t st, const float* mask, int a_kshift, int b_kshift)
+                     cudaStream_t st, const void* mask, int a_kshift, int b_kshift, int bias_row, int mask_bf16)
 {
     HOPK_REQUIRE((a_kshift == 0 || a_mn) && (b_kshift == 0 || b_mn), "a row shift needs an MN-major operand");
     HOPK_REQUIRE(!(mask && (accumulate || splits > 1)), "a mask cannot be combined with accumulation / split-K");
@@ -328,7 +362,7 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     const int BN = wide ? 256 : 128;
     if (int rc = b_mn ? make_map(&tmB, B, K, N, ldb, GT_BK) : make_map(&tmB, B, N, K, ldb, BN)) return rc;
     GtArgs g;
-    g.C = C; g.bias = bias; g.addend = addend; g.mask = mask; g.a_kshift = a_kshift; g.b_kshift = b_kshift; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
+    g.C = C; g.bias = bias; g.addend = addend; g.mask = mask; g.bias_row = bias_row; g.mask_bf16 = mask_bf16; g.a_kshift = a_kshift; g.b_kshift = b_kshift; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
     g.out_bf16 = out_bf16; g.accumulate = accumulate; g.act = act; g.slope = slope;
     if (splits < 1) splits = 1;
     int kper = ((cdiv(K, splits) + GT_BK - 1) / GT_BK) * GT_BK;
@@ -356,13 +390,14 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
 
 using namespace hopk;
 
-extern "C" int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, const float* mask,
+extern "C" int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, const void* mask,
                               int M, int N, int K, long lda, long ldb, long ldc, int flags, float slope, int splits, void* stream)
 {
     const int a_mn = (flags & HOPK_GEMM_A_MN) ? 1 : 0, b_mn = (flags & HOPK_GEMM_B_MN) ? 1 : 0;
     const int act = (flags & HOPK_GEMM_RELU) ? 1 : (flags & HOPK_GEMM_LEAKY) ? 2 : (flags & HOPK_GEMM_GELU) ? 3 : 0;
     return gemm_bf16_launch(A, B, C, bias, addend, M, N, K, lda, ldb, ldc, a_mn, b_mn, (flags & HOPK_GEMM_OUT_BF16) ? 1 : 0,
-                            (flags & HOPK_GEMM_ACCUMULATE) ? 1 : 0, act, slope, splits, (cudaStream_t)stream, mask, 0, 0);
+                            (flags & HOPK_GEMM_ACCUMULATE) ? 1 : 0, act, slope, splits, (cudaStream_t)stream, mask, 0, 0,
+                            (flags & HOPK_GEMM_BIAS_ROW) ? 1 : 0, (flags & HOPK_GEMM_MASK_BF16) ? 1 : 0);
 }
 
 extern "C" int hopk_cast_bf16(const float* src, void* dst, long rows, int cols, long lds, int cols_out, long ldd, int relu, void* stream)
@@ -373,6 +408,18 @@ extern "C" int hopk_cast_bf16(const float* src, void* dst, long rows, int cols, 
     if (blocks > 148 * 16) blocks = 148 * 16;
     cast_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, rows, cols, lds, cols_out, ldd, relu);
     HOPK_LAUNCH_CHECK("cast_bf16");
+    return 0;
+}
+
+extern "C" int hopk_unfold_bf16(const float* x, void* out, int B, int nwin, int win, int hop, long ldx, long ldo, void* stream)
+{
+    HOPK_REQUIRE(B > 0 && nwin > 0 && win > 0 && hop > 0 && ldo % 8 == 0 && ldo >= win, "unfold_bf16 sizes (ldo multiple of 8, >= win)");
+    HOPK_REQUIRE((long)(nwin - 1) * hop + win <= ldx, "unfold_bf16: windows exceed the signal length");
+    const long n = (long)B * nwin * (ldo / 8);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    unfold_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, B, nwin, win, hop, ldx, ldo);
+    HOPK_LAUNCH_CHECK("unfold_bf16");
     return 0;
 }
 

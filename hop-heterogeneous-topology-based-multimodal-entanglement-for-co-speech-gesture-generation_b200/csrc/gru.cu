@@ -49,8 +49,6 @@ constexpr uint32_t GRU_BA_BYTES = GRU_BA_NSLAB * GRU_BA_SLAB;               // 1
 constexpr uint32_t GRU_BB_BYTES = GRU_BA_NSLAB * GRU_B_SLAB;                // 34816 per buffer
 constexpr int GRU_XLD = GRU_NB + 1;                                         // fp32 pitch of the TMEM -> thread exchange tile
 
-constexpr size_t gru_fwd_smem() { return GRU_FA_BYTES + 2 * GRU_FB_BYTES + 132 * GRU_XLD * 4 + 1024; }
-constexpr size_t gru_bwd_smem() { return GRU_BA_BYTES + 2 * GRU_BB_BYTES + 64 * GRU_XLD * 4 + 1024; }
 
 // ---------------------------------------------------------------- cluster primitives
 __device__ __forceinline__ uint32_t cluster_ctarank()
@@ -88,6 +86,30 @@ __device__ __forceinline__ uint32_t bop_off(int gb, int k)
     return (uint32_t)(k >> 6) * GRU_B_SLAB + (uint32_t)gb * 128u + (uint32_t)((((k & 63) >> 3) ^ (gb & 7)) << 4) + (uint32_t)(k & 7) * 2u;
 }
 
+// ---------------------------------------------------------------- warp roles and CTA-level synchronisation
+// warps 0-5  gate warps (176 gate threads = (sample, group of 4 units); warps 0-3 also drain TMEM): on-chip work only
+// warps 6-7  I/O warps: every global load / store of the step, through shared-memory staging, so that the threads that
+//            execute the cluster-scope fences (MEMBAR.ALL.GPU in SASS) never have global traffic in flight
+// warp 8     MMA issuer
+constexpr int GRU_IO_T0 = 192, GRU_IO_THREADS = 64;
+constexpr int GRU_BAR_IN = 1, GRU_BAR_OUT = 2;          // named barriers: step inputs staged / step results staged (256 threads)
+constexpr int GRU_ROW4 = GRU_UNITS / 4;                 // 11 groups of 4 units per sample row
+constexpr int GRU_TILE4 = GRU_NB * GRU_ROW4;            // 176 float4 per staged array
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_cluster() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// K-major descriptor of a slab at `addr`; advancing the start address by `bytes` adds bytes >> 4 to the low word
+__device__ __forceinline__ uint64_t desc_base(uint32_t addr) { return tc::desc_kmajor(addr, 0); }
+__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
 // ---------------------------------------------------------------- forward recurrence
 struct GruFwdArgs {
     const float* Gi;            // [T*B][2*1056]: input projections + b_ih (+ b_hr, b_hz)
@@ -99,6 +121,11 @@ struct GruFwdArgs {
     int B, T, H;
 };
 
+constexpr size_t GRU_F_XCHG = 132 * GRU_XLD * 4;                           // 8976
+constexpr size_t GRU_F_SIN = 3 * GRU_TILE4 * 16;                           // staged gi_r | gi_z | gi_n       8448
+constexpr size_t GRU_F_SOUT = 5 * GRU_TILE4 * 16;                          // staged h | r | z | n | hn      14080
+constexpr size_t gru_fwd_smem() { return GRU_FA_BYTES + 2 * GRU_FB_BYTES + GRU_F_XCHG + 16 + GRU_F_SIN + GRU_F_SOUT + 1024; }
+
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(const GruFwdArgs a)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -108,6 +135,8 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     uint8_t* sA = smem;
     uint8_t* sB = smem + GRU_FA_BYTES;
     float* xchg = reinterpret_cast<float*>(sB + 2 * GRU_FB_BYTES);
+    float4* sin4 = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(xchg) + ((GRU_F_XCHG + 15) & ~size_t(15)));
+    float4* sout4 = sin4 + 3 * GRU_TILE4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int cl = blockIdx.x / GRU_CL;
@@ -133,126 +162,167 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     cluster_arrive();
     cluster_wait();                                   // every CTA's operand buffers are initialised before a peer writes into them
 
-    const bool gate_thr = tid < GRU_GATE_THREADS;
-    const int gb = tid & 15, grp = tid >> 4;
-    const int b = b0 + gb;
-    const bool act = gate_thr && b < B;
-    const int ju = (int)rank * GRU_UNITS + grp * 4;   // first of this thread's 4 hidden units (padded index)
-    float h[4] = {0.f, 0.f, 0.f, 0.f};
-    float4 bhn = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t raddr[GRU_CL];
-    if (gate_thr) {
-        const uint32_t local = tc::smem_u32(sB) + bop_off(gb, ju);
-#pragma unroll
-        for (int r = 0; r < GRU_CL; ++r) raddr[r] = mapa(local, (uint32_t)r);
-        bhn = __ldg(reinterpret_cast<const float4*>(a.bhn + dir * GRU_HP + ju));
-    }
-    float4 gi_r = make_float4(0.f, 0.f, 0.f, 0.f), gi_z = gi_r, gi_n = gi_r;
-    if (act) {
-        const int t0 = dir ? T - 1 : 0;
-        const float* p = a.Gi + ((size_t)t0 * B + b) * (2 * GRU_G) + dir * GRU_G + ju;
-        gi_r = __ldg(reinterpret_cast<const float4*>(p));
-        gi_z = __ldg(reinterpret_cast<const float4*>(p + GRU_HP));
-        gi_n = __ldg(reinterpret_cast<const float4*>(p + 2 * GRU_HP));
-    }
-    uint32_t mphase = 0;
+    if (warp == 8) {
+        // ============================================================ MMA issuer
+        const uint64_t dA = desc_base(tc::smem_u32(sA));
+        const uint64_t dB0 = desc_base(tc::smem_u32(sB)), dB1 = desc_base(tc::smem_u32(sB) + GRU_FB_BYTES);
+        constexpr uint32_t idesc = tc::idesc_bf16(128, GRU_NB, 0, 0);
+        tc::mbar_wait(&wbar, 0);                      // W_hh slice resident
 #pragma unroll 1
-    for (int step = 0; step < T; ++step) {
-        const int t = dir ? T - 1 - step : step;
-        const int cur = step & 1;
-        // ---- D[gate row][sample] = W_slice . h_{t-1}^T on the tensor core
-        if (warp == 8) {
-            if (lane == 0) {
-                if (step == 0) tc::mbar_wait(&wbar, 0);
-                fence_proxy_async_all();
-                tc::fence_after_sync();
-                constexpr uint32_t idesc = tc::idesc_bf16(128, GRU_NB, 0, 0);
-                const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB) + cur * GRU_FB_BYTES;
-#pragma unroll 2
+        for (int step = 0; step < T; ++step) {
+            tc::fence_after_sync();
+            if (elect_one()) {
+                const uint64_t dB = (step & 1) ? dB1 : dB0;
+#pragma unroll
                 for (int kt = 0; kt < GRU_HP / 16; ++kt) {
-                    const uint32_t sa = a_base + (kt >> 2) * GRU_FA_SLAB, sb = b_base + (kt >> 2) * GRU_B_SLAB;
-                    const uint64_t db = tc::desc_kmajor(sb, kt & 3);
-                    tc::mma_bf16(tmem, tc::desc_kmajor(sa, kt & 3), db, idesc, kt != 0);                        // gate rows 0..127
-                    tc::mma_bf16(tmem + 16, tc::desc_kmajor(sa + 128 * 128, kt & 3), db, idesc, kt != 0);       // gate rows 128..131
+                    const uint64_t da = desc_adv(dA, (kt >> 2) * GRU_FA_SLAB + (kt & 3) * 32);
+                    const uint64_t db = desc_adv(dB, (kt >> 2) * GRU_B_SLAB + (kt & 3) * 32);
+                    tc::mma_bf16(tmem, da, db, idesc, kt != 0);                                  // gate rows 0..127
+                    tc::mma_bf16(tmem + 16, desc_adv(da, 128 * 128), db, idesc, kt != 0);        // gate rows 128..131
                 }
                 tc::mma_commit(&mbar);
             }
             __syncwarp();
+            cluster_arrive_relaxed();
+            cluster_wait();                           // h_t of every CTA has landed in the operand buffer of step + 1
         }
-        tc::mbar_wait(&mbar, mphase);
-        mphase ^= 1;
-        tc::fence_after_sync();
-        if (warp < 4) {
-            float v[16];
-            tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
-            float* dst = xchg + (warp * 32 + lane) * GRU_XLD;
+    } else if (warp >= 6) {
+        // ============================================================ I/O warps: global <-> staging
+        const int it = tid - GRU_IO_T0;
+        float4 g[3][3];                               // up to 3 float4 per thread per array (176 float4 over 64 threads)
+        auto load_gi = [&](int t) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dst[j] = v[j];
-            if (warp == 0) {
-                tc::tmem_ld16(tmem + 16, v);
-                if (lane < 4) {
-                    float* d2 = xchg + (128 + lane) * GRU_XLD;
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                const int gb = i / GRU_ROW4, grp = i - gb * GRU_ROW4;
+                const bool ok = i < GRU_TILE4 && b0 + gb < B;
+                const float* p = a.Gi + ((size_t)t * B + (b0 + gb)) * (2 * GRU_G) + dir * GRU_G + (int)rank * GRU_UNITS + grp * 4;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) d2[j] = v[j];
+                for (int q = 0; q < 3; ++q) g[q][k] = ok ? __ldg(reinterpret_cast<const float4*>(p + q * GRU_HP)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto stage_gi = [&]() {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                if (i < GRU_TILE4) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) sin4[q * GRU_TILE4 + i] = g[q][k];
                 }
             }
-            tc::fence_before_sync();
+        };
+        load_gi(dir ? T - 1 : 0);
+        stage_gi();
+        bar_arrive(GRU_BAR_IN, 256);
+#pragma unroll 1
+        for (int step = 0; step < T; ++step) {
+            const int t = dir ? T - 1 - step : step;
+            cluster_arrive_relaxed();
+            if (step + 1 < T) load_gi(dir ? t - 1 : t + 1);                  // in flight while the gate warps work
+            bar_sync(GRU_BAR_OUT, 256);                                       // results of this step staged
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                const int gb = i / GRU_ROW4, grp = i - gb * GRU_ROW4;
+                if (i < GRU_TILE4 && b0 + gb < B) {
+                    const int b = b0 + gb, ju = (int)rank * GRU_UNITS + grp * 4;
+                    const size_t o = ((size_t)t * B + b) * (2 * GRU_HP) + dir * GRU_HP + ju;
+                    const float4 h = sout4[i];
+                    uint2 hb;
+                    hb.x = tc::pack_bf16x2(h.x, h.y); hb.y = tc::pack_bf16x2(h.z, h.w);
+                    *reinterpret_cast<uint2*>(a.Y + o) = hb;
+                    if (a.R) {
+                        *reinterpret_cast<float4*>(a.R + o) = sout4[GRU_TILE4 + i];
+                        *reinterpret_cast<float4*>(a.Z + o) = sout4[2 * GRU_TILE4 + i];
+                        *reinterpret_cast<float4*>(a.N + o) = sout4[3 * GRU_TILE4 + i];
+                        *reinterpret_cast<float4*>(a.HN + o) = sout4[4 * GRU_TILE4 + i];
+                    }
+                    if (a.out) {
+                        float* po = a.out + ((size_t)b * T + t) * (2 * a.H) + dir * a.H + ju;
+                        const float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) if (ju + e < a.H) po[e] = hv[e];
+                    }
+                }
+            }
+            if (step + 1 < T) stage_gi();
+            bar_arrive(GRU_BAR_IN, 256);                                      // inputs of step + 1 staged (and the results tile is free)
+            cluster_wait();
         }
-        __syncthreads();
-        // ---- gates (fp32), new h
-        float rr[4], zz[4], nn[4], hn[4];
+    } else {
+        // ============================================================ gate warps
+        const bool gate_thr = tid < GRU_GATE_THREADS;
+        const int gb = tid & 15, grp = tid >> 4;
+        const bool act = gate_thr && b0 + gb < B;
+        const int ju = (int)rank * GRU_UNITS + grp * 4;   // first of this thread's 4 hidden units (padded index)
+        const int si = gb * GRU_ROW4 + grp;               // this thread's float4 slot in a staged array
+        float h[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 bhn = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t raddr[GRU_CL];
         if (gate_thr) {
-            const float gir[4] = {gi_r.x, gi_r.y, gi_r.z, gi_r.w}, giz[4] = {gi_z.x, gi_z.y, gi_z.z, gi_z.w};
-            const float gin[4] = {gi_n.x, gi_n.y, gi_n.z, gi_n.w}, bh[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
+            const uint32_t local = tc::smem_u32(sB) + bop_off(gb, ju);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float gr = xchg[(grp * 4 + i) * GRU_XLD + gb];
-                const float gz = xchg[(GRU_UNITS + grp * 4 + i) * GRU_XLD + gb];
-                const float gn = xchg[(2 * GRU_UNITS + grp * 4 + i) * GRU_XLD + gb];
-                rr[i] = sigmoid_approx(gir[i] + gr);
-                zz[i] = sigmoid_approx(giz[i] + gz);
-                hn[i] = gn + bh[i];
-                nn[i] = tanh_approx(fmaf(rr[i], hn[i], gin[i]));
-                h[i] = act ? fmaf(zz[i], h[i] - nn[i], nn[i]) : 0.f;            // (1 - z) n + z h
-            }
-            if (step + 1 < T) {                                                 // h_t into every CTA's operand buffer of step + 1
-                const uint32_t lo = tc::pack_bf16x2(h[0], h[1]), hi = tc::pack_bf16x2(h[2], h[3]);
-                const uint32_t boff = (cur ^ 1) * GRU_FB_BYTES;
-#pragma unroll
-                for (int r = 0; r < GRU_CL; ++r) st_cluster_v2(raddr[r] + boff, lo, hi);
-            }
+            for (int r = 0; r < GRU_CL; ++r) raddr[r] = mapa(local, (uint32_t)r);
+            bhn = __ldg(reinterpret_cast<const float4*>(a.bhn + dir * GRU_HP + ju));
         }
-        fence_proxy_async_all();
-        __syncwarp();
-        cluster_arrive();
-        // ---- results to global memory and next step's input projections while the barrier completes
-        if (act) {
-            const size_t row = (size_t)t * B + b;
-            const size_t o = row * (2 * GRU_HP) + dir * GRU_HP + ju;
-            uint2 hb;
-            hb.x = tc::pack_bf16x2(h[0], h[1]); hb.y = tc::pack_bf16x2(h[2], h[3]);
-            *reinterpret_cast<uint2*>(a.Y + o) = hb;
-            if (a.R) {
-                *reinterpret_cast<float4*>(a.R + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
-                *reinterpret_cast<float4*>(a.Z + o) = make_float4(zz[0], zz[1], zz[2], zz[3]);
-                *reinterpret_cast<float4*>(a.N + o) = make_float4(nn[0], nn[1], nn[2], nn[3]);
-                *reinterpret_cast<float4*>(a.HN + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            }
-            if (a.out) {
-                float* po = a.out + ((size_t)b * T + t) * (2 * a.H) + dir * a.H + ju;
+        uint32_t mphase = 0;
+#pragma unroll 1
+        for (int step = 0; step < T; ++step) {
+            const int cur = step & 1;
+            tc::mbar_wait(&mbar, mphase);
+            mphase ^= 1;
+            tc::fence_after_sync();
+            if (warp < 4) {
+                float v[16];
+                tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+                float* dst = xchg + (warp * 32 + lane) * GRU_XLD;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) if (ju + i < a.H) po[i] = h[i];
+                for (int j = 0; j < 16; ++j) dst[j] = v[j];
+                if (warp == 0) {
+                    tc::tmem_ld16(tmem + 16, v);
+                    if (lane < 4) {
+                        float* d2 = xchg + (128 + lane) * GRU_XLD;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) d2[j] = v[j];
+                    }
+                }
+                tc::fence_before_sync();
             }
-            if (step + 1 < T) {
-                const int tn = dir ? t - 1 : t + 1;
-                const float* p = a.Gi + ((size_t)tn * B + b) * (2 * GRU_G) + dir * GRU_G + ju;
-                gi_r = __ldg(reinterpret_cast<const float4*>(p));
-                gi_z = __ldg(reinterpret_cast<const float4*>(p + GRU_HP));
-                gi_n = __ldg(reinterpret_cast<const float4*>(p + 2 * GRU_HP));
+            bar_sync(GRU_BAR_IN, 256);                    // exchange tile complete + this step's input projections staged
+            if (gate_thr) {
+                const float4 g_r = sin4[si], g_z = sin4[GRU_TILE4 + si], g_n = sin4[2 * GRU_TILE4 + si];
+                const float gir[4] = {g_r.x, g_r.y, g_r.z, g_r.w}, giz[4] = {g_z.x, g_z.y, g_z.z, g_z.w};
+                const float gin[4] = {g_n.x, g_n.y, g_n.z, g_n.w}, bh[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
+                float rr[4], zz[4], nn[4], hn[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float gr = xchg[(grp * 4 + i) * GRU_XLD + gb];
+                    const float gz = xchg[(GRU_UNITS + grp * 4 + i) * GRU_XLD + gb];
+                    const float gn = xchg[(2 * GRU_UNITS + grp * 4 + i) * GRU_XLD + gb];
+                    rr[i] = sigmoid_approx(gir[i] + gr);
+                    zz[i] = sigmoid_approx(giz[i] + gz);
+                    hn[i] = gn + bh[i];
+                    nn[i] = tanh_approx(fmaf(rr[i], hn[i], gin[i]));
+                    h[i] = act ? fmaf(zz[i], h[i] - nn[i], nn[i]) : 0.f;            // (1 - z) n + z h
+                }
+                if (step + 1 < T) {                                                 // h_t into every CTA's operand buffer of step + 1
+                    const uint32_t lo = tc::pack_bf16x2(h[0], h[1]), hi = tc::pack_bf16x2(h[2], h[3]);
+                    const uint32_t boff = (cur ^ 1) * GRU_FB_BYTES;
+#pragma unroll
+                    for (int r = 0; r < GRU_CL; ++r) st_cluster_v2(raddr[r] + boff, lo, hi);
+                }
+                sout4[si] = make_float4(h[0], h[1], h[2], h[3]);
+                sout4[GRU_TILE4 + si] = make_float4(rr[0], rr[1], rr[2], rr[3]);
+                sout4[2 * GRU_TILE4 + si] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+                sout4[3 * GRU_TILE4 + si] = make_float4(nn[0], nn[1], nn[2], nn[3]);
+                sout4[4 * GRU_TILE4 + si] = make_float4(hn[0], hn[1], hn[2], hn[3]);
             }
+            __syncwarp();
+            bar_arrive(GRU_BAR_OUT, 256);                 // the I/O warps take it from here
+            fence_proxy_async_cluster();                  // remote operand writes -> visible to the peers' tensor cores
+            cluster_arrive();
+            cluster_wait();
         }
-        __syncwarp();
-        cluster_wait();
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -270,6 +340,11 @@ struct GruBwdArgs {
     int B, T;
 };
 
+constexpr size_t GRU_B_XCHG = 64 * GRU_XLD * 4;                            // 4352
+constexpr size_t GRU_B_SIN = 5 * GRU_TILE4 * 16 + GRU_TILE4 * 8;           // staged r | z | n | hn | dy (fp32) + h_prev (bf16 x 4)
+constexpr size_t GRU_B_SOUT = 4 * GRU_TILE4 * 8;                           // staged dg_r | dg_z | dg_n(input) | dg_n(hidden), bf16 x 4
+constexpr size_t gru_bwd_smem() { return GRU_BA_BYTES + 2 * GRU_BB_BYTES + GRU_B_XCHG + GRU_B_SIN + GRU_B_SOUT + 1024; }
+
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdArgs a)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -279,6 +354,9 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     uint8_t* sA = smem;
     uint8_t* sB = smem + GRU_BA_BYTES;
     float* xchg = reinterpret_cast<float*>(sB + 2 * GRU_BB_BYTES);
+    float4* sin4 = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(xchg) + GRU_B_XCHG);
+    uint2* shp = reinterpret_cast<uint2*>(sin4 + 5 * GRU_TILE4);
+    uint2* sout2 = shp + GRU_TILE4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int cl = blockIdx.x / GRU_CL;
@@ -304,107 +382,159 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     cluster_arrive();
     cluster_wait();
 
-    const bool gate_thr = tid < GRU_GATE_THREADS;
-    const int gb = tid & 15, grp = tid >> 4;
-    const int b = b0 + gb;
-    const bool act = gate_thr && b < B;
-    const int ju = (int)rank * GRU_UNITS + grp * 4;
-    uint32_t loff[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) loff[q] = tc::smem_u32(sB) + bop_off(gb, q * GRU_HP + ju);
-    float carry[4] = {0.f, 0.f, 0.f, 0.f};             // dh * z of the step before (direct path to h_{t-1})
-    uint32_t mphase = 0;
+    if (warp == 8) {
+        // ============================================================ MMA issuer: (dGh of the step before) . W_hh -> D[unit k][sample]
+        const uint64_t dA = desc_base(tc::smem_u32(sA));
+        const uint64_t dB0 = desc_base(tc::smem_u32(sB)), dB1 = desc_base(tc::smem_u32(sB) + GRU_BB_BYTES);
+        constexpr uint32_t idesc = tc::idesc_bf16(128, GRU_NB, 0, 0);
+        tc::mbar_wait(&wbar, 0);
 #pragma unroll 1
-    for (int step = 0; step < T; ++step) {
-        const int t = dir ? step : T - 1 - step;       // reverse of the forward order
-        const int cur = step & 1;
-        // ---- (dGh of the step before) . W_hh  ->  D[unit k][sample]
-        if (warp == 8) {
-            if (lane == 0) {
-                if (step == 0) tc::mbar_wait(&wbar, 0);
-                fence_proxy_async_all();
-                tc::fence_after_sync();
-                constexpr uint32_t idesc = tc::idesc_bf16(128, GRU_NB, 0, 0);
-                const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB) + cur * GRU_BB_BYTES;
-#pragma unroll 2
-                for (int kt = 0; kt < GRU_G / 16; ++kt) {
-                    const uint32_t sa = a_base + (kt >> 2) * GRU_BA_SLAB, sb = b_base + (kt >> 2) * GRU_B_SLAB;
-                    tc::mma_bf16(tmem, tc::desc_kmajor(sa, kt & 3), tc::desc_kmajor(sb, kt & 3), idesc, kt != 0);
-                }
+        for (int step = 0; step < T; ++step) {
+            tc::fence_after_sync();
+            if (elect_one()) {
+                const uint64_t dB = (step & 1) ? dB1 : dB0;
+#pragma unroll
+                for (int kt = 0; kt < GRU_G / 16; ++kt)
+                    tc::mma_bf16(tmem, desc_adv(dA, (kt >> 2) * GRU_BA_SLAB + (kt & 3) * 32), desc_adv(dB, (kt >> 2) * GRU_B_SLAB + (kt & 3) * 32),
+                                 idesc, kt != 0);
                 tc::mma_commit(&mbar);
             }
             __syncwarp();
+            cluster_arrive_relaxed();
+            cluster_wait();
         }
-        // ---- this step's saved values (in flight while the MMA runs)
-        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), z4 = r4, n4 = r4, hn4 = r4, dy4 = r4;
-        uint2 hp = make_uint2(0u, 0u);
-        if (act) {
-            const size_t o = ((size_t)t * B + b) * (2 * GRU_HP) + dir * GRU_HP + ju;
-            r4 = __ldg(reinterpret_cast<const float4*>(a.R + o));
-            z4 = __ldg(reinterpret_cast<const float4*>(a.Z + o));
-            n4 = __ldg(reinterpret_cast<const float4*>(a.N + o));
-            hn4 = __ldg(reinterpret_cast<const float4*>(a.HN + o));
-            dy4 = __ldg(reinterpret_cast<const float4*>(a.dY + o));
-            const int tp = dir ? t + 1 : t - 1;        // the time step whose output was this step's h_{t-1}
-            if (tp >= 0 && tp < T) hp = __ldg(reinterpret_cast<const uint2*>(a.Y + ((size_t)tp * B + b) * (2 * GRU_HP) + dir * GRU_HP + ju));
-        }
-        tc::mbar_wait(&mbar, mphase);
-        mphase ^= 1;
-        tc::fence_after_sync();
-        if (warp < 2) {
-            float v[16];
-            tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
-            float* dst = xchg + (warp * 32 + lane) * GRU_XLD;
+    } else if (warp >= 6) {
+        // ============================================================ I/O warps
+        const int it = tid - GRU_IO_T0;
+        float4 g[5][3];
+        uint2 hp[3];
+        auto load_in = [&](int t) {
+            const int tp = dir ? t + 1 : t - 1;          // the time step whose output was this step's h_{t-1}
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dst[j] = v[j];
-            tc::fence_before_sync();
-        }
-        __syncthreads();
-        float dgr[4], dgz[4], dgni[4], dgnh[4];
-        if (gate_thr) {
-            const float r[4] = {r4.x, r4.y, r4.z, r4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w}, n[4] = {n4.x, n4.y, n4.z, n4.w};
-            const float hn[4] = {hn4.x, hn4.y, hn4.z, hn4.w}, dy[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
-            const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hp.x), h23 = *reinterpret_cast<const __nv_bfloat162*>(&hp.y);
-            const float hprev[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float dh = act ? dy[i] + carry[i] + xchg[(grp * 4 + i) * GRU_XLD + gb] : 0.f;
-                const float dn = dh * (1.f - z[i]);
-                const float dz = dh * (hprev[i] - n[i]);
-                const float dnp = dn * (1.f - n[i] * n[i]);
-                dgni[i] = dnp;
-                dgnh[i] = dnp * r[i];
-                dgr[i] = dnp * hn[i] * r[i] * (1.f - r[i]);
-                dgz[i] = dz * z[i] * (1.f - z[i]);
-                carry[i] = dh * z[i];
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                const int gb = i / GRU_ROW4, grp = i - gb * GRU_ROW4;
+                const bool ok = i < GRU_TILE4 && b0 + gb < B;
+                const size_t col = dir * GRU_HP + (int)rank * GRU_UNITS + grp * 4;
+                const size_t o = ((size_t)t * B + (b0 + gb)) * (2 * GRU_HP) + col;
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                g[0][k] = ok ? __ldg(reinterpret_cast<const float4*>(a.R + o)) : zero;
+                g[1][k] = ok ? __ldg(reinterpret_cast<const float4*>(a.Z + o)) : zero;
+                g[2][k] = ok ? __ldg(reinterpret_cast<const float4*>(a.N + o)) : zero;
+                g[3][k] = ok ? __ldg(reinterpret_cast<const float4*>(a.HN + o)) : zero;
+                g[4][k] = ok ? __ldg(reinterpret_cast<const float4*>(a.dY + o)) : zero;
+                hp[k] = (ok && tp >= 0 && tp < T) ? __ldg(reinterpret_cast<const uint2*>(a.Y + ((size_t)tp * B + (b0 + gb)) * (2 * GRU_HP) + col))
+                                                  : make_uint2(0u, 0u);
             }
-            if (step + 1 < T) {
-                const uint32_t boff = (cur ^ 1) * GRU_BB_BYTES;
-                const uint32_t w0[3] = {tc::pack_bf16x2(dgr[0], dgr[1]), tc::pack_bf16x2(dgz[0], dgz[1]), tc::pack_bf16x2(dgnh[0], dgnh[1])};
-                const uint32_t w1[3] = {tc::pack_bf16x2(dgr[2], dgr[3]), tc::pack_bf16x2(dgz[2], dgz[3]), tc::pack_bf16x2(dgnh[2], dgnh[3])};
+        };
+        auto stage_in = [&]() {
 #pragma unroll
-                for (int q = 0; q < 3; ++q)
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                if (i < GRU_TILE4) {
 #pragma unroll
-                    for (int rk = 0; rk < GRU_CL; ++rk) st_cluster_v2(mapa(loff[q], (uint32_t)rk) + boff, w0[q], w1[q]);
+                    for (int q = 0; q < 5; ++q) sin4[q * GRU_TILE4 + i] = g[q][k];
+                    shp[i] = hp[k];
+                }
             }
+        };
+        load_in(dir ? 0 : T - 1);
+        stage_in();
+        bar_arrive(GRU_BAR_IN, 256);
+#pragma unroll 1
+        for (int step = 0; step < T; ++step) {
+            const int t = dir ? step : T - 1 - step;     // reverse of the forward order
+            cluster_arrive_relaxed();
+            if (step + 1 < T) load_in(dir ? t + 1 : t - 1);
+            bar_sync(GRU_BAR_OUT, 256);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                const int gb = i / GRU_ROW4, grp = i - gb * GRU_ROW4;
+                if (i < GRU_TILE4 && b0 + gb < B) {
+                    const size_t o = ((size_t)t * B + (b0 + gb)) * (2 * GRU_G) + dir * GRU_G + (int)rank * GRU_UNITS + grp * 4;
+                    const uint2 vr = sout2[i], vz = sout2[GRU_TILE4 + i], vni = sout2[2 * GRU_TILE4 + i], vnh = sout2[3 * GRU_TILE4 + i];
+                    *reinterpret_cast<uint2*>(a.dGi + o) = vr; *reinterpret_cast<uint2*>(a.dGh + o) = vr;
+                    *reinterpret_cast<uint2*>(a.dGi + o + GRU_HP) = vz; *reinterpret_cast<uint2*>(a.dGh + o + GRU_HP) = vz;
+                    *reinterpret_cast<uint2*>(a.dGi + o + 2 * GRU_HP) = vni;
+                    *reinterpret_cast<uint2*>(a.dGh + o + 2 * GRU_HP) = vnh;
+                }
+            }
+            if (step + 1 < T) stage_in();
+            bar_arrive(GRU_BAR_IN, 256);
+            cluster_wait();
         }
-        fence_proxy_async_all();
-        __syncwarp();
-        cluster_arrive();
-        if (act) {
-            const size_t o = ((size_t)t * B + b) * (2 * GRU_G) + dir * GRU_G + ju;
-            uint2 v;
-            v.x = tc::pack_bf16x2(dgr[0], dgr[1]); v.y = tc::pack_bf16x2(dgr[2], dgr[3]);
-            *reinterpret_cast<uint2*>(a.dGi + o) = v; *reinterpret_cast<uint2*>(a.dGh + o) = v;
-            v.x = tc::pack_bf16x2(dgz[0], dgz[1]); v.y = tc::pack_bf16x2(dgz[2], dgz[3]);
-            *reinterpret_cast<uint2*>(a.dGi + o + GRU_HP) = v; *reinterpret_cast<uint2*>(a.dGh + o + GRU_HP) = v;
-            v.x = tc::pack_bf16x2(dgni[0], dgni[1]); v.y = tc::pack_bf16x2(dgni[2], dgni[3]);
-            *reinterpret_cast<uint2*>(a.dGi + o + 2 * GRU_HP) = v;
-            v.x = tc::pack_bf16x2(dgnh[0], dgnh[1]); v.y = tc::pack_bf16x2(dgnh[2], dgnh[3]);
-            *reinterpret_cast<uint2*>(a.dGh + o + 2 * GRU_HP) = v;
+    } else {
+        // ============================================================ gate warps
+        const bool gate_thr = tid < GRU_GATE_THREADS;
+        const int gb = tid & 15, grp = tid >> 4;
+        const bool act = gate_thr && b0 + gb < B;
+        const int ju = (int)rank * GRU_UNITS + grp * 4;
+        const int si = gb * GRU_ROW4 + grp;
+        uint32_t loff[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) loff[q] = tc::smem_u32(sB) + bop_off(gb, q * GRU_HP + ju);
+        float carry[4] = {0.f, 0.f, 0.f, 0.f};             // dh * z of the step before (direct path to h_{t-1})
+        uint32_t mphase = 0;
+#pragma unroll 1
+        for (int step = 0; step < T; ++step) {
+            const int cur = step & 1;
+            tc::mbar_wait(&mbar, mphase);
+            mphase ^= 1;
+            tc::fence_after_sync();
+            if (warp < 2) {
+                float v[16];
+                tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+                float* dst = xchg + (warp * 32 + lane) * GRU_XLD;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[j] = v[j];
+                tc::fence_before_sync();
+            }
+            bar_sync(GRU_BAR_IN, 256);
+            if (gate_thr) {
+                const float4 r4 = sin4[si], z4 = sin4[GRU_TILE4 + si], n4 = sin4[2 * GRU_TILE4 + si], hn4 = sin4[3 * GRU_TILE4 + si],
+                             dy4 = sin4[4 * GRU_TILE4 + si];
+                const uint2 hp = shp[si];
+                const float r[4] = {r4.x, r4.y, r4.z, r4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w}, n[4] = {n4.x, n4.y, n4.z, n4.w};
+                const float hn[4] = {hn4.x, hn4.y, hn4.z, hn4.w}, dy[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
+                const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hp.x), h23 = *reinterpret_cast<const __nv_bfloat162*>(&hp.y);
+                const float hprev[4] = {__low2float(h01), __high2float(h01), __low2float(h23), __high2float(h23)};
+                float dgr[4], dgz[4], dgni[4], dgnh[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float dh = act ? dy[i] + carry[i] + xchg[(grp * 4 + i) * GRU_XLD + gb] : 0.f;
+                    const float dn = dh * (1.f - z[i]);
+                    const float dz = dh * (hprev[i] - n[i]);
+                    const float dnp = dn * (1.f - n[i] * n[i]);
+                    dgni[i] = dnp;
+                    dgnh[i] = dnp * r[i];
+                    dgr[i] = dnp * hn[i] * r[i] * (1.f - r[i]);
+                    dgz[i] = dz * z[i] * (1.f - z[i]);
+                    carry[i] = dh * z[i];
+                }
+                const uint2 vr = make_uint2(tc::pack_bf16x2(dgr[0], dgr[1]), tc::pack_bf16x2(dgr[2], dgr[3]));
+                const uint2 vz = make_uint2(tc::pack_bf16x2(dgz[0], dgz[1]), tc::pack_bf16x2(dgz[2], dgz[3]));
+                const uint2 vnh = make_uint2(tc::pack_bf16x2(dgnh[0], dgnh[1]), tc::pack_bf16x2(dgnh[2], dgnh[3]));
+                if (step + 1 < T) {
+                    const uint32_t boff = (cur ^ 1) * GRU_BB_BYTES;
+#pragma unroll
+                    for (int rk = 0; rk < GRU_CL; ++rk) {
+                        st_cluster_v2(mapa(loff[0], (uint32_t)rk) + boff, vr.x, vr.y);
+                        st_cluster_v2(mapa(loff[1], (uint32_t)rk) + boff, vz.x, vz.y);
+                        st_cluster_v2(mapa(loff[2], (uint32_t)rk) + boff, vnh.x, vnh.y);
+                    }
+                }
+                sout2[si] = vr;
+                sout2[GRU_TILE4 + si] = vz;
+                sout2[2 * GRU_TILE4 + si] = make_uint2(tc::pack_bf16x2(dgni[0], dgni[1]), tc::pack_bf16x2(dgni[2], dgni[3]));
+                sout2[3 * GRU_TILE4 + si] = vnh;
+            }
+            __syncwarp();
+            bar_arrive(GRU_BAR_OUT, 256);
+            fence_proxy_async_cluster();
+            cluster_arrive();
+            cluster_wait();
         }
-        __syncwarp();
-        cluster_wait();
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -451,7 +581,8 @@ __global__ void gru_pack_whh_kernel(const float* __restrict__ w0, const float* _
     const int dir = blockIdx.y, c = blockIdx.x;
     const float* w = dir ? w1 : w0;
     uint8_t* fi = fimg + (size_t)(dir * GRU_CL + c) * GRU_FA_BYTES;
-    for (int idx = threadIdx.x; idx < GRU_FA_ROWS * GRU_FA_NSLAB * 64; idx += blockDim.x) {
+    const int t0 = blockIdx.z * blockDim.x + threadIdx.x, tstride = gridDim.z * blockDim.x;
+    for (int idx = t0; idx < GRU_FA_ROWS * GRU_FA_NSLAB * 64; idx += tstride) {
         const int row = idx / (GRU_FA_NSLAB * 64), k = idx % (GRU_FA_NSLAB * 64);
         float v = 0.f;
         if (row < 3 * GRU_UNITS) {
@@ -463,7 +594,7 @@ __global__ void gru_pack_whh_kernel(const float* __restrict__ w0, const float* _
     }
     if (!bimg) return;
     uint8_t* bi = bimg + (size_t)(dir * GRU_CL + c) * GRU_BA_BYTES;
-    for (int idx = threadIdx.x; idx < GRU_BA_ROWS * GRU_BA_NSLAB * 64; idx += blockDim.x) {
+    for (int idx = t0; idx < GRU_BA_ROWS * GRU_BA_NSLAB * 64; idx += tstride) {
         const int row = idx / (GRU_BA_NSLAB * 64), g = idx % (GRU_BA_NSLAB * 64);
         float v = 0.f;
         if (row < GRU_UNITS && g < GRU_G) {
@@ -548,7 +679,7 @@ static GruLayout gru_layout(const HopkGruShape* s)
     memset(&g, 0, sizeof(g));
     const size_t TB = (size_t)s->T * s->B;
     size_t cur = 0;
-    int ipmax = 0;
+    int ipmax = 2 * GRU_HP;                          // the dY buffers also hold the packed output gradient (704 wide)
     for (int l = 0; l < s->L; ++l) { g.Ipad[l] = gru_in_pad(l, s->I); if (g.Ipad[l] > ipmax) ipmax = g.Ipad[l]; }
     g.xb = gbump(cur, TB * g.Ipad[0] * 2);
     g.gi = gbump(cur, TB * 2 * GRU_G * 4);
@@ -615,7 +746,7 @@ extern "C" int hopk_gru_forward(const HopkGruShape* s, const HopkGruParams* p, c
         gru_pack_wih_kernel<<<2 * GRU_G, 128, 0, st>>>(p->w_ih[l][0], p->w_ih[l][1], p->b_ih[l][0], p->b_ih[l][1], p->b_hh[l][0],
                                                         p->b_hh[l][1], wih, bias, bhn, l, s->I, Iin, H);
         HOPK_LAUNCH_CHECK("gru_pack_wih");
-        gru_pack_whh_kernel<<<dim3(GRU_CL, 2), 256, 0, st>>>(p->w_hh[l][0], p->w_hh[l][1], (uint8_t*)(ws + g.whh[l]), nullptr, H);
+        gru_pack_whh_kernel<<<dim3(GRU_CL, 2, 24), 256, 0, st>>>(p->w_hh[l][0], p->w_hh[l][1], (uint8_t*)(ws + g.whh[l]), nullptr, H);
         HOPK_LAUNCH_CHECK("gru_pack_whh");
         const __nv_bfloat16* X = l == 0 ? (const __nv_bfloat16*)(ws + g.xb) : (const __nv_bfloat16*)(ws + g.y[l - 1]);
         // Gi = X . W_ih^T + bias   (both directions: N = 2112)
@@ -660,7 +791,7 @@ extern "C" int hopk_gru_backward(const HopkGruShape* s, const HopkGruParams* p, 
     for (int l = L - 1; l >= 0; --l) {
         const int Iin = l == 0 ? s->I : 2 * H;
         const int Ipad = g.Ipad[l];
-        gru_pack_whh_kernel<<<dim3(GRU_CL, 2), 256, 0, st>>>(p->w_hh[l][0], p->w_hh[l][1], (uint8_t*)(ws + g.whh[l]), (uint8_t*)(sc + g.s_whhT), H);
+        gru_pack_whh_kernel<<<dim3(GRU_CL, 2, 24), 256, 0, st>>>(p->w_hh[l][0], p->w_hh[l][1], (uint8_t*)(ws + g.whh[l]), (uint8_t*)(sc + g.s_whhT), H);
         HOPK_LAUNCH_CHECK("gru_pack_whhT");
         GruBwdArgs a;
         a.dY = dy_cur; a.whhT = (const uint8_t*)(sc + g.s_whhT); a.Y = (const __nv_bfloat16*)(ws + g.y[l]);

@@ -139,7 +139,8 @@ int hopk_conv1x1_nchw_bwd(const float* x, const float* w, const float* dy, float
  * x @ W^T with nn.Linear's weight, HOP.py:130-134,200,202,262-265); HOPK_GEMM_A_MN / _B_MN say the operand is stored with
  * the contraction index as the row ([K][M] / [K][N]), which covers dX = dY @ W and dW = dY^T @ X without transposes.
  * C: fp32 (default) or bf16 (HOPK_GEMM_OUT_BF16), leading dimension ldc.  addend: optional fp32 [M][ldc] added before the
- * activation.  mask: optional fp32 [M][ldc]; elements with mask <= 0 are written as 0 (gradient of a fused ReLU).
+ * activation.  mask: optional [M][ldc] (fp32, or bf16 with HOPK_GEMM_MASK_BF16); elements with mask <= 0 are multiplied by
+ * `slope` (0: gradient of a fused ReLU; 0.2: of LeakyReLU(0.2)).
  * splits > 1: split-K with vector atomics into an fp32 C (cleared by the call unless HOPK_GEMM_ACCUMULATE). */
 #define HOPK_GEMM_A_MN 1
 #define HOPK_GEMM_B_MN 2
@@ -148,10 +149,15 @@ int hopk_conv1x1_nchw_bwd(const float* x, const float* w, const float* dy, float
 #define HOPK_GEMM_RELU 16
 #define HOPK_GEMM_LEAKY 32     /* LeakyReLU(slope) */
 #define HOPK_GEMM_GELU 64      /* exact (erf) GELU */
-int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, const float* mask,
+#define HOPK_GEMM_BIAS_ROW 128 /* bias indexed by the output row m (length M) instead of the column n */
+#define HOPK_GEMM_MASK_BF16 256 /* mask is stored as bf16 */
+int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, const void* mask,
                    int M, int N, int K, long lda, long ldb, long ldc, int flags, float slope, int splits, void* stream);
 /* fp32 (rows x cols, ld lds) -> bf16 (rows x cols_out, ld ldd), zero padding for cols <= c < cols_out, optional ReLU */
 int hopk_cast_bf16(const float* src, void* dst, long rows, int cols, long lds, int cols_out, long ldd, int relu, void* stream);
+/* overlapping windows of B signals as a bf16 matrix: out[b*nwin + k][c] = x[b][k*hop + c], c < win (in_audio.unfold(1, 3400,
+ * 2191) of HOP.py:210 plus the cast); ldx / ldo: leading dimensions of x and out in elements (ldo % 8 == 0) */
+int hopk_unfold_bf16(const float* x, void* out, int B, int nwin, int win, int hop, long ldx, long ldo, void* stream);
 /* out[c] = sum_r src[r][c] (bias gradients); src fp32 or bf16 */
 int hopk_colsum(const void* src, float* out, long rows, int cols, long ld, int src_bf16, void* stream);
 
