@@ -82,6 +82,8 @@ SIGNATURES = {
     'hopk_cast_bf16': (_i, [_vp, _vp, C.c_long, _i, C.c_long, _i, C.c_long, _i, _vp]),
     'hopk_unfold_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, C.c_long, C.c_long, _vp]),
     'hopk_colsum': (_i, [_vp, _vp, C.c_long, _i, C.c_long, _i, _vp]),
+    'hopk_beat_rows_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    'hopk_beat_rows_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, C.c_long, _vp]),
     'hopk_gru_workspace_bytes': (_sz, [C.POINTER(GruShape)]),
     'hopk_gru_scratch_bytes': (_sz, [C.POINTER(GruShape)]),
     'hopk_gru_forward': (_i, [C.POINTER(GruShape), C.POINTER(GruParams), _vp, _vp, _vp, _vp]),

@@ -47,6 +47,8 @@ constexpr uint32_t GRU_BA_SLAB = GRU_BA_ROWS * 128;
 constexpr int GRU_BA_NSLAB = 17;
 constexpr uint32_t GRU_BA_BYTES = GRU_BA_NSLAB * GRU_BA_SLAB;               // 104448
 constexpr uint32_t GRU_BB_BYTES = GRU_BA_NSLAB * GRU_B_SLAB;                // 34816 per buffer
+constexpr uint32_t GRU_F_TX = GRU_NB * GRU_HP * 2;                           // bytes of h_t a CTA receives per step (11264)
+constexpr uint32_t GRU_B_TX = GRU_NB * GRU_G * 2;                            // bytes of dGh a CTA receives per step (33792)
 constexpr int GRU_XLD = GRU_NB + 1;                                         // fp32 pitch of the TMEM -> thread exchange tile
 
 
@@ -68,6 +70,13 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank)
 __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_t b)
 {
     asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// asynchronous remote store: 8 bytes into a peer CTA's shared memory, completion counted (complete_tx) on THAT CTA's mbarrier.
+// The sender neither fences nor waits; the receiver's MMA issuer waits on its own barrier for the expected byte count.
+__device__ __forceinline__ void st_async_v2(uint32_t addr, uint32_t a, uint32_t b, uint32_t mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                 ::"r"(addr), "r"(a), "r"(b), "r"(mbar) : "memory");
 }
 // generic-proxy writes (own and remote shared memory) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -130,6 +139,7 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t wbar, mbar;
+    __shared__ __align__(16) uint64_t hbar[2];        // operand buffer b complete: 8 CTAs x 176 threads x 8 bytes of st.async
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -146,7 +156,11 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     if (tid == 0) {
         tc::mbar_init(&wbar, 1);
         tc::mbar_init(&mbar, 1);
+        tc::mbar_init(&hbar[0], 1);
+        tc::mbar_init(&hbar[1], 1);
         tc::fence_barrier_init();
+        tc::mbar_expect_tx(&hbar[0], GRU_F_TX);       // armed for their first fill (steps 2 and 1)
+        tc::mbar_expect_tx(&hbar[1], GRU_F_TX);
         tc::mbar_expect_tx(&wbar, GRU_FA_BYTES);
         const uint8_t* src = a.whh + (size_t)(dir * GRU_CL + rank) * GRU_FA_BYTES;
 #pragma unroll 1
@@ -170,6 +184,12 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
         tc::mbar_wait(&wbar, 0);                      // W_hh slice resident
 #pragma unroll 1
         for (int step = 0; step < T; ++step) {
+            if (step > 0) {                           // h_{t-1}: every CTA's slice has landed in buffer step & 1
+                uint64_t* hb = &hbar[step & 1];
+                tc::mbar_wait(hb, (uint32_t)((step - 1) >> 1) & 1u);
+                if (lane == 0 && step + 2 < T) tc::mbar_expect_tx(hb, GRU_F_TX);      // re-arm for its next fill
+                tc::fence_async_smem();               // the st.async data -> async proxy (operand reads of the MMAs below)
+            }
             tc::fence_after_sync();
             if (elect_one()) {
                 const uint64_t dB = (step & 1) ? dB1 : dB0;
@@ -183,8 +203,6 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
                 tc::mma_commit(&mbar);
             }
             __syncwarp();
-            cluster_arrive_relaxed();
-            cluster_wait();                           // h_t of every CTA has landed in the operand buffer of step + 1
         }
     } else if (warp >= 6) {
         // ============================================================ I/O warps: global <-> staging
@@ -217,7 +235,6 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
 #pragma unroll 1
         for (int step = 0; step < T; ++step) {
             const int t = dir ? T - 1 - step : step;
-            cluster_arrive_relaxed();
             if (step + 1 < T) load_gi(dir ? t - 1 : t + 1);                  // in flight while the gate warps work
             bar_sync(GRU_BAR_OUT, 256);                                       // results of this step staged
 #pragma unroll
@@ -247,7 +264,6 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
             }
             if (step + 1 < T) stage_gi();
             bar_arrive(GRU_BAR_IN, 256);                                      // inputs of step + 1 staged (and the results tile is free)
-            cluster_wait();
         }
     } else {
         // ============================================================ gate warps
@@ -258,11 +274,11 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
         const int si = gb * GRU_ROW4 + grp;               // this thread's float4 slot in a staged array
         float h[4] = {0.f, 0.f, 0.f, 0.f};
         float4 bhn = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t raddr[GRU_CL];
+        uint32_t raddr[GRU_CL], rbar[GRU_CL];
         if (gate_thr) {
-            const uint32_t local = tc::smem_u32(sB) + bop_off(gb, ju);
+            const uint32_t local = tc::smem_u32(sB) + bop_off(gb, ju), lbar = tc::smem_u32(&hbar[0]);
 #pragma unroll
-            for (int r = 0; r < GRU_CL; ++r) raddr[r] = mapa(local, (uint32_t)r);
+            for (int r = 0; r < GRU_CL; ++r) { raddr[r] = mapa(local, (uint32_t)r); rbar[r] = mapa(lbar, (uint32_t)r); }
             bhn = __ldg(reinterpret_cast<const float4*>(a.bhn + dir * GRU_HP + ju));
         }
         uint32_t mphase = 0;
@@ -307,9 +323,9 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
                 }
                 if (step + 1 < T) {                                                 // h_t into every CTA's operand buffer of step + 1
                     const uint32_t lo = tc::pack_bf16x2(h[0], h[1]), hi = tc::pack_bf16x2(h[2], h[3]);
-                    const uint32_t boff = (cur ^ 1) * GRU_FB_BYTES;
+                    const uint32_t boff = (cur ^ 1) * GRU_FB_BYTES, moff = (cur ^ 1) * 8;
 #pragma unroll
-                    for (int r = 0; r < GRU_CL; ++r) st_cluster_v2(raddr[r] + boff, lo, hi);
+                    for (int r = 0; r < GRU_CL; ++r) st_async_v2(raddr[r] + boff, lo, hi, rbar[r] + moff);
                 }
                 sout4[si] = make_float4(h[0], h[1], h[2], h[3]);
                 sout4[GRU_TILE4 + si] = make_float4(rr[0], rr[1], rr[2], rr[3]);
@@ -319,13 +335,12 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
             }
             __syncwarp();
             bar_arrive(GRU_BAR_OUT, 256);                 // the I/O warps take it from here
-            fence_proxy_async_cluster();                  // remote operand writes -> visible to the peers' tensor cores
-            cluster_arrive();
-            cluster_wait();
         }
     }
     tc::fence_before_sync();
     __syncthreads();
+    cluster_arrive();                                     // nobody leaves while a peer may still address its shared memory
+    cluster_wait();
     if (warp == 8) tc::tmem_dealloc(tmem, 32);
 }
 
@@ -349,6 +364,7 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t wbar, mbar;
+    __shared__ __align__(16) uint64_t hbar[2];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -366,7 +382,11 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     if (tid == 0) {
         tc::mbar_init(&wbar, 1);
         tc::mbar_init(&mbar, 1);
+        tc::mbar_init(&hbar[0], 1);
+        tc::mbar_init(&hbar[1], 1);
         tc::fence_barrier_init();
+        tc::mbar_expect_tx(&hbar[0], GRU_B_TX);
+        tc::mbar_expect_tx(&hbar[1], GRU_B_TX);
         tc::mbar_expect_tx(&wbar, GRU_BA_BYTES);
         const uint8_t* src = a.whhT + (size_t)(dir * GRU_CL + rank) * GRU_BA_BYTES;
 #pragma unroll 1
@@ -390,6 +410,12 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
         tc::mbar_wait(&wbar, 0);
 #pragma unroll 1
         for (int step = 0; step < T; ++step) {
+            if (step > 0) {
+                uint64_t* hb = &hbar[step & 1];
+                tc::mbar_wait(hb, (uint32_t)((step - 1) >> 1) & 1u);
+                if (lane == 0 && step + 2 < T) tc::mbar_expect_tx(hb, GRU_B_TX);
+                tc::fence_async_smem();
+            }
             tc::fence_after_sync();
             if (elect_one()) {
                 const uint64_t dB = (step & 1) ? dB1 : dB0;
@@ -400,8 +426,6 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
                 tc::mma_commit(&mbar);
             }
             __syncwarp();
-            cluster_arrive_relaxed();
-            cluster_wait();
         }
     } else if (warp >= 6) {
         // ============================================================ I/O warps
@@ -444,7 +468,6 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
 #pragma unroll 1
         for (int step = 0; step < T; ++step) {
             const int t = dir ? step : T - 1 - step;     // reverse of the forward order
-            cluster_arrive_relaxed();
             if (step + 1 < T) load_in(dir ? t + 1 : t - 1);
             bar_sync(GRU_BAR_OUT, 256);
 #pragma unroll
@@ -462,7 +485,6 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
             }
             if (step + 1 < T) stage_in();
             bar_arrive(GRU_BAR_IN, 256);
-            cluster_wait();
         }
     } else {
         // ============================================================ gate warps
@@ -516,12 +538,13 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
                 const uint2 vz = make_uint2(tc::pack_bf16x2(dgz[0], dgz[1]), tc::pack_bf16x2(dgz[2], dgz[3]));
                 const uint2 vnh = make_uint2(tc::pack_bf16x2(dgnh[0], dgnh[1]), tc::pack_bf16x2(dgnh[2], dgnh[3]));
                 if (step + 1 < T) {
-                    const uint32_t boff = (cur ^ 1) * GRU_BB_BYTES;
+                    const uint32_t boff = (cur ^ 1) * GRU_BB_BYTES, lbar = tc::smem_u32(&hbar[cur ^ 1]);
 #pragma unroll
                     for (int rk = 0; rk < GRU_CL; ++rk) {
-                        st_cluster_v2(mapa(loff[0], (uint32_t)rk) + boff, vr.x, vr.y);
-                        st_cluster_v2(mapa(loff[1], (uint32_t)rk) + boff, vz.x, vz.y);
-                        st_cluster_v2(mapa(loff[2], (uint32_t)rk) + boff, vnh.x, vnh.y);
+                        const uint32_t rb = mapa(lbar, (uint32_t)rk);
+                        st_async_v2(mapa(loff[0], (uint32_t)rk) + boff, vr.x, vr.y, rb);
+                        st_async_v2(mapa(loff[1], (uint32_t)rk) + boff, vz.x, vz.y, rb);
+                        st_async_v2(mapa(loff[2], (uint32_t)rk) + boff, vnh.x, vnh.y, rb);
                     }
                 }
                 sout2[si] = vr;
@@ -531,13 +554,12 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
             }
             __syncwarp();
             bar_arrive(GRU_BAR_OUT, 256);
-            fence_proxy_async_cluster();
-            cluster_arrive();
-            cluster_wait();
         }
     }
     tc::fence_before_sync();
     __syncthreads();
+    cluster_arrive();
+    cluster_wait();
     if (warp == 8) tc::tmem_dealloc(tmem, 32);
 }
 

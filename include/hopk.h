@@ -161,6 +161,13 @@ int hopk_unfold_bf16(const float* x, void* out, int B, int nwin, int win, int ho
 /* out[c] = sum_r src[r][c] (bias gradients); src fp32 or bf16 */
 int hopk_colsum(const void* src, float* out, long rows, int cols, long ld, int src_bf16, void* stream);
 
+/* ------------------------------------------------------------------ beat features -> Graph-WaveNet rows (model/HOP.py:210-217)
+ * feat: (B*16, F) beat-MLP output per audio window; seed: (B, 16, 3J) seed bones; rows: (B, 16, J, 3 + F) with
+ * rows[b,t,j,:3] = seed[b,t,3j:3j+3] and rows[b,t,j,3:] = feat[b*16 + (t*J + j) % 16]  (the reference's repeat + view).
+ * Backward: dfeat (bf16, leading dimension ldd) = the J-fold gather-sum of drows[..., 3:]; dbias (nullable) = its column sums. */
+int hopk_beat_rows_fwd(const float* feat, const float* seed, float* rows, int B, int J, int F, void* stream);
+int hopk_beat_rows_bwd(const float* drows, void* dfeat_bf16, float* dbias, int B, int J, int F, long ldd, void* stream);
+
 /* ------------------------------------------------------------------ GRU decoder (model/HOP.py:166-167, 248)
  * Multi-layer bidirectional GRU, batch_first, zero initial state, PyTorch gate order (r, z, n); dtype-1 arithmetic (bf16
  * tensor-core operands, fp32 accumulation and fp32 recurrent state).  Hidden size <= 352 (HOP: 350).
