@@ -18,6 +18,7 @@ from math import sqrt
 import torch
 import torch.nn as nn
 
+from . import dense
 from . import gru as hgru
 from . import gwnet, profiler
 from ._lib import check, f32c, lib, ptr, stream_ptr
@@ -158,15 +159,18 @@ class ReprogrammingLayer(nn.Module):
         B, L, _ = target_embedding.shape
         S, _ = source_embedding.shape
         H = self.n_heads
-        tc = 0x100 if self.precision == 'bf16' else 0
-        q = _LinearFn.apply(target_embedding, self.query_projection.weight, self.query_projection.bias, tc).view(B, L, H, -1)
-        k = _LinearFn.apply(source_embedding, self.key_projection.weight, self.key_projection.bias, tc).view(S, H, -1)
-        v = _LinearFn.apply(value_embedding, self.value_projection.weight, self.value_projection.bias, tc).view(S, H, -1)
+        if self.precision == 'bf16':                      # projections on the TMA + tcgen05 GEMM (hop_b200/dense.py)
+            lin = lambda x, m, relu_in=False: dense.linear(x, m.weight, m.bias, relu_in)
+        else:                                             # fp32 FFMA kernels (reference numerics)
+            lin = lambda x, m, relu_in=False: _LinearFn.apply(x, m.weight, m.bias, 1 if relu_in else 0)
+        q = lin(target_embedding, self.query_projection).view(B, L, H, -1)
+        k = lin(source_embedding, self.key_projection).view(S, H, -1)
+        v = lin(value_embedding, self.value_projection).view(S, H, -1)
         out = self.reprogramming(q, k, v).reshape(B, L, -1)
         if getattr(self, '_keep_attn', False):            # tests / tools: the attention output the ReLU below gates
             self._last_attn = out.detach()
-        # ReLU (HOP.py:284) is fused into the out-projection's operand load (flag 1)
-        return _LinearFn.apply(out, self.out_projection.weight, self.out_projection.bias, 1 | tc)
+        # ReLU (HOP.py:284) is fused into the out-projection's operand load / cast
+        return lin(out, self.out_projection, True)
 
     def reprogramming(self, target_embedding, source_embedding, value_embedding):
         p = self.dropout.p if self.training else 0.0
@@ -256,6 +260,7 @@ class Model(nn.Module):
         self._source_reducer = None
         self.amp_dtype = None          # None: everything fp32 like the reference; torch.bfloat16: see set_precision
         self.own_gru = True            # bf16 mode: decoder GRU on the hand-written kernels (False: stock cuDNN, for A/B timing)
+        self.own_dense = True          # bf16 mode: mapping / align / beat GEMMs on the hand-written TMA GEMM (False: cuBLAS)
         self._we_cast = None
 
     def set_source_grad_reducer(self, fn):
@@ -328,8 +333,10 @@ class Model(nn.Module):
         we = self.word_embeddings
         if dt != we.dtype:
             if self._we_cast is None or self._we_cast.device != we.device:
-                self._we_cast = we.detach().to(dt)          # frozen: cast once
+                self._we_cast = we.detach().to(dt).contiguous()          # frozen: cast once
             we = self._we_cast
+        if self.amp_dtype is not None and self.own_dense:                # bf16 mode: TMA + tcgen05 GEMM (hop_b200/dense.py)
+            return dense.source(self.mapping_layer.weight, self.mapping_layer.bias, we, self._source_reducer)
         return _SourceFn.apply(self.mapping_layer.weight, self.mapping_layer.bias, we, self._source_reducer, dt)
 
     def forecast(self, in_audio, x_enc, text, pre_seq, vid_indices, source=None, shared=None):
@@ -353,7 +360,10 @@ class Model(nn.Module):
         if source is None:
             source = self.source_embeddings()
         enc_out = self.reprogramming_layer(x_enc, source, source)
-        llama_enc_out = self.align_layer(torch.cat([enc_out, text_embeddings], dim=2))
+        if self.amp_dtype is not None and self.own_dense:
+            llama_enc_out = dense.linear(torch.cat([enc_out, text_embeddings.float()], dim=2), self.align_layer.weight, self.align_layer.bias)
+        else:
+            llama_enc_out = self.align_layer(torch.cat([enc_out, text_embeddings], dim=2))
         dec_out = self._llm()(inputs_embeds=llama_enc_out).last_hidden_state
 
         # beat features: the reference runs the MLP on J identical copies of the 16 windows and then
@@ -367,10 +377,15 @@ class Model(nn.Module):
         else:
             if shared is not None and self.training:
                 shared['bn_prev'] = [b.clone() for b in self._gwnet_bn_buffers()]
-            windows = in_audio.unfold(1, 3400, 2191)                         # (B, 16, 3400)
-            feat = self.beat(windows)                                        # (B, 16, 170)
-            feat = feat[:, self._window_index(J, feat.device)]               # (B, 16, J, 170)
-            seq_audio = torch.cat([pre_seq.view(B, 16, -1, 3), feat.float()], dim=3)  # (B, 16, J, 173) == rows layout
+            if self.amp_dtype is not None and self.own_dense:
+                # unfold + beat MLP (once per window) + the (t*J+j)%16 gather + concat with the seed bones, written straight
+                # into Graph-WaveNet's rows buffer (hop_b200/dense.py::beat_rows, csrc/glue.cu)
+                seq_audio = dense.beat_rows(in_audio, pre_seq, self.beat, J)     # (B, 16, J, 173)
+            else:
+                windows = in_audio.unfold(1, 3400, 2191)                         # (B, 16, 3400)
+                feat = self.beat(windows)                                        # (B, 16, 170)
+                feat = feat[:, self._window_index(J, feat.device)]               # (B, 16, J, 170)
+                seq_audio = torch.cat([pre_seq.view(B, 16, -1, 3), feat.float()], dim=3)  # (B, 16, J, 173) == rows layout
             feature = self.gwnet(seq_audio.permute(0, 3, 2, 1))               # strided view, read in place
             if shared is not None:
                 shared['feature'], shared['feature_has_graph'] = feature, torch.is_grad_enabled()
