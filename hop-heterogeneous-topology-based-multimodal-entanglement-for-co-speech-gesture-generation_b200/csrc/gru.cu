@@ -31,13 +31,13 @@ constexpr int GRU_UNITS = 44;                  // hidden units per CTA
 constexpr int GRU_HP = GRU_CL * GRU_UNITS;     // 352: padded hidden size
 constexpr int GRU_G = 3 * GRU_HP;              // 1056 gate columns per direction
 constexpr int GRU_NB = 16;                     // samples per cluster
-constexpr int GRU_THREADS = 224;               // 6 gate warps + 1 MMA-issue warp
+constexpr int GRU_THREADS = 288;               // 8 worker warps + 1 MMA-issue warp
 constexpr int GRU_GATE_THREADS = GRU_NB * (GRU_UNITS / 4);      // 176: (sample, group of 4 units)
 
 // forward A operand (the CTA's rows [r 44 | z 44 | n 44] of W_hh, K = 352) lives in TENSOR MEMORY for the whole kernel:
 // lane = gate row, 32-bit column j = the bf16 pair k = 2j, 2j+1.  Block 0 = rows 0..127, block 1 = rows 128..131 (lanes 0..3).
-// Streaming a 128-row A tile from shared memory costs 4 KB per K=16 step and made the N = 16 MMAs smem-bound (round 2
-// profile: ~90 cycles per MMA); from TMEM the tensor core only reads the 512-byte B tile.
+// Streaming a 128-row A tile from shared memory costs 4 KB per K = 16 step; from TMEM the tensor core only reads the
+// 512-byte B tile.
 constexpr int GRU_FA_NSLAB = 6;                                             // K = 352 -> 5.5 slabs of 64 (B operand)
 constexpr uint32_t GRU_FT_COLS = GRU_HP / 2;                                // 176 columns per block
 constexpr uint32_t GRU_FT_A0 = 32, GRU_FT_A1 = GRU_FT_A0 + GRU_FT_COLS;     // D in columns [0, 32), blocks at 32 and 208
@@ -48,14 +48,7 @@ constexpr uint32_t GRU_FB_BYTES = GRU_FA_NSLAB * GRU_B_SLAB;                // 1
 constexpr int GRU_BA_ROWS = 48;
 constexpr uint32_t GRU_BA_SLAB = GRU_BA_ROWS * 128;
 constexpr int GRU_BA_NSLAB = 17;
-// ... of which K = 0..959 lives in TENSOR MEMORY (480 columns, lanes 0..63) and only the last two K-slabs (k = 960..1087) stay
-// in shared memory: 480 + 16 accumulator columns fill the 512-column allocation
-constexpr int GRU_BT_K = 960;
-constexpr uint32_t GRU_BT_COLS = GRU_BT_K / 2;                              // 480
-constexpr uint32_t GRU_BT_A0 = 16;                                          // D in columns [0, 16)
-constexpr uint32_t GRU_BT_IMG = 64 * GRU_BT_COLS * 4;                       // 122880: image of 64 rows x 480 u32
-constexpr int GRU_BS_SLABS = 2;
-constexpr uint32_t GRU_BS_BYTES = 16384;                                    // 2 slabs of [48][64] (12288) + in-range room for the M = 128 read
+constexpr uint32_t GRU_BA_BYTES = GRU_BA_NSLAB * GRU_BA_SLAB;               // 104448
 constexpr uint32_t GRU_BB_BYTES = GRU_BA_NSLAB * GRU_B_SLAB;                // 34816 per buffer
 constexpr uint32_t GRU_F_TX = GRU_NB * GRU_HP * 2;                           // bytes of h_t a CTA receives per step (11264)
 constexpr uint32_t GRU_B_TX = GRU_NB * GRU_G * 2;                            // bytes of dGh a CTA receives per step (33792)
@@ -105,16 +98,20 @@ __device__ __forceinline__ uint32_t bop_off(int gb, int k)
     return (uint32_t)(k >> 6) * GRU_B_SLAB + (uint32_t)gb * 128u + (uint32_t)((((k & 63) >> 3) ^ (gb & 7)) << 4) + (uint32_t)(k & 7) * 2u;
 }
 
-// ---------------------------------------------------------------- warp roles
-// warps 0-5  gate warps: 176 gate threads = (sample, group of 4 units); warps 0-3 also drain TMEM.  They read the next
-//            step's inputs straight from global memory into registers one step ahead and write the step's results straight
-//            to global memory: with the st.async exchange no thread executes a membar any more, so global traffic in
-//            flight costs nothing
-// warp 6     MMA issuer
-constexpr int GRU_ISSUER = 6;
-constexpr int GRU_GATE_T = 192;
+// ---------------------------------------------------------------- warp roles and CTA-level synchronisation
+// warps 0-5  gate warps (176 gate threads = (sample, group of 4 units); warps 0-3 also drain TMEM): on-chip work only
+// warps 6-7  I/O warps: every global load / store of the step, through shared-memory staging, so that the threads that
+//            execute the cluster-scope fences (MEMBAR.ALL.GPU in SASS) never have global traffic in flight
+// warp 8     MMA issuer
+constexpr int GRU_IO_T0 = 192, GRU_IO_THREADS = 64;
+constexpr int GRU_BAR_IN = 1, GRU_BAR_OUT = 2;          // named barriers: step inputs staged / step results staged (256 threads)
+constexpr int GRU_ROW4 = GRU_UNITS / 4;                 // 11 groups of 4 units per sample row
+constexpr int GRU_TILE4 = GRU_NB * GRU_ROW4;            // 176 float4 per staged array
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_cluster() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
@@ -154,11 +151,13 @@ struct GruFwdArgs {
 };
 
 constexpr size_t GRU_F_XCHG = 132 * GRU_XLD * 4;                           // 8976
+constexpr size_t GRU_F_SIN = 3 * GRU_TILE4 * 16;                           // staged gi_r | gi_z | gi_n       8448
+constexpr size_t GRU_F_SOUT = 5 * GRU_TILE4 * 16;                          // staged h | r | z | n | hn      14080
 // one CTA per SM is REQUIRED (each CTA allocates all 512 tensor-memory columns; a second resident CTA of the same cluster would
 // wait for them forever): the request is padded past half of the SM's shared memory
 constexpr size_t GRU_SMEM_FLOOR = 120 * 1024;
 constexpr size_t gru_fwd_smem() { return GRU_SMEM_FLOOR; }
-static_assert(2 * GRU_FB_BYTES + GRU_F_XCHG + 1024 <= GRU_SMEM_FLOOR, "forward smem");
+static_assert(2 * GRU_FB_BYTES + GRU_F_XCHG + 16 + GRU_F_SIN + GRU_F_SOUT + 1024 <= GRU_SMEM_FLOOR, "forward smem");
 
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1) gru_fwd_kernel(const GruFwdArgs a)
 {
@@ -169,6 +168,8 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sB = smem;
     float* xchg = reinterpret_cast<float*>(sB + 2 * GRU_FB_BYTES);
+    float4* sin4 = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(xchg) + ((GRU_F_XCHG + 15) & ~size_t(15)));
+    float4* sout4 = sin4 + 3 * GRU_TILE4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int cl = blockIdx.x / GRU_CL;
@@ -183,7 +184,7 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
         tc::mbar_expect_tx(&hbar[0], GRU_F_TX);       // armed for their first fill (steps 2 and 1)
         tc::mbar_expect_tx(&hbar[1], GRU_F_TX);
     }
-    if (warp == GRU_ISSUER) tc::tmem_alloc(&tmem_slot, 512);
+    if (warp == 8) tc::tmem_alloc(&tmem_slot, 512);
     for (int i = tid; i < (int)(2 * GRU_FB_BYTES / 16); i += GRU_THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0, 0, 0, 0);   // h_{-1} = 0
     fence_proxy_async_all();
     tc::fence_before_sync();
@@ -203,7 +204,7 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     cluster_arrive();
     cluster_wait();                                   // every CTA's operand buffers are initialised before a peer writes into them
 
-    if (warp == GRU_ISSUER) {
+    if (warp == 8) {
         // ============================================================ MMA issuer
         const uint64_t dB0 = desc_base(tc::smem_u32(sB)), dB1 = desc_base(tc::smem_u32(sB) + GRU_FB_BYTES);
         constexpr uint32_t idesc = tc::idesc_bf16(128, GRU_NB, 0, 0);
@@ -228,13 +229,74 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
             }
             __syncwarp();
         }
+    } else if (warp >= 6) {
+        // ============================================================ I/O warps: global <-> staging
+        const int it = tid - GRU_IO_T0;
+        float4 g[3][3];                               // up to 3 float4 per thread per array (176 float4 over 64 threads)
+        auto load_gi = [&](int t) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                const int gb = i / GRU_ROW4, grp = i - gb * GRU_ROW4;
+                const bool ok = i < GRU_TILE4 && b0 + gb < B;
+                const float* p = a.Gi + ((size_t)t * B + (b0 + gb)) * (2 * GRU_G) + dir * GRU_G + (int)rank * GRU_UNITS + grp * 4;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) g[q][k] = ok ? __ldg(reinterpret_cast<const float4*>(p + q * GRU_HP)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto stage_gi = [&]() {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                if (i < GRU_TILE4) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) sin4[q * GRU_TILE4 + i] = g[q][k];
+                }
+            }
+        };
+        load_gi(dir ? T - 1 : 0);
+        stage_gi();
+        bar_arrive(GRU_BAR_IN, 256);
+#pragma unroll 1
+        for (int step = 0; step < T; ++step) {
+            const int t = dir ? T - 1 - step : step;
+            if (step + 1 < T) load_gi(dir ? t - 1 : t + 1);                  // in flight while the gate warps work
+            bar_sync(GRU_BAR_OUT, 256);                                       // results of this step staged
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                const int gb = i / GRU_ROW4, grp = i - gb * GRU_ROW4;
+                if (i < GRU_TILE4 && b0 + gb < B) {
+                    const int b = b0 + gb, ju = (int)rank * GRU_UNITS + grp * 4;
+                    const size_t o = ((size_t)t * B + b) * (2 * GRU_HP) + dir * GRU_HP + ju;
+                    const float4 h = sout4[i];
+                    uint2 hb;
+                    hb.x = tc::pack_bf16x2(h.x, h.y); hb.y = tc::pack_bf16x2(h.z, h.w);
+                    *reinterpret_cast<uint2*>(a.Y + o) = hb;
+                    if (a.R) {
+                        *reinterpret_cast<float4*>(a.R + o) = sout4[GRU_TILE4 + i];
+                        *reinterpret_cast<float4*>(a.Z + o) = sout4[2 * GRU_TILE4 + i];
+                        *reinterpret_cast<float4*>(a.N + o) = sout4[3 * GRU_TILE4 + i];
+                        *reinterpret_cast<float4*>(a.HN + o) = sout4[4 * GRU_TILE4 + i];
+                    }
+                    if (a.out) {
+                        float* po = a.out + ((size_t)b * T + t) * (2 * a.H) + dir * a.H + ju;
+                        const float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) if (ju + e < a.H) po[e] = hv[e];
+                    }
+                }
+            }
+            if (step + 1 < T) stage_gi();
+            bar_arrive(GRU_BAR_IN, 256);                                      // inputs of step + 1 staged (and the results tile is free)
+        }
     } else {
         // ============================================================ gate warps
         const bool gate_thr = tid < GRU_GATE_THREADS;
         const int gb = tid & 15, grp = tid >> 4;
-        const int b = b0 + gb;
-        const bool act = gate_thr && b < B;
+        const bool act = gate_thr && b0 + gb < B;
         const int ju = (int)rank * GRU_UNITS + grp * 4;   // first of this thread's 4 hidden units (padded index)
+        const int si = gb * GRU_ROW4 + grp;               // this thread's float4 slot in a staged array
         float h[4] = {0.f, 0.f, 0.f, 0.f};
         float4 bhn = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t raddr[GRU_CL], rbar[GRU_CL];
@@ -244,17 +306,9 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
             for (int r = 0; r < GRU_CL; ++r) { raddr[r] = mapa(local, (uint32_t)r); rbar[r] = mapa(lbar, (uint32_t)r); }
             bhn = __ldg(reinterpret_cast<const float4*>(a.bhn + dir * GRU_HP + ju));
         }
-        float4 gi_r = make_float4(0.f, 0.f, 0.f, 0.f), gi_z = gi_r, gi_n = gi_r;
-        if (act) {
-            const float* p = a.Gi + ((size_t)(dir ? T - 1 : 0) * B + b) * (2 * GRU_G) + dir * GRU_G + ju;
-            gi_r = __ldg(reinterpret_cast<const float4*>(p));
-            gi_z = __ldg(reinterpret_cast<const float4*>(p + GRU_HP));
-            gi_n = __ldg(reinterpret_cast<const float4*>(p + 2 * GRU_HP));
-        }
         uint32_t mphase = 0;
 #pragma unroll 1
         for (int step = 0; step < T; ++step) {
-            const int t = dir ? T - 1 - step : step;
             const int cur = step & 1;
             tc::mbar_wait(&mbar, mphase);
             mphase ^= 1;
@@ -275,10 +329,11 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
                 }
                 tc::fence_before_sync();
             }
-            bar_sync(1, GRU_GATE_T);                      // exchange tile complete (gate warps only)
+            bar_sync(GRU_BAR_IN, 256);                    // exchange tile complete + this step's input projections staged
             if (gate_thr) {
-                const float gir[4] = {gi_r.x, gi_r.y, gi_r.z, gi_r.w}, giz[4] = {gi_z.x, gi_z.y, gi_z.z, gi_z.w};
-                const float gin[4] = {gi_n.x, gi_n.y, gi_n.z, gi_n.w}, bh[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
+                const float4 g_r = sin4[si], g_z = sin4[GRU_TILE4 + si], g_n = sin4[2 * GRU_TILE4 + si];
+                const float gir[4] = {g_r.x, g_r.y, g_r.z, g_r.w}, giz[4] = {g_z.x, g_z.y, g_z.z, g_z.w};
+                const float gin[4] = {g_n.x, g_n.y, g_n.z, g_n.w}, bh[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
                 float rr[4], zz[4], nn[4], hn[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -297,44 +352,27 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
 #pragma unroll
                     for (int r = 0; r < GRU_CL; ++r) st_async_v2(raddr[r] + boff, lo, hi, rbar[r] + moff);
                 }
-                if (act) {
-                    if (step + 1 < T) {                                             // next step's input projections (a step ahead)
-                        const int tn = dir ? t - 1 : t + 1;
-                        const float* p = a.Gi + ((size_t)tn * B + b) * (2 * GRU_G) + dir * GRU_G + ju;
-                        gi_r = __ldg(reinterpret_cast<const float4*>(p));
-                        gi_z = __ldg(reinterpret_cast<const float4*>(p + GRU_HP));
-                        gi_n = __ldg(reinterpret_cast<const float4*>(p + 2 * GRU_HP));
-                    }
-                    const size_t o = ((size_t)t * B + b) * (2 * GRU_HP) + dir * GRU_HP + ju;
-                    uint2 hb;
-                    hb.x = tc::pack_bf16x2(h[0], h[1]); hb.y = tc::pack_bf16x2(h[2], h[3]);
-                    *reinterpret_cast<uint2*>(a.Y + o) = hb;
-                    if (a.R) {
-                        *reinterpret_cast<float4*>(a.R + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
-                        *reinterpret_cast<float4*>(a.Z + o) = make_float4(zz[0], zz[1], zz[2], zz[3]);
-                        *reinterpret_cast<float4*>(a.N + o) = make_float4(nn[0], nn[1], nn[2], nn[3]);
-                        *reinterpret_cast<float4*>(a.HN + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    }
-                    if (a.out) {
-                        float* po = a.out + ((size_t)b * T + t) * (2 * a.H) + dir * a.H + ju;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) if (ju + i < a.H) po[i] = h[i];
-                    }
-                }
+                sout4[si] = make_float4(h[0], h[1], h[2], h[3]);
+                sout4[GRU_TILE4 + si] = make_float4(rr[0], rr[1], rr[2], rr[3]);
+                sout4[2 * GRU_TILE4 + si] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+                sout4[3 * GRU_TILE4 + si] = make_float4(nn[0], nn[1], nn[2], nn[3]);
+                sout4[4 * GRU_TILE4 + si] = make_float4(hn[0], hn[1], hn[2], hn[3]);
             }
+            __syncwarp();
+            bar_arrive(GRU_BAR_OUT, 256);                 // the I/O warps take it from here
         }
     }
     tc::fence_before_sync();
     __syncthreads();
     cluster_arrive();                                     // nobody leaves while a peer may still address its shared memory
     cluster_wait();
-    if (warp == GRU_ISSUER) tc::tmem_dealloc(tmem, 512);
+    if (warp == 8) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------- backward recurrence (BPTT)
 struct GruBwdArgs {
     const float* dY;             // [T*B][704] gradient w.r.t. this layer's outputs
-    const uint8_t* whhT;         // [2][8][GRU_BT_IMG + GRU_BS_BYTES] packed W_hh^T slices (tensor-memory image | smem tail slabs)
+    const uint8_t* whhT;         // [2][8][GRU_BA_BYTES] packed W_hh^T slices
     const __nv_bfloat16* Y;      // [T*B][704] forward outputs
     const float *R, *Z, *N, *HN;
     __nv_bfloat16* dGi;          // [T*B][2*1056] gradient w.r.t. the input projections
@@ -343,8 +381,9 @@ struct GruBwdArgs {
 };
 
 constexpr size_t GRU_B_XCHG = 64 * GRU_XLD * 4;                            // 4352
-constexpr size_t gru_bwd_smem() { return GRU_SMEM_FLOOR; }
-static_assert(GRU_BS_BYTES + 2 * GRU_BB_BYTES + GRU_B_XCHG + 1024 <= GRU_SMEM_FLOOR, "backward smem");
+constexpr size_t GRU_B_SIN = 5 * GRU_TILE4 * 16 + GRU_TILE4 * 8;           // staged r | z | n | hn | dy (fp32) + h_prev (bf16 x 4)
+constexpr size_t GRU_B_SOUT = 4 * GRU_TILE4 * 8;                           // staged dg_r | dg_z | dg_n(input) | dg_n(hidden), bf16 x 4
+constexpr size_t gru_bwd_smem() { return GRU_BA_BYTES + 2 * GRU_BB_BYTES + GRU_B_XCHG + GRU_B_SIN + GRU_B_SOUT + 1024; }   // 201 KB: one CTA per SM
 
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdArgs a)
 {
@@ -353,15 +392,17 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     __shared__ __align__(16) uint64_t hbar[2];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;                                   // the last GRU_BS_SLABS K-slabs of W_hh^T (the rest lives in TMEM)
-    uint8_t* sB = smem + GRU_BS_BYTES;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + GRU_BA_BYTES;
     float* xchg = reinterpret_cast<float*>(sB + 2 * GRU_BB_BYTES);
+    float4* sin4 = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(xchg) + GRU_B_XCHG);
+    uint2* shp = reinterpret_cast<uint2*>(sin4 + 5 * GRU_TILE4);
+    uint2* sout2 = shp + GRU_TILE4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int cl = blockIdx.x / GRU_CL;
     const int dir = cl & 1, b0 = (cl >> 1) * GRU_NB;
     const int B = a.B, T = a.T;
-    const uint8_t* wimg = a.whhT + (size_t)(dir * GRU_CL + rank) * (GRU_BT_IMG + GRU_BS_BYTES);
 
     if (tid == 0) {
         tc::mbar_init(&wbar, 1);
@@ -371,27 +412,22 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
         tc::fence_barrier_init();
         tc::mbar_expect_tx(&hbar[0], GRU_B_TX);
         tc::mbar_expect_tx(&hbar[1], GRU_B_TX);
-        tc::mbar_expect_tx(&wbar, GRU_BS_BYTES);
-        tc::bulk_g2s(sA, wimg + GRU_BT_IMG, GRU_BS_BYTES, &wbar);
+        tc::mbar_expect_tx(&wbar, GRU_BA_BYTES);
+        const uint8_t* src = a.whhT + (size_t)(dir * GRU_CL + rank) * GRU_BA_BYTES;
+#pragma unroll 1
+        for (int s = 0; s < GRU_BA_NSLAB; ++s) tc::bulk_g2s(sA + s * GRU_BA_SLAB, src + s * GRU_BA_SLAB, GRU_BA_SLAB, &wbar);
     }
-    if (warp == GRU_ISSUER) tc::tmem_alloc(&tmem_slot, 512);
+    if (warp == 8) tc::tmem_alloc(&tmem_slot, 32);
     for (int i = tid; i < (int)(2 * GRU_BB_BYTES / 16); i += GRU_THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_all();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    if (warp < 2) {                                       // rows 0..63 of W_hh^T (44 valid), K = 0..959 -> 480 TMEM columns
-        tmem_load_image(tmem + ((uint32_t)(warp * 32) << 16) + GRU_BT_A0, reinterpret_cast<const uint32_t*>(wimg), 64, GRU_BT_COLS, warp * 32 + lane);
-        tc::tmem_wait_st();
-        tc::fence_before_sync();
-    }
-    __syncthreads();
-    tc::fence_after_sync();
     cluster_arrive();
     cluster_wait();
 
-    if (warp == GRU_ISSUER) {
+    if (warp == 8) {
         // ============================================================ MMA issuer: (dGh of the step before) . W_hh -> D[unit k][sample]
         const uint64_t dA = desc_base(tc::smem_u32(sA));
         const uint64_t dB0 = desc_base(tc::smem_u32(sB)), dB1 = desc_base(tc::smem_u32(sB) + GRU_BB_BYTES);
@@ -409,47 +445,86 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
             if (elect_one()) {
                 const uint64_t dB = (step & 1) ? dB1 : dB0;
 #pragma unroll
-                for (int kt = 0; kt < GRU_BT_K / 16; ++kt)                             // A from tensor memory
-                    tc::mma_bf16_ts(tmem, tmem + GRU_BT_A0 + kt * 8, desc_adv(dB, (kt >> 2) * GRU_B_SLAB + (kt & 3) * 32), idesc, kt != 0);
-#pragma unroll
-                for (int kt = GRU_BT_K / 16; kt < GRU_G / 16; ++kt) {                  // the K tail from shared memory
-                    const int ks = kt - GRU_BT_K / 16;
-                    tc::mma_bf16(tmem, desc_adv(dA, (ks >> 2) * GRU_BA_SLAB + (ks & 3) * 32), desc_adv(dB, (kt >> 2) * GRU_B_SLAB + (kt & 3) * 32),
-                                 idesc, true);
-                }
+                for (int kt = 0; kt < GRU_G / 16; ++kt)
+                    tc::mma_bf16(tmem, desc_adv(dA, (kt >> 2) * GRU_BA_SLAB + (kt & 3) * 32), desc_adv(dB, (kt >> 2) * GRU_B_SLAB + (kt & 3) * 32),
+                                 idesc, kt != 0);
                 tc::mma_commit(&mbar);
             }
             __syncwarp();
+        }
+    } else if (warp >= 6) {
+        // ============================================================ I/O warps
+        const int it = tid - GRU_IO_T0;
+        float4 g[5][3];
+        uint2 hp[3];
+        auto load_in = [&](int t) {
+            const int tp = dir ? t + 1 : t - 1;          // the time step whose output was this step's h_{t-1}
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                const int gb = i / GRU_ROW4, grp = i - gb * GRU_ROW4;
+                const bool ok = i < GRU_TILE4 && b0 + gb < B;
+                const size_t col = dir * GRU_HP + (int)rank * GRU_UNITS + grp * 4;
+                const size_t o = ((size_t)t * B + (b0 + gb)) * (2 * GRU_HP) + col;
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                g[0][k] = ok ? __ldg(reinterpret_cast<const float4*>(a.R + o)) : zero;
+                g[1][k] = ok ? __ldg(reinterpret_cast<const float4*>(a.Z + o)) : zero;
+                g[2][k] = ok ? __ldg(reinterpret_cast<const float4*>(a.N + o)) : zero;
+                g[3][k] = ok ? __ldg(reinterpret_cast<const float4*>(a.HN + o)) : zero;
+                g[4][k] = ok ? __ldg(reinterpret_cast<const float4*>(a.dY + o)) : zero;
+                hp[k] = (ok && tp >= 0 && tp < T) ? __ldg(reinterpret_cast<const uint2*>(a.Y + ((size_t)tp * B + (b0 + gb)) * (2 * GRU_HP) + col))
+                                                  : make_uint2(0u, 0u);
+            }
+        };
+        auto stage_in = [&]() {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                if (i < GRU_TILE4) {
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) sin4[q * GRU_TILE4 + i] = g[q][k];
+                    shp[i] = hp[k];
+                }
+            }
+        };
+        load_in(dir ? 0 : T - 1);
+        stage_in();
+        bar_arrive(GRU_BAR_IN, 256);
+#pragma unroll 1
+        for (int step = 0; step < T; ++step) {
+            const int t = dir ? step : T - 1 - step;     // reverse of the forward order
+            if (step + 1 < T) load_in(dir ? t + 1 : t - 1);
+            bar_sync(GRU_BAR_OUT, 256);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = it + k * GRU_IO_THREADS;
+                const int gb = i / GRU_ROW4, grp = i - gb * GRU_ROW4;
+                if (i < GRU_TILE4 && b0 + gb < B) {
+                    const size_t o = ((size_t)t * B + (b0 + gb)) * (2 * GRU_G) + dir * GRU_G + (int)rank * GRU_UNITS + grp * 4;
+                    const uint2 vr = sout2[i], vz = sout2[GRU_TILE4 + i], vni = sout2[2 * GRU_TILE4 + i], vnh = sout2[3 * GRU_TILE4 + i];
+                    *reinterpret_cast<uint2*>(a.dGi + o) = vr; *reinterpret_cast<uint2*>(a.dGh + o) = vr;
+                    *reinterpret_cast<uint2*>(a.dGi + o + GRU_HP) = vz; *reinterpret_cast<uint2*>(a.dGh + o + GRU_HP) = vz;
+                    *reinterpret_cast<uint2*>(a.dGi + o + 2 * GRU_HP) = vni;
+                    *reinterpret_cast<uint2*>(a.dGh + o + 2 * GRU_HP) = vnh;
+                }
+            }
+            if (step + 1 < T) stage_in();
+            bar_arrive(GRU_BAR_IN, 256);
         }
     } else {
         // ============================================================ gate warps
         const bool gate_thr = tid < GRU_GATE_THREADS;
         const int gb = tid & 15, grp = tid >> 4;
-        const int b = b0 + gb;
-        const bool act = gate_thr && b < B;
+        const bool act = gate_thr && b0 + gb < B;
         const int ju = (int)rank * GRU_UNITS + grp * 4;
+        const int si = gb * GRU_ROW4 + grp;
         uint32_t loff[3];
 #pragma unroll
         for (int q = 0; q < 3; ++q) loff[q] = tc::smem_u32(sB) + bop_off(gb, q * GRU_HP + ju);
         float carry[4] = {0.f, 0.f, 0.f, 0.f};             // dh * z of the step before (direct path to h_{t-1})
-        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), z4 = r4, n4 = r4, hn4 = r4, dy4 = r4;
-        uint2 hp = make_uint2(0u, 0u);
-        auto load_in = [&](int t) {
-            const size_t o = ((size_t)t * B + b) * (2 * GRU_HP) + dir * GRU_HP + ju;
-            r4 = __ldg(reinterpret_cast<const float4*>(a.R + o));
-            z4 = __ldg(reinterpret_cast<const float4*>(a.Z + o));
-            n4 = __ldg(reinterpret_cast<const float4*>(a.N + o));
-            hn4 = __ldg(reinterpret_cast<const float4*>(a.HN + o));
-            dy4 = __ldg(reinterpret_cast<const float4*>(a.dY + o));
-            const int tp = dir ? t + 1 : t - 1;          // the time step whose output was this step's h_{t-1}
-            hp = (tp >= 0 && tp < T) ? __ldg(reinterpret_cast<const uint2*>(a.Y + ((size_t)tp * B + b) * (2 * GRU_HP) + dir * GRU_HP + ju))
-                                     : make_uint2(0u, 0u);
-        };
-        if (act) load_in(dir ? 0 : T - 1);
         uint32_t mphase = 0;
 #pragma unroll 1
         for (int step = 0; step < T; ++step) {
-            const int t = dir ? step : T - 1 - step;     // reverse of the forward order
             const int cur = step & 1;
             tc::mbar_wait(&mbar, mphase);
             mphase ^= 1;
@@ -462,8 +537,11 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
                 for (int j = 0; j < 16; ++j) dst[j] = v[j];
                 tc::fence_before_sync();
             }
-            bar_sync(1, GRU_GATE_T);
+            bar_sync(GRU_BAR_IN, 256);
             if (gate_thr) {
+                const float4 r4 = sin4[si], z4 = sin4[GRU_TILE4 + si], n4 = sin4[2 * GRU_TILE4 + si], hn4 = sin4[3 * GRU_TILE4 + si],
+                             dy4 = sin4[4 * GRU_TILE4 + si];
+                const uint2 hp = shp[si];
                 const float r[4] = {r4.x, r4.y, r4.z, r4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w}, n[4] = {n4.x, n4.y, n4.z, n4.w};
                 const float hn[4] = {hn4.x, hn4.y, hn4.z, hn4.w}, dy[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
                 const __nv_bfloat162 h01 = *reinterpret_cast<const __nv_bfloat162*>(&hp.x), h23 = *reinterpret_cast<const __nv_bfloat162*>(&hp.y);
@@ -494,22 +572,20 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
                         st_async_v2(mapa(loff[2], (uint32_t)rk) + boff, vnh.x, vnh.y, rb);
                     }
                 }
-                if (act) {
-                    if (step + 1 < T) load_in(dir ? t + 1 : t - 1);                  // next step's saved values, a step ahead
-                    const size_t o = ((size_t)t * B + b) * (2 * GRU_G) + dir * GRU_G + ju;
-                    *reinterpret_cast<uint2*>(a.dGi + o) = vr; *reinterpret_cast<uint2*>(a.dGh + o) = vr;
-                    *reinterpret_cast<uint2*>(a.dGi + o + GRU_HP) = vz; *reinterpret_cast<uint2*>(a.dGh + o + GRU_HP) = vz;
-                    *reinterpret_cast<uint2*>(a.dGi + o + 2 * GRU_HP) = make_uint2(tc::pack_bf16x2(dgni[0], dgni[1]), tc::pack_bf16x2(dgni[2], dgni[3]));
-                    *reinterpret_cast<uint2*>(a.dGh + o + 2 * GRU_HP) = vnh;
-                }
+                sout2[si] = vr;
+                sout2[GRU_TILE4 + si] = vz;
+                sout2[2 * GRU_TILE4 + si] = make_uint2(tc::pack_bf16x2(dgni[0], dgni[1]), tc::pack_bf16x2(dgni[2], dgni[3]));
+                sout2[3 * GRU_TILE4 + si] = vnh;
             }
+            __syncwarp();
+            bar_arrive(GRU_BAR_OUT, 256);
         }
     }
     tc::fence_before_sync();
     __syncthreads();
     cluster_arrive();
     cluster_wait();
-    if (warp == GRU_ISSUER) tc::tmem_dealloc(tmem, 512);
+    if (warp == 8) tc::tmem_dealloc(tmem, 32);
 }
 
 // ---------------------------------------------------------------- packing / unpacking
@@ -545,9 +621,8 @@ __global__ void gru_pack_wih_kernel(const float* __restrict__ w0, const float* _
     }
 }
 
-// W_hh -> per (dir, CTA) operand images.  Forward: tensor-memory image of the rows [r | z | n] of the CTA's 44 units
-// (block 0 = rows 0..127, block 1 = rows 128..159, see tmem_load_image).  Backward: tensor-memory image of W_hh^T rows (the
-// CTA's units k, gate columns 0..959) followed by the shared-memory slabs of gate columns 960..1087.
+// W_hh -> per (dir, CTA) operand images: forward = tensor-memory image of the rows [r|z|n] of the CTA's units; backward =
+// shared-memory slabs [unit k][gate column] of W_hh^T
 __global__ void gru_pack_whh_kernel(const float* __restrict__ w0, const float* __restrict__ w1, uint8_t* __restrict__ fimg,
                                     uint8_t* __restrict__ bimg, int H)
 {
@@ -555,7 +630,7 @@ __global__ void gru_pack_whh_kernel(const float* __restrict__ w0, const float* _
     const float* w = dir ? w1 : w0;
     const int t0 = blockIdx.z * blockDim.x + threadIdx.x, tstride = gridDim.z * blockDim.x;
     uint32_t* fi = reinterpret_cast<uint32_t*>(fimg + (size_t)(dir * GRU_CL + c) * GRU_FT_IMG);
-    for (int idx = t0; idx < 160 * (int)GRU_FT_COLS; idx += tstride) {
+    for (int idx = t0; idx < 160 * (int)GRU_FT_COLS; idx += tstride) {       // tensor-memory image, see tmem_load_image
         const int row = idx / (int)GRU_FT_COLS, kp = idx % (int)GRU_FT_COLS;
         float v0 = 0.f, v1 = 0.f;
         if (row < 3 * GRU_UNITS) {
@@ -571,30 +646,16 @@ __global__ void gru_pack_whh_kernel(const float* __restrict__ w0, const float* _
         fi[at] = tc::pack_bf16x2(v0, v1);
     }
     if (!bimg) return;
-    uint8_t* bi = bimg + (size_t)(dir * GRU_CL + c) * (GRU_BT_IMG + GRU_BS_BYTES);
-    uint32_t* bt = reinterpret_cast<uint32_t*>(bi);
-    auto wt = [&](int row, int g) -> float {               // W_hh^T element: unit k = c*44 + row, gate column g
-        if (row >= GRU_UNITS || g >= GRU_G) return 0.f;
-        const int k = c * GRU_UNITS + row, q = g / GRU_HP, u = g % GRU_HP;
-        return (k < H && u < H) ? w[(size_t)(q * H + u) * H + k] : 0.f;
-    };
-    for (int idx = t0; idx < 64 * (int)GRU_BT_COLS; idx += tstride) {
-        const int row = idx / (int)GRU_BT_COLS, kp = idx % (int)GRU_BT_COLS;
-        bt[((size_t)(kp >> 4) * 64 + row) * 16 + (kp & 15)] = tc::pack_bf16x2(wt(row, 2 * kp), wt(row, 2 * kp + 1));
-    }
-    uint8_t* bs = bi + GRU_BT_IMG;
-    for (int idx = t0; idx < (int)GRU_BS_BYTES / 2; idx += tstride) {
+    uint8_t* bi = bimg + (size_t)(dir * GRU_CL + c) * GRU_BA_BYTES;
+    for (int idx = t0; idx < GRU_BA_ROWS * GRU_BA_NSLAB * 64; idx += tstride) {
+        const int row = idx / (GRU_BA_NSLAB * 64), g = idx % (GRU_BA_NSLAB * 64);
         float v = 0.f;
-        const int e = idx;                                 // bf16 element index inside the 16 KB tail region
-        const int slab = e / (GRU_BA_ROWS * 64);
-        if (slab < GRU_BS_SLABS) {
-            const int row = (e % (GRU_BA_ROWS * 64)) / 64, col = e % 64;
-            v = wt(row, GRU_BT_K + slab * 64 + col);
-            const uint32_t off = (uint32_t)slab * GRU_BA_SLAB + tc::slab_chunk_off(row, col >> 3) + (uint32_t)(col & 7) * 2u;
-            *reinterpret_cast<__nv_bfloat16*>(bs + off) = __float2bfloat16_rn(v);
-        } else {
-            *reinterpret_cast<__nv_bfloat16*>(bs + (size_t)e * 2) = __float2bfloat16_rn(0.f);
+        if (row < GRU_UNITS && g < GRU_G) {
+            const int k = c * GRU_UNITS + row, q = g / GRU_HP, u = g % GRU_HP;
+            if (k < H && u < H) v = w[(size_t)(q * H + u) * H + k];
         }
+        const uint32_t off = (uint32_t)(g >> 6) * GRU_BA_SLAB + tc::slab_chunk_off(row, (g & 63) >> 3) + (uint32_t)(g & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(bi + off) = __float2bfloat16_rn(v);
     }
 }
 
@@ -688,7 +749,7 @@ static GruLayout gru_layout(const HopkGruShape* s)
     }
     g.total = cur;
     cur = 0;
-    g.s_whhT = gbump(cur, (size_t)2 * GRU_CL * (GRU_BT_IMG + GRU_BS_BYTES));
+    g.s_whhT = gbump(cur, (size_t)2 * GRU_CL * GRU_BA_BYTES);
     g.s_dya = gbump(cur, TB * ipmax * 4);
     g.s_dyb = gbump(cur, TB * ipmax * 4);
     g.s_dgi = gbump(cur, TB * 2 * GRU_G * 2);

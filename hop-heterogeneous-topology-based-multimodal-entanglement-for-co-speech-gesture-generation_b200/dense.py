@@ -20,6 +20,8 @@ from . import _lib, profiler
 from ._lib import check, f32c, lib, ptr, stream_ptr
 
 _SMS = 148
+KEEP = False          # tests / tools: keep references to intermediate activations in LAST (gate patterns for pinned oracles)
+LAST = {}
 
 
 def _pad8(n):
@@ -154,6 +156,8 @@ class _BeatRowsFn(torch.autograd.Function):
             rows = torch.empty((B, NWIN, J, 3 + F2), device=dev, dtype=torch.float32)
             check(lib().hopk_beat_rows_fwd(ptr(feat), ptr(seed), ptr(rows), B, J, F2, stream_ptr()))
         ctx.save_for_backward(win, w1b, w2b, h1)
+        if KEEP:
+            LAST['beat_h1'] = h1[:, :F1]
         ctx.dims = (B, J, F1, F2)
         return rows
 
