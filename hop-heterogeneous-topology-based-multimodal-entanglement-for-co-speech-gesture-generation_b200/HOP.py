@@ -18,6 +18,7 @@ from math import sqrt
 import torch
 import torch.nn as nn
 
+from . import bert as hbert
 from . import dense
 from . import gru as hgru
 from . import gwnet, profiler
@@ -260,6 +261,7 @@ class Model(nn.Module):
         self._source_reducer = None
         self.amp_dtype = None          # None: everything fp32 like the reference; torch.bfloat16: see set_precision
         self.own_gru = True            # bf16 mode: decoder GRU on the hand-written kernels (False: stock cuDNN, for A/B timing)
+        self.own_bert = True           # bf16 mode: frozen BERT encoder on the hand-written kernels (False: stock Hugging Face module)
         self.own_dense = True          # bf16 mode: mapping / align / beat GEMMs on the hand-written TMA GEMM (False: cuBLAS)
         self._we_cast = None
 
@@ -306,6 +308,7 @@ class Model(nn.Module):
         out = super().load_state_dict(*args, **kwargs)
         self.__dict__['_llm_shadow'] = None                 # frozen-weight caches follow the loaded weights
         self._we_cast = None
+        hbert.invalidate(self.llm_model)
         return out
 
     def _gwnet_bn_buffers(self):
@@ -364,7 +367,11 @@ class Model(nn.Module):
             llama_enc_out = dense.linear(torch.cat([enc_out, text_embeddings.float()], dim=2), self.align_layer.weight, self.align_layer.bias)
         else:
             llama_enc_out = self.align_layer(torch.cat([enc_out, text_embeddings], dim=2))
-        dec_out = self._llm()(inputs_embeds=llama_enc_out).last_hidden_state
+        if self.amp_dtype is not None and self.own_bert and hbert.supported(self.llm_model, llama_enc_out.shape[1]):
+            # frozen encoder on the hand-written path (hop_b200/bert.py: TMA GEMMs + csrc/bert.cu), gradient to the input only
+            dec_out = hbert.run(self.llm_model, llama_enc_out.float())
+        else:
+            dec_out = self._llm()(inputs_embeds=llama_enc_out).last_hidden_state
 
         # beat features: the reference runs the MLP on J identical copies of the 16 windows and then
         # *reinterprets* (B,J,16,170) as (B,16,J,170) (HOP.py:210-212); equal to MLP-once + gather.

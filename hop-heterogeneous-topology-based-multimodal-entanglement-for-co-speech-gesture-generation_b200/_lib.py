@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libhopk.so')
 MAX_LAYERS = 16
 GEMM_A_MN, GEMM_B_MN, GEMM_OUT_BF16, GEMM_ACCUMULATE, GEMM_RELU, GEMM_LEAKY, GEMM_GELU = 1, 2, 4, 8, 16, 32, 64
-GEMM_BIAS_ROW, GEMM_MASK_BF16 = 128, 256
+GEMM_BIAS_ROW, GEMM_MASK_BF16, GEMM_MASK_GELU = 128, 256, 512
 
 _vp = C.c_void_p
 _LAYER_ARR = _vp * MAX_LAYERS
@@ -82,6 +82,11 @@ SIGNATURES = {
     'hopk_cast_bf16': (_i, [_vp, _vp, C.c_long, _i, C.c_long, _i, C.c_long, _i, _vp]),
     'hopk_unfold_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, C.c_long, C.c_long, _vp]),
     'hopk_colsum': (_i, [_vp, _vp, C.c_long, _i, C.c_long, _i, _vp]),
+    'hopk_ln_fwd': (_i, [_vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp]),
+    'hopk_ln_bwd': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    'hopk_gelu_bf16': (_i, [_vp, _vp, C.c_long, _vp]),
+    'hopk_bert_attn_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'hopk_bert_attn_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'hopk_beat_rows_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'hopk_beat_rows_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, C.c_long, _vp]),
     'hopk_gru_workspace_bytes': (_sz, [C.POINTER(GruShape)]),

@@ -11,7 +11,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libhopk.so')
-SOURCES = ['api.cu', 'gwnet.cu', 'linear.cu', 'xattn.cu', 'xattn_tc.cu', 'gemm_tma.cu', 'gru.cu', 'glue.cu']
+SOURCES = ['api.cu', 'gwnet.cu', 'linear.cu', 'xattn.cu', 'xattn_tc.cu', 'gemm_tma.cu', 'gru.cu', 'glue.cu', 'bert.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
 

@@ -35,7 +35,7 @@ cudaError_t configure_smem_once(const void* func, size_t bytes);
 // dense bf16 GEMM on tcgen05 + TMA (gemm_tma.cu); see hopk_gemm_bf16 in include/hopk.h for the operand conventions
 int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, const void* addend, int M, int N, int K, long lda,
                      long ldb, long ldc, int a_mn, int b_mn, int out_bf16, int accumulate, int act, float slope, int splits,
-                     cudaStream_t st, const void* mask = nullptr, int a_kshift = 0, int b_kshift = 0, int bias_row = 0, int mask_bf16 = 0);
+                     cudaStream_t st, const void* mask = nullptr, int a_kshift = 0, int b_kshift = 0, int bias_row = 0, int mask_bf16 = 0, int mask_gelu = 0);
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 

@@ -33,7 +33,7 @@ template <int BN> constexpr size_t gt_smem_bytes() { return (size_t)gt_stages<BN
 
 struct GtArgs {
     void* C; const float* bias; const void* addend; const void* mask;
-    int bias_row, mask_bf16;                            // bias indexed by the output row m instead of the column n; mask stored as bf16
+    int bias_row, mask_bf16, mask_gelu;                            // bias indexed by the output row m instead of the column n; mask stored as bf16
     int a_kshift, b_kshift;                             // added to the contraction (row) coordinate of an MN-major operand; rows
                                                         // that fall outside the matrix read as zero (TMA out-of-bounds fill)
     int M, N, K;
@@ -192,7 +192,14 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         for (int j = 0; j < 32; ++j) v[j] = gt_act(v[j], g.act, g.slope);
                     }
                     if (g.mask) {                                  // out *= mask > 0 ? 1 : slope  (gradient of a fused (Leaky)ReLU)
-                        if (g.mask_bf16) {
+                        if (g.mask_gelu) {                         // out *= gelu'(mask): the mask is the saved bf16 pre-activation
+                            const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(g.mask) + (size_t)m * g.ldc + nb;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) {
+                                const float xx = __bfloat162float(mk[j]);
+                                v[j] *= 0.5f * (1.f + erff(xx * 0.70710678118654752f)) + xx * 0.3989422804014327f * __expf(-0.5f * xx * xx);
+                            }
+                        } else if (g.mask_bf16) {
                             const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(g.mask) + (size_t)m * g.ldc + nb;
 #pragma unroll
                             for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] = __bfloat162float(mk[j]) > 0.f ? v[j] : g.slope * v[j];
@@ -346,7 +353,7 @@ static int make_map(CUtensorMap* tm, const void* base, long rows, long cols, lon
 
 int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, const void* addend, int M, int N, int K, long lda,
                      long ldb, long ldc, int a_mn, int b_mn, int out_bf16, int accumulate, int act, float slope, int splits,
-                     cudaStream_t st, const void* mask, int a_kshift, int b_kshift, int bias_row, int mask_bf16)
+                     cudaStream_t st, const void* mask, int a_kshift, int b_kshift, int bias_row, int mask_bf16, int mask_gelu)
 {
     HOPK_REQUIRE((a_kshift == 0 || a_mn) && (b_kshift == 0 || b_mn), "a row shift needs an MN-major operand");
     HOPK_REQUIRE(!(mask && (accumulate || splits > 1)), "a mask cannot be combined with accumulation / split-K");
@@ -362,7 +369,7 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     const int BN = wide ? 256 : 128;
     if (int rc = b_mn ? make_map(&tmB, B, K, N, ldb, GT_BK) : make_map(&tmB, B, N, K, ldb, BN)) return rc;
     GtArgs g;
-    g.C = C; g.bias = bias; g.addend = addend; g.mask = mask; g.bias_row = bias_row; g.mask_bf16 = mask_bf16; g.a_kshift = a_kshift; g.b_kshift = b_kshift; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
+    g.C = C; g.bias = bias; g.addend = addend; g.mask = mask; g.bias_row = bias_row; g.mask_bf16 = mask_bf16; g.mask_gelu = mask_gelu; g.a_kshift = a_kshift; g.b_kshift = b_kshift; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
     g.out_bf16 = out_bf16; g.accumulate = accumulate; g.act = act; g.slope = slope;
     if (splits < 1) splits = 1;
     int kper = ((cdiv(K, splits) + GT_BK - 1) / GT_BK) * GT_BK;
@@ -397,7 +404,8 @@ extern "C" int hopk_gemm_bf16(const void* A, const void* B, void* C, const float
     const int act = (flags & HOPK_GEMM_RELU) ? 1 : (flags & HOPK_GEMM_LEAKY) ? 2 : (flags & HOPK_GEMM_GELU) ? 3 : 0;
     return gemm_bf16_launch(A, B, C, bias, addend, M, N, K, lda, ldb, ldc, a_mn, b_mn, (flags & HOPK_GEMM_OUT_BF16) ? 1 : 0,
                             (flags & HOPK_GEMM_ACCUMULATE) ? 1 : 0, act, slope, splits, (cudaStream_t)stream, mask, 0, 0,
-                            (flags & HOPK_GEMM_BIAS_ROW) ? 1 : 0, (flags & HOPK_GEMM_MASK_BF16) ? 1 : 0);
+                            (flags & HOPK_GEMM_BIAS_ROW) ? 1 : 0, (flags & HOPK_GEMM_MASK_BF16) ? 1 : 0,
+                            (flags & HOPK_GEMM_MASK_GELU) ? 1 : 0);
 }
 
 extern "C" int hopk_cast_bf16(const float* src, void* dst, long rows, int cols, long lds, int cols_out, long ldd, int relu, void* stream)

@@ -36,14 +36,15 @@ def cast_bf16(x2, relu=False):
     return out
 
 
-def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, addend=None, mask=None, mask_bf16=False, out=None, out_bf16=False,
-         act=0, slope=0.0, splits=1, bias_row=False, accumulate=False, ldc=None):
+def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, addend=None, mask=None, mask_bf16=False, mask_gelu=False, out=None,
+         out_bf16=False, act=0, slope=0.0, splits=1, bias_row=False, accumulate=False, ldc=None):
     """C[M, N] = A . B^T-style contraction over K (see include/hopk.h: hopk_gemm_bf16)."""
     ldc = ldc or (out.stride(0) if out is not None else (_pad8(N) if out_bf16 else N))
     if out is None:
         out = torch.empty((M, ldc), device=A.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
     flags = ((_lib.GEMM_A_MN if a_mn else 0) | (_lib.GEMM_B_MN if b_mn else 0) | (_lib.GEMM_OUT_BF16 if out_bf16 else 0) | act |
-             (_lib.GEMM_BIAS_ROW if bias_row else 0) | (_lib.GEMM_MASK_BF16 if mask_bf16 else 0) | (_lib.GEMM_ACCUMULATE if accumulate else 0))
+             (_lib.GEMM_BIAS_ROW if bias_row else 0) | (_lib.GEMM_MASK_BF16 if mask_bf16 else 0) | (_lib.GEMM_MASK_GELU if mask_gelu else 0) |
+             (_lib.GEMM_ACCUMULATE if accumulate else 0))
     check(lib().hopk_gemm_bf16(ptr(A), ptr(B), ptr(out), ptr(bias), ptr(addend), ptr(mask), M, N, K, A.stride(0), B.stride(0), ldc,
                                flags, float(slope), int(splits), stream_ptr()))
     return out

@@ -151,6 +151,7 @@ int hopk_conv1x1_nchw_bwd(const float* x, const float* w, const float* dy, float
 #define HOPK_GEMM_GELU 64      /* exact (erf) GELU */
 #define HOPK_GEMM_BIAS_ROW 128 /* bias indexed by the output row m (length M) instead of the column n */
 #define HOPK_GEMM_MASK_BF16 256 /* mask is stored as bf16 */
+#define HOPK_GEMM_MASK_GELU 512 /* mask is a bf16 pre-activation x: the result is multiplied by gelu'(x) (exact erf form) */
 int hopk_gemm_bf16(const void* A, const void* B, void* C, const float* bias, const float* addend, const void* mask,
                    int M, int N, int K, long lda, long ldb, long ldc, int flags, float slope, int splits, void* stream);
 /* fp32 (rows x cols, ld lds) -> bf16 (rows x cols_out, ld ldd), zero padding for cols <= c < cols_out, optional ReLU */
@@ -167,6 +168,21 @@ int hopk_colsum(const void* src, float* out, long rows, int cols, long ld, int s
  * Backward: dfeat (bf16, leading dimension ldd) = the J-fold gather-sum of drows[..., 3:]; dbias (nullable) = its column sums. */
 int hopk_beat_rows_fwd(const float* feat, const float* seed, float* rows, int B, int J, int F, void* stream);
 int hopk_beat_rows_bwd(const float* drows, void* dfeat_bf16, float* dbias, int B, int J, int F, long ldd, void* stream);
+
+/* ------------------------------------------------------------------ frozen BERT encoder: the kernels between its GEMMs
+ * (model/HOP.py:204 `self.llm_model(inputs_embeds=...)`; weights frozen, HOP.py:90-91: backward = dX only)
+ * layer norm over rows of C = 128 k columns: v = x (+ add[row % period]); y = (v - mean) * rstd * gamma + beta; fp32 and / or
+ * bf16 copies of y; stat[row] = {mean, rstd} for backward.  hopk_ln_bwd: dX of the same (fp32 and / or bf16). */
+int hopk_ln_fwd(const float* x, const float* add, int period, const float* gamma, const float* beta, float eps, float* y32,
+                void* y16, float* stat, int M, int C, void* stream);
+int hopk_ln_bwd(const float* dy, const float* x, const float* add, int period, const float* gamma, const float* stat,
+                float* dx32, void* dx16, int M, int C, void* stream);
+/* exact GELU on n bf16 elements (n % 8 == 0) */
+int hopk_gelu_bf16(const void* pre, void* out, long n, void* stream);
+/* BertSelfAttention core without mask / dropout: qkv bf16 (B*S, 3*H*D) = [q heads | k heads | v heads] per row; ctx bf16
+ * (B*S, H*D); P fp32 (B*H, S, S) softmax probabilities (saved for backward; NULL: not stored).  D = 64, S <= 64. */
+int hopk_bert_attn_fwd(const void* qkv, void* ctx, float* P, int B, int S, int H, int D, void* stream);
+int hopk_bert_attn_bwd(const void* qkv, const void* dctx, const float* P, void* dqkv, int B, int S, int H, int D, void* stream);
 
 /* ------------------------------------------------------------------ GRU decoder (model/HOP.py:166-167, 248)
  * Multi-layer bidirectional GRU, batch_first, zero initial state, PyTorch gate order (r, z, n); dtype-1 arithmetic (bf16
