@@ -72,6 +72,15 @@ SIGNATURES = {
     'hopk_gwnet_ws_field': (_i, [_SHP, C.c_char_p, _i, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
     'hopk_gwnet_forward': (_i, [_SHP, _PRM, _vp, _I64x4, _vp, _vp, _vp]),
     'hopk_gwnet_backward': (_i, [_SHP, _PRM, _vp, _I64x4, _vp, _vp, _vp, _GRD, _vp, _vp]),
+    'hopk_adp_softmax_fwd': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    'hopk_adp_softmax_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    'hopk_gated_tcn_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'hopk_gated_tcn_bwd_scratch_bytes': (_sz, [_i, _i, _i, _i, _i]),
+    'hopk_gated_tcn_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'hopk_gcn_scratch_bytes': (_sz, [_i, _i, _i, _i]),
+    'hopk_gcn_diffuse_mlp_res_bnstat_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'hopk_gcn_diffuse_mlp_res_bnstat_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'hopk_bn_finalize': (_i, [_vp, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp]),
     'hopk_nconv_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'hopk_nconv_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'hopk_linear_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -13,7 +13,8 @@
 //            completion by mbarrier complete_tx
 //   warp 1   MMA issuer: one lane issues tcgen05.mma (M 128, N = BN, K 16, 4 per 64-wide K block) into one of two TMEM
 //            accumulators; tcgen05.commit releases the ring slot / publishes the accumulator
-//   warps 2-5  epilogue: tcgen05.ld of their TMEM lane quarter (row per thread), bias / activation / conversion, 256-bit
+//   warps 2-9  epilogue (two warps per TMEM lane quarter, alternating 32-column chunks): tcgen05.ld (row per thread), bias /
+//            residual / activation / conversion, 256-bit
 //            (fp32) or 128-bit (bf16) global stores, or vector atomics for split-K
 // The second accumulator lets the MMAs of tile i+1 run under the epilogue of tile i.
 #include <cuda.h>
@@ -25,7 +26,7 @@
 namespace hopk {
 
 constexpr int GT_BM = 128, GT_BK = 64;
-constexpr int GT_THREADS = 192;                         // producer warp, MMA warp, 4 epilogue warps
+constexpr int GT_THREADS = 320;                         // producer warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 
 template <int BN> constexpr int gt_stages() { return BN == 128 ? 6 : 4; }
 template <int BN> constexpr uint32_t gt_stage_bytes() { return tc::slab_bytes(GT_BM) + tc::slab_bytes(BN); }
@@ -82,7 +83,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 8); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * BN);
@@ -151,8 +152,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else {
-        // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
-        const int quarter = warp & 3;
+        // ===================================================== epilogue: warps 2..9; warp w drains TMEM lane quarter w & 3 (the
+        // quarter a warp may access) and, of the tile's 32-column chunks, those with chunk parity (w - 2) >> 2
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         int acc = 0; uint32_t acc_phase = 0;
@@ -165,7 +167,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc::fence_after_sync();
             const uint32_t src = tmem + acc * BN + lane_off;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = chalf; c < BN / 32; c += 2) {
                 const int nb = n0 + c * 32;
                 if (nb >= g.N) break;                              // uniform across the warp
                 float v[32];
@@ -177,6 +179,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const float bm = __ldg(g.bias + m);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] += bm;
+                        } else if (fullw && ((reinterpret_cast<uintptr_t>(g.bias + nb) & 15) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
+                                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+                            }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] += __ldg(g.bias + nb + j);
@@ -184,8 +192,16 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if (g.addend && first_split) {                                // fp32 residual / accumulate-from tensor with C's layout
                         const float* ad = reinterpret_cast<const float*>(g.addend) + (size_t)m * g.ldc + nb;
+                        if (fullw && ((reinterpret_cast<uintptr_t>(ad) & 15) == 0)) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] += __ldg(ad + j);
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 aa = __ldg(reinterpret_cast<const float4*>(ad + j));
+                                v[j] += aa.x; v[j + 1] += aa.y; v[j + 2] += aa.z; v[j + 3] += aa.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] += __ldg(ad + j);
+                        }
                     }
                     if (g.act) {
 #pragma unroll
@@ -365,8 +381,15 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     CUtensorMap tmA, tmB;
     // K-major: matrix is (M rows x K cols), box {64 k, 128 rows}; MN-major: matrix is (K rows x M cols), box {64 m, 64 k-rows}
     if (int rc = a_mn ? make_map(&tmA, A, K, M, lda, GT_BK) : make_map(&tmA, A, M, K, lda, GT_BM)) return rc;
-    const bool wide = N > 128 && ((long)cdiv(M, GT_BM) * cdiv(N, 128) * (splits > 1 ? splits : 1)) > 2 * 148;   // enough tiles: 128 x 256
-    const int BN = wide ? 256 : 128;
+    // tile width: 128 x 256 tiles read less of A per flop but cost ~1.75x a 128 x 128 tile; the persistent grid runs
+    // ceil(tiles / SMs) waves, so take whichever finishes first (wave quantisation decides at these sizes)
+    int dev0 = 0, sms0 = 148;
+    cudaGetDevice(&dev0);
+    cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+    const long sp = splits > 1 ? splits : 1;
+    const long t128 = (long)cdiv(M, GT_BM) * cdiv(N, 128) * sp, t256 = (long)cdiv(M, GT_BM) * cdiv(N, 256) * sp;
+    const double c128 = (double)cdiv(t128, sms0), c256 = 1.75 * (double)cdiv(t256, sms0);
+    const int BN = (N > 128 && c256 < c128) ? 256 : 128;
     if (int rc = b_mn ? make_map(&tmB, B, K, N, ldb, GT_BK) : make_map(&tmB, B, N, K, ldb, BN)) return rc;
     GtArgs g;
     g.C = C; g.bias = bias; g.addend = addend; g.mask = mask; g.bias_row = bias_row; g.mask_bf16 = mask_bf16; g.mask_gelu = mask_gelu; g.a_kshift = a_kshift; g.b_kshift = b_kshift; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
@@ -377,9 +400,7 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     g.splits = splits; g.kper = kper;
     g.tiles_m = cdiv(M, GT_BM); g.tiles_n = cdiv(N, BN);
     const long ntiles = (long)g.tiles_m * g.tiles_n * splits;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sms0;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     if (splits > 1 && !accumulate) HOPK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
     if (BN == 256) {

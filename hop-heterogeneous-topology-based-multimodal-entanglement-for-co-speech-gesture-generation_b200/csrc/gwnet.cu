@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ TF,
         const float4* zp = reinterpret_cast<const float4*>(SG + (size_t)g0 * V * C);
         const float4* gp = reinterpret_cast<const float4*>(G + (size_t)g0 * V * 2 * C);
         for (int i = threadIdx.x; i < ng * V * C / 4; i += blockDim.x) {
-            float4 x = __ldg(yp + i); const float4 z = __ldg(zp + i);
+            float4 x = __ldg(yp + i); const float4 z = SG ? __ldg(zp + i) : make_float4(1.f, 1.f, 1.f, 1.f);
             x.x *= z.x; x.y *= z.y; x.z *= z.z; x.w *= z.w;
             int e = i * 4; int r = e / C, c = e - r * C;
             float* d = sy + r * ldy + c; d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
@@ -1629,5 +1629,224 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
         HOPK_CUDA(cudaEventRecord(sd->ev_join[k], sd->s[k]));
         HOPK_CUDA(cudaStreamWaitEvent(st, sd->ev_join[k], 0));
     }
+    return 0;
+}
+
+
+// ============================================================================ per-op entry points
+// The same kernels that hopk_gwnet_forward / backward chain together (the generic, non-fused path), exposed one operator at
+// a time so that each can be tested and timed in isolation through the C ABI.  All activations in the rows layout.
+namespace hopk {
+__global__ void gate_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ tf, const float* __restrict__ sg,
+                                float* __restrict__ df, float* __restrict__ dg, size_t n4)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 d = reinterpret_cast<const float4*>(dy)[i], t = reinterpret_cast<const float4*>(tf)[i], s = reinterpret_cast<const float4*>(sg)[i];
+        reinterpret_cast<float4*>(df)[i] = make_float4(d.x * s.x * (1.f - t.x * t.x), d.y * s.y * (1.f - t.y * t.y), d.z * s.z * (1.f - t.z * t.z),
+                                                       d.w * s.w * (1.f - t.w * t.w));
+        reinterpret_cast<float4*>(dg)[i] = make_float4(d.x * t.x * s.x * (1.f - s.x), d.y * t.y * s.y * (1.f - s.y), d.z * t.z * s.z * (1.f - s.z),
+                                                       d.w * t.w * s.w * (1.f - s.w));
+    }
+}
+// dA = M1 + A^T M2 + M2 A^T  (two diffusion hops, Appendix A)
+__global__ void da_combine_kernel(const float* __restrict__ A, const float* __restrict__ M1, const float* __restrict__ M2, float* __restrict__ dA, int V)
+{
+    for (int idx = threadIdx.x; idx < V * V; idx += blockDim.x) {
+        const int v = idx / V, w = idx % V;
+        float acc = M1[idx];
+        for (int k = 0; k < V; ++k) acc += A[k * V + v] * M2[k * V + w] + M2[v * V + k] * A[w * V + k];
+        dA[idx] = acc;
+    }
+}
+}  // namespace hopk
+
+static int op_check(int B, int V, int Ti, int d, int C, int dtype)
+{
+    HOPK_REQUIRE(B >= 1 && V >= 1 && V <= 45 && d >= 1 && Ti > d, "op sizes (V <= 45, Ti > d)");
+    HOPK_REQUIRE(C % 4 == 0 && C >= 4 && C <= 256, "C must be a multiple of 4, <= 256");
+    HOPK_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 or 1");
+    HOPK_REQUIRE((long)B * V * Ti * 256 < (1L << 31), "tensor too large for 32-bit row indices");
+    return 0;
+}
+
+extern "C" int hopk_adp_softmax_fwd(const float* e1, const float* e2, int V, int R, float* A5, void* stream)
+{
+    HOPK_REQUIRE(V >= 1 && V <= 45 && R >= 1, "adp_softmax sizes");
+    const size_t vv = (size_t)V * V;
+    adp_fwd_kernel<<<1, 256, V * V * sizeof(float), (cudaStream_t)stream>>>(e1, e2, V, R, A5, A5 + vv, A5 + 2 * vv, A5 + 3 * vv, A5 + 4 * vv);
+    HOPK_LAUNCH_CHECK("adp_softmax_fwd");
+    return 0;
+}
+
+extern "C" int hopk_adp_softmax_bwd(const float* e1, const float* e2, const float* A5, const float* dA, int V, int R, float* de1, float* de2,
+                                    void* stream)
+{
+    HOPK_REQUIRE(V >= 1 && V <= 45 && R >= 1, "adp_softmax sizes");
+    const size_t vv = (size_t)V * V;
+    adp_bwd_kernel<<<1, 256, V * V * sizeof(float), (cudaStream_t)stream>>>(e1, e2, A5, A5 + 4 * vv, dA, nullptr, V, R, de1, de2);
+    HOPK_LAUNCH_CHECK("adp_softmax_bwd");
+    return 0;
+}
+
+extern "C" int hopk_gated_tcn_fwd(const float* x, const float* ss, const float* wf, const float* bf, const float* wg, const float* bg, int B,
+                                  int V, int Ti, int d, int C, int dtype, float* tf, float* sg, float* y, void* stream)
+{
+    if (int rc = op_check(B, V, Ti, d, C, dtype)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc = dtype == 1;
+    LayerGeom lg{V, C, Ti, Ti - d, d};
+    const int M = B * lg.To * V;
+    GateA a{x, ss, lg};
+    GateB b{wf, wg, C, tc ? 1 : 0};
+    GateEpi e{bf, bg, tf, sg, y, nullptr, lg, 0, 1, 0};          // Tl = 0: no skip slice
+    const int Nlog = tc ? cdiv(C, 16) * 32 : cdiv(C, 64) * 128;
+    launch_gemm<2, 2>(tc, M, Nlog, 2 * C, 1, a, b, e, st);
+    HOPK_LAUNCH_CHECK("gated_tcn_fwd");
+    return 0;
+}
+
+extern "C" size_t hopk_gated_tcn_bwd_scratch_bytes(int B, int V, int Ti, int d, int C) { return (size_t)2 * B * (Ti - d) * V * C * sizeof(float); }
+
+extern "C" int hopk_gated_tcn_bwd(const float* x, const float* ss, const float* wf, const float* wg, const float* tf, const float* sg,
+                                  const float* dy, int B, int V, int Ti, int d, int C, int dtype, void* scratch, float* dx, float* dwf,
+                                  float* dbf, float* dwg, float* dbg, void* stream)
+{
+    if (int rc = op_check(B, V, Ti, d, C, dtype)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc = dtype == 1;
+    LayerGeom lg{V, C, Ti, Ti - d, d};
+    const int M = B * lg.To * V, Min = B * Ti * V;
+    float* DF = (float*)scratch;
+    float* DG = DF + (size_t)M * C;
+    const size_t n4 = (size_t)M * C / 4;
+    gate_bwd_kernel<<<cdiv((long)n4, 256) > 148 * 8 ? 148 * 8 : cdiv((long)n4, 256), 256, 0, st>>>(dy, tf, sg, DF, DG, n4);
+    HOPK_LAUNCH_CHECK("gate_bwd");
+    HOPK_CUDA(cudaMemsetAsync(dwf, 0, (size_t)C * 2 * C * sizeof(float), st));
+    HOPK_CUDA(cudaMemsetAsync(dwg, 0, (size_t)C * 2 * C * sizeof(float), st));
+    HOPK_CUDA(cudaMemsetAsync(dbf, 0, (size_t)C * sizeof(float), st));
+    HOPK_CUDA(cudaMemsetAsync(dbg, 0, (size_t)C * sizeof(float), st));
+    if (tc && C % 8 == 0) {
+        W8Seg3 a{DF, DG, DG, C, 2 * C};
+        W8GateXI b{x, ss, lg, 2 * C};
+        GateWgEpi2 e{dwf, dwg, dbf, dbg, C};
+        HOPK_CUDA(launch_gemm_tc_wgrad<128>(M, 2 * C, 2 * C, a, b, e, true, st));
+    } else {
+        GateWgA a{DF, DG, C};
+        GateWgB b{x, ss, lg};
+        GateWgEpi<2> e{dwf, dwg, dbf, dbg, C};
+        launch_gemm<2, 2>(tc, 2 * C, 2 * C + 1, M, pick_splits(tc, 2 * C, 2 * C + 1, M, 2, 2), a, b, e, st);
+    }
+    HOPK_LAUNCH_CHECK("gated_tcn_wgrad");
+    if (dx) {
+        DxA a{DF, DG, lg};
+        DxB b{wf, wg, C};
+        if (C <= 64) {
+            DxEpi<1> e; memset(&e, 0, sizeof(e));
+            e.DX = dx; e.g = lg; e.tc_bn = 64;
+            launch_gemm<2, 1>(tc, Min, C, 4 * C, 1, a, b, e, st);
+        } else {
+            DxEpi<2> e; memset(&e, 0, sizeof(e));
+            e.DX = dx; e.g = lg; e.tc_bn = 128;
+            launch_gemm<2, 2>(tc, Min, C, 4 * C, 1, a, b, e, st);
+        }
+        HOPK_LAUNCH_CHECK("gated_tcn_dx");
+    }
+    return 0;
+}
+
+extern "C" size_t hopk_gcn_scratch_bytes(int B, int V, int To, int C)
+{
+    return ((size_t)4 * B * To * V * C + (size_t)3 * V * V) * sizeof(float) + 1024;
+}
+
+/* u = Wm . [y | A^T y | (A^2)^T y] + bm + BN-folded residual x[t + d]; stats = per-channel sum / sum^2 of u (doubles, 2C) */
+extern "C" int hopk_gcn_diffuse_mlp_res_bnstat_fwd(const float* y, const float* A5, const float* xres, const float* ss, const float* wm,
+                                                   const float* bm, int B, int V, int Ti, int d, int C, int dtype, float* x1, float* x2,
+                                                   float* u, double* stats, void* stream)
+{
+    if (int rc = op_check(B, V, Ti, d, C, dtype)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc = dtype == 1;
+    LayerGeom lg{V, C, Ti, Ti - d, d};
+    const int M = B * lg.To * V;
+    const size_t vv = (size_t)V * V;
+    HOPK_CUDA(cudaMemsetAsync(stats, 0, (size_t)2 * C * sizeof(double), st));
+    if (int rc = launch_node_mix(y, A5, A5 + vv, x1, x2, B * lg.To, V, C, st)) return rc;
+    Seg3A a{y, x1, x2, C};
+    Ld2D<true, 0> b{wm, nullptr, 3 * C};
+    if (C <= 64) {
+        MlpEpi<1> e; memset(&e, 0, sizeof(e));
+        e.bm = bm; e.up = xres; e.ss = ss; e.U = u; e.stats = stats; e.g = lg; e.tc_bn = 64;
+        launch_gemm<2, 1>(tc, M, C, 3 * C, 1, a, b, e, st);
+    } else {
+        MlpEpi<2> e; memset(&e, 0, sizeof(e));
+        e.bm = bm; e.up = xres; e.ss = ss; e.U = u; e.stats = stats; e.g = lg; e.tc_bn = 128;
+        launch_gemm<2, 2>(tc, M, C, 3 * C, 1, a, b, e, st);
+    }
+    HOPK_LAUNCH_CHECK("gcn_mlp_fwd");
+    return 0;
+}
+
+/* given du (gradient w.r.t. u; also the gradient of the residual branch): dy, dWm, dbm, dA */
+extern "C" int hopk_gcn_diffuse_mlp_res_bnstat_bwd(const float* du, const float* y, const float* x1, const float* x2, const float* A5,
+                                                   const float* wm, int B, int V, int To, int C, int dtype, void* scratch, float* dy,
+                                                   float* dwm, float* dbm, float* dA, void* stream)
+{
+    if (int rc = op_check(B, V, To + 1, 1, C, dtype)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc = dtype == 1;
+    const int M = B * To * V, groups = B * To;
+    const size_t vv = (size_t)V * V;
+    float* P1 = (float*)(((uintptr_t)scratch + 255) & ~uintptr_t(255));
+    float* P2 = P1 + (size_t)M * C;
+    float* G = P2 + (size_t)M * C;
+    float* m12 = G + (size_t)2 * M * C;
+    if (int rc = launch_node_mix(du, A5 + 2 * vv, A5 + 3 * vv, P1, P2, groups, V, C, st)) return rc;      // A du, A^2 du
+    {
+        Seg3A a{du, P1, P2, C};
+        DyB b{wm, C};
+        if (C <= 64) { EpiStore<1> e{dy, C, nullptr, nullptr, C, 0}; launch_gemm<2, 1>(tc, M, C, 3 * C, 1, a, b, e, st); }
+        else { EpiStore<2> e{dy, C, nullptr, nullptr, C, 0}; launch_gemm<2, 2>(tc, M, C, 3 * C, 1, a, b, e, st); }
+        HOPK_LAUNCH_CHECK("gcn_dy");
+    }
+    HOPK_CUDA(cudaMemsetAsync(dwm, 0, (size_t)C * 3 * C * sizeof(float), st));
+    HOPK_CUDA(cudaMemsetAsync(dbm, 0, (size_t)C * sizeof(float), st));
+    {
+        Ld2D<false, 0> a{du, nullptr, C};
+        Seg3AT b{y, x1, x2, C};
+        EpiWgrad<2> e{dwm, (long)3 * C, dbm, 3 * C, C};
+        if (C <= 64) launch_gemm<1, 2>(tc, C, 3 * C + 1, M, pick_splits(tc, C, 3 * C + 1, M, 1, 2), a, b, e, st);
+        else launch_gemm<2, 2>(tc, C, 3 * C + 1, M, pick_splits(tc, C, 3 * C + 1, M, 2, 2), a, b, e, st);
+        HOPK_LAUNCH_CHECK("gcn_wgrad");
+    }
+    {
+        Ld2D<true, 0> a{du, nullptr, C};
+        Ld2D<false, 0> b{wm + C, nullptr, (long)3 * C};
+        EpiStore<2> e{G, (long)2 * C, nullptr, nullptr, 2 * C, 0};
+        launch_gemm<2, 2>(tc, M, 2 * C, C, 1, a, b, e, st);
+        HOPK_LAUNCH_CHECK("gcn_g");
+        HOPK_CUDA(cudaMemsetAsync(m12, 0, 2 * vv * sizeof(float), st));
+        int gpi = GRAM_GPI;
+        auto gram_smem = [&](int n) { return ((size_t)n * V * (3 * C + 2) + 2 * (size_t)V * V) * sizeof(float); };
+        while (gpi > 1 && gram_smem(gpi) > 200 * 1024) --gpi;
+        const size_t smem3 = gram_smem(gpi);
+        HOPK_REQUIRE(smem3 <= 200 * 1024, "gram kernel: V * C too large for shared memory");
+        if (smem3 > 48 * 1024) HOPK_CUDA(configure_smem_once((const void*)gram_kernel, 200 * 1024));
+        int gblocks = cdiv(groups, gpi); if (gblocks > 148) gblocks = 148;
+        gram_kernel<<<gblocks, 256, smem3, st>>>(y, nullptr, G, m12, groups, V, C, gpi);
+        HOPK_LAUNCH_CHECK("gcn_gram");
+        da_combine_kernel<<<1, 256, 0, st>>>(A5, m12, m12 + vv, dA, V);
+        HOPK_LAUNCH_CHECK("gcn_dA");
+    }
+    return 0;
+}
+
+extern "C" int hopk_bn_finalize(const double* stats, double count, const float* gamma, const float* beta, float* rmean, float* rvar,
+                                int64_t* nbt, float* mean_rstd, float* scale_shift, int C, int training, float momentum, float eps, void* stream)
+{
+    HOPK_REQUIRE(C >= 1 && count >= 1 && eps > 0.f, "bn_finalize sizes");
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, count, gamma, beta, rmean, rvar, (long long*)nbt, mean_rstd,
+                                                                        scale_shift, C, training, momentum, eps);
+    HOPK_LAUNCH_CHECK("bn_finalize");
     return 0;
 }

@@ -112,6 +112,37 @@ int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParams* p,
                         const float* x, const int64_t xs[4], const float* dout,
                         void* ws, void* scratch, const HopkGwnetGrads* g, float* dx, void* stream);
 
+/* ------------------------------------------------------------------ Graph-WaveNet operators one at a time
+ * The kernels hopk_gwnet_forward / backward chain together, exposed per operator for isolated tests and timing.  Rows layout
+ * everywhere: x (B, Ti, V, C), outputs of a layer (B, To = Ti - d, V, C).  ss = BatchNorm scale | shift (2C floats) folded into
+ * every read of x (pass ones | zeros for a plain input).  dtype as above.
+ *
+ * adaptive adjacency (gwnet.py:161-164): A5 = [A | A^2 | A^T | (A^2)^T | Z = E1 E2], 5 V*V floats, A = softmax(relu(Z), dim=1) */
+int hopk_adp_softmax_fwd(const float* e1, const float* e2, int V, int R, float* A5, void* stream);
+int hopk_adp_softmax_bwd(const float* e1, const float* e2, const float* A5, const float* dA, int V, int R, float* de1, float* de2, void* stream);
+/* gated dilated conv (gwnet.py:186-200): tf = tanh(filter conv), sg = sigmoid(gate conv), y = tf * sg; weights (C, C, 1, 2).
+ * bwd: dx = gradient w.r.t. the BN-folded input (nullable), dw / db overwritten; scratch = hopk_gated_tcn_bwd_scratch_bytes */
+int hopk_gated_tcn_fwd(const float* x, const float* ss, const float* wf, const float* bf, const float* wg, const float* bg, int B, int V,
+                       int Ti, int d, int C, int dtype, float* tf, float* sg, float* y, void* stream);
+size_t hopk_gated_tcn_bwd_scratch_bytes(int B, int V, int Ti, int d, int C);
+int hopk_gated_tcn_bwd(const float* x, const float* ss, const float* wf, const float* wg, const float* tf, const float* sg, const float* dy,
+                       int B, int V, int Ti, int d, int C, int dtype, void* scratch, float* dx, float* dwf, float* dbf, float* dwg,
+                       float* dbg, void* stream);
+/* graph convolution + residual + BatchNorm statistics (gwnet.py:33-46, 233, 237): x1 = A^T y, x2 = (A^2)^T y (per node group),
+ * u = Wm [y | x1 | x2] + bm + (ss-folded) xres[t + d]; stats = per-channel sum | sum of squares of u (2C doubles).
+ * bwd (from du): dy, dWm (C, 3C), dbm, dA (V, V); the residual branch receives du itself.  scratch = hopk_gcn_scratch_bytes */
+size_t hopk_gcn_scratch_bytes(int B, int V, int To, int C);
+int hopk_gcn_diffuse_mlp_res_bnstat_fwd(const float* y, const float* A5, const float* xres, const float* ss, const float* wm,
+                                        const float* bm, int B, int V, int Ti, int d, int C, int dtype, float* x1, float* x2, float* u,
+                                        double* stats, void* stream);
+int hopk_gcn_diffuse_mlp_res_bnstat_bwd(const float* du, const float* y, const float* x1, const float* x2, const float* A5,
+                                        const float* wm, int B, int V, int To, int C, int dtype, void* scratch, float* dy, float* dwm,
+                                        float* dbm, float* dA, void* stream);
+/* BatchNorm2d finalize (gwnet.py:120, 237): statistics -> mean | rstd, folded scale | shift for the next layer's reads,
+ * running-statistics update (training) */
+int hopk_bn_finalize(const double* stats, double count, const float* gamma, const float* beta, float* rmean, float* rvar, int64_t* nbt,
+                     float* mean_rstd, float* scale_shift, int C, int training, float momentum, float eps, void* stream);
+
 /* nconv.forward (model/gwnet.py:12-14): out[n,c,w,l] = sum_v x[n,c,v,l] * A[v,w], contiguous NCHW.
  * hopk_nconv_bwd: dx (same layout) and dA (V x V, overwritten). */
 int hopk_nconv_fwd(const float* x, const float* A, float* out, int N, int C, int V, int T, void* stream);
