@@ -113,9 +113,7 @@ class _ModuleDP:
             b.work.wait()                                       # orders the current stream after the collective
         if self.o.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.o.comm_stream)
-        inv = 1.0 / self.o.world
-        for b in self.buckets:
-            b.flat.mul_(inv)
+        for b in self.buckets:                                  # already averaged: the all-reduce runs with ReduceOp.AVG
             for v, p in zip(b.views, b.params):
                 if p.grad is not None:
                     p.grad = v                                  # hand the averaged view to the optimiser (no copy back)
@@ -130,10 +128,12 @@ class DataParallel:
         self.stats = dict(allreduce_bytes=0, buckets=0)
         self.comm_stream = None
         self.parts = []
+        self._avg = dist.ReduceOp.SUM
         if self.world > 1:
             dev = next(self.modules[0].parameters()).device
             if dev.type == 'cuda':
                 self.comm_stream = torch.cuda.Stream(device=dev)
+                self._avg = dist.ReduceOp.AVG                   # NCCL averages inside the collective: no separate scaling pass
             if broadcast:
                 for m in self.modules:
                     for t in list(m.parameters()) + list(m.buffers()):
@@ -143,8 +143,9 @@ class DataParallel:
     def _reduce_now(self, t):
         """Stream-ordered mean all-reduce used inside autograd for the small dSource tensor."""
         if self.world > 1:
-            dist.all_reduce(t, group=self.group)
-            t.div_(self.world)
+            dist.all_reduce(t, op=self._avg, group=self.group)
+            if self._avg is dist.ReduceOp.SUM:
+                t.div_(self.world)
             self.stats['allreduce_bytes'] += t.numel() * t.element_size()
         return t
 
@@ -154,9 +155,12 @@ class DataParallel:
             ev.record()                                         # gradients of this bucket are complete here
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
-                b.work = dist.all_reduce(b.flat, group=self.group, async_op=True)
+                b.work = dist.all_reduce(b.flat, op=self._avg, group=self.group, async_op=True)
         else:
-            b.work = dist.all_reduce(b.flat, group=self.group, async_op=True)
+            b.work = dist.all_reduce(b.flat, op=self._avg, group=self.group, async_op=True)
+            if self._avg is dist.ReduceOp.SUM:                  # gloo (CPU tests) has no AVG: scale after the sum
+                b.work.wait()
+                b.flat.div_(self.world)
         self.stats['allreduce_bytes'] += b.numel * 4
         self.stats['buckets'] += 1
 
