@@ -37,6 +37,7 @@ def launches(path, steps=None):
     with open(path) as f:
         lines = [ln for ln in f if not ln.startswith('==')]
     tot, cnt = collections.Counter(), collections.Counter()
+    ours_names = set()
     for row in csv.DictReader(lines):
         try:
             v = float(row['Metric Value'].replace(',', ''))
@@ -45,6 +46,8 @@ def launches(path, steps=None):
         unit = row.get('Metric Unit', 'ns')
         v *= {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}.get(unit, 1e-3)
         k = short(row['Kernel Name'])
+        if 'hopk::' in row['Kernel Name']:
+            ours_names.add(k)
         tot[k] += v
         cnt[k] += 1
     total = sum(tot.values())
@@ -52,11 +55,12 @@ def launches(path, steps=None):
     print(f'# {path}: {n} launches, {total / 1e3:.3f} ms of kernel time (ncu: serialised, cold caches)')
     if steps:
         print(f'# per step ({steps} steps captured): {n / steps:.0f} launches, {total / steps / 1e3:.3f} ms')
-    ours = sum(v for k, v in tot.items() if any(s in k for s in ('gemm_tc', 'xattn', 'fz_', 'gw_', 'node_mix', 'gram_', 'bn_', 'adp_', 'nchw_', 'fill_', 'linear_', 'gemm_kernel')))
-    print(f'# hand-written kernels (libhopk.so): {ours / 1e3:.3f} ms = {100 * ours / max(total, 1e-9):.1f} % of the kernel time')
-    print(f'{"us total":>10} {"share":>6} {"count":>6} {"us avg":>8}  kernel')
+    ours = sum(v for k, v in tot.items() if k in ours_names)
+    nours = sum(c for k, c in cnt.items() if k in ours_names)
+    print(f'# hand-written kernels (namespace hopk, libhopk.so): {nours} launches, {ours / 1e3:.3f} ms = {100 * ours / max(total, 1e-9):.1f} % of the kernel time')
+    print(f'{"us total":>10} {"share":>6} {"count":>6} {"us avg":>8}  kernel   (* = hand-written, namespace hopk)')
     for k, v in tot.most_common():
-        print(f'{v:10.1f} {100 * v / total:5.1f}% {cnt[k]:6d} {v / cnt[k]:8.1f}  {k}')
+        print(f'{v:10.1f} {100 * v / total:5.1f}% {cnt[k]:6d} {v / cnt[k]:8.1f}  {"*" if k in ours_names else " "} {k}')
 
 
 def full(path):
