@@ -3,7 +3,7 @@
     python scripts/sass_opcodes.py [out.txt]
 
 Counts SASS mnemonics of `cuobjdump -sass libhopk.so` (no GPU needed): tcgen05 MMA (UTCHMMA / UTCQMMA / UTCIMMA ...), TMEM
-traffic (LDTM / STTM / UTCCP), tensor-core barriers (UTCBAR), bulk copies without a tensor map (UBLKCP), TMA tensor
+traffic (LDTM / STTM / UTCCP), tensor-core barriers (UTCBAR), bulk copies without a tensor map (UBLKCP), remote st.async (STAS), TMA tensor
 copies (UTMALDG / UTMASTG / UTMAPF), mbarrier (SYNCS), cluster barriers (UCGABAR), legacy tensor instructions (HMMA / WGMMA:
 must be absent), and per-kernel counts of the tensor-core instructions.
 """
@@ -16,7 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'hop-heterogeneous-topology-based-multimodal-entanglement-for-co-speech-gesture-generation_b200', 'libhopk.so')
 WATCH = ['UTCHMMA', 'UTCQMMA', 'UTCIMMA', 'UTCOMMA', 'LDTM', 'STTM', 'UTCCP', 'UTCBAR', 'UBLKCP', 'UTMALDG', 'UTMASTG', 'UTMAPF',
-         'UTMACCTL', 'SYNCS', 'UCGABAR', 'HMMA', 'WGMMA', 'BMMA', 'MUFU.TANH', 'MUFU.EX2', 'REDG', 'ATOMG', 'STG.E.ENL2.256',
+         'UTMACCTL', 'SYNCS', 'UCGABAR', 'STAS', 'HMMA', 'WGMMA', 'BMMA', 'MUFU.TANH', 'MUFU.EX2', 'REDG', 'ATOMG', 'STG.E.ENL2.256',
          'LDG.E.ENL2.256', 'FENCE.VIEW.ASYNC']
 
 
@@ -35,7 +35,7 @@ def main():
             continue
         op = m.group(1)
         for w in WATCH:
-            if op == w or op.startswith(w + '.') or (('.' in w) and op.startswith(w)):
+            if op.startswith(w):
                 total[w] += 1
                 per_kernel[kernel][w] += 1
     lines = [f'# cuobjdump -sass {os.path.basename(LIB)} | opcode counts (sm_100a); HMMA / WGMMA / BMMA must be 0',
@@ -43,13 +43,13 @@ def main():
     for w in WATCH:
         lines.append(f'{w:20s} {total[w]:7d}')
     lines.append('')
-    lines.append('# per kernel (demangled prefix): UTCHMMA LDTM STTM UBLKCP UTMALDG UTMASTG SYNCS UCGABAR')
+    lines.append('# per kernel (demangled prefix): UTCHMMA LDTM STTM UBLKCP UTMALDG STAS SYNCS UCGABAR')
     names = subprocess.run(['c++filt'], input='\n'.join(per_kernel), capture_output=True, text=True).stdout.splitlines()
     for k, nm in zip(per_kernel, names):
         c = per_kernel[k]
         if c['UTCHMMA'] or c['UTMALDG'] or c['UBLKCP'] or c['UCGABAR']:
             short = re.sub(r'\(.*', '', nm).replace('hopk::', '')[:110]
-            lines.append(f'{c["UTCHMMA"]:5d} {c["LDTM"]:5d} {c["STTM"]:5d} {c["UBLKCP"]:5d} {c["UTMALDG"]:5d} {c["UTMASTG"]:5d} '
+            lines.append(f'{c["UTCHMMA"]:5d} {c["LDTM"]:5d} {c["STTM"]:5d} {c["UBLKCP"]:5d} {c["UTMALDG"]:5d} {c["STAS"]:5d} '
                          f'{c["SYNCS"]:5d} {c["UCGABAR"]:5d}  {short}')
     text = '\n'.join(lines) + '\n'
     if len(sys.argv) > 1:
