@@ -116,38 +116,81 @@ __global__ void gelu_bf16_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfl
 
 // ---------------------------------------------------------------- self-attention, one CTA per (sample, head)
 // qkv: bf16 [B*S][3*H*D] rows = (b, t): [q heads | k heads | v heads]; ctx: bf16 [B*S][H*D]; P: fp32 [B*H][S][S] (saved)
-constexpr int AT_MAXS = 64, AT_D = 64;
+// Every product is register-tiled (2 rows x 2 columns of the S x S matrices, 2 rows x 4 columns of the S x D ones) with
+// 128-bit shared-memory reads along the contraction index: one LDS.128 per 4-8 FMAs instead of two LDS per FMA (the first
+// version was shared-memory-bandwidth bound: 78 us per call at B = 128).
+constexpr int AT_MAXS = 64, AT_D = 64, AT_LD = AT_D + 4;      // fp32 row pitch 68: 16-byte aligned rows
+
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+
+// out[r][c] = sum_e X[r][e] Y[c][e] for r, c < S (X, Y: [S][AT_LD]); 2 x 2 register tiles; out pitch ldo; scaled
+__device__ __forceinline__ void tile_xyT(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ out, int ldo, int S, float scale)
+{
+    const int TS = (S + 1) >> 1;
+    for (int i = threadIdx.x; i < TS * TS; i += blockDim.x) {
+        const int r0 = (i / TS) * 2, c0 = (i % TS) * 2;
+        const int r1 = min(r0 + 1, S - 1), c1 = min(c0 + 1, S - 1);
+        float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+#pragma unroll 4
+        for (int e = 0; e < AT_D; e += 4) {
+            const float4 x0 = *reinterpret_cast<const float4*>(X + r0 * AT_LD + e), x1 = *reinterpret_cast<const float4*>(X + r1 * AT_LD + e);
+            const float4 y0 = *reinterpret_cast<const float4*>(Y + c0 * AT_LD + e), y1 = *reinterpret_cast<const float4*>(Y + c1 * AT_LD + e);
+            a00 += dot4(x0, y0); a01 += dot4(x0, y1); a10 += dot4(x1, y0); a11 += dot4(x1, y1);
+        }
+        out[r0 * ldo + c0] = a00 * scale;
+        if (c0 + 1 < S) out[r0 * ldo + c0 + 1] = a01 * scale;
+        if (r0 + 1 < S) {
+            out[(r0 + 1) * ldo + c0] = a10 * scale;
+            if (c0 + 1 < S) out[(r0 + 1) * ldo + c0 + 1] = a11 * scale;
+        }
+    }
+}
+
+// acc[2][4] = sum_j W(r, j) * Z[j][c..c+3] for rows r0, r0 + 1: W(r, j) = Wm[r * ldw + j] or (transposed) Wm[j * ldw + r]
+template <bool TRANS>
+__device__ __forceinline__ void tile_wz(const float* __restrict__ Wm, int ldw, const float* __restrict__ Z, int S, int r0, int r1, int c,
+                                        float (&acc)[2][4])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { acc[0][q] = 0.f; acc[1][q] = 0.f; }
+    for (int j = 0; j < S; ++j) {
+        const float w0 = TRANS ? Wm[j * ldw + r0] : Wm[r0 * ldw + j], w1 = TRANS ? Wm[j * ldw + r1] : Wm[r1 * ldw + j];
+        const float4 z = *reinterpret_cast<const float4*>(Z + j * AT_LD + c);
+        acc[0][0] = fmaf(w0, z.x, acc[0][0]); acc[0][1] = fmaf(w0, z.y, acc[0][1]); acc[0][2] = fmaf(w0, z.z, acc[0][2]); acc[0][3] = fmaf(w0, z.w, acc[0][3]);
+        acc[1][0] = fmaf(w1, z.x, acc[1][0]); acc[1][1] = fmaf(w1, z.y, acc[1][1]); acc[1][2] = fmaf(w1, z.z, acc[1][2]); acc[1][3] = fmaf(w1, z.w, acc[1][3]);
+    }
+}
+
+__device__ __forceinline__ void load_head(float* dst, const __nv_bfloat16* __restrict__ src, size_t ld, int S)
+{
+    for (int i = threadIdx.x; i < S * (AT_D / 8); i += blockDim.x) {          // 8 bf16 (16 bytes) per thread
+        const int t = i / (AT_D / 8), c = (i % (AT_D / 8)) * 8;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)t * ld + c));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+        float* d = dst + t * AT_LD + c;
+        *reinterpret_cast<float4*>(d) = make_float4(__low2float(h[0]), __high2float(h[0]), __low2float(h[1]), __high2float(h[1]));
+        *reinterpret_cast<float4*>(d + 4) = make_float4(__low2float(h[2]), __high2float(h[2]), __low2float(h[3]), __high2float(h[3]));
+    }
+}
 
 __global__ void __launch_bounds__(128) bert_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx,
                                                             float* __restrict__ P, int S, int H)
 {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const int b = blockIdx.x / H, h = blockIdx.x % H;
-    float* q = sm;                          // [S][D+1]
-    float* k = q + S * (AT_D + 1);          // [S][D+1]
-    float* v = k + S * (AT_D + 1);          // [S][D]
-    float* p = v + S * AT_D;                // [S][S+1]
-    const int ld = 3 * H * AT_D;
-    for (int i = threadIdx.x; i < S * (AT_D / 2); i += blockDim.x) {
-        const int t = i / (AT_D / 2), c = (i % (AT_D / 2)) * 2;
-        const __nv_bfloat16* row = qkv + (size_t)(b * S + t) * ld + h * AT_D + c;
-        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(row);
-        const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(row + H * AT_D);
-        const __nv_bfloat162 cc = *reinterpret_cast<const __nv_bfloat162*>(row + 2 * H * AT_D);
-        q[t * (AT_D + 1) + c] = __low2float(a); q[t * (AT_D + 1) + c + 1] = __high2float(a);
-        k[t * (AT_D + 1) + c] = __low2float(bb); k[t * (AT_D + 1) + c + 1] = __high2float(bb);
-        v[t * AT_D + c] = __low2float(cc); v[t * AT_D + c + 1] = __high2float(cc);
-    }
+    float* q = sm;                          // [S][AT_LD]
+    float* k = q + S * AT_LD;
+    float* v = k + S * AT_LD;
+    float* p = v + S * AT_LD;               // [S][S+1]
+    const size_t ld = (size_t)3 * H * AT_D;
+    const __nv_bfloat16* base = qkv + (size_t)b * S * ld + h * AT_D;
+    load_head(q, base, ld, S);
+    load_head(k, base + H * AT_D, ld, S);
+    load_head(v, base + 2 * H * AT_D, ld, S);
     __syncthreads();
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
-        const int r = i / S, c = i % S;
-        float acc = 0.f;
-#pragma unroll 16
-        for (int e = 0; e < AT_D; ++e) acc = fmaf(q[r * (AT_D + 1) + e], k[c * (AT_D + 1) + e], acc);
-        p[r * (S + 1) + c] = acc * 0.125f;                      // 1 / sqrt(64)
-    }
+    tile_xyT(q, k, p, S + 1, S, 0.125f);                        // scores / sqrt(64)
     __syncthreads();
-    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {   // one warp per row
+    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {   // softmax: one warp per row
         const int lane = threadIdx.x & 31;
         float m = -INFINITY;
         for (int c = lane; c < S; c += 32) m = fmaxf(m, p[r * (S + 1) + c]);
@@ -163,53 +206,40 @@ __global__ void __launch_bounds__(128) bert_attn_fwd_kernel(const __nv_bfloat16*
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < S * (AT_D / 2); i += blockDim.x) {
-        const int r = i / (AT_D / 2), c = (i % (AT_D / 2)) * 2;
-        float a0 = 0.f, a1 = 0.f;
-        for (int j = 0; j < S; ++j) {
-            const float pv = p[r * (S + 1) + j];
-            a0 = fmaf(pv, v[j * AT_D + c], a0); a1 = fmaf(pv, v[j * AT_D + c + 1], a1);
-        }
-        *reinterpret_cast<uint32_t*>(ctx + (size_t)(b * S + r) * (H * AT_D) + h * AT_D + c) = bf2(a0, a1);
+    const int TR = (S + 1) >> 1;
+    for (int i = threadIdx.x; i < TR * (AT_D / 4); i += blockDim.x) {            // ctx = P V, 2 rows x 4 columns per thread
+        const int r0 = (i / (AT_D / 4)) * 2, c = (i % (AT_D / 4)) * 4, r1 = min(r0 + 1, S - 1);
+        float acc[2][4];
+        tile_wz<false>(p, S + 1, v, S, r0, r1, c, acc);
+        __nv_bfloat16* o = ctx + (size_t)(b * S + r0) * (H * AT_D) + h * AT_D + c;
+        *reinterpret_cast<uint2*>(o) = make_uint2(bf2(acc[0][0], acc[0][1]), bf2(acc[0][2], acc[0][3]));
+        if (r0 + 1 < S) *reinterpret_cast<uint2*>(o + H * AT_D) = make_uint2(bf2(acc[1][0], acc[1][1]), bf2(acc[1][2], acc[1][3]));
     }
 }
 
-// dqkv from dctx: dV = P^T dO, dP = dO V^T, dS = P * (dP - rowsum(dP * P)), dQ = dS K / 8, dK = dS^T Q / 8
+// dqkv from dctx: dV = P^T dO, dP = dO V^T, dS = P * (dP - rowsum(dP * P)) / 8, dQ = dS K, dK = dS^T Q
 __global__ void __launch_bounds__(128) bert_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx,
                                                             const float* __restrict__ P, __nv_bfloat16* __restrict__ dqkv, int S, int H)
 {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const int b = blockIdx.x / H, h = blockIdx.x % H;
-    float* q = sm;                          // [S][D+1]
-    float* k = q + S * (AT_D + 1);
-    float* v = k + S * (AT_D + 1);          // [S][D+1]
-    float* d = v + S * (AT_D + 1);          // dO [S][D+1]
-    float* p = d + S * (AT_D + 1);          // P  [S][S+1]
+    float* q = sm;                          // [S][AT_LD]
+    float* k = q + S * AT_LD;
+    float* v = k + S * AT_LD;
+    float* d = v + S * AT_LD;               // dO
+    float* p = d + S * AT_LD;               // P  [S][S+1]
     float* ds = p + S * (S + 1);            // dS [S][S+1]
-    const int ld = 3 * H * AT_D;
-    for (int i = threadIdx.x; i < S * (AT_D / 2); i += blockDim.x) {
-        const int t = i / (AT_D / 2), c = (i % (AT_D / 2)) * 2;
-        const __nv_bfloat16* row = qkv + (size_t)(b * S + t) * ld + h * AT_D + c;
-        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(row);
-        const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(row + H * AT_D);
-        const __nv_bfloat162 cc = *reinterpret_cast<const __nv_bfloat162*>(row + 2 * H * AT_D);
-        const __nv_bfloat162 dd = *reinterpret_cast<const __nv_bfloat162*>(dctx + (size_t)(b * S + t) * (H * AT_D) + h * AT_D + c);
-        q[t * (AT_D + 1) + c] = __low2float(a); q[t * (AT_D + 1) + c + 1] = __high2float(a);
-        k[t * (AT_D + 1) + c] = __low2float(bb); k[t * (AT_D + 1) + c + 1] = __high2float(bb);
-        v[t * (AT_D + 1) + c] = __low2float(cc); v[t * (AT_D + 1) + c + 1] = __high2float(cc);
-        d[t * (AT_D + 1) + c] = __low2float(dd); d[t * (AT_D + 1) + c + 1] = __high2float(dd);
-    }
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) p[(i / S) * (S + 1) + i % S] = P[(size_t)blockIdx.x * S * S + i];
+    const size_t ld = (size_t)3 * H * AT_D;
+    const __nv_bfloat16* base = qkv + (size_t)b * S * ld + h * AT_D;
+    load_head(q, base, ld, S);
+    load_head(k, base + H * AT_D, ld, S);
+    load_head(v, base + 2 * H * AT_D, ld, S);
+    load_head(d, dctx + (size_t)b * S * (H * AT_D) + h * AT_D, (size_t)H * AT_D, S);
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) p[(i / S) * (S + 1) + i % S] = __ldg(P + (size_t)blockIdx.x * S * S + i);
     __syncthreads();
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) {                 // dP = dO V^T
-        const int r = i / S, c = i % S;
-        float acc = 0.f;
-#pragma unroll 16
-        for (int e = 0; e < AT_D; ++e) acc = fmaf(d[r * (AT_D + 1) + e], v[c * (AT_D + 1) + e], acc);
-        ds[r * (S + 1) + c] = acc;
-    }
+    tile_xyT(d, v, ds, S + 1, S, 1.f);                          // dP = dO V^T
     __syncthreads();
-    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {           // dS = P * (dP - sum(dP * P)) / 8
+    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {
         const int lane = threadIdx.x & 31;
         float s = 0.f;
         for (int c = lane; c < S; c += 32) s += ds[r * (S + 1) + c] * p[r * (S + 1) + c];
@@ -217,19 +247,23 @@ __global__ void __launch_bounds__(128) bert_attn_bwd_kernel(const __nv_bfloat16*
         for (int c = lane; c < S; c += 32) ds[r * (S + 1) + c] = p[r * (S + 1) + c] * (ds[r * (S + 1) + c] - s) * 0.125f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < S * (AT_D / 2); i += blockDim.x) {
-        const int r = i / (AT_D / 2), c = (i % (AT_D / 2)) * 2;
-        float q0 = 0.f, q1 = 0.f, k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
-        for (int j = 0; j < S; ++j) {
-            const float s_rj = ds[r * (S + 1) + j], s_jr = ds[j * (S + 1) + r], p_jr = p[j * (S + 1) + r];
-            q0 = fmaf(s_rj, k[j * (AT_D + 1) + c], q0); q1 = fmaf(s_rj, k[j * (AT_D + 1) + c + 1], q1);
-            k0 = fmaf(s_jr, q[j * (AT_D + 1) + c], k0); k1 = fmaf(s_jr, q[j * (AT_D + 1) + c + 1], k1);
-            v0 = fmaf(p_jr, d[j * (AT_D + 1) + c], v0); v1 = fmaf(p_jr, d[j * (AT_D + 1) + c + 1], v1);
+    const int TR = (S + 1) >> 1;
+    for (int i = threadIdx.x; i < TR * (AT_D / 4); i += blockDim.x) {
+        const int r0 = (i / (AT_D / 4)) * 2, c = (i % (AT_D / 4)) * 4, r1 = min(r0 + 1, S - 1);
+        float aq[2][4], ak[2][4], av[2][4];
+        tile_wz<false>(ds, S + 1, k, S, r0, r1, c, aq);         // dQ = dS K
+        tile_wz<true>(ds, S + 1, q, S, r0, r1, c, ak);          // dK = dS^T Q
+        tile_wz<true>(p, S + 1, d, S, r0, r1, c, av);           // dV = P^T dO
+        __nv_bfloat16* o = dqkv + (size_t)(b * S + r0) * ld + h * AT_D + c;
+        *reinterpret_cast<uint2*>(o) = make_uint2(bf2(aq[0][0], aq[0][1]), bf2(aq[0][2], aq[0][3]));
+        *reinterpret_cast<uint2*>(o + H * AT_D) = make_uint2(bf2(ak[0][0], ak[0][1]), bf2(ak[0][2], ak[0][3]));
+        *reinterpret_cast<uint2*>(o + 2 * H * AT_D) = make_uint2(bf2(av[0][0], av[0][1]), bf2(av[0][2], av[0][3]));
+        if (r0 + 1 < S) {
+            o += ld;
+            *reinterpret_cast<uint2*>(o) = make_uint2(bf2(aq[1][0], aq[1][1]), bf2(aq[1][2], aq[1][3]));
+            *reinterpret_cast<uint2*>(o + H * AT_D) = make_uint2(bf2(ak[1][0], ak[1][1]), bf2(ak[1][2], ak[1][3]));
+            *reinterpret_cast<uint2*>(o + 2 * H * AT_D) = make_uint2(bf2(av[1][0], av[1][1]), bf2(av[1][2], av[1][3]));
         }
-        __nv_bfloat16* row = dqkv + (size_t)(b * S + r) * ld + h * AT_D + c;
-        *reinterpret_cast<uint32_t*>(row) = bf2(q0, q1);
-        *reinterpret_cast<uint32_t*>(row + H * AT_D) = bf2(k0, k1);
-        *reinterpret_cast<uint32_t*>(row + 2 * H * AT_D) = bf2(v0, v1);
     }
 }
 
@@ -288,7 +322,7 @@ extern "C" int hopk_gelu_bf16(const void* pre, void* out, long n, void* stream)
 extern "C" int hopk_bert_attn_fwd(const void* qkv, void* ctx, float* P, int B, int S, int H, int D, void* stream)
 {
     HOPK_REQUIRE(B > 0 && H > 0 && S >= 1 && S <= AT_MAXS && D == AT_D, "bert attention: head dim 64, sequence <= 64");
-    const size_t smem = ((size_t)2 * S * (AT_D + 1) + (size_t)S * AT_D + (size_t)S * (S + 1)) * sizeof(float);
+    const size_t smem = ((size_t)3 * S * AT_LD + (size_t)S * (S + 1)) * sizeof(float) + 16;
     HOPK_CUDA(configure_smem_once((const void*)bert_attn_fwd_kernel, 96 * 1024));
     bert_attn_fwd_kernel<<<B * H, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, P, S, H);
     HOPK_LAUNCH_CHECK("bert_attn_fwd");
@@ -298,7 +332,7 @@ extern "C" int hopk_bert_attn_fwd(const void* qkv, void* ctx, float* P, int B, i
 extern "C" int hopk_bert_attn_bwd(const void* qkv, const void* dctx, const float* P, void* dqkv, int B, int S, int H, int D, void* stream)
 {
     HOPK_REQUIRE(B > 0 && H > 0 && S >= 1 && S <= AT_MAXS && D == AT_D && P, "bert attention backward: head dim 64, sequence <= 64, saved P");
-    const size_t smem = ((size_t)4 * S * (AT_D + 1) + (size_t)2 * S * (S + 1)) * sizeof(float);
+    const size_t smem = ((size_t)4 * S * AT_LD + (size_t)2 * S * (S + 1)) * sizeof(float) + 16;
     HOPK_CUDA(configure_smem_once((const void*)bert_attn_bwd_kernel, 128 * 1024));
     bert_attn_bwd_kernel<<<B * H, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dctx, P, (__nv_bfloat16*)dqkv, S, H);
     HOPK_LAUNCH_CHECK("bert_attn_bwd");
