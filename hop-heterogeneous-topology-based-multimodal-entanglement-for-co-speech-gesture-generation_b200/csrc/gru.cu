@@ -48,7 +48,14 @@ constexpr uint32_t GRU_FB_BYTES = GRU_FA_NSLAB * GRU_B_SLAB;                // 1
 constexpr int GRU_BA_ROWS = 48;
 constexpr uint32_t GRU_BA_SLAB = GRU_BA_ROWS * 128;
 constexpr int GRU_BA_NSLAB = 17;
-constexpr uint32_t GRU_BA_BYTES = GRU_BA_NSLAB * GRU_BA_SLAB;               // 104448
+// ... of which K = 0..959 lives in TENSOR MEMORY (480 columns, lanes 0..63) and only the last two K-slabs (k = 960..1087) stay
+// in shared memory: 480 + 16 accumulator columns fill the 512-column allocation
+constexpr int GRU_BT_K = 960;
+constexpr uint32_t GRU_BT_COLS = GRU_BT_K / 2;                              // 480
+constexpr uint32_t GRU_BT_A0 = 16;                                          // D in columns [0, 16)
+constexpr uint32_t GRU_BT_IMG = 64 * GRU_BT_COLS * 4;                       // 122880: image of 64 rows x 480 u32
+constexpr int GRU_BS_SLABS = 2;
+constexpr uint32_t GRU_BS_BYTES = 16384;                                    // 2 slabs of [48][64] (12288) + in-range room for the M = 128 read
 constexpr uint32_t GRU_BB_BYTES = GRU_BA_NSLAB * GRU_B_SLAB;                // 34816 per buffer
 constexpr uint32_t GRU_F_TX = GRU_NB * GRU_HP * 2;                           // bytes of h_t a CTA receives per step (11264)
 constexpr uint32_t GRU_B_TX = GRU_NB * GRU_G * 2;                            // bytes of dGh a CTA receives per step (33792)
@@ -372,7 +379,7 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
 // ---------------------------------------------------------------- backward recurrence (BPTT)
 struct GruBwdArgs {
     const float* dY;             // [T*B][704] gradient w.r.t. this layer's outputs
-    const uint8_t* whhT;         // [2][8][GRU_BA_BYTES] packed W_hh^T slices
+    const uint8_t* whhT;         // [2][8][GRU_BT_IMG + GRU_BS_BYTES] packed W_hh^T slices (tensor-memory image | smem tail slabs)
     const __nv_bfloat16* Y;      // [T*B][704] forward outputs
     const float *R, *Z, *N, *HN;
     __nv_bfloat16* dGi;          // [T*B][2*1056] gradient w.r.t. the input projections
@@ -383,7 +390,8 @@ struct GruBwdArgs {
 constexpr size_t GRU_B_XCHG = 64 * GRU_XLD * 4;                            // 4352
 constexpr size_t GRU_B_SIN = 5 * GRU_TILE4 * 16 + GRU_TILE4 * 8;           // staged r | z | n | hn | dy (fp32) + h_prev (bf16 x 4)
 constexpr size_t GRU_B_SOUT = 4 * GRU_TILE4 * 8;                           // staged dg_r | dg_z | dg_n(input) | dg_n(hidden), bf16 x 4
-constexpr size_t gru_bwd_smem() { return GRU_BA_BYTES + 2 * GRU_BB_BYTES + GRU_B_XCHG + GRU_B_SIN + GRU_B_SOUT + 1024; }   // 201 KB: one CTA per SM
+constexpr size_t gru_bwd_smem() { return GRU_SMEM_FLOOR; }
+static_assert(GRU_BS_BYTES + 2 * GRU_BB_BYTES + GRU_B_XCHG + GRU_B_SIN + GRU_B_SOUT + 1024 <= GRU_SMEM_FLOOR, "backward smem");
 
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1) gru_bwd_kernel(const GruBwdArgs a)
 {
@@ -392,8 +400,8 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     __shared__ __align__(16) uint64_t hbar[2];
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + GRU_BA_BYTES;
+    uint8_t* sA = smem;                                   // the last GRU_BS_SLABS K-slabs of W_hh^T (the rest lives in TMEM)
+    uint8_t* sB = smem + GRU_BS_BYTES;
     float* xchg = reinterpret_cast<float*>(sB + 2 * GRU_BB_BYTES);
     float4* sin4 = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(xchg) + GRU_B_XCHG);
     uint2* shp = reinterpret_cast<uint2*>(sin4 + 5 * GRU_TILE4);
@@ -403,6 +411,7 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     const int cl = blockIdx.x / GRU_CL;
     const int dir = cl & 1, b0 = (cl >> 1) * GRU_NB;
     const int B = a.B, T = a.T;
+    const uint8_t* wimg = a.whhT + (size_t)(dir * GRU_CL + rank) * (GRU_BT_IMG + GRU_BS_BYTES);
 
     if (tid == 0) {
         tc::mbar_init(&wbar, 1);
@@ -412,18 +421,23 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
         tc::fence_barrier_init();
         tc::mbar_expect_tx(&hbar[0], GRU_B_TX);
         tc::mbar_expect_tx(&hbar[1], GRU_B_TX);
-        tc::mbar_expect_tx(&wbar, GRU_BA_BYTES);
-        const uint8_t* src = a.whhT + (size_t)(dir * GRU_CL + rank) * GRU_BA_BYTES;
-#pragma unroll 1
-        for (int s = 0; s < GRU_BA_NSLAB; ++s) tc::bulk_g2s(sA + s * GRU_BA_SLAB, src + s * GRU_BA_SLAB, GRU_BA_SLAB, &wbar);
+        tc::mbar_expect_tx(&wbar, GRU_BS_BYTES);
+        tc::bulk_g2s(sA, wimg + GRU_BT_IMG, GRU_BS_BYTES, &wbar);
     }
-    if (warp == 8) tc::tmem_alloc(&tmem_slot, 32);
+    if (warp == 8) tc::tmem_alloc(&tmem_slot, 512);
     for (int i = tid; i < (int)(2 * GRU_BB_BYTES / 16); i += GRU_THREADS) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_all();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
+    if (warp < 2) {                                       // rows 0..63 of W_hh^T (44 valid), K = 0..959 -> 480 TMEM columns
+        tmem_load_image(tmem + ((uint32_t)(warp * 32) << 16) + GRU_BT_A0, reinterpret_cast<const uint32_t*>(wimg), 64, GRU_BT_COLS, warp * 32 + lane);
+        tc::tmem_wait_st();
+        tc::fence_before_sync();
+    }
+    __syncthreads();
+    tc::fence_after_sync();
     cluster_arrive();
     cluster_wait();
 
@@ -445,9 +459,14 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
             if (elect_one()) {
                 const uint64_t dB = (step & 1) ? dB1 : dB0;
 #pragma unroll
-                for (int kt = 0; kt < GRU_G / 16; ++kt)
-                    tc::mma_bf16(tmem, desc_adv(dA, (kt >> 2) * GRU_BA_SLAB + (kt & 3) * 32), desc_adv(dB, (kt >> 2) * GRU_B_SLAB + (kt & 3) * 32),
-                                 idesc, kt != 0);
+                for (int kt = 0; kt < GRU_BT_K / 16; ++kt)                             // A from tensor memory
+                    tc::mma_bf16_ts(tmem, tmem + GRU_BT_A0 + kt * 8, desc_adv(dB, (kt >> 2) * GRU_B_SLAB + (kt & 3) * 32), idesc, kt != 0);
+#pragma unroll
+                for (int kt = GRU_BT_K / 16; kt < GRU_G / 16; ++kt) {                  // the K tail from shared memory
+                    const int ks = kt - GRU_BT_K / 16;
+                    tc::mma_bf16(tmem, desc_adv(dA, (ks >> 2) * GRU_BA_SLAB + (ks & 3) * 32), desc_adv(dB, (kt >> 2) * GRU_B_SLAB + (kt & 3) * 32),
+                                 idesc, true);
+                }
                 tc::mma_commit(&mbar);
             }
             __syncwarp();
@@ -585,7 +604,7 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(GRU_THREADS, 1)
     __syncthreads();
     cluster_arrive();
     cluster_wait();
-    if (warp == 8) tc::tmem_dealloc(tmem, 32);
+    if (warp == 8) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------- packing / unpacking
@@ -646,16 +665,30 @@ __global__ void gru_pack_whh_kernel(const float* __restrict__ w0, const float* _
         fi[at] = tc::pack_bf16x2(v0, v1);
     }
     if (!bimg) return;
-    uint8_t* bi = bimg + (size_t)(dir * GRU_CL + c) * GRU_BA_BYTES;
-    for (int idx = t0; idx < GRU_BA_ROWS * GRU_BA_NSLAB * 64; idx += tstride) {
-        const int row = idx / (GRU_BA_NSLAB * 64), g = idx % (GRU_BA_NSLAB * 64);
+    uint8_t* bi = bimg + (size_t)(dir * GRU_CL + c) * (GRU_BT_IMG + GRU_BS_BYTES);
+    uint32_t* bt = reinterpret_cast<uint32_t*>(bi);
+    auto wt = [&](int row, int g) -> float {               // W_hh^T element: unit k = c*44 + row, gate column g
+        if (row >= GRU_UNITS || g >= GRU_G) return 0.f;
+        const int k = c * GRU_UNITS + row, q = g / GRU_HP, u = g % GRU_HP;
+        return (k < H && u < H) ? w[(size_t)(q * H + u) * H + k] : 0.f;
+    };
+    for (int idx = t0; idx < 64 * (int)GRU_BT_COLS; idx += tstride) {
+        const int row = idx / (int)GRU_BT_COLS, kp = idx % (int)GRU_BT_COLS;
+        bt[((size_t)(kp >> 4) * 64 + row) * 16 + (kp & 15)] = tc::pack_bf16x2(wt(row, 2 * kp), wt(row, 2 * kp + 1));
+    }
+    uint8_t* bs = bi + GRU_BT_IMG;
+    for (int idx = t0; idx < (int)GRU_BS_BYTES / 2; idx += tstride) {
         float v = 0.f;
-        if (row < GRU_UNITS && g < GRU_G) {
-            const int k = c * GRU_UNITS + row, q = g / GRU_HP, u = g % GRU_HP;
-            if (k < H && u < H) v = w[(size_t)(q * H + u) * H + k];
+        const int e = idx;                                 // bf16 element index inside the 16 KB tail region
+        const int slab = e / (GRU_BA_ROWS * 64);
+        if (slab < GRU_BS_SLABS) {
+            const int row = (e % (GRU_BA_ROWS * 64)) / 64, col = e % 64;
+            v = wt(row, GRU_BT_K + slab * 64 + col);
+            const uint32_t off = (uint32_t)slab * GRU_BA_SLAB + tc::slab_chunk_off(row, col >> 3) + (uint32_t)(col & 7) * 2u;
+            *reinterpret_cast<__nv_bfloat16*>(bs + off) = __float2bfloat16_rn(v);
+        } else {
+            *reinterpret_cast<__nv_bfloat16*>(bs + (size_t)e * 2) = __float2bfloat16_rn(0.f);
         }
-        const uint32_t off = (uint32_t)(g >> 6) * GRU_BA_SLAB + tc::slab_chunk_off(row, (g & 63) >> 3) + (uint32_t)(g & 7) * 2u;
-        *reinterpret_cast<__nv_bfloat16*>(bi + off) = __float2bfloat16_rn(v);
     }
 }
 
@@ -749,7 +782,7 @@ static GruLayout gru_layout(const HopkGruShape* s)
     }
     g.total = cur;
     cur = 0;
-    g.s_whhT = gbump(cur, (size_t)2 * GRU_CL * GRU_BA_BYTES);
+    g.s_whhT = gbump(cur, (size_t)2 * GRU_CL * (GRU_BT_IMG + GRU_BS_BYTES));
     g.s_dya = gbump(cur, TB * ipmax * 4);
     g.s_dyb = gbump(cur, TB * ipmax * 4);
     g.s_dgi = gbump(cur, TB * 2 * GRU_G * 2);
