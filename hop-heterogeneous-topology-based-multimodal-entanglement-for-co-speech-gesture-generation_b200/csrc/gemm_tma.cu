@@ -18,6 +18,7 @@
 //            (fp32) or 128-bit (bf16) global stores, or vector atomics for split-K
 // The second accumulator lets the MMAs of tile i+1 run under the epilogue of tile i.
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include "tc_core.cuh"
 #include "common.cuh"
@@ -51,6 +52,30 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
                  ::"r"(tc::smem_u32(smem_dst)), "l"(tm), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// the same box delivered to the same shared-memory offset (and signalled on the same-offset mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(tm), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+                 : "memory");
+}
+// tcgen05.commit arriving on the same-offset mbarrier of every CTA in `mask`
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(tc::smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t gt_cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void gt_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
@@ -63,7 +88,11 @@ __device__ __forceinline__ float gt_act(float x, int act, float slope)
     return x;
 }
 
-template <int BN>
+// MC = true (experiment, off by default): launched as clusters of 2 CTAs that own vertically adjacent tiles (same columns n0,
+// rows m0 and m0 + 128) and run in lockstep; each CTA fetches HALF of the shared B tile and multicasts it into both CTAs.  A
+// ring slot is free when BOTH CTAs' MMAs have read it: commits arrive on both CTAs' barriers.  (ncu on the 1-CTA kernel: the
+// MMA issuer waits for operand data 74 % of the time, tensor pipe 32 % busy: the kernel is bound by L2 -> SM delivery.)
+template <int BN, bool MC>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GtArgs g)
 {
@@ -82,7 +111,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], MC ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 8); }
         tc::fence_barrier_init();
     }
@@ -91,15 +120,22 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+    const uint32_t crank = MC ? gt_cluster_rank() : 0u;
+    if (MC) gt_cluster_sync();                                      // the peer's barriers exist before anything is sent to them
 
-    const int ntiles = g.tiles_m * g.tiles_n * g.splits;
+    // work items: tile index `tile` (1-CTA) or super-tile (MC: two vertically adjacent tiles, this CTA takes row block + rank)
+    const int tiles_mw = MC ? (g.tiles_m + 1) / 2 : g.tiles_m;      // work items along M
+    const int per_split = tiles_mw * g.tiles_n;
+    const int ntiles = per_split * g.splits;
+    const int w0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, wstride = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto tile_m0 = [&](int t2) { return ((t2 / g.tiles_n) * (MC ? 2 : 1) + (int)crank) * GT_BM; };
     if (warp == 0) {
         // ===================================================== producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int sp = tile / (g.tiles_m * g.tiles_n), t2 = tile - sp * g.tiles_m * g.tiles_n;
-                const int m0 = (t2 / g.tiles_n) * GT_BM, n0 = (t2 % g.tiles_n) * BN;
+            for (int tile = w0; tile < ntiles; tile += wstride) {
+                const int sp = tile / per_split, t2 = tile - sp * per_split;
+                const int m0 = tile_m0(t2), n0 = (t2 % g.tiles_n) * BN;
                 const int k_begin = sp * g.kper, k_end = min(g.K, k_begin + g.kper);
                 for (int k = k_begin; k < k_end; k += GT_BK) {
                     tc::mbar_wait(&empty[stage], phase ^ 1);
@@ -111,7 +147,16 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                         for (int s = 0; s < GT_BM / 64; ++s) tma_load_2d(sa + s * tc::slab_bytes(GT_BK), &tmA, m0 + 64 * s, k + g.a_kshift, &full[stage]);   // box {64 m, 64 k-rows}
                     }
-                    if (!g.b_mn) tma_load_2d(sb, &tmB, k, n0, &full[stage]);
+                    if (MC) {                                      // this CTA's half of B, delivered to both CTAs
+                        if (!g.b_mn) tma_load_2d_mc(sb + crank * tc::slab_bytes(BN / 2), &tmB, k, n0 + (int)crank * (BN / 2), &full[stage], 3);
+                        else {
+#pragma unroll
+                            for (int s = 0; s < BN / 128; ++s) {
+                                const int sl = (int)crank * (BN / 128) + s;
+                                tma_load_2d_mc(sb + sl * tc::slab_bytes(GT_BK), &tmB, n0 + 64 * sl, k + g.b_kshift, &full[stage], 3);
+                            }
+                        }
+                    } else if (!g.b_mn) tma_load_2d(sb, &tmB, k, n0, &full[stage]);
                     else {
 #pragma unroll
                         for (int s = 0; s < BN / 64; ++s) tma_load_2d(sb + s * tc::slab_bytes(GT_BK), &tmB, n0 + 64 * s, k + g.b_kshift, &full[stage]);
@@ -126,8 +171,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t idesc = tc::idesc_bf16(GT_BM, BN, g.a_mn, g.b_mn);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int sp = tile / (g.tiles_m * g.tiles_n);
+            for (int tile = w0; tile < ntiles; tile += wstride) {
+                const int sp = tile / per_split;
                 const int k_begin = sp * g.kper, k_end = min(g.K, k_begin + g.kper);
                 tc::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                 tc::fence_after_sync();
@@ -144,7 +189,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         tc::mma_bf16(d, da, db, idesc, !first);
                         first = false;
                     }
-                    tc::mma_commit(&empty[stage]);                 // ring slot free once these MMAs have read it
+                    if (MC) mma_commit_mc(&empty[stage], 3);       // ring slot free once BOTH CTAs' MMAs have read it
+                    else tc::mma_commit(&empty[stage]);            // ring slot free once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc::mma_commit(&acc_full[acc]);                    // accumulator complete
@@ -158,10 +204,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int row = quarter * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int t2 = tile % (g.tiles_m * g.tiles_n);
-            const bool first_split = tile < g.tiles_m * g.tiles_n;         // bias / addend enter once, with K-split 0
-            const int m0 = (t2 / g.tiles_n) * GT_BM, n0 = (t2 % g.tiles_n) * BN;
+        for (int tile = w0; tile < ntiles; tile += wstride) {
+            const int t2 = tile % per_split;
+            const bool first_split = tile < per_split;                     // bias / addend enter once, with K-split 0
+            const int m0 = tile_m0(t2), n0 = (t2 % g.tiles_n) * BN;
             const int m = m0 + row;
             tc::mbar_wait(&acc_full[acc], acc_phase);
             tc::fence_after_sync();
@@ -269,6 +315,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     tc::fence_before_sync();
     __syncthreads();
+    if (MC) gt_cluster_sync();                                      // nobody leaves while the peer may still signal its barriers
     if (warp == 1) tc::tmem_dealloc(tmem, 2 * BN);
 }
 
@@ -411,25 +458,52 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     const long t128 = (long)cdiv(M, GT_BM) * cdiv(N, 128) * sp, t256 = (long)cdiv(M, GT_BM) * cdiv(N, 256) * sp;
     const double c128 = (double)cdiv(t128, sms0), c256 = 1.75 * (double)cdiv(t256, sms0);
     const int BN = (N > 128 && c256 < c128) ? 256 : 128;
-    if (int rc = b_mn ? make_map(&tmB, B, K, N, ldb, GT_BK) : make_map(&tmB, B, N, K, ldb, BN)) return rc;
-    GtArgs g;
-    g.C = C; g.bias = bias; g.addend = addend; g.mask = mask; g.bias_row = bias_row; g.mask_bf16 = mask_bf16; g.mask_gelu = mask_gelu; g.a_kshift = a_kshift; g.b_kshift = b_kshift; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
-    g.out_bf16 = out_bf16; g.accumulate = accumulate; g.act = act; g.slope = slope;
     if (splits < 1) splits = 1;
     int kper = ((cdiv(K, splits) + GT_BK - 1) / GT_BK) * GT_BK;
     splits = cdiv(K, kper);
+    const int tiles_m = cdiv(M, GT_BM), tiles_n = cdiv(N, BN);
+    // Cluster pairs with a multicast B tile (MC = true).  Measured on B200 (profiles/README.md): no gain at cluster size 2 -- the
+    // 37 us FFN GEMM stays at 37 us -- which matches the microarchitecture note that TMA multicast only de-duplicates L2 reads
+    // for clusters larger than 4.  Kept selectable (HOPK_GEMM_MULTICAST=1) and parity-tested; off by default.
+    static const bool mc_on = getenv("HOPK_GEMM_MULTICAST") != nullptr;
+    const bool mc = mc_on && tiles_m >= 2 && (long)tiles_m * tiles_n * splits >= sms0;
+    if (int rc = b_mn ? make_map(&tmB, B, K, N, ldb, GT_BK) : make_map(&tmB, B, N, K, ldb, mc ? BN / 2 : BN)) return rc;
+    GtArgs g;
+    g.C = C; g.bias = bias; g.addend = addend; g.mask = mask; g.bias_row = bias_row; g.mask_bf16 = mask_bf16; g.mask_gelu = mask_gelu;
+    g.a_kshift = a_kshift; g.b_kshift = b_kshift; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
+    g.out_bf16 = out_bf16; g.accumulate = accumulate; g.act = act; g.slope = slope;
     g.splits = splits; g.kper = kper;
-    g.tiles_m = cdiv(M, GT_BM); g.tiles_n = cdiv(N, BN);
-    const long ntiles = (long)g.tiles_m * g.tiles_n * splits;
+    g.tiles_m = tiles_m; g.tiles_n = tiles_n;
     const int sms = sms0;
-    const int grid = (int)(ntiles < sms ? ntiles : sms);
     if (splits > 1 && !accumulate) HOPK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
-    if (BN == 256) {
-        HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<256>, gt_smem_bytes<256>()));
-        gemm_tma_kernel<256><<<grid, GT_THREADS, gt_smem_bytes<256>(), st>>>(tmA, tmB, g);
+    if (mc) {
+        const long nsuper = (long)((tiles_m + 1) / 2) * tiles_n * splits;
+        const int pairs = (int)(nsuper < sms / 2 ? nsuper : sms / 2);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GT_THREADS); cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+        if (BN == 256) {
+            HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<256, true>, gt_smem_bytes<256>()));
+            cfg.dynamicSmemBytes = gt_smem_bytes<256>();
+            HOPK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<256, true>, tmA, tmB, g));
+        } else {
+            HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<128, true>, gt_smem_bytes<128>()));
+            cfg.dynamicSmemBytes = gt_smem_bytes<128>();
+            HOPK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<128, true>, tmA, tmB, g));
+        }
     } else {
-        HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<128>, gt_smem_bytes<128>()));
-        gemm_tma_kernel<128><<<grid, GT_THREADS, gt_smem_bytes<128>(), st>>>(tmA, tmB, g);
+        const long ntiles = (long)tiles_m * tiles_n * splits;
+        const int grid = (int)(ntiles < sms ? ntiles : sms);
+        if (BN == 256) {
+            HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<256, false>, gt_smem_bytes<256>()));
+            gemm_tma_kernel<256, false><<<grid, GT_THREADS, gt_smem_bytes<256>(), st>>>(tmA, tmB, g);
+        } else {
+            HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<128, false>, gt_smem_bytes<128>()));
+            gemm_tma_kernel<128, false><<<grid, GT_THREADS, gt_smem_bytes<128>(), st>>>(tmA, tmB, g);
+        }
     }
     HOPK_LAUNCH_CHECK("gemm_tma");
     return 0;

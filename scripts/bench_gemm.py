@@ -33,7 +33,9 @@ def main():
     rows = []
     pad8 = lambda n: (n + 7) // 8 * 8
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for name, M, N, K, a_mn, b_mn, splits in SHAPES:
+    only = [a for a in sys.argv[1:] if a.startswith('--only=')]
+    shapes = [sh for sh in SHAPES if not only or only[0][7:] in sh[0]]
+    for name, M, N, K, a_mn, b_mn, splits in shapes:
         A = torch.randn((K, pad8(M)) if a_mn else (M, pad8(K)), device=dev).bfloat16()
         B = torch.randn((K, pad8(N)) if b_mn else (N, pad8(K)), device=dev).bfloat16()
         C = torch.empty(M, pad8(N), device=dev)
@@ -65,7 +67,7 @@ def main():
         rows.append({'shape': name, 'ours_us': round(res['ours'] * 1e3, 1), 'cublas_us': round(res['cublas'] * 1e3, 1),
                      'ours_tflops': round(fl / res['ours'] / 1e9, 1), 'cublas_tflops': round(fl / res['cublas'] / 1e9, 1)})
         print(rows[-1], flush=True)
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and not sys.argv[1].startswith('--'):
         json.dump(rows, open(sys.argv[1], 'w'), indent=1)
 
 
