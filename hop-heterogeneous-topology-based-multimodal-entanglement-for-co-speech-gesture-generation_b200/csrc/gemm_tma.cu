@@ -13,7 +13,7 @@
 //            completion by mbarrier complete_tx
 //   warp 1   MMA issuer: one lane issues tcgen05.mma (M 128, N = BN, K 16, 4 per 64-wide K block) into one of two TMEM
 //            accumulators; tcgen05.commit releases the ring slot / publishes the accumulator
-//   warps 2-9  epilogue (two warps per TMEM lane quarter, alternating 32-column chunks): tcgen05.ld (row per thread), bias /
+//   warps 2-9  epilogue (two warps per TMEM lane quarter, interleaved 32-column chunks): tcgen05.ld (row per thread), bias /
 //            residual / activation / conversion, 256-bit
 //            (fp32) or 128-bit (bf16) global stores, or vector atomics for split-K
 // The second accumulator lets the MMAs of tile i+1 run under the epilogue of tile i.
@@ -27,7 +27,8 @@
 namespace hopk {
 
 constexpr int GT_BM = 128, GT_BK = 64;
-constexpr int GT_THREADS = 320;                         // producer warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int GT_EPI_WARPS = 8;                         // 2 per TMEM lane quarter (16 were measured: no gain)
+constexpr int GT_THREADS = 64 + 32 * GT_EPI_WARPS;      // producer warp, MMA warp, epilogue warps
 
 template <int BN> constexpr int gt_stages() { return BN == 128 ? 6 : 4; }
 template <int BN> constexpr uint32_t gt_stage_bytes() { return tc::slab_bytes(GT_BM) + tc::slab_bytes(BN); }
@@ -52,30 +53,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
                  ::"r"(tc::smem_u32(smem_dst)), "l"(tm), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
-// the same box delivered to the same shared-memory offset (and signalled on the same-offset mbarrier) of every CTA in `mask`
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint16_t mask)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-                 ::"r"(tc::smem_u32(smem_dst)), "l"(tm), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-                 : "memory");
-}
-// tcgen05.commit arriving on the same-offset mbarrier of every CTA in `mask`
-__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(tc::smem_u32(bar)), "h"(mask) : "memory");
-}
-__device__ __forceinline__ uint32_t gt_cluster_rank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void gt_cluster_sync()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
@@ -88,11 +65,12 @@ __device__ __forceinline__ float gt_act(float x, int act, float slope)
     return x;
 }
 
-// MC = true (experiment, off by default): launched as clusters of 2 CTAs that own vertically adjacent tiles (same columns n0,
-// rows m0 and m0 + 128) and run in lockstep; each CTA fetches HALF of the shared B tile and multicasts it into both CTAs.  A
-// ring slot is free when BOTH CTAs' MMAs have read it: commits arrive on both CTAs' barriers.  (ncu on the 1-CTA kernel: the
-// MMA issuer waits for operand data 74 % of the time, tensor pipe 32 % busy: the kernel is bound by L2 -> SM delivery.)
-template <int BN, bool MC>
+// The operand majors are template parameters: the single MMA-issuing thread is the busiest warp of the kernel (ncu, round 2:
+// ~180 instructions per K block with run-time layout branches against 512 tensor-pipe cycles), so its loop is straight-line:
+// one 64-bit add per descriptor, four tcgen05.mma, one commit.
+// (A cluster-pair variant with a multicast B tile was measured too: no gain at cluster size 2 -- TMA multicast only
+// de-duplicates L2 reads for larger clusters -- and it was removed again.)
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GtArgs g)
 {
@@ -111,8 +89,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], MC ? 2 : 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 8); }
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], GT_EPI_WARPS); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * BN);
@@ -120,15 +98,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t crank = MC ? gt_cluster_rank() : 0u;
-    if (MC) gt_cluster_sync();                                      // the peer's barriers exist before anything is sent to them
-
-    // work items: tile index `tile` (1-CTA) or super-tile (MC: two vertically adjacent tiles, this CTA takes row block + rank)
-    const int tiles_mw = MC ? (g.tiles_m + 1) / 2 : g.tiles_m;      // work items along M
-    const int per_split = tiles_mw * g.tiles_n;
+    const int per_split = g.tiles_m * g.tiles_n;
     const int ntiles = per_split * g.splits;
-    const int w0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, wstride = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    auto tile_m0 = [&](int t2) { return ((t2 / g.tiles_n) * (MC ? 2 : 1) + (int)crank) * GT_BM; };
+    const int w0 = (int)blockIdx.x, wstride = (int)gridDim.x;
+    auto tile_m0 = [&](int t2) { return (t2 / g.tiles_n) * GT_BM; };
     if (warp == 0) {
         // ===================================================== producer
         if (lane == 0) {
@@ -142,21 +115,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint8_t* sa = smem + (size_t)stage * STAGE;
                     uint8_t* sb = sa + A_BYTES;
                     tc::mbar_expect_tx(&full[stage], STAGE);
-                    if (!g.a_mn) tma_load_2d(sa, &tmA, k, m0, &full[stage]);                    // box {64 k, 128 rows}
+                    if (!A_MN) tma_load_2d(sa, &tmA, k, m0, &full[stage]);                    // box {64 k, 128 rows}
                     else {
 #pragma unroll
                         for (int s = 0; s < GT_BM / 64; ++s) tma_load_2d(sa + s * tc::slab_bytes(GT_BK), &tmA, m0 + 64 * s, k + g.a_kshift, &full[stage]);   // box {64 m, 64 k-rows}
                     }
-                    if (MC) {                                      // this CTA's half of B, delivered to both CTAs
-                        if (!g.b_mn) tma_load_2d_mc(sb + crank * tc::slab_bytes(BN / 2), &tmB, k, n0 + (int)crank * (BN / 2), &full[stage], 3);
-                        else {
-#pragma unroll
-                            for (int s = 0; s < BN / 128; ++s) {
-                                const int sl = (int)crank * (BN / 128) + s;
-                                tma_load_2d_mc(sb + sl * tc::slab_bytes(GT_BK), &tmB, n0 + 64 * sl, k + g.b_kshift, &full[stage], 3);
-                            }
-                        }
-                    } else if (!g.b_mn) tma_load_2d(sb, &tmB, k, n0, &full[stage]);
+                    if (!B_MN) tma_load_2d(sb, &tmB, k, n0, &full[stage]);
                     else {
 #pragma unroll
                         for (int s = 0; s < BN / 64; ++s) tma_load_2d(sb + s * tc::slab_bytes(GT_BK), &tmB, n0 + 64 * s, k + g.b_kshift, &full[stage]);
@@ -168,7 +132,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else if (warp == 1) {
         // ===================================================== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = tc::idesc_bf16(GT_BM, BN, g.a_mn, g.b_mn);
+            constexpr uint32_t idesc = tc::idesc_bf16(GT_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            // descriptors of stage 0; a later stage / K = 16 step only moves the 14-bit start-address field (bytes >> 4)
+            const uint32_t s0 = tc::smem_u32(smem);
+            const uint64_t dA0 = A_MN ? tc::desc_mnmajor(s0, tc::slab_bytes(GT_BK), 0) : tc::desc_kmajor(s0, 0);
+            const uint64_t dB0 = B_MN ? tc::desc_mnmajor(s0 + A_BYTES, tc::slab_bytes(GT_BK), 0) : tc::desc_kmajor(s0 + A_BYTES, 0);
+            constexpr uint64_t STEP_A = (A_MN ? 2048u : 32u) >> 4, STEP_B = (B_MN ? 2048u : 32u) >> 4, STEP_STAGE = STAGE >> 4;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = w0; tile < ntiles; tile += wstride) {
@@ -177,20 +146,17 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tc::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                 tc::fence_after_sync();
                 const uint32_t d = tmem + acc * BN;
-                bool first = true;
+                uint32_t accumulate = 0;
                 for (int k = k_begin; k < k_end; k += GT_BK) {
                     tc::mbar_wait(&full[stage], phase);
                     tc::fence_after_sync();
-                    const uint32_t sa = tc::smem_u32(smem + (size_t)stage * STAGE), sb = sa + A_BYTES;
-#pragma unroll
-                    for (int t = 0; t < GT_BK / 16; ++t) {
-                        const uint64_t da = g.a_mn ? tc::desc_mnmajor(sa, tc::slab_bytes(GT_BK), t) : tc::desc_kmajor(sa, t);
-                        const uint64_t db = g.b_mn ? tc::desc_mnmajor(sb, tc::slab_bytes(GT_BK), t) : tc::desc_kmajor(sb, t);
-                        tc::mma_bf16(d, da, db, idesc, !first);
-                        first = false;
-                    }
-                    if (MC) mma_commit_mc(&empty[stage], 3);       // ring slot free once BOTH CTAs' MMAs have read it
-                    else tc::mma_commit(&empty[stage]);            // ring slot free once these MMAs have read it
+                    const uint64_t da = dA0 + (uint64_t)stage * STEP_STAGE, db = dB0 + (uint64_t)stage * STEP_STAGE;
+                    tc::mma_bf16(d, da, db, idesc, accumulate != 0);
+                    tc::mma_bf16(d, da + STEP_A, db + STEP_B, idesc, true);
+                    tc::mma_bf16(d, da + 2 * STEP_A, db + 2 * STEP_B, idesc, true);
+                    tc::mma_bf16(d, da + 3 * STEP_A, db + 3 * STEP_B, idesc, true);
+                    accumulate = 1;
+                    tc::mma_commit(&empty[stage]);                 // ring slot free once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc::mma_commit(&acc_full[acc]);                    // accumulator complete
@@ -198,8 +164,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else {
-        // ===================================================== epilogue: warps 2..9; warp w drains TMEM lane quarter w & 3 (the
-        // quarter a warp may access) and, of the tile's 32-column chunks, those with chunk parity (w - 2) >> 2
+        // ===================================================== epilogue: warps 2..; warp w drains TMEM lane quarter w & 3 (the
+        // quarter a warp may access) and, of the tile's 32-column chunks, every (GT_EPI_WARPS / 4)-th one starting at (w - 2) >> 2
         const int quarter = warp & 3, chalf = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
@@ -213,7 +179,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc::fence_after_sync();
             const uint32_t src = tmem + acc * BN + lane_off;
 #pragma unroll 1
-            for (int c = chalf; c < BN / 32; c += 2) {
+            for (int c = chalf; c < BN / 32; c += GT_EPI_WARPS / 4) {
                 const int nb = n0 + c * 32;
                 if (nb >= g.N) break;                              // uniform across the warp
                 float v[32];
@@ -315,7 +281,6 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (MC) gt_cluster_sync();                                      // nobody leaves while the peer may still signal its barriers
     if (warp == 1) tc::tmem_dealloc(tmem, 2 * BN);
 }
 
@@ -462,49 +427,33 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     int kper = ((cdiv(K, splits) + GT_BK - 1) / GT_BK) * GT_BK;
     splits = cdiv(K, kper);
     const int tiles_m = cdiv(M, GT_BM), tiles_n = cdiv(N, BN);
-    // Cluster pairs with a multicast B tile (MC = true).  Measured on B200 (profiles/README.md): no gain at cluster size 2 -- the
-    // 37 us FFN GEMM stays at 37 us -- which matches the microarchitecture note that TMA multicast only de-duplicates L2 reads
-    // for clusters larger than 4.  Kept selectable (HOPK_GEMM_MULTICAST=1) and parity-tested; off by default.
-    static const bool mc_on = getenv("HOPK_GEMM_MULTICAST") != nullptr;
-    const bool mc = mc_on && tiles_m >= 2 && (long)tiles_m * tiles_n * splits >= sms0;
-    if (int rc = b_mn ? make_map(&tmB, B, K, N, ldb, GT_BK) : make_map(&tmB, B, N, K, ldb, mc ? BN / 2 : BN)) return rc;
+    if (int rc = b_mn ? make_map(&tmB, B, K, N, ldb, GT_BK) : make_map(&tmB, B, N, K, ldb, BN)) return rc;
     GtArgs g;
     g.C = C; g.bias = bias; g.addend = addend; g.mask = mask; g.bias_row = bias_row; g.mask_bf16 = mask_bf16; g.mask_gelu = mask_gelu;
     g.a_kshift = a_kshift; g.b_kshift = b_kshift; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.a_mn = a_mn; g.b_mn = b_mn;
     g.out_bf16 = out_bf16; g.accumulate = accumulate; g.act = act; g.slope = slope;
     g.splits = splits; g.kper = kper;
     g.tiles_m = tiles_m; g.tiles_n = tiles_n;
-    const int sms = sms0;
     if (splits > 1 && !accumulate) HOPK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
-    if (mc) {
-        const long nsuper = (long)((tiles_m + 1) / 2) * tiles_n * splits;
-        const int pairs = (int)(nsuper < sms / 2 ? nsuper : sms / 2);
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GT_THREADS); cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
-        if (BN == 256) {
-            HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<256, true>, gt_smem_bytes<256>()));
-            cfg.dynamicSmemBytes = gt_smem_bytes<256>();
-            HOPK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<256, true>, tmA, tmB, g));
-        } else {
-            HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<128, true>, gt_smem_bytes<128>()));
-            cfg.dynamicSmemBytes = gt_smem_bytes<128>();
-            HOPK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<128, true>, tmA, tmB, g));
-        }
-    } else {
-        const long ntiles = (long)tiles_m * tiles_n * splits;
-        const int grid = (int)(ntiles < sms ? ntiles : sms);
-        if (BN == 256) {
-            HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<256, false>, gt_smem_bytes<256>()));
-            gemm_tma_kernel<256, false><<<grid, GT_THREADS, gt_smem_bytes<256>(), st>>>(tmA, tmB, g);
-        } else {
-            HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<128, false>, gt_smem_bytes<128>()));
-            gemm_tma_kernel<128, false><<<grid, GT_THREADS, gt_smem_bytes<128>(), st>>>(tmA, tmB, g);
-        }
+    const long ntiles = (long)tiles_m * tiles_n * splits;
+    const int grid = (int)(ntiles < sms0 ? ntiles : sms0);
+#define HOPK_GT_LAUNCH(BNV, AM, BM_)                                                                                      \
+    do {                                                                                                                  \
+        HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<BNV, AM, BM_>, gt_smem_bytes<BNV>()));                  \
+        gemm_tma_kernel<BNV, AM, BM_><<<grid, GT_THREADS, gt_smem_bytes<BNV>(), st>>>(tmA, tmB, g);                        \
+    } while (0)
+    const int variant = (BN == 256 ? 4 : 0) | (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
+    switch (variant) {
+        case 0: HOPK_GT_LAUNCH(128, false, false); break;
+        case 1: HOPK_GT_LAUNCH(128, false, true); break;
+        case 2: HOPK_GT_LAUNCH(128, true, false); break;
+        case 3: HOPK_GT_LAUNCH(128, true, true); break;
+        case 4: HOPK_GT_LAUNCH(256, false, false); break;
+        case 5: HOPK_GT_LAUNCH(256, false, true); break;
+        case 6: HOPK_GT_LAUNCH(256, true, false); break;
+        default: HOPK_GT_LAUNCH(256, true, true); break;
     }
+#undef HOPK_GT_LAUNCH
     HOPK_LAUNCH_CHECK("gemm_tma");
     return 0;
 }
