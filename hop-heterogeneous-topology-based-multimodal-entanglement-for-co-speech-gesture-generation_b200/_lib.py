@@ -95,7 +95,7 @@ SIGNATURES = {
     'hopk_ln_bwd': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     'hopk_gelu_bf16': (_i, [_vp, _vp, C.c_long, _vp]),
     'hopk_bert_attn_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    'hopk_bert_attn_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'hopk_bert_attn_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'hopk_beat_rows_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'hopk_beat_rows_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, C.c_long, _vp]),
     'hopk_gru_workspace_bytes': (_sz, [C.POINTER(GruShape)]),

@@ -105,8 +105,7 @@ class _BertFn(torch.autograd.Function):
             for p in W.L:
                 qkv = gemm(h16, p['wqkv'], M, 3 * C, C, bias=p['bqkv'], out_bf16=True)
                 cx = torch.empty((M, C), device=dev, dtype=torch.bfloat16)
-                P = torch.empty((B * H, S, S), device=dev, dtype=torch.float32) if save else None
-                check(l.hopk_bert_attn_fwd(ptr(qkv), ptr(cx), ptr(P), B, S, H, C // H, stream_ptr()))
+                check(l.hopk_bert_attn_fwd(ptr(qkv), ptr(cx), None, B, S, H, C // H, stream_ptr()))
                 a = gemm(cx, p['wo'], M, C, C, bias=p['bo'], addend=h32)                       # + residual
                 y32, y16, st1 = _ln_fwd(a, None, 0, p['g1'], p['b1'], W.eps, M, C)
                 if save:
@@ -118,7 +117,7 @@ class _BertFn(torch.autograd.Function):
                 f = gemm(hh, p['w2'], M, C, I, bias=p['c2'], addend=y32)                       # + residual
                 h32, h16, st2 = _ln_fwd(f, None, 0, p['g2'], p['b2'], W.eps, M, C)
                 if save:
-                    keep += [qkv, P, a, st1, pre, f, st2]
+                    keep += [qkv, a, st1, pre, f, st2]
         if save:
             ctx.save_for_backward(x2, st0, *keep)
         ctx.W, ctx.dims = W, (B, S, C)
@@ -135,7 +134,7 @@ class _BertFn(torch.autograd.Function):
         with profiler.span('bert_bwd'):
             for li in range(len(W.L) - 1, -1, -1):
                 p = W.L[li]
-                qkv, P, a, st1, pre, f, st2 = keep[7 * li:7 * li + 7]
+                qkv, a, st1, pre, f, st2 = keep[6 * li:6 * li + 6]
                 d2_32, d2_16 = _ln_bwd(d, f, None, 0, p['g2'], st2, M, C)
                 # dY @ W2 through GELU': the saved pre-activation rides the epilogue
                 dpre = gemm(d2_16, p['w2'], M, I, C, b_mn=True, mask=pre, mask_gelu=True, out_bf16=True)
@@ -143,7 +142,7 @@ class _BertFn(torch.autograd.Function):
                 d1_32, d1_16 = _ln_bwd(dy1, a, None, 0, p['g1'], st1, M, C)
                 dcx = gemm(d1_16, p['wo'], M, C, C, b_mn=True, out_bf16=True)
                 dqkv = torch.empty_like(qkv)
-                check(l.hopk_bert_attn_bwd(ptr(qkv), ptr(dcx), ptr(P), ptr(dqkv), B, S, H, C // H, stream_ptr()))
+                check(l.hopk_bert_attn_bwd(ptr(qkv), ptr(dcx), ptr(dqkv), B, S, H, C // H, stream_ptr()))
                 d = gemm(dqkv, p['wqkv'], M, C, 3 * C, b_mn=True, addend=d1_32)
             dx, _ = _ln_bwd(d, x2, W.table, S, W.g0, st0, M, C, want16=False)
         return dx.view(B, S, C), None

@@ -2,11 +2,12 @@
 // `self.llm_model(inputs_embeds=llama_enc_out).last_hidden_state`; the encoder is frozen, HOP.py:90-91, so backward only
 // needs dX).  The GEMMs themselves (QKV / output / FFN projections and their dX products) run on gemm_tma.cu; here:
 //   layer norm forward / backward (dX)        BertEmbeddings.LayerNorm, BertSelfOutput.LayerNorm, BertOutput.LayerNorm
-//   self-attention forward / backward         12 heads x 64, sequence 34: one CTA per (sample, head), everything in smem
+//   self-attention forward / backward         12 heads x 64, sequence 34: two (sample, head) pairs per CTA on tcgen05 UMMAs
 //   GELU                                      BertIntermediate (exact erf form)
 // dtype-1 arithmetic: bf16 operands for the tensor-core GEMMs, fp32 statistics / softmax / residual stream.
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "tc_core.cuh"
 #include "../../include/hopk.h"
 
 namespace hopk {
@@ -114,157 +115,252 @@ __global__ void gelu_bf16_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfl
     }
 }
 
-// ---------------------------------------------------------------- self-attention, one CTA per (sample, head)
-// qkv: bf16 [B*S][3*H*D] rows = (b, t): [q heads | k heads | v heads]; ctx: bf16 [B*S][H*D]; P: fp32 [B*H][S][S] (saved)
-// Every product is register-tiled (2 rows x 2 columns of the S x S matrices, 2 rows x 4 columns of the S x D ones) with
-// 128-bit shared-memory reads along the contraction index: one LDS.128 per 4-8 FMAs instead of two LDS per FMA (the first
-// version was shared-memory-bandwidth bound: 78 us per call at B = 128).
-constexpr int AT_MAXS = 64, AT_D = 64, AT_LD = AT_D + 4;      // fp32 row pitch 68: 16-byte aligned rows
+// ---------------------------------------------------------------- self-attention on the tensor core
+// qkv: bf16 [B*S][3*H*D] rows = (b, t): [q heads | k heads | v heads]; ctx: bf16 [B*S][H*D]   (BertSelfAttention, D = 64)
+// A CTA owns two consecutive (sample, head) pairs; pair g occupies rows 64 g .. 64 g + S - 1 of every 128-row operand slab
+// (S <= 64), rows beyond S are zero.
+//   forward:  S = Q K^T as one 128 x 128 x 64 UMMA (only the two 64 x 64 diagonal blocks are used) -> TMEM; thread = row:
+//             softmax over its S columns in registers; P (bf16) becomes a block-diagonal A operand; O = P V (128 x 64 x 128)
+//             -> TMEM -> bf16 context rows.
+//   backward: recomputes S and the softmax (only qkv is saved), dP = dO V^T beside it; dS = P (dP - sum P dP) / 8;
+//             dQ = dS K, dK = dS^T Q, dV = P^T dO read P / dS through K-major and MN-major descriptors of one image.
+// A block-diagonal operand is stored compactly as [block 0: 64 rows][64 zero rows][block 1: 64 rows] (8 KB each): its
+// k < 64 half is the 128-row view at byte 0 and its k >= 64 half the 128-row view at byte 8192.
+constexpr int AT_MAXS = 64, AT_D = 64;
+constexpr uint32_t AT_SLAB = tc::slab_bytes(128);             // 16 KB
+constexpr uint32_t AT_HALF = tc::slab_bytes(64);              // 8 KB
+constexpr uint32_t AT_BD = 3 * AT_HALF;                       // block-diagonal operand
+constexpr size_t AT_FWD_SMEM = 3 * AT_SLAB + 1024, AT_BWD_SMEM = 4 * AT_SLAB + 2 * AT_BD + 1024;
 
-__device__ __forceinline__ float dot4(const float4 a, const float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
-
-// out[r][c] = sum_e X[r][e] Y[c][e] for r, c < S (X, Y: [S][AT_LD]); 2 x 2 register tiles; out pitch ldo; scaled
-__device__ __forceinline__ void tile_xyT(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ out, int ldo, int S, float scale)
+// one matrix (Q, K, V or dO) of both pairs -> slab rows 64 g + t; 8 x 16 bytes per thread, loads first
+__device__ __forceinline__ void at_load(uint8_t* slab, const __nv_bfloat16* __restrict__ src, size_t ld, int pair0, int npairs, int S, int H)
 {
-    const int TS = (S + 1) >> 1;
-    for (int i = threadIdx.x; i < TS * TS; i += blockDim.x) {
-        const int r0 = (i / TS) * 2, c0 = (i % TS) * 2;
-        const int r1 = min(r0 + 1, S - 1), c1 = min(c0 + 1, S - 1);
-        float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
-#pragma unroll 4
-        for (int e = 0; e < AT_D; e += 4) {
-            const float4 x0 = *reinterpret_cast<const float4*>(X + r0 * AT_LD + e), x1 = *reinterpret_cast<const float4*>(X + r1 * AT_LD + e);
-            const float4 y0 = *reinterpret_cast<const float4*>(Y + c0 * AT_LD + e), y1 = *reinterpret_cast<const float4*>(Y + c1 * AT_LD + e);
-            a00 += dot4(x0, y0); a01 += dot4(x0, y1); a10 += dot4(x1, y0); a11 += dot4(x1, y1);
-        }
-        out[r0 * ldo + c0] = a00 * scale;
-        if (c0 + 1 < S) out[r0 * ldo + c0 + 1] = a01 * scale;
-        if (r0 + 1 < S) {
-            out[(r0 + 1) * ldo + c0] = a10 * scale;
-            if (c0 + 1 < S) out[(r0 + 1) * ldo + c0 + 1] = a11 * scale;
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = threadIdx.x + i * 128;
+        const int ch = idx & 7, t = (idx >> 3) & 63, pr = pair0 + (idx >> 9);
+        v[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (t < S && pr < npairs) {
+            const int b = pr / H, h = pr - b * H;
+            v[i] = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)b * S + t) * ld + h * AT_D) + ch);
         }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = threadIdx.x + i * 128;
+        *reinterpret_cast<uint4*>(slab + tc::slab_chunk_off(idx >> 3, idx & 7)) = v[i];
+    }
 }
-
-// acc[2][4] = sum_j W(r, j) * Z[j][c..c+3] for rows r0, r0 + 1: W(r, j) = Wm[r * ldw + j] or (transposed) Wm[j * ldw + r]
-template <bool TRANS>
-__device__ __forceinline__ void tile_wz(const float* __restrict__ Wm, int ldw, const float* __restrict__ Z, int S, int r0, int r1, int c,
-                                        float (&acc)[2][4])
+__device__ __forceinline__ void at_zero_half(uint8_t* p)     // 8 KB
 {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { acc[0][q] = 0.f; acc[1][q] = 0.f; }
-    for (int j = 0; j < S; ++j) {
-        const float w0 = TRANS ? Wm[j * ldw + r0] : Wm[r0 * ldw + j], w1 = TRANS ? Wm[j * ldw + r1] : Wm[r1 * ldw + j];
-        const float4 z = *reinterpret_cast<const float4*>(Z + j * AT_LD + c);
-        acc[0][0] = fmaf(w0, z.x, acc[0][0]); acc[0][1] = fmaf(w0, z.y, acc[0][1]); acc[0][2] = fmaf(w0, z.z, acc[0][2]); acc[0][3] = fmaf(w0, z.w, acc[0][3]);
-        acc[1][0] = fmaf(w1, z.x, acc[1][0]); acc[1][1] = fmaf(w1, z.y, acc[1][1]); acc[1][2] = fmaf(w1, z.z, acc[1][2]); acc[1][3] = fmaf(w1, z.w, acc[1][3]);
-    }
+    for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(p)[threadIdx.x + i * 128] = make_uint4(0u, 0u, 0u, 0u);
 }
-
-__device__ __forceinline__ void load_head(float* dst, const __nv_bfloat16* __restrict__ src, size_t ld, int S)
+template <int SP>
+__device__ __forceinline__ void at_ld_row(uint32_t taddr, float (&v)[SP])
 {
-    for (int i = threadIdx.x; i < S * (AT_D / 8); i += blockDim.x) {          // 8 bf16 (16 bytes) per thread
-        const int t = i / (AT_D / 8), c = (i % (AT_D / 8)) * 8;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (size_t)t * ld + c));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-        float* d = dst + t * AT_LD + c;
-        *reinterpret_cast<float4*>(d) = make_float4(__low2float(h[0]), __high2float(h[0]), __low2float(h[1]), __high2float(h[1]));
-        *reinterpret_cast<float4*>(d + 4) = make_float4(__low2float(h[2]), __high2float(h[2]), __low2float(h[3]), __high2float(h[3]));
+    float a[32];
+    tc::tmem_ld32(taddr, a);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = a[i];
+    if constexpr (SP == 64) {
+        tc::tmem_ld32(taddr + 32, a);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[32 + i] = a[i];
+    } else {
+        float c[8];
+        tc::tmem_ld8(taddr + 32, c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[32 + i] = c[i];
+    }
+}
+// a thread's row of a block-diagonal operand: 64 bf16 (columns >= SP are zero) into block g
+template <int SP>
+__device__ __forceinline__ void at_store_row(uint8_t* bd, int g, int t, const float (&v)[SP])
+{
+    uint8_t* blk = bd + (g ? 2 * AT_HALF : 0);
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (ch * 8 < SP) u = make_uint4(bf2(v[ch * 8], v[ch * 8 + 1]), bf2(v[ch * 8 + 2], v[ch * 8 + 3]), bf2(v[ch * 8 + 4], v[ch * 8 + 5]), bf2(v[ch * 8 + 6], v[ch * 8 + 7]));
+        *reinterpret_cast<uint4*>(blk + tc::slab_chunk_off(t, ch)) = u;
+    }
+}
+// softmax(s / 8) over the first S entries, in place (entries >= S become 0)
+template <int SP>
+__device__ __forceinline__ void at_softmax(float (&s)[SP], int S, bool valid)
+{
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < SP; ++c) if (c < S) m = fmaxf(m, s[c]);
+    constexpr float kf = 0.125f * 1.4426950408889634f;
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < SP; ++c) { const float e = c < S ? exp2f((s[c] - m) * kf) : 0.f; s[c] = e; sum += e; }
+    const float inv = valid ? 1.f / sum : 0.f;
+#pragma unroll
+    for (int c = 0; c < SP; ++c) s[c] *= inv;
+}
+// TMEM row (64 fp32) -> 64 bf16 in global memory
+__device__ __forceinline__ void at_store_out(uint32_t taddr, __nv_bfloat16* dst, bool valid)
+{
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float o[32];
+        tc::tmem_ld32(taddr + half * 32, o);
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                reinterpret_cast<uint4*>(dst + half * 32)[q] = make_uint4(bf2(o[8 * q], o[8 * q + 1]), bf2(o[8 * q + 2], o[8 * q + 3]),
+                                                                           bf2(o[8 * q + 4], o[8 * q + 5]), bf2(o[8 * q + 6], o[8 * q + 7]));
+        }
     }
 }
 
+template <int SP>
 __global__ void __launch_bounds__(128) bert_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx,
-                                                            float* __restrict__ P, int S, int H)
+                                                            float* __restrict__ P, int S, int H, int npairs)
 {
-    extern __shared__ __align__(16) float sm[];
-    const int b = blockIdx.x / H, h = blockIdx.x % H;
-    float* q = sm;                          // [S][AT_LD]
-    float* k = q + S * AT_LD;
-    float* v = k + S * AT_LD;
-    float* p = v + S * AT_LD;               // [S][S+1]
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = smem, *sK = smem + AT_SLAB, *sV = smem + 2 * AT_SLAB;
+    uint8_t* sP = smem;                                        // over Q and the first half of K once S = Q K^T is complete
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int pair0 = blockIdx.x * 2;
     const size_t ld = (size_t)3 * H * AT_D;
-    const __nv_bfloat16* base = qkv + (size_t)b * S * ld + h * AT_D;
-    load_head(q, base, ld, S);
-    load_head(k, base + H * AT_D, ld, S);
-    load_head(v, base + 2 * H * AT_D, ld, S);
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 128);
+    at_load(sQ, qkv, ld, pair0, npairs, S, H);
+    at_load(sK, qkv + H * AT_D, ld, pair0, npairs, S, H);
+    at_load(sV, qkv + 2 * H * AT_D, ld, pair0, npairs, S, H);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
     __syncthreads();
-    tile_xyT(q, k, p, S + 1, S, 0.125f);                        // scores / sqrt(64)
-    __syncthreads();
-    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {   // softmax: one warp per row
-        const int lane = threadIdx.x & 31;
-        float m = -INFINITY;
-        for (int c = lane; c < S; c += 32) m = fmaxf(m, p[r * (S + 1) + c]);
+    tc::fence_after_sync();
+    const uint32_t tm = tmem_base_smem;
+    if (tid == 0) {
+        constexpr uint32_t idesc = tc::idesc_bf16(128, 128, 0, 0);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        float s = 0.f;
-        for (int c = lane; c < S; c += 32) { const float e = __expf(p[r * (S + 1) + c] - m); p[r * (S + 1) + c] = e; s += e; }
-        s = 1.f / warp_sum(s);
-        for (int c = lane; c < S; c += 32) {
-            const float pv = p[r * (S + 1) + c] * s;
-            p[r * (S + 1) + c] = pv;
-            if (P) P[((size_t)blockIdx.x * S + r) * S + c] = pv;
-        }
+        for (int k = 0; k < 4; ++k) tc::mma_bf16(tm, tc::desc_kmajor(tc::smem_u32(sQ), k), tc::desc_kmajor(tc::smem_u32(sK), k), idesc, k != 0);
+        tc::mma_commit(&bar);
     }
+    const int g = tid >> 6, t = tid & 63, pr = pair0 + g;
+    const bool valid = t < S && pr < npairs;
+    const int b = pr / H, h = pr - b * H;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    float s[SP];
+    at_ld_row<SP>(tm + lane_off + g * 64, s);
+    at_softmax<SP>(s, S, valid);
+    if (P && valid) {
+        float* prow = P + ((size_t)pr * S + t) * S;
+#pragma unroll
+        for (int c = 0; c < SP; ++c) if (c < S) prow[c] = s[c];
+    }
+    at_zero_half(sP + AT_HALF);
+    at_store_row<SP>(sP, g, t, s);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
     __syncthreads();
-    const int TR = (S + 1) >> 1;
-    for (int i = threadIdx.x; i < TR * (AT_D / 4); i += blockDim.x) {            // ctx = P V, 2 rows x 4 columns per thread
-        const int r0 = (i / (AT_D / 4)) * 2, c = (i % (AT_D / 4)) * 4, r1 = min(r0 + 1, S - 1);
-        float acc[2][4];
-        tile_wz<false>(p, S + 1, v, S, r0, r1, c, acc);
-        __nv_bfloat16* o = ctx + (size_t)(b * S + r0) * (H * AT_D) + h * AT_D + c;
-        *reinterpret_cast<uint2*>(o) = make_uint2(bf2(acc[0][0], acc[0][1]), bf2(acc[0][2], acc[0][3]));
-        if (r0 + 1 < S) *reinterpret_cast<uint2*>(o + H * AT_D) = make_uint2(bf2(acc[1][0], acc[1][1]), bf2(acc[1][2], acc[1][3]));
+    if (tid == 0) {
+        tc::fence_after_sync();
+        constexpr uint32_t idesc = tc::idesc_bf16(128, 64, 0, 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            tc::mma_bf16(tm, tc::desc_kmajor(tc::smem_u32(sP) + (k >> 2) * AT_HALF, k & 3), tc::desc_mnmajor(tc::smem_u32(sV), 0, k), idesc, k != 0);
+        tc::mma_commit(&bar);
     }
+    tc::mbar_wait(&bar, 1);
+    tc::fence_after_sync();
+    at_store_out(tm + lane_off, ctx + ((size_t)b * S + t) * ((size_t)H * AT_D) + h * AT_D, valid);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tm, 128);
 }
 
-// dqkv from dctx: dV = P^T dO, dP = dO V^T, dS = P * (dP - rowsum(dP * P)) / 8, dQ = dS K, dK = dS^T Q
+template <int SP>
 __global__ void __launch_bounds__(128) bert_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx,
-                                                            const float* __restrict__ P, __nv_bfloat16* __restrict__ dqkv, int S, int H)
+                                                            __nv_bfloat16* __restrict__ dqkv, int S, int H, int npairs)
 {
-    extern __shared__ __align__(16) float sm[];
-    const int b = blockIdx.x / H, h = blockIdx.x % H;
-    float* q = sm;                          // [S][AT_LD]
-    float* k = q + S * AT_LD;
-    float* v = k + S * AT_LD;
-    float* d = v + S * AT_LD;               // dO
-    float* p = d + S * AT_LD;               // P  [S][S+1]
-    float* ds = p + S * (S + 1);            // dS [S][S+1]
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_smem;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = smem, *sK = smem + AT_SLAB, *sD = smem + 2 * AT_SLAB, *sV = smem + 3 * AT_SLAB;
+    uint8_t* sP = sV;                                          // P: over V (dead after dP = dO V^T) and 8 KB more
+    uint8_t* sS = sP + AT_BD;                                  // dS
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int pair0 = blockIdx.x * 2;
     const size_t ld = (size_t)3 * H * AT_D;
-    const __nv_bfloat16* base = qkv + (size_t)b * S * ld + h * AT_D;
-    load_head(q, base, ld, S);
-    load_head(k, base + H * AT_D, ld, S);
-    load_head(v, base + 2 * H * AT_D, ld, S);
-    load_head(d, dctx + (size_t)b * S * (H * AT_D) + h * AT_D, (size_t)H * AT_D, S);
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) p[(i / S) * (S + 1) + i % S] = __ldg(P + (size_t)blockIdx.x * S * S + i);
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 256);
+    at_load(sQ, qkv, ld, pair0, npairs, S, H);
+    at_load(sK, qkv + H * AT_D, ld, pair0, npairs, S, H);
+    at_load(sV, qkv + 2 * H * AT_D, ld, pair0, npairs, S, H);
+    at_load(sD, dctx, (size_t)H * AT_D, pair0, npairs, S, H);
+    at_zero_half(sS + AT_HALF);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
     __syncthreads();
-    tile_xyT(d, v, ds, S + 1, S, 1.f);                          // dP = dO V^T
-    __syncthreads();
-    for (int r = threadIdx.x >> 5; r < S; r += blockDim.x >> 5) {
-        const int lane = threadIdx.x & 31;
-        float s = 0.f;
-        for (int c = lane; c < S; c += 32) s += ds[r * (S + 1) + c] * p[r * (S + 1) + c];
-        s = warp_sum(s);
-        for (int c = lane; c < S; c += 32) ds[r * (S + 1) + c] = p[r * (S + 1) + c] * (ds[r * (S + 1) + c] - s) * 0.125f;
+    tc::fence_after_sync();
+    const uint32_t tm = tmem_base_smem;
+    if (tid == 0) {
+        constexpr uint32_t idesc = tc::idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc::mma_bf16(tm, tc::desc_kmajor(tc::smem_u32(sQ), k), tc::desc_kmajor(tc::smem_u32(sK), k), idesc, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc::mma_bf16(tm + 128, tc::desc_kmajor(tc::smem_u32(sD), k), tc::desc_kmajor(tc::smem_u32(sV), k), idesc, k != 0);
+        tc::mma_commit(&bar);
     }
+    const int g = tid >> 6, t = tid & 63, pr = pair0 + g;
+    const bool valid = t < S && pr < npairs;
+    const int b = pr / H, h = pr - b * H;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    float p[SP], dp[SP];
+    at_ld_row<SP>(tm + lane_off + g * 64, p);
+    at_softmax<SP>(p, S, valid);
+    at_ld_row<SP>(tm + lane_off + 128 + g * 64, dp);
+    float delta = 0.f;
+#pragma unroll
+    for (int c = 0; c < SP; ++c) delta = fmaf(p[c], dp[c], delta);
+#pragma unroll
+    for (int c = 0; c < SP; ++c) dp[c] = p[c] * (dp[c] - delta) * 0.125f;
+    at_zero_half(sP + AT_HALF);                                // rows 64..127 of the V slab
+    at_store_row<SP>(sP, g, t, p);
+    at_store_row<SP>(sS, g, t, dp);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
     __syncthreads();
-    const int TR = (S + 1) >> 1;
-    for (int i = threadIdx.x; i < TR * (AT_D / 4); i += blockDim.x) {
-        const int r0 = (i / (AT_D / 4)) * 2, c = (i % (AT_D / 4)) * 4, r1 = min(r0 + 1, S - 1);
-        float aq[2][4], ak[2][4], av[2][4];
-        tile_wz<false>(ds, S + 1, k, S, r0, r1, c, aq);         // dQ = dS K
-        tile_wz<true>(ds, S + 1, q, S, r0, r1, c, ak);          // dK = dS^T Q
-        tile_wz<true>(p, S + 1, d, S, r0, r1, c, av);           // dV = P^T dO
-        __nv_bfloat16* o = dqkv + (size_t)(b * S + r0) * ld + h * AT_D + c;
-        *reinterpret_cast<uint2*>(o) = make_uint2(bf2(aq[0][0], aq[0][1]), bf2(aq[0][2], aq[0][3]));
-        *reinterpret_cast<uint2*>(o + H * AT_D) = make_uint2(bf2(ak[0][0], ak[0][1]), bf2(ak[0][2], ak[0][3]));
-        *reinterpret_cast<uint2*>(o + 2 * H * AT_D) = make_uint2(bf2(av[0][0], av[0][1]), bf2(av[0][2], av[0][3]));
-        if (r0 + 1 < S) {
-            o += ld;
-            *reinterpret_cast<uint2*>(o) = make_uint2(bf2(aq[1][0], aq[1][1]), bf2(aq[1][2], aq[1][3]));
-            *reinterpret_cast<uint2*>(o + H * AT_D) = make_uint2(bf2(ak[1][0], ak[1][1]), bf2(ak[1][2], ak[1][3]));
-            *reinterpret_cast<uint2*>(o + 2 * H * AT_D) = make_uint2(bf2(av[1][0], av[1][1]), bf2(av[1][2], av[1][3]));
-        }
+    if (tid == 0) {
+        tc::fence_after_sync();
+        constexpr uint32_t i_kn = tc::idesc_bf16(128, 64, 0, 1), i_nn = tc::idesc_bf16(128, 64, 1, 1);
+        const uint32_t aS = tc::smem_u32(sS), aP = tc::smem_u32(sP);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)                            // dQ = dS K
+            tc::mma_bf16(tm, tc::desc_kmajor(aS + (k >> 2) * AT_HALF, k & 3), tc::desc_mnmajor(tc::smem_u32(sK), 0, k), i_kn, k != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)                            // dK = dS^T Q
+            tc::mma_bf16(tm + 64, tc::desc_mnmajor(aS, AT_HALF, k), tc::desc_mnmajor(tc::smem_u32(sQ), 0, k), i_nn, k != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)                            // dV = P^T dO
+            tc::mma_bf16(tm + 128, tc::desc_mnmajor(aP, AT_HALF, k), tc::desc_mnmajor(tc::smem_u32(sD), 0, k), i_nn, k != 0);
+        tc::mma_commit(&bar);
     }
+    tc::mbar_wait(&bar, 1);
+    tc::fence_after_sync();
+    __nv_bfloat16* o = dqkv + ((size_t)b * S + t) * ld + h * AT_D;
+    at_store_out(tm + lane_off, o, valid);
+    at_store_out(tm + lane_off + 64, o + H * AT_D, valid);
+    at_store_out(tm + lane_off + 128, o + 2 * H * AT_D, valid);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tm, 256);
 }
 
 static int grid_for(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : b); }
@@ -322,19 +418,31 @@ extern "C" int hopk_gelu_bf16(const void* pre, void* out, long n, void* stream)
 extern "C" int hopk_bert_attn_fwd(const void* qkv, void* ctx, float* P, int B, int S, int H, int D, void* stream)
 {
     HOPK_REQUIRE(B > 0 && H > 0 && S >= 1 && S <= AT_MAXS && D == AT_D, "bert attention: head dim 64, sequence <= 64");
-    const size_t smem = ((size_t)3 * S * AT_LD + (size_t)S * (S + 1)) * sizeof(float) + 16;
-    HOPK_CUDA(configure_smem_once((const void*)bert_attn_fwd_kernel, 96 * 1024));
-    bert_attn_fwd_kernel<<<B * H, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, P, S, H);
+    const int npairs = B * H, grid = (npairs + 1) / 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (S <= 40) {
+        HOPK_CUDA(configure_smem_once((const void*)bert_attn_fwd_kernel<40>, AT_FWD_SMEM));
+        bert_attn_fwd_kernel<40><<<grid, 128, AT_FWD_SMEM, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, P, S, H, npairs);
+    } else {
+        HOPK_CUDA(configure_smem_once((const void*)bert_attn_fwd_kernel<64>, AT_FWD_SMEM));
+        bert_attn_fwd_kernel<64><<<grid, 128, AT_FWD_SMEM, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, P, S, H, npairs);
+    }
     HOPK_LAUNCH_CHECK("bert_attn_fwd");
     return 0;
 }
 
-extern "C" int hopk_bert_attn_bwd(const void* qkv, const void* dctx, const float* P, void* dqkv, int B, int S, int H, int D, void* stream)
+extern "C" int hopk_bert_attn_bwd(const void* qkv, const void* dctx, void* dqkv, int B, int S, int H, int D, void* stream)
 {
-    HOPK_REQUIRE(B > 0 && H > 0 && S >= 1 && S <= AT_MAXS && D == AT_D && P, "bert attention backward: head dim 64, sequence <= 64, saved P");
-    const size_t smem = ((size_t)4 * S * AT_LD + (size_t)2 * S * (S + 1)) * sizeof(float) + 16;
-    HOPK_CUDA(configure_smem_once((const void*)bert_attn_bwd_kernel, 128 * 1024));
-    bert_attn_bwd_kernel<<<B * H, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dctx, P, (__nv_bfloat16*)dqkv, S, H);
+    HOPK_REQUIRE(B > 0 && H > 0 && S >= 1 && S <= AT_MAXS && D == AT_D, "bert attention backward: head dim 64, sequence <= 64");
+    const int npairs = B * H, grid = (npairs + 1) / 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (S <= 40) {
+        HOPK_CUDA(configure_smem_once((const void*)bert_attn_bwd_kernel<40>, AT_BWD_SMEM));
+        bert_attn_bwd_kernel<40><<<grid, 128, AT_BWD_SMEM, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dctx, (__nv_bfloat16*)dqkv, S, H, npairs);
+    } else {
+        HOPK_CUDA(configure_smem_once((const void*)bert_attn_bwd_kernel<64>, AT_BWD_SMEM));
+        bert_attn_bwd_kernel<64><<<grid, 128, AT_BWD_SMEM, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dctx, (__nv_bfloat16*)dqkv, S, H, npairs);
+    }
     HOPK_LAUNCH_CHECK("bert_attn_bwd");
     return 0;
 }

@@ -211,9 +211,10 @@ int hopk_ln_bwd(const float* dy, const float* x, const float* add, int period, c
 /* exact GELU on n bf16 elements (n % 8 == 0) */
 int hopk_gelu_bf16(const void* pre, void* out, long n, void* stream);
 /* BertSelfAttention core without mask / dropout: qkv bf16 (B*S, 3*H*D) = [q heads | k heads | v heads] per row; ctx bf16
- * (B*S, H*D); P fp32 (B*H, S, S) softmax probabilities (saved for backward; NULL: not stored).  D = 64, S <= 64. */
+ * (B*S, H*D); P fp32 (B*H, S, S): optional copy of the softmax probabilities for tools (NULL: not stored).  Backward
+ * recomputes the probabilities from qkv and writes dqkv (same layout as qkv) from dctx.  D = 64, S <= 64. */
 int hopk_bert_attn_fwd(const void* qkv, void* ctx, float* P, int B, int S, int H, int D, void* stream);
-int hopk_bert_attn_bwd(const void* qkv, const void* dctx, const float* P, void* dqkv, int B, int S, int H, int D, void* stream);
+int hopk_bert_attn_bwd(const void* qkv, const void* dctx, void* dqkv, int B, int S, int H, int D, void* stream);
 
 /* ------------------------------------------------------------------ GRU decoder (model/HOP.py:166-167, 248)
  * Multi-layer bidirectional GRU, batch_first, zero initial state, PyTorch gate order (r, z, n); dtype-1 arithmetic (bf16
