@@ -5,6 +5,7 @@
 //   self-attention forward / backward         12 heads x 64, sequence 34: two (sample, head) pairs per CTA on tcgen05 UMMAs
 //   GELU                                      BertIntermediate (exact erf form)
 // dtype-1 arithmetic: bf16 operands for the tensor-core GEMMs, fp32 statistics / softmax / residual stream.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc_core.cuh"
@@ -130,32 +131,23 @@ constexpr int AT_MAXS = 64, AT_D = 64;
 constexpr uint32_t AT_SLAB = tc::slab_bytes(128);             // 16 KB
 constexpr uint32_t AT_HALF = tc::slab_bytes(64);              // 8 KB
 constexpr uint32_t AT_BD = 3 * AT_HALF;                       // block-diagonal operand
-constexpr size_t AT_FWD_SMEM = 3 * AT_SLAB + 1024, AT_BWD_SMEM = 4 * AT_SLAB + 2 * AT_BD + 1024;
+constexpr size_t AT_FWD_SMEM = 3 * AT_SLAB + 1024, AT_BWD_SMEM = 3 * AT_SLAB + 2 * AT_BD + 1024;   // P starts on the V slab
 
-// one matrix (Q, K, V or dO) of both pairs -> slab rows 64 g + t; 8 x 16 bytes per thread, loads first
-__device__ __forceinline__ void at_load(uint8_t* slab, const __nv_bfloat16* __restrict__ src, size_t ld, int pair0, int npairs, int S, int H)
-{
-    uint4 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int idx = threadIdx.x + i * 128;
-        const int ch = idx & 7, t = (idx >> 3) & 63, pr = pair0 + (idx >> 9);
-        v[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (t < S && pr < npairs) {
-            const int b = pr / H, h = pr - b * H;
-            v[i] = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)b * S + t) * ld + h * AT_D) + ch);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int idx = threadIdx.x + i * 128;
-        *reinterpret_cast<uint4*>(slab + tc::slab_chunk_off(idx >> 3, idx & 7)) = v[i];
-    }
-}
+constexpr int AT_PITCH = 144;                                 // staging row pitch: 128 data bytes + 16 (conflict-free 16-byte stores)
+
+// Q, K, V (and dO) of one pair are 64-row boxes of the row-major activations loaded by the TMA engine straight into the 128B
+// swizzled slabs.  Rows S..63 of a box belong to the next sample (or are zero past the end): finite values that only meet
+// zero probabilities / masked score columns, so nothing has to be cleared.
 __device__ __forceinline__ void at_zero_half(uint8_t* p)     // 8 KB
 {
 #pragma unroll
     for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(p)[threadIdx.x + i * 128] = make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ float ex2_fast(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 template <int SP>
 __device__ __forceinline__ void at_ld_row(uint32_t taddr, float (&v)[SP])
@@ -187,7 +179,7 @@ __device__ __forceinline__ void at_store_row(uint8_t* bd, int g, int t, const fl
         *reinterpret_cast<uint4*>(blk + tc::slab_chunk_off(t, ch)) = u;
     }
 }
-// softmax(s / 8) over the first S entries, in place (entries >= S become 0)
+// softmax(s / 8) over the first S entries, in place (entries >= S become 0; an invalid row becomes all zero)
 template <int SP>
 __device__ __forceinline__ void at_softmax(float (&s)[SP], int S, bool valid)
 {
@@ -197,61 +189,69 @@ __device__ __forceinline__ void at_softmax(float (&s)[SP], int S, bool valid)
     constexpr float kf = 0.125f * 1.4426950408889634f;
     float sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < SP; ++c) { const float e = c < S ? exp2f((s[c] - m) * kf) : 0.f; s[c] = e; sum += e; }
+    for (int c = 0; c < SP; ++c) { const float e = c < S ? ex2_fast((s[c] - m) * kf) : 0.f; s[c] = e; sum += e; }
     const float inv = valid ? 1.f / sum : 0.f;
 #pragma unroll
     for (int c = 0; c < SP; ++c) s[c] *= inv;
 }
-// TMEM row (64 fp32) -> 64 bf16 in global memory
-__device__ __forceinline__ void at_store_out(uint32_t taddr, __nv_bfloat16* dst, bool valid)
+// TMEM row (64 fp32) -> 64 bf16 in the thread's staging row -> one 128-byte bulk store to global memory
+__device__ __forceinline__ void at_store_out(uint32_t taddr, uint8_t* stage_row, __nv_bfloat16* dst, bool valid)
 {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         float o[32];
         tc::tmem_ld32(taddr + half * 32, o);
-        if (valid) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                reinterpret_cast<uint4*>(dst + half * 32)[q] = make_uint4(bf2(o[8 * q], o[8 * q + 1]), bf2(o[8 * q + 2], o[8 * q + 3]),
-                                                                           bf2(o[8 * q + 4], o[8 * q + 5]), bf2(o[8 * q + 6], o[8 * q + 7]));
-        }
+        for (int q = 0; q < 4; ++q)
+            reinterpret_cast<uint4*>(stage_row + half * 64)[q] = make_uint4(bf2(o[8 * q], o[8 * q + 1]), bf2(o[8 * q + 2], o[8 * q + 3]),
+                                                                            bf2(o[8 * q + 4], o[8 * q + 5]), bf2(o[8 * q + 6], o[8 * q + 7]));
     }
+    tc::fence_async_smem();                                    // this thread's row -> visible to the bulk copy it issues
+    if (valid) tc::bulk_s2g(dst, stage_row, 128);
 }
 
 template <int SP>
-__global__ void __launch_bounds__(128) bert_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx,
+__global__ void __launch_bounds__(128) bert_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ ctx,
                                                             float* __restrict__ P, int S, int H, int npairs)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[2];                               // 0: operands landed, 1: UMMA completion
     __shared__ uint32_t tmem_base_smem;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sQ = smem, *sK = smem + AT_SLAB, *sV = smem + 2 * AT_SLAB;
     uint8_t* sP = smem;                                        // over Q and the first half of K once S = Q K^T is complete
     const int tid = threadIdx.x, warp = tid >> 5;
     const int pair0 = blockIdx.x * 2;
-    const size_t ld = (size_t)3 * H * AT_D;
-    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    if (tid == 0) {
+        tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&bars[0], 6 * AT_HALF);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int pr = pair0 + g, b = pr / H, h = pr - b * H;
+            tc::tma_load_2d(sQ + g * AT_HALF, &tmQKV, h * AT_D, b * S, &bars[0]);
+            tc::tma_load_2d(sK + g * AT_HALF, &tmQKV, (H + h) * AT_D, b * S, &bars[0]);
+            tc::tma_load_2d(sV + g * AT_HALF, &tmQKV, (2 * H + h) * AT_D, b * S, &bars[0]);
+        }
+    }
     if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 128);
-    at_load(sQ, qkv, ld, pair0, npairs, S, H);
-    at_load(sK, qkv + H * AT_D, ld, pair0, npairs, S, H);
-    at_load(sV, qkv + 2 * H * AT_D, ld, pair0, npairs, S, H);
-    tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tm = tmem_base_smem;
     if (tid == 0) {
+        tc::mbar_wait(&bars[0], 0);
         constexpr uint32_t idesc = tc::idesc_bf16(128, 128, 0, 0);
+        const uint64_t dq = tc::desc_kmajor(tc::smem_u32(sQ), 0), dk = tc::desc_kmajor(tc::smem_u32(sK), 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc::mma_bf16(tm, tc::desc_kmajor(tc::smem_u32(sQ), k), tc::desc_kmajor(tc::smem_u32(sK), k), idesc, k != 0);
-        tc::mma_commit(&bar);
+        for (int k = 0; k < 4; ++k) tc::mma_bf16(tm, tc::desc_adv(dq, 32 * k), tc::desc_adv(dk, 32 * k), idesc, k != 0);
+        tc::mma_commit(&bars[1]);
     }
     const int g = tid >> 6, t = tid & 63, pr = pair0 + g;
     const bool valid = t < S && pr < npairs;
     const int b = pr / H, h = pr - b * H;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    tc::mbar_wait(&bar, 0);
+    tc::mbar_wait(&bars[1], 0);
     tc::fence_after_sync();
     float s[SP];
     at_ld_row<SP>(tm + lane_off + g * 64, s);
@@ -269,25 +269,27 @@ __global__ void __launch_bounds__(128) bert_attn_fwd_kernel(const __nv_bfloat16*
     if (tid == 0) {
         tc::fence_after_sync();
         constexpr uint32_t idesc = tc::idesc_bf16(128, 64, 0, 1);
+        const uint64_t dp = tc::desc_kmajor(tc::smem_u32(sP), 0), dv = tc::desc_mnmajor(tc::smem_u32(sV), 0, 0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            tc::mma_bf16(tm, tc::desc_kmajor(tc::smem_u32(sP) + (k >> 2) * AT_HALF, k & 3), tc::desc_mnmajor(tc::smem_u32(sV), 0, k), idesc, k != 0);
-        tc::mma_commit(&bar);
+        for (int k = 0; k < 8; ++k) tc::mma_bf16(tm, tc::desc_adv(dp, (k >> 2) * AT_HALF + (k & 3) * 32), tc::desc_adv(dv, 2048 * k), idesc, k != 0);
+        tc::mma_commit(&bars[1]);
     }
-    tc::mbar_wait(&bar, 1);
+    tc::mbar_wait(&bars[1], 1);
     tc::fence_after_sync();
-    at_store_out(tm + lane_off, ctx + ((size_t)b * S + t) * ((size_t)H * AT_D) + h * AT_D, valid);
+    at_store_out(tm + lane_off, smem + tid * AT_PITCH, ctx + ((size_t)b * S + t) * ((size_t)H * AT_D) + h * AT_D, valid);
+    tc::bulk_commit();
+    tc::bulk_wait_read();
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tm, 128);
 }
 
 template <int SP>
-__global__ void __launch_bounds__(128) bert_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx,
+__global__ void __launch_bounds__(128) bert_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                                                             __nv_bfloat16* __restrict__ dqkv, int S, int H, int npairs)
 {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[2];
     __shared__ uint32_t tmem_base_smem;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sQ = smem, *sK = smem + AT_SLAB, *sD = smem + 2 * AT_SLAB, *sV = smem + 3 * AT_SLAB;
@@ -296,31 +298,41 @@ __global__ void __launch_bounds__(128) bert_attn_bwd_kernel(const __nv_bfloat16*
     const int tid = threadIdx.x, warp = tid >> 5;
     const int pair0 = blockIdx.x * 2;
     const size_t ld = (size_t)3 * H * AT_D;
-    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    if (tid == 0) {
+        tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&bars[0], 8 * AT_HALF);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int pr = pair0 + g, b = pr / H, h = pr - b * H;
+            tc::tma_load_2d(sQ + g * AT_HALF, &tmQKV, h * AT_D, b * S, &bars[0]);
+            tc::tma_load_2d(sK + g * AT_HALF, &tmQKV, (H + h) * AT_D, b * S, &bars[0]);
+            tc::tma_load_2d(sV + g * AT_HALF, &tmQKV, (2 * H + h) * AT_D, b * S, &bars[0]);
+            tc::tma_load_2d(sD + g * AT_HALF, &tmDO, h * AT_D, b * S, &bars[0]);
+        }
+    }
     if (warp == 0) tc::tmem_alloc(&tmem_base_smem, 256);
-    at_load(sQ, qkv, ld, pair0, npairs, S, H);
-    at_load(sK, qkv + H * AT_D, ld, pair0, npairs, S, H);
-    at_load(sV, qkv + 2 * H * AT_D, ld, pair0, npairs, S, H);
-    at_load(sD, dctx, (size_t)H * AT_D, pair0, npairs, S, H);
     at_zero_half(sS + AT_HALF);
-    tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tm = tmem_base_smem;
     if (tid == 0) {
+        tc::mbar_wait(&bars[0], 0);
         constexpr uint32_t idesc = tc::idesc_bf16(128, 128, 0, 0);
+        const uint64_t dq = tc::desc_kmajor(tc::smem_u32(sQ), 0), dk = tc::desc_kmajor(tc::smem_u32(sK), 0);
+        const uint64_t dd = tc::desc_kmajor(tc::smem_u32(sD), 0), dv = tc::desc_kmajor(tc::smem_u32(sV), 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc::mma_bf16(tm, tc::desc_kmajor(tc::smem_u32(sQ), k), tc::desc_kmajor(tc::smem_u32(sK), k), idesc, k != 0);
+        for (int k = 0; k < 4; ++k) tc::mma_bf16(tm, tc::desc_adv(dq, 32 * k), tc::desc_adv(dk, 32 * k), idesc, k != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc::mma_bf16(tm + 128, tc::desc_kmajor(tc::smem_u32(sD), k), tc::desc_kmajor(tc::smem_u32(sV), k), idesc, k != 0);
-        tc::mma_commit(&bar);
+        for (int k = 0; k < 4; ++k) tc::mma_bf16(tm + 128, tc::desc_adv(dd, 32 * k), tc::desc_adv(dv, 32 * k), idesc, k != 0);
+        tc::mma_commit(&bars[1]);
     }
     const int g = tid >> 6, t = tid & 63, pr = pair0 + g;
     const bool valid = t < S && pr < npairs;
     const int b = pr / H, h = pr - b * H;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    tc::mbar_wait(&bar, 0);
+    tc::mbar_wait(&bars[1], 0);
     tc::fence_after_sync();
     float p[SP], dp[SP];
     at_ld_row<SP>(tm + lane_off + g * 64, p);
@@ -340,24 +352,29 @@ __global__ void __launch_bounds__(128) bert_attn_bwd_kernel(const __nv_bfloat16*
     if (tid == 0) {
         tc::fence_after_sync();
         constexpr uint32_t i_kn = tc::idesc_bf16(128, 64, 0, 1), i_nn = tc::idesc_bf16(128, 64, 1, 1);
-        const uint32_t aS = tc::smem_u32(sS), aP = tc::smem_u32(sP);
+        const uint64_t ds_k = tc::desc_kmajor(tc::smem_u32(sS), 0), ds_n = tc::desc_mnmajor(tc::smem_u32(sS), AT_HALF, 0);
+        const uint64_t dp_n = tc::desc_mnmajor(tc::smem_u32(sP), AT_HALF, 0);
+        const uint64_t bk = tc::desc_mnmajor(tc::smem_u32(sK), 0, 0), bq = tc::desc_mnmajor(tc::smem_u32(sQ), 0, 0), bd = tc::desc_mnmajor(tc::smem_u32(sD), 0, 0);
 #pragma unroll
         for (int k = 0; k < 8; ++k)                            // dQ = dS K
-            tc::mma_bf16(tm, tc::desc_kmajor(aS + (k >> 2) * AT_HALF, k & 3), tc::desc_mnmajor(tc::smem_u32(sK), 0, k), i_kn, k != 0);
+            tc::mma_bf16(tm, tc::desc_adv(ds_k, (k >> 2) * AT_HALF + (k & 3) * 32), tc::desc_adv(bk, 2048 * k), i_kn, k != 0);
 #pragma unroll
         for (int k = 0; k < 8; ++k)                            // dK = dS^T Q
-            tc::mma_bf16(tm + 64, tc::desc_mnmajor(aS, AT_HALF, k), tc::desc_mnmajor(tc::smem_u32(sQ), 0, k), i_nn, k != 0);
+            tc::mma_bf16(tm + 64, tc::desc_adv(ds_n, 2048 * k), tc::desc_adv(bq, 2048 * k), i_nn, k != 0);
 #pragma unroll
         for (int k = 0; k < 8; ++k)                            // dV = P^T dO
-            tc::mma_bf16(tm + 128, tc::desc_mnmajor(aP, AT_HALF, k), tc::desc_mnmajor(tc::smem_u32(sD), 0, k), i_nn, k != 0);
-        tc::mma_commit(&bar);
+            tc::mma_bf16(tm + 128, tc::desc_adv(dp_n, 2048 * k), tc::desc_adv(bd, 2048 * k), i_nn, k != 0);
+        tc::mma_commit(&bars[1]);
     }
-    tc::mbar_wait(&bar, 1);
+    tc::mbar_wait(&bars[1], 1);
     tc::fence_after_sync();
     __nv_bfloat16* o = dqkv + ((size_t)b * S + t) * ld + h * AT_D;
-    at_store_out(tm + lane_off, o, valid);
-    at_store_out(tm + lane_off + 64, o + H * AT_D, valid);
-    at_store_out(tm + lane_off + 128, o + 2 * H * AT_D, valid);
+    uint8_t* stage = smem + tid * AT_PITCH;
+    at_store_out(tm + lane_off, stage, o, valid);
+    at_store_out(tm + lane_off + 64, stage + 128 * AT_PITCH, o + H * AT_D, valid);
+    at_store_out(tm + lane_off + 128, stage + 256 * AT_PITCH, o + 2 * H * AT_D, valid);
+    tc::bulk_commit();
+    tc::bulk_wait_read();
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tm, 256);
@@ -420,12 +437,14 @@ extern "C" int hopk_bert_attn_fwd(const void* qkv, void* ctx, float* P, int B, i
     HOPK_REQUIRE(B > 0 && H > 0 && S >= 1 && S <= AT_MAXS && D == AT_D, "bert attention: head dim 64, sequence <= 64");
     const int npairs = B * H, grid = (npairs + 1) / 2;
     cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap tq;
+    if (int rc = make_tensor_map_bf16(&tq, qkv, (long)B * S, 3L * H * D, 3L * H * D, 64)) return rc;
     if (S <= 40) {
         HOPK_CUDA(configure_smem_once((const void*)bert_attn_fwd_kernel<40>, AT_FWD_SMEM));
-        bert_attn_fwd_kernel<40><<<grid, 128, AT_FWD_SMEM, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, P, S, H, npairs);
+        bert_attn_fwd_kernel<40><<<grid, 128, AT_FWD_SMEM, st>>>(tq, (__nv_bfloat16*)ctx, P, S, H, npairs);
     } else {
         HOPK_CUDA(configure_smem_once((const void*)bert_attn_fwd_kernel<64>, AT_FWD_SMEM));
-        bert_attn_fwd_kernel<64><<<grid, 128, AT_FWD_SMEM, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, P, S, H, npairs);
+        bert_attn_fwd_kernel<64><<<grid, 128, AT_FWD_SMEM, st>>>(tq, (__nv_bfloat16*)ctx, P, S, H, npairs);
     }
     HOPK_LAUNCH_CHECK("bert_attn_fwd");
     return 0;
@@ -436,12 +455,15 @@ extern "C" int hopk_bert_attn_bwd(const void* qkv, const void* dctx, void* dqkv,
     HOPK_REQUIRE(B > 0 && H > 0 && S >= 1 && S <= AT_MAXS && D == AT_D, "bert attention backward: head dim 64, sequence <= 64");
     const int npairs = B * H, grid = (npairs + 1) / 2;
     cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap tq, td;
+    if (int rc = make_tensor_map_bf16(&tq, qkv, (long)B * S, 3L * H * D, 3L * H * D, 64)) return rc;
+    if (int rc = make_tensor_map_bf16(&td, dctx, (long)B * S, (long)H * D, (long)H * D, 64)) return rc;
     if (S <= 40) {
         HOPK_CUDA(configure_smem_once((const void*)bert_attn_bwd_kernel<40>, AT_BWD_SMEM));
-        bert_attn_bwd_kernel<40><<<grid, 128, AT_BWD_SMEM, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dctx, (__nv_bfloat16*)dqkv, S, H, npairs);
+        bert_attn_bwd_kernel<40><<<grid, 128, AT_BWD_SMEM, st>>>(tq, td, (__nv_bfloat16*)dqkv, S, H, npairs);
     } else {
         HOPK_CUDA(configure_smem_once((const void*)bert_attn_bwd_kernel<64>, AT_BWD_SMEM));
-        bert_attn_bwd_kernel<64><<<grid, 128, AT_BWD_SMEM, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dctx, (__nv_bfloat16*)dqkv, S, H, npairs);
+        bert_attn_bwd_kernel<64><<<grid, 128, AT_BWD_SMEM, st>>>(tq, td, (__nv_bfloat16*)dqkv, S, H, npairs);
     }
     HOPK_LAUNCH_CHECK("bert_attn_bwd");
     return 0;

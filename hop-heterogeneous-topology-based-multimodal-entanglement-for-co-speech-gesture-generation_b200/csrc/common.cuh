@@ -37,6 +37,9 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
                      long ldb, long ldc, int a_mn, int b_mn, int out_bf16, int accumulate, int act, float slope, int splits,
                      cudaStream_t st, const void* mask = nullptr, int a_kshift = 0, int b_kshift = 0, int bias_row = 0, int mask_bf16 = 0, int mask_gelu = 0);
 
+// bf16 row-major matrix (rows x cols, pitch ld elements) -> CUtensorMap with {64 columns, box_rows rows} boxes, 128B swizzle
+int make_tensor_map_bf16(void* tmap, const void* base, long rows, long cols, long ld, int box_rows);
+
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace hopk

@@ -47,16 +47,6 @@ struct GtArgs {
     int tiles_m, tiles_n;
 };
 
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(tc::smem_u32(smem_dst)), "l"(tm), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
-{
-    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
-}
 __device__ __forceinline__ float gt_act(float x, int act, float slope)
 {
     if (act == 1) return fmaxf(x, 0.f);
@@ -87,8 +77,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], GT_EPI_WARPS); }
         tc::fence_barrier_init();
@@ -115,15 +105,15 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint8_t* sa = smem + (size_t)stage * STAGE;
                     uint8_t* sb = sa + A_BYTES;
                     tc::mbar_expect_tx(&full[stage], STAGE);
-                    if (!A_MN) tma_load_2d(sa, &tmA, k, m0, &full[stage]);                    // box {64 k, 128 rows}
+                    if (!A_MN) tc::tma_load_2d(sa, &tmA, k, m0, &full[stage]);                    // box {64 k, 128 rows}
                     else {
 #pragma unroll
-                        for (int s = 0; s < GT_BM / 64; ++s) tma_load_2d(sa + s * tc::slab_bytes(GT_BK), &tmA, m0 + 64 * s, k + g.a_kshift, &full[stage]);   // box {64 m, 64 k-rows}
+                        for (int s = 0; s < GT_BM / 64; ++s) tc::tma_load_2d(sa + s * tc::slab_bytes(GT_BK), &tmA, m0 + 64 * s, k + g.a_kshift, &full[stage]);   // box {64 m, 64 k-rows}
                     }
-                    if (!B_MN) tma_load_2d(sb, &tmB, k, n0, &full[stage]);
+                    if (!B_MN) tc::tma_load_2d(sb, &tmB, k, n0, &full[stage]);
                     else {
 #pragma unroll
-                        for (int s = 0; s < BN / 64; ++s) tma_load_2d(sb + s * tc::slab_bytes(GT_BK), &tmB, n0 + 64 * s, k + g.b_kshift, &full[stage]);
+                        for (int s = 0; s < BN / 64; ++s) tc::tma_load_2d(sb + s * tc::slab_bytes(GT_BK), &tmB, n0 + 64 * s, k + g.b_kshift, &full[stage]);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -380,9 +370,10 @@ static EncodeTiledFn encode_tiled()
     return fn;
 }
 
-// 2-D bf16 tensor map over a row-major (rows x cols) matrix with leading dimension ld (elements); box = {64 cols, box_rows}
-static int make_map(CUtensorMap* tm, const void* base, long rows, long cols, long ld, int box_rows)
+// bf16 row-major matrix (rows x cols, pitch ld elements) as a 2-D tensor map with {64 columns, box_rows rows} boxes, 128B swizzle
+int make_tensor_map_bf16(void* tmap, const void* base, long rows, long cols, long ld, int box_rows)
 {
+    CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(tmap);
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail(3, "cuTensorMapEncodeTiled", "driver entry point not found");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -398,6 +389,11 @@ static int make_map(CUtensorMap* tm, const void* base, long rows, long cols, lon
         return fail(3, "cuTensorMapEncodeTiled failed:", msg);
     }
     return 0;
+}
+
+static int make_map(CUtensorMap* tm, const void* base, long rows, long cols, long ld, int box_rows)
+{
+    return make_tensor_map_bf16(tm, base, rows, cols, ld, box_rows);
 }
 
 int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, const void* addend, int M, int N, int K, long lda,
