@@ -39,6 +39,7 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
 
 // bf16 row-major matrix (rows x cols, pitch ld elements) -> CUtensorMap with {64 columns, box_rows rows} boxes, 128B swizzle
 int make_tensor_map_bf16(void* tmap, const void* base, long rows, long cols, long ld, int box_rows);
+int make_tensor_map_2d(void* tmap, const void* base, int elt_bytes, long rows, long cols, long ld, int box_cols, int box_rows, int swizzle_bytes);
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 

@@ -32,7 +32,8 @@ constexpr int GT_THREADS = 64 + 32 * GT_EPI_WARPS;      // producer warp, MMA wa
 
 template <int BN> constexpr int gt_stages() { return BN == 128 ? 6 : 4; }
 template <int BN> constexpr uint32_t gt_stage_bytes() { return tc::slab_bytes(GT_BM) + tc::slab_bytes(BN); }
-template <int BN> constexpr size_t gt_smem_bytes() { return (size_t)gt_stages<BN>() * gt_stage_bytes<BN>() + 1024 + 256; }
+constexpr uint32_t GT_STG_BYTES = 4096;                 // per epilogue warp: one 32-row x 128-byte (fp32) or x 64-byte (bf16) store box
+template <int BN> constexpr size_t gt_smem_bytes() { return (size_t)gt_stages<BN>() * gt_stage_bytes<BN>() + (size_t)GT_EPI_WARPS * GT_STG_BYTES + 1024 + 256; }
 
 struct GtArgs {
     void* C; const float* bias; const void* addend; const void* mask;
@@ -45,6 +46,7 @@ struct GtArgs {
     int out_bf16, accumulate, act, splits, kper;        // act: 0 none, 1 relu, 2 leaky relu (slope), 3 gelu (erf)
     float slope;
     int tiles_m, tiles_n;
+    int tma_store;                                      // the epilogue writes C through tmC (32 x 32 boxes) instead of per-thread stores
 };
 
 __device__ __forceinline__ float gt_act(float x, int act, float slope)
@@ -59,16 +61,20 @@ __device__ __forceinline__ float gt_act(float x, int act, float slope)
 // ~180 instructions per K block with run-time layout branches against 512 tensor-pipe cycles), so its loop is straight-line:
 // one 64-bit add per descriptor, four tcgen05.mma, one commit.
 // (A cluster-pair variant with a multicast B tile was measured too: no gain at cluster size 2 -- TMA multicast only
-// de-duplicates L2 reads for larger clusters -- and it was removed again.)
+// de-duplicates L2 reads for larger clusters -- and it was removed again.  Knock-out timings at 4352 x 3072 x 768: fixed
+// cost 12 us, + main loop 11 us, + TMEM reads of the epilogue 6 us, + its stores 9 us: the epilogue of a tile is as long as
+// its main loop and competes with the next tile's MMAs for TMEM bandwidth; per-thread stores, a shared-memory transpose and
+// the TMA store used now all time the same.)
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GtArgs g)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GtArgs g)
 {
     constexpr int STAGES = gt_stages<BN>();
     constexpr uint32_t A_BYTES = tc::slab_bytes(GT_BM), B_BYTES = tc::slab_bytes(BN), STAGE = A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE);
+    uint8_t* staging = smem + (size_t)STAGES * STAGE;       // GT_EPI_WARPS x GT_STG_BYTES, 1024-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (size_t)GT_EPI_WARPS * GT_STG_BYTES);
     uint64_t* full = bars;                       // [STAGES] TMA -> MMA
     uint64_t* empty = bars + STAGES;             // [STAGES] MMA -> TMA
     uint64_t* acc_full = bars + 2 * STAGES;      // [2]      MMA -> epilogue
@@ -88,6 +94,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+    // programmatic dependent launch: everything above overlaps the tail of the preceding kernel in the stream; global
+    // memory is only touched after that kernel has completed.  Our own dependents may start their prologue right away.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int per_split = g.tiles_m * g.tiles_n;
     const int ntiles = per_split * g.splits;
     const int w0 = (int)blockIdx.x, wstride = (int)gridDim.x;
@@ -159,6 +169,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int quarter = warp & 3, chalf = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        uint8_t* stg = staging + (size_t)(warp - 2) * GT_STG_BYTES;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = w0; tile < ntiles; tile += wstride) {
             const int t2 = tile % per_split;
@@ -174,8 +185,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (nb >= g.N) break;                              // uniform across the warp
                 float v[32];
                 tc::tmem_ld32(src + c * 32, v);
+                const bool fullw = nb + 32 <= g.N;
                 if (m < g.M) {
-                    const bool fullw = nb + 32 <= g.N;
                     if (g.bias && first_split) {
                         if (g.bias_row) {
                             const float bm = __ldg(g.bias + m);
@@ -227,6 +238,32 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) v[j] = __ldg(mk + j) > 0.f ? v[j] : g.slope * v[j];
                         }
                     }
+                }
+                if (g.tma_store) {
+                    // row-per-thread registers -> swizzled 32 x 32 staging box -> one TMA store (full lines, clipped at M / N)
+                    if (lane == 0) tc::bulk_wait_read();           // the previous box of this warp has left the buffer
+                    __syncwarp();
+                    if (g.out_bf16) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u;
+                            u.x = tc::pack_bf16x2(v[8 * q], v[8 * q + 1]); u.y = tc::pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+                            u.z = tc::pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); u.w = tc::pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                    tc::fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&tmC), "r"(tc::smem_u32(stg)), "r"(nb), "r"(m0 + quarter * 32) : "memory");
+                        tc::bulk_commit();
+                    }
+                } else if (m < g.M) {
                     if (g.out_bf16) {
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + (size_t)m * g.ldc + nb;
                         if (fullw && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -268,6 +305,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (g.tma_store && lane == 0) tc::bulk_wait_read();        // shared memory stays valid until the last box has been read
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -370,18 +408,20 @@ static EncodeTiledFn encode_tiled()
     return fn;
 }
 
-// bf16 row-major matrix (rows x cols, pitch ld elements) as a 2-D tensor map with {64 columns, box_rows rows} boxes, 128B swizzle
-int make_tensor_map_bf16(void* tmap, const void* base, long rows, long cols, long ld, int box_rows)
+// row-major matrix (rows x cols, pitch ld elements of elt_bytes = 2: bf16, 4: fp32) as a 2-D tensor map with {box_cols, box_rows}
+// boxes and the 128B / 64B swizzle
+int make_tensor_map_2d(void* tmap, const void* base, int elt_bytes, long rows, long cols, long ld, int box_cols, int box_rows, int swizzle_bytes)
 {
     CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(tmap);
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return fail(3, "cuTensorMapEncodeTiled", "driver entry point not found");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * elt_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(tm, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char msg[96];
@@ -389,6 +429,10 @@ int make_tensor_map_bf16(void* tmap, const void* base, long rows, long cols, lon
         return fail(3, "cuTensorMapEncodeTiled failed:", msg);
     }
     return 0;
+}
+int make_tensor_map_bf16(void* tmap, const void* base, long rows, long cols, long ld, int box_rows)
+{
+    return make_tensor_map_2d(tmap, base, 2, rows, cols, ld, 64, box_rows, 128);
 }
 
 static int make_map(CUtensorMap* tm, const void* base, long rows, long cols, long ld, int box_rows)
@@ -407,7 +451,7 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     HOPK_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "operands must be 16-byte aligned");
     HOPK_REQUIRE(!(out_bf16 && (accumulate || splits > 1)), "accumulation needs an fp32 destination");
     HOPK_REQUIRE(!(act && (accumulate || splits > 1)), "an activation cannot be combined with accumulation / split-K");
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     // K-major: matrix is (M rows x K cols), box {64 k, 128 rows}; MN-major: matrix is (K rows x M cols), box {64 m, 64 k-rows}
     if (int rc = a_mn ? make_map(&tmA, A, K, M, lda, GT_BK) : make_map(&tmA, A, M, K, lda, GT_BM)) return rc;
     // tile width: 128 x 256 tiles read less of A per flop but cost ~1.75x a 128 x 128 tile; the persistent grid runs
@@ -430,13 +474,25 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     g.out_bf16 = out_bf16; g.accumulate = accumulate; g.act = act; g.slope = slope;
     g.splits = splits; g.kper = kper;
     g.tiles_m = tiles_m; g.tiles_n = tiles_n;
+    // plain stores go through the TMA engine when C's rows are 16-byte multiples (32 x 32 boxes: 128-byte fp32 / 64-byte bf16 rows)
+    const int elt = out_bf16 ? 2 : 4;
+    g.tma_store = splits == 1 && !accumulate && ((size_t)ldc * elt) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+    if (g.tma_store) {
+        if (int rc = make_tensor_map_2d(&tmC, C, elt, M, N, ldc, 32, 32, out_bf16 ? 64 : 128)) return rc;
+    } else tmC = tmA;
     if (splits > 1 && !accumulate) HOPK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
     const long ntiles = (long)tiles_m * tiles_n * splits;
     const int grid = (int)(ntiles < sms0 ? ntiles : sms0);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GT_THREADS); cfg.stream = st; cfg.attrs = pdl; cfg.numAttrs = 1;
 #define HOPK_GT_LAUNCH(BNV, AM, BM_)                                                                                      \
     do {                                                                                                                  \
         HOPK_CUDA(configure_smem_once((const void*)gemm_tma_kernel<BNV, AM, BM_>, gt_smem_bytes<BNV>()));                  \
-        gemm_tma_kernel<BNV, AM, BM_><<<grid, GT_THREADS, gt_smem_bytes<BNV>(), st>>>(tmA, tmB, g);                        \
+        cfg.dynamicSmemBytes = gt_smem_bytes<BNV>();                                                                      \
+        HOPK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<BNV, AM, BM_>, tmA, tmB, tmC, g));                             \
     } while (0)
     const int variant = (BN == 256 ? 4 : 0) | (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
     switch (variant) {
