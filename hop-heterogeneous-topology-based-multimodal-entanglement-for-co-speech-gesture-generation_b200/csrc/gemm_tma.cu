@@ -89,7 +89,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], GT_EPI_WARPS); }
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, 2 * BN);
+    constexpr uint32_t TMEM_COLS = BN <= 128 ? 256 : 512;  // two accumulators of BN columns (allocation sizes are powers of two)
+    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -309,7 +310,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem, 2 * BN);
+    if (warp == 1) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ small helper kernels
@@ -459,10 +460,18 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     int dev0 = 0, sms0 = 148;
     cudaGetDevice(&dev0);
     cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+    // tile width: a wider tile reads less of A per flop but costs more per tile (about 0.25 + 0.75 BN / 128 of a 128-wide
+    // one); the persistent grid runs ceil(tiles / SMs) rounds, so take whichever finishes first -- wave quantisation decides
+    // at these sizes (N = 768 fills 136 of 148 SMs with 192-wide tiles, 102 with 256-wide ones)
     const long sp = splits > 1 ? splits : 1;
-    const long t128 = (long)cdiv(M, GT_BM) * cdiv(N, 128) * sp, t256 = (long)cdiv(M, GT_BM) * cdiv(N, 256) * sp;
-    const double c128 = (double)cdiv(t128, sms0), c256 = 1.75 * (double)cdiv(t256, sms0);
-    const int BN = (N > 128 && c256 < c128) ? 256 : 128;
+    int BN = 128;
+    double best = 1e30;
+    for (int bn = 128; bn <= 256; bn += 64) {
+        if (bn > 128 && N <= bn - 64) break;
+        const long tiles = (long)cdiv(M, GT_BM) * cdiv(N, bn) * sp;
+        const double cost = (double)cdiv(tiles, sms0) * (0.25 + 0.75 * bn / 128.0);
+        if (cost < best - 1e-9) { best = cost; BN = bn; }
+    }
     if (splits < 1) splits = 1;
     int kper = ((cdiv(K, splits) + GT_BK - 1) / GT_BK) * GT_BK;
     splits = cdiv(K, kper);
@@ -494,15 +503,19 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
         cfg.dynamicSmemBytes = gt_smem_bytes<BNV>();                                                                      \
         HOPK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<BNV, AM, BM_>, tmA, tmB, tmC, g));                             \
     } while (0)
-    const int variant = (BN == 256 ? 4 : 0) | (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
+    const int variant = (BN == 256 ? 8 : BN == 192 ? 4 : 0) | (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
     switch (variant) {
         case 0: HOPK_GT_LAUNCH(128, false, false); break;
         case 1: HOPK_GT_LAUNCH(128, false, true); break;
         case 2: HOPK_GT_LAUNCH(128, true, false); break;
         case 3: HOPK_GT_LAUNCH(128, true, true); break;
-        case 4: HOPK_GT_LAUNCH(256, false, false); break;
-        case 5: HOPK_GT_LAUNCH(256, false, true); break;
-        case 6: HOPK_GT_LAUNCH(256, true, false); break;
+        case 4: HOPK_GT_LAUNCH(192, false, false); break;
+        case 5: HOPK_GT_LAUNCH(192, false, true); break;
+        case 6: HOPK_GT_LAUNCH(192, true, false); break;
+        case 7: HOPK_GT_LAUNCH(192, true, true); break;
+        case 8: HOPK_GT_LAUNCH(256, false, false); break;
+        case 9: HOPK_GT_LAUNCH(256, false, true); break;
+        case 10: HOPK_GT_LAUNCH(256, true, false); break;
         default: HOPK_GT_LAUNCH(256, true, true); break;
     }
 #undef HOPK_GT_LAUNCH
