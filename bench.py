@@ -265,6 +265,14 @@ def run_ours(a):
             losses.append(W.step(W.resident)['loss'])
         torch.cuda.synchronize()
         spans = profiler.summary()
+        profiler.enable(True, fine=True)                            # second pass: every dense GEMM launch on its own (nested spans)
+        for _ in range(prof_steps):
+            losses.append(W.step(W.resident)['loss'])
+        torch.cuda.synchronize()
+        fine = profiler.summary()
+        spans_work = profiler.work_summary()
+        if 'gemm_tma' in fine:
+            spans['gemm_tma'] = fine['gemm_tma']
         profiler.enable(False)
         run = W.step
         if a.graph:
@@ -301,7 +309,7 @@ def run_ours(a):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = W.graphed.launches_per_step * steps if W.graphed is not None else lib.hopk_launch_count() - launches0
-        res = {'ms': ms, 'launches': int(launches), 'spans': spans, 'prof_steps': prof_steps, 'losses': losses, 'out_len': 0,
+        res = {'ms': ms, 'launches': int(launches), 'spans': spans, 'spans_work': spans_work, 'prof_steps': prof_steps, 'losses': losses, 'out_len': 0,
                'e2e_ms': None}
         if not with_e2e:
             return res
@@ -388,8 +396,8 @@ def run_ours(a):
                         'd2h_bytes_per_step': 4 * r['out_len']},
                 'gpu_launches': r['launches'],
                 'loss_first_last': [r['losses'][0], r['losses'][-1]],
-                'roofline': roofline(r['spans'], a, a.datasets, r['prof_steps']),
-                'kernel_ms_per_step': {k: round(v[1] / r['prof_steps'], 4) for k, v in sorted(r['spans'].items())},
+                'roofline': roofline(r['spans'], a, a.datasets, r['prof_steps'], r['spans_work']),
+                'kernel_ms_per_step': {k: round(v[1] / r['prof_steps'], 4) for k, v in sorted(r['spans'].items())},   # gemm_tma is nested inside bert_* / linear_* / beat_* / mapping_*
                 'dp': W.engine.stats if world > 1 else None}
     # ---- N = 1 extras: Expressive configuration, stock-PyTorch-CUDA speed bar, CPU baseline
     if world == 1:
@@ -407,7 +415,7 @@ def run_ours(a):
                     'e2e': {'value': a.batch * ksteps / (re_['e2e_ms'] * 1e-3), 'unit': 'samples/s'},
                     'cuda_graph': WE.graphed is not None, 'gpu_launches': re_['launches'],
                     'kernel_ms_per_step': {k: round(v[1] / re_['prof_steps'], 4) for k, v in sorted(re_['spans'].items())},
-                    'roofline': roofline(re_['spans'], a, 'TED_expressive', re_['prof_steps'])}
+                    'roofline': roofline(re_['spans'], a, 'TED_expressive', re_['prof_steps'], re_['spans_work'])}
                 WE.release()
                 del WE
             except Exception as exc:                            # noqa: BLE001
@@ -581,9 +589,10 @@ def measured_traffic():
         return {}
 
 
-def roofline(spans, a, datasets, nsteps):
+def roofline(spans, a, datasets, nsteps, spans_work=None):
     """Roofline position of every hand-written kernel group timed inside the step (CUDA events around the C-ABI calls);
-    the top-level entry is the group that takes the most time per step.
+    the top-level entry is the group that takes the most time per step -- the dense TMA + tcgen05 GEMM (`gemm_tma`: every
+    hopk_gemm_bf16 launch of the encoder / projections / beat MLP / mapping layer, 2*M*N*K FLOPs each, timed per launch).
 
     Algorithmic work per call:
       gwnet forward  : fused-floor bytes of SURVEY 8(d) with s = 4 (fp32 activations), backward = 2x    -> HBM roofline
@@ -599,6 +608,15 @@ def roofline(spans, a, datasets, nsteps):
             'gwnet_fwd': ('hbm', float(floor_fwd), None), 'gwnet_bwd': ('hbm', 2.0 * floor_fwd, None)}
     traffic = measured_traffic() if (datasets == 'TED' and a.batch == 128) else {}
     groups = {}
+    if spans_work and spans.get('gemm_tma') and a.precision == 'bf16':
+        calls, total_ms = spans['gemm_tma']
+        flops = spans_work['gemm_tma']
+        ach = flops / (total_ms * 1e-3) / 1e12
+        groups['gemm_tma'] = {'bound': 'tensor', 'achieved': ach, 'peak': tf, 'unit': 'TFLOP/s', 'frac': ach / tf,
+                              'traffic': traffic.get('gemm_tma'), 'avg_ms': total_ms / calls, 'launches_timed': calls,
+                              'ms_per_step': total_ms / nsteps, 'algorithmic_flops': flops / calls,
+                              'arithmetic': 'bf16 tcgen05 UMMA (TMA operands, fp32 accumulate in TMEM); FLOPs = 2*M*N*K summed over the '
+                                            'launches, time = sum of their CUDA-event durations (eager launches: includes host gaps)'}
     for k, (bound, amount, executed) in work.items():
         if k not in spans:
             continue

@@ -110,7 +110,7 @@ __global__ void gelu_bf16_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfl
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float a = __low2float(h[j]), b = __high2float(h[j]);
-            o[j] = bf2(0.5f * a * (1.f + erff(a * 0.70710678118654752f)), 0.5f * b * (1.f + erff(b * 0.70710678118654752f)));
+            o[j] = bf2(gelu_fast(a), gelu_fast(b));
         }
         reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }

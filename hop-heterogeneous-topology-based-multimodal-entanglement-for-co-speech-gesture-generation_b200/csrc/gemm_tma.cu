@@ -53,7 +53,7 @@ __device__ __forceinline__ float gt_act(float x, int act, float slope)
 {
     if (act == 1) return fmaxf(x, 0.f);
     if (act == 2) return x > 0.f ? x : slope * x;
-    if (act == 3) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    if (act == 3) return gelu_fast(x);
     return x;
 }
 
@@ -227,7 +227,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 32; ++j) if (fullw || nb + j < g.N) {
                                 const float xx = __bfloat162float(mk[j]);
-                                v[j] *= 0.5f * (1.f + erff(xx * 0.70710678118654752f)) + xx * 0.3989422804014327f * __expf(-0.5f * xx * xx);
+                                v[j] *= gelu_grad_fast(xx);
                             }
                         } else if (g.mask_bf16) {
                             const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(g.mask) + (size_t)m * g.ldc + nb;
@@ -371,18 +371,28 @@ __global__ void colsum_kernel(const T* __restrict__ src, float* __restrict__ out
 #pragma unroll
     for (int j = 0; j < W; ++j) acc[j] = 0.f;
     const bool vec = c + W <= cols && (ld % W) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-    for (long r = r0; r < r1; ++r) {
-        const T* p = src + r * ld + c;
-        if (vec) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-            if constexpr (sizeof(T) == 2) {
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    auto add16 = [&](const uint4& u) {
+        if constexpr (sizeof(T) == 2) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { acc[2 * j] += __low2float(h[j]); acc[2 * j + 1] += __high2float(h[j]); }
-            } else {
-                acc[0] += __uint_as_float(u.x); acc[1] += __uint_as_float(u.y); acc[2] += __uint_as_float(u.z); acc[3] += __uint_as_float(u.w);
-            }
+            for (int j = 0; j < 4; ++j) { acc[2 * j] += __low2float(h[j]); acc[2 * j + 1] += __high2float(h[j]); }
         } else {
+            acc[0] += __uint_as_float(u.x); acc[1] += __uint_as_float(u.y); acc[2] += __uint_as_float(u.z); acc[3] += __uint_as_float(u.w);
+        }
+    };
+    long r = r0;
+    if (vec) {
+        for (; r + 8 <= r1; r += 8) {                              // eight independent 16-byte loads in flight per thread
+            uint4 u[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (r + k) * ld + c));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) add16(u[k]);
+        }
+        for (; r < r1; ++r) add16(__ldg(reinterpret_cast<const uint4*>(src + r * ld + c)));
+    } else {
+        for (; r < r1; ++r) {
+            const T* p = src + r * ld + c;
 #pragma unroll
             for (int j = 0; j < W; ++j) if (c + j < cols) acc[j] += (float)p[j];
         }
@@ -568,7 +578,7 @@ extern "C" int hopk_colsum(const void* src, float* out, long rows, int cols, lon
     HOPK_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), st));
     const int W = src_bf16 ? 8 : 4;                       // columns per thread
     const int tx = cdiv(cols, W) < 64 ? 32 : 64;
-    long per = rows / 96 > 16 ? rows / 96 : 16;            // about 96 row blocks
+    long per = rows / 128 > 16 ? (rows / 128 + 7) / 8 * 8 : 16;   // about 128 row blocks, batches of 8 rows
     dim3 grid(cdiv(cdiv(cols, W), tx), cdiv(rows, per));
     if (src_bf16) colsum_kernel<__nv_bfloat16><<<grid, tx, 0, st>>>((const __nv_bfloat16*)src, out, rows, cols, ld, per);
     else colsum_kernel<float><<<grid, tx, 0, st>>>((const float*)src, out, rows, cols, ld, per);

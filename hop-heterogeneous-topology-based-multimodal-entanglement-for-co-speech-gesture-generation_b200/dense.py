@@ -45,8 +45,9 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, bias=None, addend=None, mask=
     flags = ((_lib.GEMM_A_MN if a_mn else 0) | (_lib.GEMM_B_MN if b_mn else 0) | (_lib.GEMM_OUT_BF16 if out_bf16 else 0) | act |
              (_lib.GEMM_BIAS_ROW if bias_row else 0) | (_lib.GEMM_MASK_BF16 if mask_bf16 else 0) | (_lib.GEMM_MASK_GELU if mask_gelu else 0) |
              (_lib.GEMM_ACCUMULATE if accumulate else 0))
-    check(lib().hopk_gemm_bf16(ptr(A), ptr(B), ptr(out), ptr(bias), ptr(addend), ptr(mask), M, N, K, A.stride(0), B.stride(0), ldc,
-                               flags, float(slope), int(splits), stream_ptr()))
+    with profiler.span('gemm_tma', 2.0 * M * N * K, fine=True):              # the step's dominant kernel: timed per launch for the roofline
+        check(lib().hopk_gemm_bf16(ptr(A), ptr(B), ptr(out), ptr(bias), ptr(addend), ptr(mask), M, N, K, A.stride(0), B.stride(0), ldc,
+                                   flags, float(slope), int(splits), stream_ptr()))
     return out
 
 

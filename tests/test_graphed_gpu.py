@@ -69,8 +69,10 @@ def test_graphed_step_follows_eager_step(cuda, monkeypatch):
     acc = types.SimpleNamespace(backward=lambda loss: loss.backward())
 
     def make(m, d):
-        go = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=4e-4, betas=(0.5, 0.999), fused=True, capturable=True)
-        do = torch.optim.Adam(d.parameters(), lr=4e-4, betas=(0.5, 0.999), fused=True, capturable=True)
+        # a tenth of the reference's learning rate: at 4e-4 the first steps of this tiny batch are chaotic (the loss jumps
+        # 130 -> 240 -> 156) and amplify the summation-order noise of the split-K reductions past any sensible tolerance
+        go = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=4e-5, betas=(0.5, 0.999), fused=True, capturable=True)
+        do = torch.optim.Adam(d.parameters(), lr=4e-5, betas=(0.5, 0.999), fused=True, capturable=True)
         return go, do
 
     m2, d2 = copy.deepcopy(model), copy.deepcopy(disc)
