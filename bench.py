@@ -360,7 +360,9 @@ def run_ours(a):
         res['out_len'] = len(out)
         return res
 
-    engine_factory = lambda mods: DataParallel(mods)
+    # dtype-1 runs put bf16 gradients on the wire (half the all-reduce bytes); the exact mode keeps fp32
+    engine_factory = lambda mods: DataParallel(mods, grad_dtype=torch.bfloat16 if a.precision == 'bf16' else torch.float32,
+                                               overlap=bool(a.dp_overlap), bucket_mb=a.dp_bucket_mb)
     W = Workload(a, a.datasets, dev, rank, engine_factory)
     if a.profile_step:
         # one eagerly launched step between cudaProfilerStart / Stop (ncu --profile-from-start off): the launch list of the
@@ -398,7 +400,7 @@ def run_ours(a):
                 'loss_first_last': [r['losses'][0], r['losses'][-1]],
                 'roofline': roofline(r['spans'], a, a.datasets, r['prof_steps'], r['spans_work']),
                 'kernel_ms_per_step': {k: round(v[1] / r['prof_steps'], 4) for k, v in sorted(r['spans'].items())},   # gemm_tma is nested inside bert_* / linear_* / beat_* / mapping_*
-                'dp': W.engine.stats if world > 1 else None}
+                'dp': (W.engine.stats | {'wire_dtype': str(W.engine.grad_dtype).replace('torch.', '')}) if world > 1 else None}
     # ---- N = 1 extras: Expressive configuration, stock-PyTorch-CUDA speed bar, CPU baseline
     if world == 1:
         W.release()
@@ -674,6 +676,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-stock-cuda', action='store_true')
     ap.add_argument('--no-expressive', action='store_true')
+    ap.add_argument('--dp-overlap', type=int, default=1, help='0: reduce the gradient buckets after backward instead of under it')
+    ap.add_argument('--dp-bucket-mb', type=float, default=25)
     ap.add_argument('--profile-step', action='store_true', help='profile one eager step (for ncu --profile-from-start off) and exit')
     ap.add_argument('--graph', type=int, default=1, help='replay the whole training step as one CUDA graph (0 = launch eagerly)')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],

@@ -105,7 +105,8 @@ def linear(x, w, b, relu_in=False):
 class _SourceTmaFn(torch.autograd.Function):
     """source = W_map @ WE + b[:, None] (HOP.py:200).  ``we_b`` is the cached bf16 copy of the frozen word embeddings.
     With data parallelism the small upstream gradient is all-reduced through ``reducer`` before dW_map is formed locally
-    (see hop_b200.dp)."""
+    (see hop_b200.dp): ``reducer(t)`` reduces in stream order; a reducer with a ``defer(t, finish)`` method
+    takes the tensor, reduces it asynchronously and calls ``finish`` itself once backward has been issued."""
 
     @staticmethod
     def forward(ctx, w_map, b_map, we_b, reducer):
@@ -123,12 +124,23 @@ class _SourceTmaFn(torch.autograd.Function):
         (we_b,) = ctx.saved_tensors
         S, Vc, D = ctx.dims
         dsrc = f32c(dsrc)
-        if ctx.reducer is not None:
-            dsrc = ctx.reducer(dsrc.clone())
-        with profiler.span('mapping_bwd'):
-            db16 = cast_bf16(dsrc)
-            dw = gemm(db16, we_b, S, Vc, D)              # dW_map[s][v] = sum_d dsrc[s][d] WE[v][d]: both K-major
-        return dw, dsrc.sum(1), None, None
+
+        def finish(d):                                   # d: the (rank-averaged) upstream gradient
+            with profiler.span('mapping_bwd'):
+                db16 = cast_bf16(d)
+                dw = gemm(db16, we_b, S, Vc, D)          # dW_map[s][v] = sum_d dsrc[s][d] WE[v][d]: both K-major
+            return dw, d.sum(1)
+
+        red = ctx.reducer
+        if red is not None and hasattr(red, 'defer'):
+            # data parallelism on CUDA: the all-reduce of dSource travels on the communication stream under the rest of
+            # backward; DataParallel.backward() finishes the two parameter gradients after it (hop_b200.dp)
+            red.defer(dsrc.clone(), finish)
+            return None, None, None, None
+        if red is not None:
+            dsrc = red(dsrc.clone())
+        dw, db = finish(dsrc)
+        return dw, db, None, None
 
 
 def source(w_map, b_map, we_b, reducer=None):

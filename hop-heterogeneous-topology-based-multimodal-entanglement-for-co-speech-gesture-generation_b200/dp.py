@@ -6,8 +6,11 @@ Replaces what the reference gets implicitly from HF Accelerate + DeepSpeed/DDP
 * replicas start identical (rank-0 broadcast of parameters and buffers); BatchNorm statistics stay
   per rank, like the reference (no SyncBatchNorm);
 * gradients are all-reduced in ~25 MB buckets on a side stream *while backward is still running*:
-  each parameter's post-accumulate hook drops the gradient into its bucket's flat buffer and the
-  bucket is launched as soon as its last member arrives;
+  each parameter's post-accumulate hook counts its bucket down; when the last member arrives ONE multi-tensor copy
+  packs the bucket's gradients into its flat wire buffer (bf16 with ``grad_dtype=torch.bfloat16``: half the bytes on
+  the wire; fp32 by default) and the all-reduce is launched;
+* after the collective one multi-tensor copy per bucket unpacks into a flat fp32 buffer whose views become ``p.grad``
+  (fp32 wire format: the wire buffer itself is handed over, no unpack);
 * tensors the reference never gives a gradient (audio_encoder.*) are discovered on the
   first step and skipped afterwards;
 * ``mapping_layer`` (183 MB of the 263 MB of gradients, produced last) is never all-reduced: its upstream
@@ -23,17 +26,62 @@ import torch.distributed as dist
 
 
 class _Bucket:
-    def __init__(self, params, device):
+    def __init__(self, params, device, wire_dtype=torch.float32):
         self.params = params
         self.numel = sum(p.numel() for p in params)
-        self.flat = torch.zeros(self.numel, device=device, dtype=torch.float32)
-        self.views, off = [], 0
+        self.flat = torch.zeros(self.numel, device=device, dtype=wire_dtype)          # what travels
+        self.flat32 = self.flat if wire_dtype == torch.float32 else torch.zeros(self.numel, device=device, dtype=torch.float32)
+        self.views, self.views32, off = [], [], 0
         for p in params:
             self.views.append(self.flat[off:off + p.numel()].view(p.shape))
+            self.views32.append(self.flat32[off:off + p.numel()].view(p.shape))
             off += p.numel()
         self.pending = len(params)
         self.work = None
         self.event = None
+
+    def pack(self):
+        """Gradients -> wire buffer: one multi-tensor copy (members without a gradient this step count as zero)."""
+        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
+        for v, p in zip(self.views, self.params):
+            if p.grad is None:
+                v.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+
+    def unpack(self):
+        """Averaged wire buffer -> the fp32 views handed to the optimiser."""
+        if self.flat32 is not self.flat:
+            self.flat32.copy_(self.flat)
+        for v, p in zip(self.views32, self.params):
+            if p.grad is not None:
+                p.grad = v
+
+
+class _SourceReducer:
+    """What ``Model.set_source_grad_reducer`` receives.  Called (``r(t)``) it all-reduces ``t`` in stream order; on CUDA it
+    also offers ``defer(t, finish)``: the all-reduce is issued on the communication stream at once, and
+    ``_ModuleDP.end`` later waits for it and turns ``finish(t) -> (dW, db)`` into the mapping layer's gradients."""
+
+    def __init__(self, owner, part):
+        self.o, self.part = owner, part
+        if owner.comm_stream is not None:
+            self.defer = self._defer
+
+    def __call__(self, t):
+        return self.o._reduce_now(t)
+
+    def _defer(self, t, finish):
+        o = self.o
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(o.comm_stream):
+            o.comm_stream.wait_event(ev)
+            work = dist.all_reduce(t, op=o._avg, group=o.group, async_op=True)
+        t.record_stream(o.comm_stream)
+        o.stats['allreduce_bytes'] += t.numel() * t.element_size()
+        self.part.deferred.append((t, work, finish))
+        self.part.fired = True
 
 
 class _ModuleDP:
@@ -46,8 +94,9 @@ class _ModuleDP:
         self._seen, self._order, self._where = set(), [], {}
         self.fired = False
         self.pre_reduced = set()
+        self.deferred = []
         if hasattr(module, 'set_source_grad_reducer'):          # the dSource trick (see module docstring)
-            module.set_source_grad_reducer(owner._reduce_now)
+            module.set_source_grad_reducer(_SourceReducer(owner, self))
             self.pre_reduced = set(id(p) for p in module.mapping_layer.parameters())
         seen = set()
         for p in module.parameters():
@@ -62,9 +111,9 @@ class _ModuleDP:
         for p in used:
             cur.append(p); size += p.numel() * 4
             if size >= self.o.bucket_bytes:
-                self.buckets.append(_Bucket(cur, device)); cur, size = [], 0
+                self.buckets.append(_Bucket(cur, device, self.o.grad_dtype)); cur, size = [], 0
         if cur:
-            self.buckets.append(_Bucket(cur, device))
+            self.buckets.append(_Bucket(cur, device, self.o.grad_dtype))
         for bi, b in enumerate(self.buckets):
             for pi, p in enumerate(b.params):
                 self._where[id(p)] = (bi, pi)
@@ -79,52 +128,64 @@ class _ModuleDP:
         if where is None:
             return
         b = self.buckets[where[0]]
-        b.views[where[1]].copy_(p.grad)
         b.pending -= 1
-        if b.pending == 0:
+        if b.pending == 0 and self.o.overlap:
+            b.pack()
             self.o._launch(b)
 
     def begin(self):
         self.fired = False
+        self.deferred = []
         if self.buckets is not None:
             for b in self.buckets:
                 b.pending = len(b.params)
                 b.work = None
 
+    def _finish_deferred(self):
+        for t, work, finish in self.deferred:                   # dSource: averaged by now (or soon: wait() orders the stream)
+            work.wait()
+            dw, db = finish(t)
+            lin = self.module.mapping_layer
+            for p, g in ((lin.weight, dw), (lin.bias, db)):
+                if p.requires_grad:
+                    p.grad = g if p.grad is None else p.grad + g
+        self.deferred = []
+
     def end(self):
         if not self.fired:
+            return
+        if self.buckets is None and not self._order:            # nothing but the deferred dSource reduction this backward
+            self._finish_deferred()
             return
         if self.buckets is None:
             # first active step: the backward was a plain one; bucket in readiness order and reduce now
             used = [p for p in self._order if p.grad is not None]
             self._build_buckets(used)
             for b in self.buckets:
-                for v, p in zip(b.views, b.params):
-                    v.copy_(p.grad)
+                b.pack()
                 self.o._launch(b)
         else:
-            for b in self.buckets:                              # members that got no gradient this step count as zero
+            for b in self.buckets:                              # a bucket some member of which got no gradient this step
                 if b.work is None:
-                    for (v, p) in zip(b.views, b.params):
-                        if self._where[id(p)] and p.grad is None:
-                            v.zero_()
+                    b.pack()
                     self.o._launch(b)
         for b in self.buckets:
             b.work.wait()                                       # orders the current stream after the collective
         if self.o.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.o.comm_stream)
         for b in self.buckets:                                  # already averaged: the all-reduce runs with ReduceOp.AVG
-            for v, p in zip(b.views, b.params):
-                if p.grad is not None:
-                    p.grad = v                                  # hand the averaged view to the optimiser (no copy back)
+            b.unpack()                                          # hand the averaged views to the optimiser
+        self._finish_deferred()
 
 
 class DataParallel:
-    def __init__(self, modules, bucket_mb=25, process_group=None, broadcast=True):
+    def __init__(self, modules, bucket_mb=25, process_group=None, broadcast=True, grad_dtype=torch.float32, overlap=True):
         self.modules = list(modules) if isinstance(modules, (list, tuple)) else [modules]
         self.group = process_group
         self.world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
         self.bucket_bytes = int(bucket_mb * (1 << 20))
+        self.grad_dtype = grad_dtype                            # wire format of the bucketed gradients (fp32 or bf16)
+        self.overlap = overlap                                  # False: every bucket is reduced after backward (no SM sharing with it)
         self.stats = dict(allreduce_bytes=0, buckets=0)
         self.comm_stream = None
         self.parts = []
@@ -161,7 +222,7 @@ class DataParallel:
             if self._avg is dist.ReduceOp.SUM:                  # gloo (CPU tests) has no AVG: scale after the sum
                 b.work.wait()
                 b.flat.div_(self.world)
-        self.stats['allreduce_bytes'] += b.numel * 4
+        self.stats['allreduce_bytes'] += b.numel * b.flat.element_size()
         self.stats['buckets'] += 1
 
     def backward(self, loss):

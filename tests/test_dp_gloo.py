@@ -38,7 +38,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, xs, ret):
+def _worker(rank, world, port, xs, ret, wire='fp32'):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     from hop_b200.dp import DataParallel
@@ -47,7 +47,7 @@ def _worker(rank, world, port, xs, ret):
         with torch.no_grad():
             for p in m.parameters():
                 p.add_(1.0)
-    eng = DataParallel([m], bucket_mb=0.0005)
+    eng = DataParallel([m], bucket_mb=0.0005, grad_dtype=torch.bfloat16 if wire == 'bf16' else torch.float32)
     out = {}
     for step in range(3):                                    # step 0 = discovery, 1-2 = bucketed/overlapped path
         m.zero_grad(set_to_none=True)
@@ -59,14 +59,18 @@ def _worker(rank, world, port, xs, ret):
     dist.destroy_process_group()
 
 
-def test_dp_two_ranks_match_single_process():
+@pytest.mark.parametrize('wire', ['fp32', 'bf16'])
+def test_dp_two_ranks_match_single_process(wire):
     world = 2
     torch.manual_seed(1)
     xs = [torch.randn(5, 6) for _ in range(world)]
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, _free_port(), xs, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), xs, ret, wire), nprocs=world, join=True)
         ret = dict(ret)
+    # bf16 wire format: every rank's gradient is rounded to bf16 before the sum (2^-8 relative to the tensor's scale);
+    # the dSource path stays fp32
+    rtol, atol_rel = (1e-5, 0.0) if wire == 'fp32' else (1e-2, 1e-2)
     # single-process reference: mean over ranks of the per-rank mean losses
     m = Toy()
     loss = sum((m(x) ** 2).mean() for x in xs) / world
@@ -79,6 +83,7 @@ def test_dp_two_ranks_match_single_process():
                 if g is None:
                     assert got[k] is None, k
                 else:
-                    assert torch.allclose(got[k], g, rtol=1e-5, atol=1e-6), (step, rank, k)
+                    assert got[k].dtype == torch.float32
+                    assert torch.allclose(got[k], g, rtol=rtol, atol=1e-6 + atol_rel * float(g.abs().max())), (step, rank, k)
     # mapping_layer.weight (12*7 floats) was never put on the wire: only dSource (7*4) and the bucketed rest
     assert ret[0]['stats']['buckets'] >= 3
