@@ -260,13 +260,19 @@ def run_ours(a):
         for _ in range(warmup):
             losses.append(W.step(W.resident)['loss'])
         prof_steps = max(1, min(steps, 5))
+        # Eagerly launched, the step is host-bound (about 2 us of GPU idle time inside every event pair).  Each profiled step
+        # therefore starts behind a ~30 ms device-side spin: the host enqueues the step while the GPU waits, and the event
+        # pairs then bracket back-to-back GPU execution only.
+        spin = int(0.030 * 1.9e9)
         profiler.enable(True)
         for _ in range(prof_steps):
+            torch.cuda._sleep(spin)
             losses.append(W.step(W.resident)['loss'])
         torch.cuda.synchronize()
         spans = profiler.summary()
         profiler.enable(True, fine=True)                            # second pass: every dense GEMM launch on its own (nested spans)
         for _ in range(prof_steps):
+            torch.cuda._sleep(spin)
             losses.append(W.step(W.resident)['loss'])
         torch.cuda.synchronize()
         fine = profiler.summary()
@@ -390,7 +396,7 @@ def run_ours(a):
                 'config': workload_config(a, world, a.datasets) | {
                     'tf32_library_gemms': bool(a.tf32), 'gan_phase': bool(a.gan), 'cuda_graph': W.graphed is not None,
                     'graph_error': W.graph_error,
-                    'kernel_group_timing': f'{r["prof_steps"]} eagerly launched steps before the timed region',
+                    'kernel_group_timing': f'{r["prof_steps"]} eagerly launched steps before the timed region, each queued behind a 30 ms device-side spin (host runs ahead: event pairs bracket GPU execution only)',
                     'precision': a.precision + (' (hand-written tcgen05 bf16 UMMA kernels, fp32 accumulate; remaining stock parts under bf16 autocast)'
                                                 if a.precision == 'bf16' else ' (FFMA kernels, reference numerics)')},
                 'clocks': clocks,
@@ -618,7 +624,7 @@ def roofline(spans, a, datasets, nsteps, spans_work=None):
                               'traffic': traffic.get('gemm_tma'), 'avg_ms': total_ms / calls, 'launches_timed': calls,
                               'ms_per_step': total_ms / nsteps, 'algorithmic_flops': flops / calls,
                               'arithmetic': 'bf16 tcgen05 UMMA (TMA operands, fp32 accumulate in TMEM); FLOPs = 2*M*N*K summed over the '
-                                            'launches, time = sum of their CUDA-event durations (eager launches: includes host gaps)'}
+                                            'launches, time = sum of their CUDA-event durations'}
     for k, (bound, amount, executed) in work.items():
         if k not in spans:
             continue
