@@ -9,6 +9,7 @@
 // Loader contract:  int ncols;  void ld8(int r, int c0, float (&f)[8]) const;   // 8 consecutive columns, 0 outside
 // Epilogue contract: row32 / finish as in gemm_tc.cuh, plus  void bias(int i, float v);  // column sum of A (atomic)
 #pragma once
+#include <math.h>
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -143,6 +144,7 @@ gemm_tc_wgrad_kernel(int R, int Mo, int No, int r_per_split, ALoad aload, BLoad 
     if (warp == 0) tc::tmem_dealloc(tmem, BN);
 }
 
+constexpr int WG_MIN_SLABS = 16;                              // contraction slabs (64 rows each) per split-K CTA at least
 template <int BN, class AL, class BL, class EP>
 static cudaError_t launch_gemm_tc_wgrad(int R, int Mo, int No, AL a, BL b, EP e, bool want_bias, cudaStream_t st)
 {
@@ -152,8 +154,12 @@ static cudaError_t launch_gemm_tc_wgrad(int R, int Mo, int No, AL a, BL b, EP e,
         if (err != cudaSuccess) return err;
     }
     const int tiles = ((Mo + TC_BM - 1) / TC_BM) * ((No + BN - 1) / BN);
-    int splits = (2 * 148 + tiles - 1) / tiles;                       // about two CTAs per SM
-    int max_splits = (R + 4 * WG_ROWS - 1) / (4 * WG_ROWS);           // at least 4 slabs per split
+    // Split-K factor, measured on the whole backward (TED B = 128 / Expressive / B = 1024, ms): 4 slabs per split 1.14 / 3.92 /
+    // 5.15, 8: 1.00 / 3.42 / -, 16: 0.94 / 3.40 / 4.18, 32: 1.38 / 4.47 / 4.10; a sqrt(R) rule fitted to TED loses 1.3 ms on
+    // Expressive.  These kernels run on side streams beside the dependent dx / dy chain: a grid that fills every SM slot
+    // delays the chain's own small kernels (and adds reduction traffic), a grid of a few dozen CTAs leaves room for them.
+    int splits = (2 * 148 + tiles - 1) / tiles;                       // about two CTAs per SM at most
+    int max_splits = (R + WG_MIN_SLABS * WG_ROWS - 1) / (WG_MIN_SLABS * WG_ROWS);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     int rper = (((R + splits - 1) / splits + WG_ROWS - 1) / WG_ROWS) * WG_ROWS;
