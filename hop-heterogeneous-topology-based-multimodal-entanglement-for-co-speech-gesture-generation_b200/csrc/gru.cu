@@ -751,7 +751,7 @@ struct GruLayout {
     size_t xb, gi, y[HOPK_GRU_MAX_LAYERS], r[HOPK_GRU_MAX_LAYERS], z[HOPK_GRU_MAX_LAYERS], n[HOPK_GRU_MAX_LAYERS], hn[HOPK_GRU_MAX_LAYERS];
     size_t wih[HOPK_GRU_MAX_LAYERS], whh[HOPK_GRU_MAX_LAYERS], bias[HOPK_GRU_MAX_LAYERS], bhn[HOPK_GRU_MAX_LAYERS], total;
     // backward scratch
-    size_t s_whhT, s_dya, s_dyb, s_dgi, s_dgh, s_dwih, s_dwhh, s_dbi, s_dbh, s_total;
+    size_t s_whhT, s_dya, s_dyb, s_dgi[2], s_dgh[2], s_dwih, s_dwhh, s_dbi, s_dbh, s_total;   // dGi / dGh double-buffered by layer parity
 };
 static size_t gbump(size_t& cur, size_t bytes)
 {
@@ -785,8 +785,10 @@ static GruLayout gru_layout(const HopkGruShape* s)
     g.s_whhT = gbump(cur, (size_t)2 * GRU_CL * (GRU_BT_IMG + GRU_BS_BYTES));
     g.s_dya = gbump(cur, TB * ipmax * 4);
     g.s_dyb = gbump(cur, TB * ipmax * 4);
-    g.s_dgi = gbump(cur, TB * 2 * GRU_G * 2);
-    g.s_dgh = gbump(cur, TB * 2 * GRU_G * 2);
+    for (int k = 0; k < 2; ++k) {
+        g.s_dgi[k] = gbump(cur, TB * 2 * GRU_G * 2);
+        g.s_dgh[k] = gbump(cur, TB * 2 * GRU_G * 2);
+    }
     g.s_dwih = gbump(cur, (size_t)2 * GRU_G * ipmax * 4);
     g.s_dwhh = gbump(cur, (size_t)2 * GRU_G * GRU_HP * 4);
     g.s_dbi = gbump(cur, (size_t)2 * GRU_G * 4);
@@ -851,6 +853,36 @@ extern "C" int hopk_gru_forward(const HopkGruShape* s, const HopkGruParams* p, c
     return 0;
 }
 
+// Side stream of the backward pass: the weight-gradient work of layer l (dW_ih, dW_hh, bias column sums, unpacking) is not
+// on the dependent chain recurrence(l) -> dX -> recurrence(l-1); it runs beside the next layer's recurrence kernel, whose
+// 128 latency-bound CTAs leave 20 SMs idle.  One stream + events per device, created on first use (same conventions as the
+// Graph-WaveNet side streams: non-blocking, calls on a device come from one host thread at a time).
+struct GruSide {
+    cudaStream_t s;
+    cudaEvent_t ev_rec[HOPK_GRU_MAX_LAYERS], ev_done[HOPK_GRU_MAX_LAYERS];
+};
+static GruSide* gru_side()
+{
+    constexpr int MAXDEV = 64;
+    static GruSide table[MAXDEV];
+    static int states[MAXDEV] = {0};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    GruSide& sd = table[dev];
+    int& state = states[dev];
+    if (state == 0) {
+        state = 1;
+        if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) state = -1;
+        for (int l = 0; l < HOPK_GRU_MAX_LAYERS; ++l) {
+            if (cudaEventCreateWithFlags(&sd.ev_rec[l], cudaEventDisableTiming) != cudaSuccess) state = -1;
+            if (cudaEventCreateWithFlags(&sd.ev_done[l], cudaEventDisableTiming) != cudaSuccess) state = -1;
+        }
+    }
+    return state == 1 ? &sd : nullptr;
+}
+
 extern "C" int hopk_gru_backward(const HopkGruShape* s, const HopkGruParams* p, const float* dout, void* ws_, void* scratch_,
                                  const HopkGruGrads* gr, float* dx, void* stream)
 {
@@ -868,40 +900,49 @@ extern "C" int hopk_gru_backward(const HopkGruShape* s, const HopkGruParams* p, 
     gru_pack_dy_kernel<<<grid_1d((size_t)TB * 2 * GRU_HP), 256, 0, st>>>(dout, dy_cur, B, T, H);
     HOPK_LAUNCH_CHECK("gru_pack_dy");
     const int slices = cdiv(B, GRU_NB);
-    __nv_bfloat16* dgi = (__nv_bfloat16*)(sc + g.s_dgi);
-    __nv_bfloat16* dgh = (__nv_bfloat16*)(sc + g.s_dgh);
     float* dwih = (float*)(sc + g.s_dwih);
     float* dwhh = (float*)(sc + g.s_dwhh);
     float* dbi = (float*)(sc + g.s_dbi);
     float* dbh = (float*)(sc + g.s_dbh);
+    GruSide* side = gru_side();
+    HOPK_REQUIRE(side != nullptr, "gru backward: side stream");
+    cudaStream_t ss = side->s;
     for (int l = L - 1; l >= 0; --l) {
         const int Iin = l == 0 ? s->I : 2 * H;
         const int Ipad = g.Ipad[l];
+        __nv_bfloat16* dgi = (__nv_bfloat16*)(sc + g.s_dgi[l & 1]);
+        __nv_bfloat16* dgh = (__nv_bfloat16*)(sc + g.s_dgh[l & 1]);
         gru_pack_whh_kernel<<<dim3(GRU_CL, 2, 24), 256, 0, st>>>(p->w_hh[l][0], p->w_hh[l][1], (uint8_t*)(ws + g.whh[l]), (uint8_t*)(sc + g.s_whhT), H);
         HOPK_LAUNCH_CHECK("gru_pack_whhT");
+        if (l + 2 < L) HOPK_CUDA(cudaStreamWaitEvent(st, side->ev_done[l + 2], 0));    // the side stream has finished with this dGi / dGh pair
         GruBwdArgs a;
         a.dY = dy_cur; a.whhT = (const uint8_t*)(sc + g.s_whhT); a.Y = (const __nv_bfloat16*)(ws + g.y[l]);
         a.R = (const float*)(ws + g.r[l]); a.Z = (const float*)(ws + g.z[l]); a.N = (const float*)(ws + g.n[l]); a.HN = (const float*)(ws + g.hn[l]);
         a.dGi = dgi; a.dGh = dgh; a.B = B; a.T = T;
         gru_bwd_kernel<<<2 * slices * GRU_CL, GRU_THREADS, gru_bwd_smem(), st>>>(a);
         HOPK_LAUNCH_CHECK("gru_bwd");
+        HOPK_CUDA(cudaEventRecord(side->ev_rec[l], st));
+        HOPK_CUDA(cudaStreamWaitEvent(ss, side->ev_rec[l], 0));
         const __nv_bfloat16* X = l == 0 ? (const __nv_bfloat16*)(ws + g.xb) : (const __nv_bfloat16*)(ws + g.y[l - 1]);
+        // ---- side stream: parameter gradients of this layer
         // dW_ih[2112][Ipad] = dGi^T . X   (contraction over the T*B rows: both operands MN-major)
-        if (int rc = gemm_bf16_launch(dgi, X, dwih, nullptr, nullptr, 2 * GRU_G, Ipad, TB, 2 * GRU_G, Ipad, Ipad, 1, 1, 0, 0, 0, 0.f, 2, st))
+        if (int rc = gemm_bf16_launch(dgi, X, dwih, nullptr, nullptr, 2 * GRU_G, Ipad, TB, 2 * GRU_G, Ipad, Ipad, 1, 1, 0, 0, 0, 0.f, 2, ss))
             return rc;
         // dW_hh[dir][1056][352] = dGh_dir^T . h_{t-1}: the stored outputs shifted by one time step (B rows), zero outside
         for (int dir = 0; dir < 2; ++dir) {
             if (int rc = gemm_bf16_launch(dgh + dir * GRU_G, (const __nv_bfloat16*)(ws + g.y[l]) + dir * GRU_HP, dwhh + (size_t)dir * GRU_G * GRU_HP,
-                                          nullptr, nullptr, GRU_G, GRU_HP, TB, 2 * GRU_G, 2 * GRU_HP, GRU_HP, 1, 1, 0, 0, 0, 0.f, 8, st,
+                                          nullptr, nullptr, GRU_G, GRU_HP, TB, 2 * GRU_G, 2 * GRU_HP, GRU_HP, 1, 1, 0, 0, 0, 0.f, 8, ss,
                                           nullptr, 0, dir ? B : -B))
                 return rc;
         }
-        if (int rc = hopk_colsum(dgi, dbi, TB, 2 * GRU_G, 2 * GRU_G, 1, stream)) return rc;
-        if (int rc = hopk_colsum(dgh, dbh, TB, 2 * GRU_G, 2 * GRU_G, 1, stream)) return rc;
-        gru_unpack_grads_kernel<<<2 * 3 * H, 128, 0, st>>>(dwih, dwhh, dbi, dbh, gr->w_ih[l][0], gr->w_ih[l][1], gr->w_hh[l][0],
+        if (int rc = hopk_colsum(dgi, dbi, TB, 2 * GRU_G, 2 * GRU_G, 1, ss)) return rc;
+        if (int rc = hopk_colsum(dgh, dbh, TB, 2 * GRU_G, 2 * GRU_G, 1, ss)) return rc;
+        gru_unpack_grads_kernel<<<2 * 3 * H, 128, 0, ss>>>(dwih, dwhh, dbi, dbh, gr->w_ih[l][0], gr->w_ih[l][1], gr->w_hh[l][0],
                                                             gr->w_hh[l][1], gr->b_ih[l][0], gr->b_ih[l][1], gr->b_hh[l][0], gr->b_hh[l][1],
                                                             l, s->I, Iin, H);
         HOPK_LAUNCH_CHECK("gru_unpack_grads");
+        HOPK_CUDA(cudaEventRecord(side->ev_done[l], ss));
+        // ---- main stream: the input gradient the next layer's recurrence waits for
         // dX[T*B][Ipad] = dGi . W_ih   (W_ih packed is [2112][Ipad] = [contraction][out]: B MN-major)
         if (l > 0 || dx) {
             if (int rc = gemm_bf16_launch(dgi, ws + g.wih[l], dy_next, nullptr, nullptr, TB, Ipad, 2 * GRU_G, 2 * GRU_G, Ipad, Ipad, 0, 1,
@@ -913,5 +954,6 @@ extern "C" int hopk_gru_backward(const HopkGruShape* s, const HopkGruParams* p, 
             float* tmp = dy_cur; dy_cur = dy_next; dy_next = tmp;
         }
     }
+    for (int l = 0; l < L && l < 2; ++l) HOPK_CUDA(cudaStreamWaitEvent(st, side->ev_done[l], 0));   // join (ev_done[l] orders all later layers)
     return 0;
 }
