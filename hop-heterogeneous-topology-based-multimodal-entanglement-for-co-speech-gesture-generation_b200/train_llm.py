@@ -10,15 +10,28 @@ change the arithmetic:
   * the beat features and the Graph-WaveNet output -- a function of the audio, the seed poses and the weights only, with
     no dropout on that branch -- are computed by the first forward of the step and reused by the others (the reference
     recomputes identical values); the BatchNorm running statistics still receive one update per forward;
+  * the random-speaker pass is issued on a second CUDA stream beside the discriminator forward and the regression terms
+    (it depends on neither; its decoder recurrence leaves SMs idle); joined before the diversity term;
   * the 2-5 ``.item()`` host syncs are folded into one device->host read at the end.
 ``accelerator`` only needs ``.backward(loss)``: hop_b200.dp.DataParallel (single- and multi-GPU) or, on ONE GPU with the
 bare module, HF Accelerate.  A DDP / DeepSpeed-wrapped model is refused (see ``_check_wrapper``).
 """
+import contextlib
+
 import torch
 import torch.nn.functional as F
 
 
 SHARE_STEP_FEATURES = True
+OVERLAP_RANDOM_SPEAKER_PASS = True
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
 
 
 def add_noise(data):
@@ -85,19 +98,34 @@ def train_llm_device(args, epoch, in_audio, log_melspec, text_token_padded, targ
     model_optim.zero_grad()                                     # generator step (train_llm.py:38-86)
     outputs, z_context, z_mu, z_logvar = _forward(core, in_audio, log_melspec, text_token_padded, pre_seq,
                                                    vid_indices, source, shared)
-    dis_output = discriminator(outputs, text_token_padded)      # computed every step, like train_llm.py:43-44
-    gen_error = -torch.mean(torch.log(dis_output + 1e-8))
-    huber_loss = F.smooth_l1_loss(outputs / 0.1, target_dir_vec / 0.1) * 0.1
-    kld = div_reg = None
-    if (args.z_type == 'speaker' or args.z_type == 'random') and args.loss_reg_weight > 0.0:
+    want_rand = (args.z_type == 'speaker' or args.z_type == 'random') and args.loss_reg_weight > 0.0
+    side = None
+    if want_rand:
         if args.z_type == 'speaker':
             rand_idx = torch.randperm(vid_indices.shape[0], device=vid_indices.device)
             rand_vids = vid_indices[rand_idx]
         else:
             rand_vids = None
-        with torch.no_grad():
-            out_dir_vec_rand_vid, z_rand_vid, _, _ = _forward(core, in_audio, log_melspec, text_token_padded, pre_seq,
-                                                              rand_vids, None if source is None else source.detach(), shared)
+        # The random-speaker pass (no autograd graph) does not depend on the discriminator / regression terms below and its
+        # decoder recurrence leaves SMs idle: on CUDA it runs on a second stream beside them (forked and joined with events,
+        # so a CUDA-graph capture of the step records the same dependency structure).
+        side = _side_stream(outputs.device) if (OVERLAP_RANDOM_SPEAKER_PASS and outputs.is_cuda) else None
+        cur = torch.cuda.current_stream() if side is not None else None
+        if side is not None:
+            side.wait_stream(cur)
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            with torch.no_grad():
+                out_dir_vec_rand_vid, z_rand_vid, _, _ = _forward(core, in_audio, log_melspec, text_token_padded, pre_seq,
+                                                                  rand_vids, None if source is None else source.detach(), shared)
+    dis_output = discriminator(outputs, text_token_padded)      # computed every step, like train_llm.py:43-44
+    gen_error = -torch.mean(torch.log(dis_output + 1e-8))
+    huber_loss = F.smooth_l1_loss(outputs / 0.1, target_dir_vec / 0.1) * 0.1
+    kld = div_reg = None
+    if want_rand:
+        if side is not None:
+            cur.wait_stream(side)
+            for t in (out_dir_vec_rand_vid, z_rand_vid):
+                t.record_stream(cur)
         beta = 0.05
         pose_l1 = F.smooth_l1_loss(outputs / beta, out_dir_vec_rand_vid.detach() / beta, reduction='none') * beta
         pose_l1 = pose_l1.sum(dim=1).sum(dim=1)
