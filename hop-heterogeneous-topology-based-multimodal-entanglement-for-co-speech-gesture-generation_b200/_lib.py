@@ -98,6 +98,8 @@ SIGNATURES = {
     'hopk_bert_attn_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'hopk_beat_rows_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     'hopk_beat_rows_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, C.c_long, _vp]),
+    'hopk_step_losses_fwd': (_i, [_vp] * 7 + [_i, _i, _i, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    'hopk_step_losses_bwd': (_i, [_vp] * 7 + [_i, _i, _i, C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
     'hopk_gru_workspace_bytes': (_sz, [C.POINTER(GruShape)]),
     'hopk_gru_scratch_bytes': (_sz, [C.POINTER(GruShape)]),
     'hopk_gru_forward': (_i, [C.POINTER(GruShape), C.POINTER(GruParams), _vp, _vp, _vp, _vp]),

@@ -24,6 +24,7 @@ import torch.nn.functional as F
 
 SHARE_STEP_FEATURES = True
 OVERLAP_RANDOM_SPEAKER_PASS = True
+FUSED_LOSSES = True
 _SIDE = {}
 
 
@@ -119,27 +120,42 @@ def train_llm_device(args, epoch, in_audio, log_melspec, text_token_padded, targ
                                                                   rand_vids, None if source is None else source.detach(), shared)
     dis_output = discriminator(outputs, text_token_padded)      # computed every step, like train_llm.py:43-44
     gen_error = -torch.mean(torch.log(dis_output + 1e-8))
-    huber_loss = F.smooth_l1_loss(outputs / 0.1, target_dir_vec / 0.1) * 0.1
     kld = div_reg = None
-    if want_rand:
-        if side is not None:
-            cur.wait_stream(side)
-            for t in (out_dir_vec_rand_vid, z_rand_vid):
-                t.record_stream(cur)
-        beta = 0.05
-        pose_l1 = F.smooth_l1_loss(outputs / beta, out_dir_vec_rand_vid.detach() / beta, reduction='none') * beta
-        pose_l1 = pose_l1.sum(dim=1).sum(dim=1)
-        pose_l1 = pose_l1.view(pose_l1.shape[0], -1).mean(1)
-        z_l1 = F.l1_loss(z_context.detach(), z_rand_vid.detach(), reduction='none')
-        z_l1 = z_l1.view(z_l1.shape[0], -1).mean(1)
-        div_reg = torch.clamp(-(pose_l1 / (z_l1 + 1.0e-5)), min=-1000).mean()
-        if args.z_type == 'speaker':
-            kld = -0.5 * torch.mean(1 + z_logvar - z_mu.pow(2) - z_logvar.exp())
-            loss = huber_loss * args.loss_regression_weight + div_reg * args.loss_reg_weight + kld * args.loss_kld_weight
-        else:
-            loss = huber_loss * args.loss_regression_weight + div_reg * args.loss_reg_weight
+    if want_rand and side is not None:
+        cur.wait_stream(side)
+        for t in (out_dir_vec_rand_vid, z_rand_vid):
+            t.record_stream(cur)
+    if FUSED_LOSSES and outputs.is_cuda:
+        # one kernel forward + one backward for the regression / diversity / KLD terms (hop_b200/losses.py)
+        from .losses import step_losses
+        speaker = want_rand and args.z_type == 'speaker'
+        loss, lv = step_losses(outputs, target_dir_vec,
+                               out_dir_vec_rand_vid if want_rand else None, z_context.detach() if want_rand else None,
+                               z_rand_vid if want_rand else None, z_mu if speaker else None, z_logvar if speaker else None,
+                               args.loss_regression_weight, args.loss_reg_weight if want_rand else 0.0,
+                               args.loss_kld_weight if speaker else 0.0)
+        huber_loss = lv[1]
+        if want_rand:
+            div_reg = lv[2]
+        if speaker:
+            kld = lv[3]
     else:
-        loss = huber_loss * args.loss_regression_weight
+        huber_loss = F.smooth_l1_loss(outputs / 0.1, target_dir_vec / 0.1) * 0.1
+        if want_rand:
+            beta = 0.05
+            pose_l1 = F.smooth_l1_loss(outputs / beta, out_dir_vec_rand_vid.detach() / beta, reduction='none') * beta
+            pose_l1 = pose_l1.sum(dim=1).sum(dim=1)
+            pose_l1 = pose_l1.view(pose_l1.shape[0], -1).mean(1)
+            z_l1 = F.l1_loss(z_context.detach(), z_rand_vid.detach(), reduction='none')
+            z_l1 = z_l1.view(z_l1.shape[0], -1).mean(1)
+            div_reg = torch.clamp(-(pose_l1 / (z_l1 + 1.0e-5)), min=-1000).mean()
+            if args.z_type == 'speaker':
+                kld = -0.5 * torch.mean(1 + z_logvar - z_mu.pow(2) - z_logvar.exp())
+                loss = huber_loss * args.loss_regression_weight + div_reg * args.loss_reg_weight + kld * args.loss_kld_weight
+            else:
+                loss = huber_loss * args.loss_regression_weight + div_reg * args.loss_reg_weight
+        else:
+            loss = huber_loss * args.loss_regression_weight
     if gan:
         loss = loss + gen_error * args.loss_gan_weight
 

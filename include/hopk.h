@@ -200,6 +200,20 @@ int hopk_colsum(const void* src, float* out, long rows, int cols, long ld, int s
 int hopk_beat_rows_fwd(const float* feat, const float* seed, float* rows, int B, int J, int F, void* stream);
 int hopk_beat_rows_bwd(const float* drows, void* dfeat_bf16, float* dbias, int B, int J, int F, long ldd, void* stream);
 
+/* The generator's loss terms of the training step, train_eval/train_llm.py:46-79, as one kernel forward and one backward:
+ *   huber = mean smooth_l1(out / 0.1, tgt / 0.1) * 0.1;  pose[b] = sum smooth_l1(out / 0.05, rnd / 0.05) * 0.05;
+ *   zl1[b] = mean |zc - zr|;  div_reg = mean_b clamp(-pose[b] / (zl1[b] + 1e-5), min = -1000);
+ *   kld = -0.5 mean(1 + logvar - mu^2 - exp(logvar));  vals = {w_reg huber + w_div div_reg + w_kld kld, huber, div_reg, kld}.
+ * out, tgt, rnd: (B, TP) fp32; zc, zr, mu, logvar: (B, Z); rnd / zc / zr NULL: no diversity term; mu / logvar NULL: no KLD.
+ * per: (B, 4) fp32 scratch kept for backward; ticket: one zero-initialised uint32 (left zero).  Backward writes the
+ * gradients of vals[0] with respect to out, mu, logvar, scaled by the device scalar *gl. */
+int hopk_step_losses_fwd(const float* out, const float* tgt, const float* rnd, const float* zc, const float* zr, const float* mu,
+                         const float* logvar, int B, int TP, int Z, float w_reg, float w_div, float w_kld, float* per, float* vals,
+                         unsigned int* ticket, void* stream);
+int hopk_step_losses_bwd(const float* out, const float* tgt, const float* rnd, const float* mu, const float* logvar, const float* per,
+                         const float* gl, int B, int TP, int Z, float w_reg, float w_div, float w_kld, float* dout, float* dmu,
+                         float* dlogvar, void* stream);
+
 /* ------------------------------------------------------------------ frozen BERT encoder: the kernels between its GEMMs
  * (model/HOP.py:204 `self.llm_model(inputs_embeds=...)`; weights frozen, HOP.py:90-91: backward = dX only)
  * layer norm over rows of C = 128 k columns: v = x (+ add[row % period]); y = (v - mean) * rstd * gamma + beta; fp32 and / or
