@@ -32,7 +32,7 @@ constexpr int GT_THREADS = 64 + 32 * GT_EPI_WARPS;      // producer warp, MMA wa
 
 template <int BN> constexpr int gt_stages() { return BN == 128 ? 6 : 4; }
 template <int BN> constexpr uint32_t gt_stage_bytes() { return tc::slab_bytes(GT_BM) + tc::slab_bytes(BN); }
-constexpr uint32_t GT_STG_BYTES = 4096;                 // per epilogue warp: one 32-row x 128-byte (fp32) or x 64-byte (bf16) store box
+constexpr uint32_t GT_STG_BYTES = 4096;                 // per epilogue warp: two 32-row x 64-byte store boxes (32 bf16 / 16 fp32 columns)
 template <int BN> constexpr size_t gt_smem_bytes() { return (size_t)gt_stages<BN>() * gt_stage_bytes<BN>() + (size_t)GT_EPI_WARPS * GT_STG_BYTES + 1024 + 256; }
 
 struct GtArgs {
@@ -46,7 +46,7 @@ struct GtArgs {
     int out_bf16, accumulate, act, splits, kper;        // act: 0 none, 1 relu, 2 leaky relu (slope), 3 gelu (erf)
     float slope;
     int tiles_m, tiles_n;
-    int tma_store;                                      // the epilogue writes C through tmC (32 x 32 boxes) instead of per-thread stores
+    int tma_store;                                      // the epilogue writes C through tmC (32-row x 64-byte boxes) instead of per-thread stores
 };
 
 __device__ __forceinline__ float gt_act(float x, int act, float slope)
@@ -64,7 +64,9 @@ __device__ __forceinline__ float gt_act(float x, int act, float slope)
 // de-duplicates L2 reads for larger clusters -- and it was removed again.  Knock-out timings at 4352 x 3072 x 768: fixed
 // cost 12 us, + main loop 11 us, + TMEM reads of the epilogue 6 us, + its stores 9 us: the epilogue of a tile is as long as
 // its main loop and competes with the next tile's MMAs for TMEM bandwidth; per-thread stores, a shared-memory transpose and
-// the TMA store used now all time the same.)
+// the TMA store all time the same with ONE staging box per warp; alternating two boxes
+// (the store of box i reads its buffer while box i + 1 is filled) gained 12 % at 4352 x 3072 x 768.  Issuing the next chunk's
+// tcgen05.ld before processing the current one made the kernel 30 % slower: more TMEM reads in flight beside the MMAs.)
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GtArgs g)
@@ -171,6 +173,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int row = quarter * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         uint8_t* stg = staging + (size_t)(warp - 2) * GT_STG_BYTES;
+        uint32_t box = 0;                                  // TMA store boxes issued by this warp (alternates the two staging halves)
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = w0; tile < ntiles; tile += wstride) {
             const int t2 = tile % per_split;
@@ -241,28 +244,44 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
                 if (g.tma_store) {
-                    // row-per-thread registers -> swizzled 32 x 32 staging box -> one TMA store (full lines, clipped at M / N)
-                    if (lane == 0) tc::bulk_wait_read();           // the previous box of this warp has left the buffer
-                    __syncwarp();
+                    // row-per-thread registers -> swizzled staging box of 32 rows x 64 bytes (32 bf16 or 16 fp32 columns) -> one TMA
+                    // store (full lines, clipped at M / N).  Two boxes per warp alternate: the store of box i reads its buffer
+                    // while box i + 1 is being filled (a single buffer serialised every chunk on the TMA read latency).
+                    auto put_box = [&](const uint4 (&u)[4], int col) {
+                        uint8_t* buf = stg + (box & 1) * (GT_STG_BYTES / 2);
+                        ++box;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // the box before last has left
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u[q];
+                        tc::fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(&tmC), "r"(tc::smem_u32(buf)), "r"(col), "r"(m0 + quarter * 32) : "memory");
+                            tc::bulk_commit();
+                        }
+                    };
                     if (g.out_bf16) {
+                        uint4 u[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            uint4 u;
-                            u.x = tc::pack_bf16x2(v[8 * q], v[8 * q + 1]); u.y = tc::pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-                            u.z = tc::pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); u.w = tc::pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = u;
+                            u[q].x = tc::pack_bf16x2(v[8 * q], v[8 * q + 1]); u[q].y = tc::pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+                            u[q].z = tc::pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); u[q].w = tc::pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
                         }
+                        put_box(u, nb);
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<float4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
-                    tc::fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     ::"l"(&tmC), "r"(tc::smem_u32(stg)), "r"(nb), "r"(m0 + quarter * 32) : "memory");
-                        tc::bulk_commit();
+                        for (int hh = 0; hh < 2; ++hh) {
+                            if (nb + 16 * hh >= g.N) break;         // uniform
+                            uint4 u[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                u[q].x = __float_as_uint(v[16 * hh + 4 * q]); u[q].y = __float_as_uint(v[16 * hh + 4 * q + 1]);
+                                u[q].z = __float_as_uint(v[16 * hh + 4 * q + 2]); u[q].w = __float_as_uint(v[16 * hh + 4 * q + 3]);
+                            }
+                            put_box(u, nb + 16 * hh);
+                        }
                     }
                 } else if (m < g.M) {
                     if (g.out_bf16) {
@@ -497,7 +516,7 @@ int gemm_bf16_launch(const void* A, const void* B, void* C, const float* bias, c
     const int elt = out_bf16 ? 2 : 4;
     g.tma_store = splits == 1 && !accumulate && ((size_t)ldc * elt) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
     if (g.tma_store) {
-        if (int rc = make_tensor_map_2d(&tmC, C, elt, M, N, ldc, 32, 32, out_bf16 ? 64 : 128)) return rc;
+        if (int rc = make_tensor_map_2d(&tmC, C, elt, M, N, ldc, out_bf16 ? 32 : 16, 32, 64)) return rc;      // 32 rows x 64 bytes
     } else tmC = tmA;
     if (splits > 1 && !accumulate) HOPK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
     const long ntiles = (long)tiles_m * tiles_n * splits;
