@@ -61,7 +61,9 @@ def test_loss_curve_tracks_reference(precision, cuda, monkeypatch):
     # exponentially (measured: 1e-6 at step 10, 1e-4 at step 20, 1e-3 at step 50) and after a loss spike near step 100
     # they sit in different basins.  So: step-for-step agreement while the trajectories are numerically comparable,
     # and the same loss level afterwards.  (profiles/r1_loss_curve_*.txt hold the measured curves.)
-    first10, first60 = (2e-4, 5e-3) if precision == 'fp32' else (3e-2, 8e-2)
+    # bf16 mode: the same code gives 2.8 %, 3.4 % and 3.5 % over the first ten steps in three consecutive runs (the order of the
+    # split-K reductions differs from run to run and steps 8-9 already amplify it): 5 % bounds the first ten, 8 % the first sixty.
+    first10, first60 = (2e-4, 5e-3) if precision == 'fp32' else (5e-2, 8e-2)
     assert rel[:10].max() < first10, rel[:10]
     assert rel[:60].max() < first60, (rel[:60].max(), int(rel[:60].argmax()))
     tail_ref, tail_got = ref[100:, 0].mean(), got[100:, 0].mean()
