@@ -49,10 +49,14 @@ class _Bucket:
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
 
-    def unpack(self):
-        """Averaged wire buffer -> the fp32 views handed to the optimiser."""
+    def widen(self):
+        """Averaged wire buffer -> the flat fp32 buffer (no-op for an fp32 wire).  Issued on the communication stream right
+        behind the bucket's all-reduce, so only the last bucket's copy is left for the end of backward."""
         if self.flat32 is not self.flat:
             self.flat32.copy_(self.flat)
+
+    def unpack(self):
+        """Hand the averaged fp32 views to the optimiser."""
         for v, p in zip(self.views32, self.params):
             if p.grad is not None:
                 p.grad = v
@@ -217,11 +221,14 @@ class DataParallel:
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
                 b.work = dist.all_reduce(b.flat, op=self._avg, group=self.group, async_op=True)
+                b.work.wait()                                   # orders the communication stream (not the host) behind the collective
+                b.widen()
         else:
             b.work = dist.all_reduce(b.flat, op=self._avg, group=self.group, async_op=True)
+            b.work.wait()
             if self._avg is dist.ReduceOp.SUM:                  # gloo (CPU tests) has no AVG: scale after the sum
-                b.work.wait()
                 b.flat.div_(self.world)
+            b.widen()
         self.stats['allreduce_bytes'] += b.numel * b.flat.element_size()
         self.stats['buckets'] += 1
 
