@@ -9,13 +9,14 @@
 // B is [K][N]) -- so dX = dY @ W (B MN-major) and dW = dY^T @ X (both MN-major) need no transposed copies.
 //
 // Kernel anatomy (persistent, warp specialised, one CTA per SM):
-//   warp 0   producer: cp.async.bulk.tensor.2d (TMA, 128B swizzle) fills a ring of STAGES x (A 16 KB | B 16/32 KB) slabs,
-//            completion by mbarrier complete_tx
+//   warp 0   producer: cp.async.bulk.tensor.2d (TMA, 128B swizzle) fills a ring of STAGES x (A 16 KB | B 16 / 24 / 32 KB)
+//            slabs, completion by mbarrier complete_tx
 //   warp 1   MMA issuer: one lane issues tcgen05.mma (M 128, N = BN, K 16, 4 per 64-wide K block) into one of two TMEM
 //            accumulators; tcgen05.commit releases the ring slot / publishes the accumulator
 //   warps 2-9  epilogue (two warps per TMEM lane quarter, interleaved 32-column chunks): tcgen05.ld (row per thread), bias /
-//            residual / activation / conversion, 256-bit
-//            (fp32) or 128-bit (bf16) global stores, or vector atomics for split-K
+//            residual / activation / derivative mask / conversion, then a TMA tensor store out of two alternating swizzled
+//            staging boxes per warp (per-thread stores when C's rows are not 16-byte multiples; vector reductions for split-K)
+// Launched with programmatic stream serialisation: the prologue overlaps the preceding kernel's tail.
 // The second accumulator lets the MMAs of tile i+1 run under the epilogue of tile i.
 #include <cuda.h>
 #include <stdlib.h>
