@@ -907,6 +907,15 @@ extern "C" int hopk_gru_backward(const HopkGruShape* s, const HopkGruParams* p, 
     GruSide* side = gru_side();
     HOPK_REQUIRE(side != nullptr, "gru backward: side stream");
     cudaStream_t ss = side->s;
+    struct JoinOnError {                                 // an early error return still joins the side stream (graph capture)
+        GruSide* sd; cudaStream_t st; bool armed;
+        ~JoinOnError()
+        {
+            if (!armed) return;
+            if (cudaEventRecord(sd->ev_done[0], sd->s) == cudaSuccess) cudaStreamWaitEvent(st, sd->ev_done[0], 0);
+            cudaGetLastError();
+        }
+    } join_guard{side, st, true};
     for (int l = L - 1; l >= 0; --l) {
         const int Iin = l == 0 ? s->I : 2 * H;
         const int Ipad = g.Ipad[l];
@@ -955,5 +964,6 @@ extern "C" int hopk_gru_backward(const HopkGruShape* s, const HopkGruParams* p, 
         }
     }
     for (int l = 0; l < L && l < 2; ++l) HOPK_CUDA(cudaStreamWaitEvent(st, side->ev_done[l], 0));   // join (ev_done[l] orders all later layers)
+    join_guard.armed = false;
     return 0;
 }

@@ -1169,6 +1169,19 @@ struct SideStreams {
 // created once per device (keyed by the current device, so a process that drives several GPUs gets streams and events
 // on the right one); non-blocking so they never serialise against stream 0.  Calls on one device are expected from one
 // host thread at a time (the autograd thread of that device's rank): events are reused from call to call.
+// Joins the side streams into `st` when a backward entry point leaves early with an error, so that a caller that is
+// capturing a CUDA graph can still end the capture cleanly (errors of the join itself are ignored: the call already failed).
+struct SideJoinOnError {
+    SideStreams* sd; cudaStream_t st; bool armed;
+    ~SideJoinOnError()
+    {
+        if (!armed) return;
+        for (int k = 0; k < 3; ++k)
+            if (cudaEventRecord(sd->ev_join[k], sd->s[k]) == cudaSuccess) cudaStreamWaitEvent(st, sd->ev_join[k], 0);
+        cudaGetLastError();
+    }
+};
+
 static SideStreams* side_streams()
 {
     constexpr int MAXDEV = 64;
@@ -1433,6 +1446,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
 
     SideStreams* sd = side_streams();
     if (!sd) return fail(3, "side streams", "cudaStreamCreate failed");
+    SideJoinOnError join_guard{sd, st, true};
 #ifdef HOPK_DEBUG
     static const bool skip_side = getenv("HOPK_BWD_SKIP_SIDE") != nullptr;     // timing experiments only: wrong gradients
 #else
@@ -1659,6 +1673,7 @@ extern "C" int hopk_gwnet_backward(const HopkGwnetShape* s, const HopkGwnetParam
         HOPK_CUDA(cudaEventRecord(sd->ev_join[k], sd->s[k]));
         HOPK_CUDA(cudaStreamWaitEvent(st, sd->ev_join[k], 0));
     }
+    join_guard.armed = false;
     return 0;
 }
 
